@@ -1,0 +1,410 @@
+// bf16 tensor-core path of avdf_conv_gemm for sm_100a: TMA-fed, warp-specialised, persistent
+// implicit-GEMM 1-D convolution on tcgen05 with the accumulator in TMEM and the whole
+// MaskedConv1D -> (+bias) -> mask -> LayerNorm -> activation -> (+PE) -> residual epilogue fused.
+//
+// Tile: 128 output tokens x BN (<=256) output channels, K stepped in 64-channel blocks per tap.
+//   warp 0      TMA producer: A = 4-D box (64 ch, parity, TT steps, BB videos) of the token-major
+//               activation -- conv taps are shifted boxes, zero padding is TMA out-of-bounds fill,
+//               stride 2 is the parity dimension; W = 2-D box (64, BN) of the [N, taps*C] weights.
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM),
+//               tcgen05.commit releases smem stages / publishes the accumulator.
+//   warp 2      TMEM allocator (512 columns = two 256-column accumulators, double buffered).
+//   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns), one output row per thread, two passes
+//               over TMEM when LayerNorm is fused (row statistics, then normalise + store).
+// smem ring: 4 stages x (16 KB A + 32 KB W), 128B-swizzled, mbarrier full/empty pairs.
+#include <cuda.h>
+#include <string.h>
+#include "gemm_common.cuh"
+
+namespace avdf {
+namespace tc {
+
+constexpr int BM = 128, BK = 64, STAGES = 4, MAX_BN = 256;
+constexpr int A_STAGE = BM * BK * 2;          // 16384
+constexpr int B_STAGE = MAX_BN * BK * 2;      // 32768
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*barriers*/ + 4 * MAX_BN * 4 /*epilogue vectors*/ + 1024 /*align slack*/;
+constexpr int THREADS = 256;
+
+struct Params {
+  CUtensorMap a_map[AVDF_MAX_LEVELS];
+  CUtensorMap w_map;
+  SegInfo seg;
+  int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
+  int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
+  int n_out, c_in, taps, stride, bn, n_tiles_n, total_tiles;
+  unsigned idesc;
+  EpiParams epi;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (surfaced as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("avdf gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
+// start address >> 4, LBO unused (0), SBO = 1024 B >> 4, descriptor version 1 (sm_100), layout SWIZZLE_128B (2).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct TileCoord { int seg, b0, t0, tt, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
+  TileCoord c;
+  const int mt = tile / p.n_tiles_n;
+  c.n0 = (tile - mt * p.n_tiles_n) * p.bn;
+  int s = 0;
+  while (s + 1 < p.seg.n_seg && mt >= p.seg_tile_start[s + 1]) ++s;
+  c.seg = s;
+  c.tt = p.seg_tt[s];
+  const int local = mt - p.seg_tile_start[s];
+  const int tblocks = p.seg.t_out[s] / c.tt;
+  const int bb = local / tblocks;
+  c.t0 = (local - bb * tblocks) * c.tt;
+  c.b0 = bb * (BM / c.tt);
+  return c;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024 B alignment for the 128B swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + STAGES * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024);   // 4 x MAX_BN floats
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.seg.n_seg; ++s)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.w_map) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int kb_per_tap = p.c_in / BK;
+  const int k_iters = p.taps * kb_per_tap;
+  const uint32_t stage_bytes = (uint32_t)A_STAGE + (uint32_t)p.bn * BK * 2;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc_ = decode_tile(p, tile);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int d = tap - (p.taps >> 1);
+          int par = 0, dt = d;
+          if (p.stride == 2) { par = d & 1; dt = (d - par) / 2; }
+          for (int kb = 0; kb < kb_per_tap; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+            tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), kb * BK, par, tc_.t0 + dt, tc_.b0);
+            tma_load_2d(smem_u32(smem_b + stage * B_STAGE), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * A_STAGE));
+          const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * B_STAGE));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)          // +32 B per K=16 step inside the swizzle atom
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (ki == k_iters - 1) umma_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue (one output row per thread)
+    const EpiParams& e = p.epi;
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int N = p.n_out;
+    const int et = threadIdx.x - 128;            // 0..127 among the epilogue threads
+    float* s_bias = epi_smem; float* s_lnw = epi_smem + MAX_BN; float* s_lnb = epi_smem + 2 * MAX_BN; float* s_gam = epi_smem + 3 * MAX_BN;
+    int it = 0, loaded_n0 = -1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc_ = decode_tile(p, tile);
+      if (tc_.n0 != loaded_n0) {                 // per-channel epilogue vectors of this n-tile -> smem
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < p.bn; i += 128) {
+          s_bias[i] = e.bias ? __ldg(e.bias + tc_.n0 + i) : 0.f;
+          s_lnw[i] = e.ln_w ? __ldg(e.ln_w + tc_.n0 + i) : 1.f;
+          s_lnb[i] = e.ln_b ? __ldg(e.ln_b + tc_.n0 + i) : 0.f;
+          s_gam[i] = e.gamma ? __ldg(e.gamma + tc_.n0 + i) : 1.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        loaded_n0 = tc_.n0;
+      }
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int b = tc_.b0 + r / tc_.tt;
+      const int t = tc_.t0 + (r & (tc_.tt - 1));
+      const bool valid = b < p.seg.batch;
+      const size_t orow = valid ? ((size_t)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t) : 0;
+      const float mk = (valid && e.row_mask) ? (e.row_mask[orow] ? 1.f : 0.f) : 1.f;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
+      const int chunks = p.bn >> 5;
+      float mean = 0.f, rstd = 1.f;
+      if (e.ln_w) {
+        float s = 0.f, ss = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) {
+          float v[32];
+          tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = (v[i] + s_bias[ch * 32 + i]) * mk;
+            s += x; ss = fmaf(x, x, ss);
+          }
+        }
+        mean = s / (float)p.bn;
+        const float var = fmaxf(ss / (float)p.bn - mean * mean, 0.f);
+        rstd = rsqrtf(var + 1e-5f);
+      }
+      for (int ch = 0; ch < chunks; ++ch) {
+        float v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        if (ch == chunks - 1) {                   // all TMEM reads of this accumulator are done
+          tcgen05_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        if (!valid) continue;
+        const int n = tc_.n0 + ch * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = (v[i] + s_bias[ch * 32 + i]) * mk;
+          if (e.ln_w) x = (x - mean) * rstd * s_lnw[ch * 32 + i] + s_lnb[ch * 32 + i];
+          v[i] = apply_act(x, e.act);
+        }
+        if (e.pe) {
+          const float4* pe = reinterpret_cast<const float4*>(e.pe + (size_t)t * N + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 f = __ldg(pe + i);
+            v[4 * i] += f.x * mk; v[4 * i + 1] += f.y * mk; v[4 * i + 2] += f.z * mk; v[4 * i + 3] += f.w * mk;
+          }
+        }
+        if (e.residual) {
+          const float4* rs = reinterpret_cast<const float4*>(e.residual + orow * N + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 f = __ldg(rs + i);
+            const float* g = s_gam + ch * 32 + 4 * i;
+            v[4 * i] = f.x * mk + g[0] * v[4 * i]; v[4 * i + 1] = f.y * mk + g[1] * v[4 * i + 1];
+            v[4 * i + 2] = f.z * mk + g[2] * v[4 * i + 2]; v[4 * i + 3] = f.w * mk + g[3] * v[4 * i + 3];
+          }
+        }
+        if (e.out_f32) {
+          float4* o = reinterpret_cast<float4*>(e.out_f32 + orow * N + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (e.out_bf16) {
+          uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + orow * N + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            o[i] = u;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace tc
+
+int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
+  using namespace tc;
+  AVDF_CHECK_ARG(a->c_in % BK == 0, "bf16 path: c_in must be a multiple of 64");
+  AVDF_CHECK_ARG(a->n_out % 32 == 0, "bf16 path: n_out must be a multiple of 32");
+  const int bn = a->n_out >= MAX_BN ? MAX_BN : a->n_out;
+  AVDF_CHECK_ARG(a->n_out % bn == 0, "bf16 path: n_out must be <= 256 or a multiple of 256");
+  AVDF_CHECK_ARG(bn % 16 == 0 && bn >= 32, "bf16 path: unsupported n_out");
+  AVDF_CHECK_ARG(!a->ln_w || a->n_out == bn, "bf16 path: fused LayerNorm needs n_out <= 256");
+  AVDF_CHECK_ARG(a->stride == 1 || a->taps == 3 || a->taps == 1, "bad stride/taps");
+  AVDF_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0, "operands must be 16-byte aligned");
+  EncodeFn encode = get_encode();
+  if (!encode) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled not available from the driver"); return AVDF_ERR_CUDA; }
+
+  static Params p;     // large; filled per call, copied into the launch by value
+  memset(&p, 0, sizeof(p));
+  fill_seg(a, p.seg);
+  fill_epi(a, p.epi);
+  p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.bn = bn;
+  p.n_tiles_n = a->n_out / bn;
+  int tiles = 0;
+  for (int s = 0; s < a->n_seg; ++s) {
+    const int T = a->seg_t_out[s];
+    int tt = T & (-T);
+    if (tt > BM) tt = BM;
+    p.seg_tt[s] = tt;
+    const int bb = BM / tt;
+    p.seg_tile_start[s] = tiles;
+    tiles += (T / tt) * ceil_div(a->batch, bb);
+    // A view of this level: dims (c, parity, t, b)
+    const cuuint64_t t_in = (cuuint64_t)T * a->stride;
+    cuuint64_t dims[4] = {(cuuint64_t)a->c_in, (cuuint64_t)a->stride, (cuuint64_t)T, (cuuint64_t)a->batch};
+    cuuint64_t strides[3] = {(cuuint64_t)a->c_in * 2, (cuuint64_t)a->c_in * 2 * a->stride, (cuuint64_t)a->a_rows_per_video * a->c_in * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, 1u, (cuuint32_t)tt, (cuuint32_t)bb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    (void)t_in;
+    void* base = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(a->a)) + (size_t)a->seg_a_row[s] * a->c_in * 2;
+    CUresult r = encode(&p.a_map[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(A, level %d) failed with %d", s, (int)r); return AVDF_ERR_CUDA; }
+  }
+  p.seg_tile_start[a->n_seg] = tiles;
+  p.total_tiles = tiles * p.n_tiles_n;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a->taps * a->c_in, (cuuint64_t)a->n_out};
+    cuuint64_t strides[1] = {(cuuint64_t)a->taps * a->c_in * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(W) failed with %d", (int)r); return AVDF_ERR_CUDA; }
+  }
+  // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+  if (p.total_tiles == 0) return AVDF_OK;
+
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    AVDF_CUDA(cudaGetDevice(&dev));
+    AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  }
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  conv_gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  return check_launch("conv_gemm_tc_kernel");
+}
+
+}  // namespace avdf

@@ -1,0 +1,101 @@
+// K1: fixed-length linear resampling + channel concat of the per-stream features.
+//
+// Replaces libs/datasets/deepfake_video_audio.py:513-547 (DeepFakeVideoAudioDatasetInfer3.__getitem__:
+// F.interpolate(size=max_seq_len, mode='linear', align_corners=False) per stream, torch.cat along C)
+// and the [C,T] -> device copy of av_fd_no_recon.py:431-479. Output is token-major [B, T_out, C_total]
+// (channel-last: what the conv-GEMM's TMA boxes want), bf16 or fp32.
+//
+// Index math is ATen's area_pixel_compute_source_index with the two FMAs its vectorised CPU kernel
+// executes, so fp32 output is bit-identical to F.interpolate (oracle/interp_ref.py):
+//   scale = T_in / T_out (fp32);  src = max(0, fma(scale, t + 0.5, -0.5));  i0 = (int)src
+//   i1 = i0 + (i0 < T_in - 1);  l1 = src - i0;  l0 = 1 - l1;  out = fma(l0, x[i0], l1 * x[i1])
+//
+// HBM-bound streaming kernel: one thread = 8 consecutive channels of one output row (2x float4 loads
+// from each of the two source rows, one 16 B (bf16) or two 16 B (fp32) stores); rows of a warp are
+// contiguous in C so every access is a fully coalesced 128 B+ line. Algorithmic bytes per video:
+// 4 * sum_s(T_s * C_s) read + T_out * C_total * sizeof(out) written.
+#include "common.cuh"
+
+namespace avdf {
+
+struct InterpParams {
+  const float* src[3];         // packed rows of all videos, per stream: [sum_b T_s(b), C_s]
+  const int* row_off[3];       // [B+1] prefix offsets (rows) per stream
+  int c[3];                    // channels per stream (0 = stream absent)
+  int c_off[3];                // channel offset in the concatenated output
+  int c_total, t_out, B;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) interp_concat_kernel(const InterpParams p, OutT* __restrict__ out) {
+  const int groups_per_row = p.c_total >> 3;
+  const long long total = (long long)p.B * p.t_out * groups_per_row;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(g % groups_per_row);
+    const long long row = g / groups_per_row;
+    const int t = (int)(row % p.t_out);
+    const int b = (int)(row / p.t_out);
+    const int ch = cg << 3;
+    const int s = (ch >= p.c_off[2] && p.c[2] > 0) ? 2 : ((ch >= p.c_off[1] && p.c[1] > 0) ? 1 : 0);
+    const int cs = ch - p.c_off[s];
+    const int r0 = p.row_off[s][b];
+    const int t_in = p.row_off[s][b + 1] - r0;
+    const float* base = p.src[s] + (size_t)r0 * p.c[s] + cs;
+    float v[8];
+    if (t_in == p.t_out) {
+      Row8<float>::load(base + (size_t)t * p.c[s], v);
+    } else {
+      const float scale = __fdiv_rn((float)t_in, (float)p.t_out);
+      float src = __fmaf_rn(scale, __fadd_rn((float)t, 0.5f), -0.5f);
+      src = src < 0.f ? 0.f : src;
+      const int i0 = (int)src;
+      const int i1 = i0 + (i0 < t_in - 1 ? 1 : 0);
+      const float l1 = __fsub_rn(src, (float)i0);
+      const float l0 = __fsub_rn(1.f, l1);
+      float a[8], c[8];
+      Row8<float>::load(base + (size_t)i0 * p.c[s], a);
+      Row8<float>::load(base + (size_t)i1 * p.c[s], c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __fmaf_rn(l0, a[k], __fmul_rn(l1, c[k]));
+    }
+    Row8<OutT>::store(out + (size_t)row * p.c_total + ch, v);
+  }
+}
+
+}  // namespace avdf
+
+using namespace avdf;
+
+extern "C" int avdf_interp_concat(const float* video, const float* byola, const float* emo,
+                                  const int32_t* video_off, const int32_t* byola_off, const int32_t* emo_off,
+                                  int32_t batch, int32_t c_video, int32_t c_byola, int32_t c_emo, int32_t t_out,
+                                  void* out, int32_t out_dtype, void* stream) {
+  AVDF_CHECK_ARG(batch >= 0 && t_out > 0, "bad batch / t_out");
+  AVDF_CHECK_ARG(c_video >= 0 && c_byola >= 0 && c_emo >= 0, "negative channel count");
+  AVDF_CHECK_ARG((c_video % 8 | c_byola % 8 | c_emo % 8) == 0, "channel counts must be multiples of 8");
+  AVDF_CHECK_ARG(c_video + c_byola + c_emo > 0, "no stream");
+  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_ARG((c_video == 0 || (video && video_off)) && (c_byola == 0 || (byola && byola_off)) &&
+                 (c_emo == 0 || (emo && emo_off)), "null stream pointer");
+  AVDF_CHECK_ARG(out != nullptr, "out is null");
+  if (batch == 0) return AVDF_OK;
+  InterpParams p{};
+  p.src[0] = video; p.src[1] = byola; p.src[2] = emo;
+  p.row_off[0] = video_off; p.row_off[1] = byola_off; p.row_off[2] = emo_off;
+  p.c[0] = c_video; p.c[1] = c_byola; p.c[2] = c_emo;
+  p.c_off[0] = 0; p.c_off[1] = c_video; p.c_off[2] = c_video + c_byola;
+  p.c_total = c_video + c_byola + c_emo; p.t_out = t_out; p.B = batch;
+  const long long total = (long long)batch * t_out * (p.c_total / 8);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long want = (total + 255) / 256;
+  int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);   // grid-stride, 16 CTAs of 256 per SM
+  if (grid < 1) grid = 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == AVDF_DTYPE_BF16)
+    interp_concat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    interp_concat_kernel<float><<<grid, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
+  return check_launch("interp_concat_kernel");
+}

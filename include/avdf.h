@@ -1,0 +1,201 @@
+/*
+ * avdf.h — C-ABI of libavdf_sm100.so: the B200 (sm_100a) kernels behind the temporal-localization
+ * inference path of audio-visual/Audio_Visual_Deepfake_Detection.
+ *
+ * Conventions
+ *   - every entry point returns AVDF_OK (0) or a negative AVDF_ERR_* code and never throws;
+ *     avdf_last_error() returns the message of the calling thread's last failure;
+ *   - all pointers are DEVICE pointers owned by the caller unless a comment says "host";
+ *     nothing is allocated behind the caller's back (scratch comes in through workspace
+ *     pointers whose size is queried with the matching *_workspace_bytes function);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - activations are token-major ("channel-last"): [batch, rows_per_video, channels], channels
+ *     contiguous; weights of a conv with k taps are [c_out, k * c_in] with the tap index outermost
+ *     inside a row (W[co][j * c_in + ci] = reference weight[co][ci][j]).
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   avdf_nms_hard / avdf_nms_soft   pybind11 module nms_1d_cpu {nms, softnms},
+ *                                   libs/utils/csrc/nms_cpu.cpp:19-58, 67-160, 172-182
+ *   avdf_postprocess                libs/modeling/av_fd_no_recon.py:760-876 (inference_single_video,
+ *                                   postprocessing) + libs/utils/nms.py:8-190 (NMSop, SoftNMSop,
+ *                                   seg_voting, batched_nms)
+ *   avdf_interp_concat              libs/datasets/deepfake_video_audio.py:513-547 (F.interpolate x3 + cat)
+ *   avdf_conv_gemm                  MaskedConv1D (libs/modeling/blocks.py:13-63) as used by the
+ *                                   embedding (backbones.py:437-445), the 1x1 projections and MLP of the
+ *                                   transformer blocks (blocks.py:1169-1171,1223,1291-1297), FPN laterals
+ *                                   (necks.py:69-73), head towers (av_fd_no_recon.py:75-89,144-159) and
+ *                                   DownBlock convs (blocks.py:1495-1516), with LayerNorm (blocks.py:70-112),
+ *                                   activation, positional encoding and residual/AffineDropPath fused
+ *   avdf_ln_dwconv_ln               LN -> depthwise MaskedConv1D(k3, stride) -> LN of LocalMaskedMHCA /
+ *                                   LocalMaskedMMHCA (blocks.py:1159-1165, 726-741) incl. the nearest
+ *                                   up/down-sampling of backbones.py:487,490 and MaxPool1d skip (blocks.py:1277-1281)
+ *   avdf_attention                  banded / global softmax attention (blocks.py:977-1224, 274-313)
+ *   avdf_ln_rows                    LayerNorm before the MLP (blocks.py:1311)
+ *   avdf_instnorm_lrelu             InstanceNorm1d + LeakyReLU of DownBlock (blocks.py:1508-1515)
+ *   avdf_fpn_fuse                   FPN1D top-down sum + depthwise conv + LN (necks.py:75-93)
+ *   avdf_head_final                 last conv of the cls / reg heads + Scale + ReLU (av_fd_no_recon.py:82-89,152-159)
+ *   avdf_vcls_exp12 / _exp13        video-level classifier tails (blocks.py:1608-1626, 1682-1700)
+ */
+#ifndef AVDF_H_
+#define AVDF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVDF_ABI_VERSION 1
+#define AVDF_MAX_LEVELS 8
+#define AVDF_MAX_SEGS 1024
+
+enum { AVDF_OK = 0, AVDF_ERR_INVALID = -1, AVDF_ERR_CUDA = -2, AVDF_ERR_UNSUPPORTED = -3 };
+enum { AVDF_DTYPE_F32 = 0, AVDF_DTYPE_BF16 = 1 };
+enum { AVDF_ACT_NONE = 0, AVDF_ACT_RELU = 1, AVDF_ACT_GELU = 2 };
+
+/* ---- runtime ---- */
+int avdf_abi_version(void);
+const char* avdf_last_error(void);
+/* fills SM count and compute capability of the current device */
+int avdf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- K1: per-stream linear resize to t_out + channel concat (video | byola | emo) ----
+ * Streams are packed row-major [sum_b T_s(b), C_s] fp32 with per-stream prefix offsets [batch+1]
+ * (rows). A stream with C_s == 0 is absent. out: [batch, t_out, c_video+c_byola+c_emo]. */
+int avdf_interp_concat(const float* video, const float* byola, const float* emo,
+                       const int32_t* video_off, const int32_t* byola_off, const int32_t* emo_off,
+                       int32_t batch, int32_t c_video, int32_t c_byola, int32_t c_emo, int32_t t_out,
+                       void* out, int32_t out_dtype, void* stream);
+
+/* ---- NMS: same contracts as nms_1d_cpu.nms / nms_1d_cpu.softnms, on device memory ----
+ * segs [n,2], scores [n]; out_idx [n] int64 (kept input indices, descending score / pick order);
+ * out_count [1]. max_num <= 0: run to completion (the reference's behaviour); max_num > 0: stop after
+ * that many picks (the wrappers consume no more, nms.py:29-30,56-63). dets [n,3] is written in place
+ * for the picks, like the reference. */
+size_t avdf_nms_workspace_bytes(int32_t n);
+int avdf_nms_hard(const float* segs, const float* scores, int32_t n, float iou_threshold, int32_t max_num,
+                  int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+int avdf_nms_soft(const float* segs, const float* scores, int32_t n, float* dets, float iou_threshold,
+                  float sigma, float min_score, int32_t method, int32_t max_num, int64_t* out_idx,
+                  int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- decode + batched_nms + seconds conversion, one CTA per video ---- */
+typedef struct avdf_postprocess_args {
+  int32_t batch;
+  /* decode inputs (logits == NULL: candidates are provided in cand_* instead) */
+  const float* logits;           /* [batch, P]      P = sum(level_len), level-major per video */
+  const float* offsets;          /* [batch, P, 2]   */
+  const uint8_t* mask;           /* [batch, P]      */
+  int32_t n_levels;
+  int32_t level_len[AVDF_MAX_LEVELS];
+  float level_stride[AVDF_MAX_LEVELS];
+  float pre_nms_thresh; int32_t pre_nms_topk; float duration_thresh;
+  /* candidates: written by decode (and read by voting), or given */
+  float* cand_segs;              /* [batch, cand_cap, 2] */
+  float* cand_scores;            /* [batch, cand_cap]    */
+  int32_t* cand_count;           /* [batch]              */
+  int32_t cand_cap;
+  /* batched_nms (class-agnostic path, nms.py:160-190) */
+  float iou_threshold, min_score, sigma, voting_thresh;
+  int32_t max_seg_num, use_soft_nms, soft_method;
+  /* seconds conversion (all NULL: stay on the feature grid) */
+  const float* vid_feat_stride;  /* [batch] */
+  const float* vid_half_nframes; /* [batch] 0.5 * feat_num_frames */
+  const float* vid_fps;          /* [batch] */
+  const float* vid_duration;     /* [batch] */
+  /* outputs, sorted by descending score */
+  float* out_segs;               /* [batch, max_seg_num, 2] */
+  float* out_scores;             /* [batch, max_seg_num]    */
+  int32_t* out_count;            /* [batch]                 */
+  void* workspace; size_t workspace_bytes;
+} avdf_postprocess_args;          /* host struct */
+size_t avdf_postprocess_workspace_bytes(int32_t batch, int32_t cand_cap);
+int avdf_postprocess(const avdf_postprocess_args* args, void* stream);
+
+/* ---- conv-as-GEMM with fused epilogue ----
+ * out[b, seg_o_row + t, n] = epi( sum_{j<taps} sum_{c<c_in} W[n, j*c_in + c] * A[b, seg_a_row + stride*t + j - taps/2, c] )
+ * (rows outside [0, stride * seg_t_out) of the level read as zero), for every level `seg`.
+ * epi(v): v += bias[n]; v *= mask[row]; v = LN_n(v) * ln_w + ln_b; v = act(v); v += pe[t, n] * mask[row];
+ *         v = residual[row, n] * mask[row] + gamma[n] * v            (each step only if its pointer is set)
+ * dtype F32 -> fp32 CUDA-core path (parity mode); BF16 -> TMA + tcgen05 tensor-core path, fp32 accumulate. */
+typedef struct avdf_conv_gemm_args {
+  int32_t batch, n_out, c_in, taps, stride, n_seg;
+  int32_t seg_t_out[AVDF_MAX_LEVELS];
+  int32_t seg_a_row[AVDF_MAX_LEVELS];
+  int32_t seg_o_row[AVDF_MAX_LEVELS];
+  int64_t a_rows_per_video, o_rows_per_video;
+  const void* a;                 /* [batch, a_rows_per_video, c_in] */
+  const void* w;                 /* [n_out, taps * c_in] */
+  int32_t dtype;
+  const float* bias; const uint8_t* row_mask; const float* ln_w; const float* ln_b; int32_t act;
+  const float* pe; const float* residual; const float* gamma;
+  float* out_f32; void* out_bf16;   /* [batch, o_rows_per_video, n_out] */
+  void* workspace; size_t workspace_bytes;
+} avdf_conv_gemm_args;            /* host struct */
+size_t avdf_conv_gemm_workspace_bytes(const avdf_conv_gemm_args* args);
+int avdf_conv_gemm(const avdf_conv_gemm_args* args, void* stream);
+
+/* ---- LN -> depthwise conv k3 (stride 1|2) * mask -> LN, for up to 3 streams sharing one source ----
+ * src [batch, t_src, C] fp32. Virtual input position p in [0, t_virt) reads source row
+ * (shift >= 0 ? p >> shift : p << -shift)  (nearest up / down-sampling of backbones.py:487,490).
+ * out_s[b, t', :] = LN_out_s( (sum_j dw_s[:, j] * u_s[stride*t' + j - 1]) * mask_out[b, t'] ),
+ * u_s[p] = LN(src[map(p)]) * ln_in_w_s + ln_in_b_s inside [0, t_virt), 0 outside.
+ * skip_out (optional, stride 2): MaxPool1d(3, 2, 1) of the raw source rows. */
+typedef struct avdf_ln_dwconv_ln_args {
+  int32_t batch, channels, t_src, t_virt, shift, stride, n_streams;
+  const float* src;
+  const uint8_t* mask_out;       /* [batch, t_virt / stride] */
+  const float* ln_in_w[3]; const float* ln_in_b[3];
+  const float* dw_w[3];          /* [C, 3] */
+  const float* ln_out_w[3]; const float* ln_out_b[3];
+  void* out[3];                  /* [batch, t_virt / stride, C] */
+  int32_t out_dtype;
+  float* skip_out;               /* [batch, t_virt / stride, C] fp32 or NULL */
+} avdf_ln_dwconv_ln_args;
+int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* args, void* stream);
+
+/* ---- multi-head attention over q,k,v [batch, t, C]; window > 1: band |i-j| <= window/2 with additive
+ * -1e4 on masked keys and zeroed masked query rows (blocks.py:1152-1224); window <= 1: global with
+ * -inf on masked keys (blocks.py:274-313). out [batch, t, C]. */
+int avdf_attention(const void* q, const void* k, const void* v, const uint8_t* kv_mask, void* out,
+                   int32_t dtype, int32_t batch, int32_t t, int32_t channels, int32_t n_head, int32_t window,
+                   void* stream);
+
+/* ---- LayerNorm over channels of fp32 rows -> fp32 or bf16 ---- */
+int avdf_ln_rows(const float* x, const float* w, const float* b, void* out, int32_t out_dtype, int64_t rows,
+                 int32_t channels, void* stream);
+
+/* ---- InstanceNorm1d over T (per video, channel; eps 1e-5, biased) + LeakyReLU(slope) ---- */
+int avdf_instnorm_lrelu(const float* x, void* out, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels,
+                        float slope, void* stream);
+
+/* ---- FPN top-down fuse: L_l[t] = sum_{j>=l} lat_j[t >> (j-l)]; F_l = LN_l(dwconv3_l(L_l) * mask) ----
+ * lat / out are pyramids [batch, P, C] with levels concatenated per video. dw_w [n_levels, C, 3],
+ * ln_w / ln_b [n_levels, C]. */
+int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float* dw_w, const float* ln_w, const float* ln_b,
+                  void* out, int32_t out_dtype, int32_t batch, int32_t channels, int32_t n_levels,
+                  const int32_t* level_len /* host */, void* stream);
+
+/* ---- last conv (k3) of both heads: logits [batch,P] = cls_w . x_cls + cls_b (* mask);
+ * offsets [batch,P,2] = relu((reg_w . x_reg + reg_b) * mask * scale_l). Towers are pyramids [batch,P,C]. */
+int avdf_head_final(const void* cls_feat, const void* reg_feat, int32_t dtype, const uint8_t* mask,
+                    const float* cls_w /* [1,3*C] */, const float* cls_b, const float* reg_w /* [2,3*C] */,
+                    const float* reg_b, const float* level_scale /* host [n_levels] */, float* logits,
+                    float* offsets, int32_t batch, int32_t channels, int32_t n_levels,
+                    const int32_t* level_len /* host */, void* stream);
+
+/* ---- video-level classifier tails ---- */
+/* exp12 (blocks.py:1608-1626): z [batch, t, C] (after the last DownBlock) -> logit [batch] */
+int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* lin1_w /* [C,2C] */,
+                    const float* ln_w, const float* ln_b, const float* lin2_w /* [C] */, const float* lin2_b,
+                    float* out, int32_t batch, int32_t t, int32_t channels, void* stream);
+/* exp13 (blocks.py:1682-1700): z [batch, t, C] -> logit [batch] */
+int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* seg_w /* [C] */,
+                    const float* seg_b, const float* cls_w /* [2] */, const float* cls_b, float* out,
+                    int32_t batch, int32_t t, int32_t channels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVDF_H_ */
