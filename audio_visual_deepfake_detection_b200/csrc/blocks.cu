@@ -1,0 +1,736 @@
+// HBM-bound kernels of the ConvTransformer blocks, the FPN and the head / video-level tails.
+// All activations are token-major [batch, T, C] with C contiguous; one warp owns one row of
+// C = 256 channels (lane l holds channels 8l .. 8l+7: a 1 KB fp32 row is one fully coalesced
+// 2 x 512 B request, a bf16 row one 512 B request), row statistics are warp shuffles.
+//
+// Reference code restated (paths relative to the reference root):
+//   ln_dwconv_ln     LayerNorm (libs/modeling/blocks.py:97-112) -> depthwise MaskedConv1D k3
+//                    (blocks.py:41-63; q/k/v convs of LocalMaskedMHCA :1159-1165, LocalMaskedMMHCA
+//                    :726-741, MaskedMHCA :291-297) -> LayerNorm; the nearest up/down-sampling between
+//                    scales (libs/modeling/backbones.py:487,490) is an index map on the source rows,
+//                    and the stride-2 skip MaxPool1d(3,2,1) (blocks.py:1277-1281) is a by-product.
+//   attention        banded softmax attention == the sliding-chunk code of blocks.py:977-1224
+//                    (verified to 1.8e-7) and the global MaskedMHCA blocks.py:299-309
+//   ln_rows          blocks.py:97-112 (ln2 before the MLP, blocks.py:1311)
+//   instnorm_lrelu   nn.InstanceNorm1d + LeakyReLU(0.2) of DownBlock, blocks.py:1508-1515
+//   fpn_fuse         FPN1D.forward top-down path + fpn_convs + fpn_norms, libs/modeling/necks.py:75-93
+//   head_final       cls_head / offset_head + Scale + ReLU, libs/modeling/av_fd_no_recon.py:82-89,152-159
+//   vcls_exp12       DeepInterpolator.classifier, blocks.py:1608-1626
+//   vcls_exp13       SegmentandCls.segment, blocks.py:1682-1700
+#include <math.h>
+#include "common.cuh"
+
+namespace avdf {
+
+constexpr float kLnEps = 1e-5f;
+constexpr int kC = 256;               // channels handled by the warp-per-row kernels
+
+// mean / 1/sqrt(var+eps) of one 256-channel row spread over a warp (8 values per lane), two-pass
+__device__ __forceinline__ void row_stats(const float (&v)[8], float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  mean = warp_sum(s) * (1.f / kC);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q = fmaf(d, d, q); }
+  rstd = 1.f / sqrtf(warp_sum(q) * (1.f / kC) + kLnEps);
+}
+
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------
+// LN -> depthwise conv k3 (stride 1|2) * mask -> LN for up to 3 streams sharing one source
+// ------------------------------------------------------------------------------------------------
+struct LdlParams {
+  const float* src; const unsigned char* mask_out;
+  const float* ln_in_w[3]; const float* ln_in_b[3]; const float* dw_w[3];
+  const float* ln_out_w[3]; const float* ln_out_b[3];
+  void* out[3]; float* skip_out;
+  int B, t_src, t_virt, shift, t_out, n_streams;
+};
+constexpr int LDL_ROWS = 8;            // output rows per warp
+constexpr int LDL_WARPS = 8;
+
+template <typename OutT, int STRIDE>
+__global__ void __launch_bounds__(LDL_WARPS * 32) ln_dwconv_ln_kernel(const LdlParams p) {
+  // per stream: ln_in_w, ln_in_b, dw tap0, tap1, tap2, ln_out_w, ln_out_b  (7 x 256 floats)
+  __shared__ __align__(16) float sp[3][7][kC];
+  for (int i = threadIdx.x; i < p.n_streams * kC; i += blockDim.x) {
+    const int s = i / kC, c = i - s * kC;
+    sp[s][0][c] = p.ln_in_w[s][c]; sp[s][1][c] = p.ln_in_b[s][c];
+    sp[s][2][c] = p.dw_w[s][3 * c]; sp[s][3][c] = p.dw_w[s][3 * c + 1]; sp[s][4][c] = p.dw_w[s][3 * c + 2];
+    sp[s][5][c] = p.ln_out_w[s][c]; sp[s][6][c] = p.ln_out_b[s][c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_per_video = (p.t_out + LDL_ROWS - 1) / LDL_ROWS;
+  const long long n_tiles = (long long)p.B * tiles_per_video;
+  const int c0 = lane * 8;
+  for (long long tile = (long long)blockIdx.x * LDL_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * LDL_WARPS) {
+    const int b = (int)(tile / tiles_per_video);
+    const int t0 = (int)(tile - (long long)b * tiles_per_video) * LDL_ROWS;
+    const int t1 = min(t0 + LDL_ROWS, p.t_out);
+    const float* src_b = p.src + (size_t)b * p.t_src * kC;
+    float raw[3][8]; float mean[3], rstd[3]; bool ok[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { ok[j] = false; mean[j] = 0.f; rstd[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) raw[j][k] = 0.f; }
+    for (int pos = STRIDE * t0 - 1; pos <= STRIDE * (t1 - 1) + 1; ++pos) {
+      // slide the 3-position window
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { raw[0][k] = raw[1][k]; raw[1][k] = raw[2][k]; }
+      mean[0] = mean[1]; mean[1] = mean[2]; rstd[0] = rstd[1]; rstd[1] = rstd[2]; ok[0] = ok[1]; ok[1] = ok[2];
+      ok[2] = pos >= 0 && pos < p.t_virt;
+      if (ok[2]) {
+        const int r = p.shift >= 0 ? (pos >> p.shift) : (pos << (-p.shift));
+        Row8<float>::load(src_b + (size_t)r * kC + c0, raw[2]);
+        row_stats(raw[2], mean[2], rstd[2]);
+      }
+      const int rel = pos - (STRIDE * t0 + 1);
+      if (rel < 0 || (rel % STRIDE) != 0) continue;
+      const int t = t0 + rel / STRIDE;          // output row whose taps are window[0..2]
+      const size_t orow = (size_t)b * p.t_out + t;
+      const float mk = p.mask_out ? (p.mask_out[orow] ? 1.f : 0.f) : 1.f;
+      for (int s = 0; s < p.n_streams; ++s) {
+        float w[8], bb[8], acc[8];
+        lds8(&sp[s][0][c0], w); lds8(&sp[s][1][c0], bb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float d[8];
+          lds8(&sp[s][2 + j][c0], d);
+          if (ok[j]) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float u = fmaf((raw[j][k] - mean[j]) * rstd[j], w[k], bb[k]);
+              acc[k] = fmaf(d[k], u, acc[k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= mk;
+        float m2, r2;
+        row_stats(acc, m2, r2);
+        lds8(&sp[s][5][c0], w); lds8(&sp[s][6][c0], bb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m2) * r2, w[k], bb[k]);
+        Row8<OutT>::store(reinterpret_cast<OutT*>(p.out[s]) + orow * kC + c0, acc);
+      }
+      if (STRIDE == 2 && p.skip_out) {           // MaxPool1d(3, 2, 1) of the raw rows, -inf padding
+        float mx[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float m = raw[1][k];
+          if (ok[0]) m = fmaxf(m, raw[0][k]);
+          if (ok[2]) m = fmaxf(m, raw[2][k]);
+          mx[k] = m;
+        }
+        Row8<float>::store(p.skip_out + orow * kC + c0, mx);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention: warp per query row, 8 lanes per head (head dim 64), online softmax in fp32
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_ROWS = 4, ATT_WARPS = 8;
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const InT* __restrict__ q, const InT* __restrict__ k,
+                                                                  const InT* __restrict__ v, const unsigned char* __restrict__ kv_mask,
+                                                                  OutT* __restrict__ out, int B, int T, int window) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * 8;
+  const int tiles_per_video = (T + ATT_ROWS - 1) / ATT_ROWS;
+  const long long n_tiles = (long long)B * tiles_per_video;
+  const int half = window > 1 ? window / 2 : 0;
+  const float scale = 0.125f;          // 1/sqrt(64)
+  for (long long tile = (long long)blockIdx.x * ATT_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * ATT_WARPS) {
+    const int b = (int)(tile / tiles_per_video);
+    const int t0 = (int)(tile - (long long)b * tiles_per_video) * ATT_ROWS;
+    const size_t base = (size_t)b * T;
+    for (int i = t0; i < min(t0 + ATT_ROWS, T); ++i) {
+      float qv[8];
+      Row8<InT>::load(q + (base + i) * kC + c0, qv);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) qv[d] *= scale;
+      const int lo = window > 1 ? max(0, i - half) : 0;
+      const int hi = window > 1 ? min(T - 1, i + half) : T - 1;
+      float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+      for (int j = lo; j <= hi; ++j) {
+        const bool mk = kv_mask ? (kv_mask[base + j] != 0) : true;
+        if (window <= 1 && !mk) continue;                 // global: masked keys are -inf
+        float kv[8], vv[8];
+        Row8<InT>::load(k + (base + j) * kC + c0, kv);
+        Row8<InT>::load(v + (base + j) * kC + c0, vv);
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) s = fmaf(qv[d], kv[d], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (!mk) s += -1e4f;                                // banded: additive -1e4 (blocks.py:1194-1195)
+        const float mn = fmaxf(m, s);
+        const float corr = expf(m - mn);                    // m = -inf on the first key -> 0
+        const float pj = expf(s - mn);
+        l = fmaf(l, corr, pj);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[d] = fmaf(acc[d], corr, pj * vv[d]);
+        m = mn;
+      }
+      const bool qok = (window > 1 && kv_mask) ? (kv_mask[base + i] != 0) : true;   // blocks.py:1208-1209
+      const float inv = (qok && l > 0.f) ? 1.f / l : 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] *= inv;
+      Row8<OutT>::store(out + (base + i) * kC + c0, acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over channels of fp32 rows (C = 256 * NCH)
+// ------------------------------------------------------------------------------------------------
+template <typename OutT, int NCH>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bvec, OutT* __restrict__ out, long long rows) {
+  const int lane = threadIdx.x & 31;
+  const int C = kC * NCH;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    float v[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+      Row8<float>::load(x + (size_t)r * C + h * kC + lane * 8, v[h]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[h][k];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float qq = 0.f;
+#pragma unroll
+    for (int h = 0; h < NCH; ++h)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[h][k] - mean; qq = fmaf(d, d, qq); }
+    const float rstd = 1.f / sqrtf(warp_sum(qq) / (float)C + kLnEps);
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+      float ww[8], bb[8];
+      Row8<float>::load(w + h * kC + lane * 8, ww);
+      Row8<float>::load(bvec + h * kC + lane * 8, bb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[h][k] = fmaf((v[h][k] - mean) * rstd, ww[k], bb[k]);
+      Row8<OutT>::store(out + (size_t)r * C + h * kC + lane * 8, v[h]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// InstanceNorm1d over T + LeakyReLU. CTA = (video, 32-channel slab); threadIdx.x = channel (128 B
+// coalesced rows), threadIdx.y splits T. Two-pass statistics (second and third pass hit L2).
+// ------------------------------------------------------------------------------------------------
+constexpr int IN_TY = 16;
+template <typename OutT>
+__global__ void __launch_bounds__(32 * IN_TY) instnorm_lrelu_kernel(const float* __restrict__ x, OutT* __restrict__ out,
+                                                                   int T, int C, float slope) {
+  __shared__ float red[IN_TY][33];
+  const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  const float* xb = x + (size_t)b * T * C + c;
+  OutT* ob = out + (size_t)b * T * C + c;
+  float s = 0.f;
+  for (int t = threadIdx.y; t < T; t += IN_TY) s += xb[(size_t)t * C];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < IN_TY; ++i) tot += red[i][threadIdx.x];
+  const float mean = tot / (float)T;
+  __syncthreads();
+  float q = 0.f;
+  for (int t = threadIdx.y; t < T; t += IN_TY) { const float d = xb[(size_t)t * C] - mean; q = fmaf(d, d, q); }
+  red[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < IN_TY; ++i) tot += red[i][threadIdx.x];
+  const float rstd = 1.f / sqrtf(tot / (float)T + kLnEps);
+  for (int t = threadIdx.y; t < T; t += IN_TY) {
+    float v = (xb[(size_t)t * C] - mean) * rstd;
+    v = v >= 0.f ? v : v * slope;
+    store1(ob + (size_t)t * C, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FPN top-down fuse + depthwise conv + LN, warp per pyramid row
+// ------------------------------------------------------------------------------------------------
+struct FpnParams {
+  const float* lat; const unsigned char* mask; const float* dw_w; const float* ln_w; const float* ln_b;
+  void* out; int B, n_levels, P;
+  int lvl_off[AVDF_MAX_LEVELS], lvl_len[AVDF_MAX_LEVELS];
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) fpn_fuse_kernel(const FpnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 8;
+  const long long rows = (long long)p.B * p.P;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    const int b = (int)(r / p.P);
+    const int pr = (int)(r - (long long)b * p.P);
+    int l = 0;
+    while (l + 1 < p.n_levels && pr >= p.lvl_off[l + 1]) ++l;
+    const int t = pr - p.lvl_off[l], T = p.lvl_len[l];
+    const float* lat_b = p.lat + (size_t)b * p.P * kC;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int tt = t + j - 1;
+      if (tt < 0 || tt >= T) continue;
+      // L_l[tt] = lat_l[tt] + (lat_{l+1}[tt>>1] + (... )) summed from the top level down (necks.py:76-80)
+      float sum[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum[k] = 0.f;
+      for (int jl = p.n_levels - 1; jl >= l; --jl) {
+        const int ts = tt >> (jl - l);
+        if (ts >= p.lvl_len[jl]) continue;
+        float a[8];
+        Row8<float>::load(lat_b + (size_t)(p.lvl_off[jl] + ts) * kC + c0, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] += a[k];
+      }
+      const float* dw = p.dw_w + (size_t)l * kC * 3;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(__ldg(dw + (c0 + k) * 3 + j), sum[k], acc[k]);
+    }
+    const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= mk;
+    if (p.ln_w) {
+      float m, rs;
+      row_stats(acc, m, rs);
+      float w[8], bb[8];
+      Row8<float>::load(p.ln_w + (size_t)l * kC + c0, w);
+      Row8<float>::load(p.ln_b + (size_t)l * kC + c0, bb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m) * rs, w[k], bb[k]);
+    }
+    Row8<OutT>::store(reinterpret_cast<OutT*>(p.out) + (size_t)r * kC + c0, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// last conv (k3) of both heads, warp per pyramid row: 1 + 2 dot products of length 3 * 256
+// ------------------------------------------------------------------------------------------------
+struct HeadParams {
+  const void* cls_feat; const void* reg_feat; const unsigned char* mask;
+  const float* cls_w; const float* cls_b; const float* reg_w; const float* reg_b;
+  float* logits; float* offsets; int B, n_levels, P;
+  int lvl_off[AVDF_MAX_LEVELS], lvl_len[AVDF_MAX_LEVELS]; float lvl_scale[AVDF_MAX_LEVELS];
+};
+
+template <typename InT>
+__global__ void __launch_bounds__(256) head_final_kernel(const HeadParams p) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 8;
+  const long long rows = (long long)p.B * p.P;
+  const InT* cf = reinterpret_cast<const InT*>(p.cls_feat);
+  const InT* rf = reinterpret_cast<const InT*>(p.reg_feat);
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    const int b = (int)(r / p.P);
+    const int pr = (int)(r - (long long)b * p.P);
+    int l = 0;
+    while (l + 1 < p.n_levels && pr >= p.lvl_off[l + 1]) ++l;
+    const int t = pr - p.lvl_off[l], T = p.lvl_len[l];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int tt = t + j - 1;
+      if (tt < 0 || tt >= T) continue;
+      const size_t row = (size_t)r + (j - 1);
+      float x[8], w[8];
+      Row8<InT>::load(cf + row * kC + c0, x);
+      Row8<float>::load(p.cls_w + j * kC + c0, w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a0 = fmaf(w[k], x[k], a0);
+      Row8<InT>::load(rf + row * kC + c0, x);
+      Row8<float>::load(p.reg_w + j * kC + c0, w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a1 = fmaf(w[k], x[k], a1);
+      Row8<float>::load(p.reg_w + 3 * kC + j * kC + c0, w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a2 = fmaf(w[k], x[k], a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) {
+      const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
+      p.logits[r] = (a0 + p.cls_b[0]) * mk;
+      const float sc = p.lvl_scale[l];
+      p.offsets[2 * r] = fmaxf(((a1 + p.reg_b[0]) * mk) * sc, 0.f);
+      p.offsets[2 * r + 1] = fmaxf(((a2 + p.reg_b[1]) * mk) * sc, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exp12 video-level tail, one CTA (256 threads) per video:
+//   g = LeakyReLU_.2(IN_T(W0 z)) [T, C]; pooled = [max_t g | mean_t g]; h = ReLU(LN(W1 pooled)); out = w2.h + b2
+// ------------------------------------------------------------------------------------------------
+constexpr int VC12_MAXT = 64;
+template <typename InT>
+__global__ void __launch_bounds__(256) vcls_exp12_kernel(const InT* __restrict__ z, const float* __restrict__ w0,
+                                                         const float* __restrict__ w1, const float* __restrict__ ln_w,
+                                                         const float* __restrict__ ln_b, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ out, int T) {
+  extern __shared__ __align__(16) float sm[];
+  float* zs = sm;                       // [T][256]
+  float* pooled = zs + (size_t)T * kC;  // [512]
+  float* hbuf = pooled + 2 * kC;        // [256]
+  __shared__ float red[2];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < T * kC; i += 256) zs[i] = (float)z[(size_t)b * T * kC + i];
+  __syncthreads();
+  // g[t][c] for c = warp, warp + 8, ...; lanes split the 256-long dot product
+  for (int c = warp; c < kC; c += 8) {
+    float w[8];
+    Row8<float>::load(w0 + (size_t)c * kC + lane * 8, w);
+    float mx = -INFINITY, sum_g = 0.f;
+    float g[VC12_MAXT];
+    float s1 = 0.f;
+    for (int t = 0; t < T; ++t) {
+      float x[8];
+      lds8(zs + t * kC + lane * 8, x);
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a = fmaf(w[k], x[k], a);
+      a = warp_sum(a);
+      g[t % VC12_MAXT] = a; s1 += a;
+    }
+    const float mean = s1 / (float)T;
+    float qv = 0.f;
+    for (int t = 0; t < T; ++t) { const float d = g[t % VC12_MAXT] - mean; qv = fmaf(d, d, qv); }
+    const float rstd = 1.f / sqrtf(qv / (float)T + kLnEps);
+    for (int t = 0; t < T; ++t) {
+      float v = (g[t % VC12_MAXT] - mean) * rstd;
+      v = v >= 0.f ? v : 0.2f * v;
+      mx = fmaxf(mx, v); sum_g += v;
+    }
+    if (lane == 0) { pooled[c] = mx; pooled[kC + c] = sum_g / (float)T; }
+  }
+  __syncthreads();
+  // h[c] = W1[c, :512] . pooled
+  for (int c = warp; c < kC; c += 8) {
+    float a = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float w[8], x[8];
+      Row8<float>::load(w1 + (size_t)c * 2 * kC + h * kC + lane * 8, w);
+      lds8(pooled + h * kC + lane * 8, x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a = fmaf(w[k], x[k], a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) hbuf[c] = a;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float v[8];
+    lds8(hbuf + lane * 8, v);
+    float m, rs;
+    row_stats(v, m, rs);
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane * 8 + k;
+      const float y = fmaxf(fmaf((v[k] - m) * rs, ln_w[c], ln_b[c]), 0.f);
+      a = fmaf(w2[c], y, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) out[b] = a + b2[0];
+  }
+  (void)red;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exp13 video-level tail, one CTA per video, C (= 64) channels:
+//   g = LeakyReLU_.2(IN_T(W0 z)) [T, C]; s_t = seg_w . g_t + seg_b; out = cls_w . [max_t s, mean_t s] + cls_b
+// thread = (channel c = tid % C, time lane tid / C); W0 transposed in smem; three passes over z (L2).
+// ------------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void __launch_bounds__(256) vcls_exp13_kernel(const InT* __restrict__ z, const float* __restrict__ w0,
+                                                         const float* __restrict__ seg_w, const float* __restrict__ seg_b,
+                                                         const float* __restrict__ cls_w, const float* __restrict__ cls_b,
+                                                         float* __restrict__ out, int T, int C) {
+  extern __shared__ __align__(16) float sm[];
+  float* w0t = sm;                         // [C][C+1]  w0t[k][c] = w0[c][k]
+  float* zt = w0t + C * (C + 1);           // [TL][C]   staged z rows
+  float* red = zt + (256 / C) * C;         // [256]
+  float* stat = red + 256;                 // mean[C], rstd[C]
+  float* sbuf = stat + 2 * C;              // s_t partials: [TL]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int c = tid % C, tl = tid / C, TL = 256 / C;
+  for (int i = tid; i < C * C; i += 256) { const int cc = i / C, kk = i - cc * C; w0t[kk * (C + 1) + cc] = w0[i]; }
+  __syncthreads();
+  const InT* zb = z + (size_t)b * T * C;
+  float acc1 = 0.f;
+  float mean = 0.f, rstd = 0.f;
+  float smax = -INFINITY, ssum = 0.f;
+  for (int pass = 0; pass < 3; ++pass) {
+    float part = 0.f;
+    for (int tb = 0; tb < T; tb += TL) {
+      const int t = tb + tl;
+      if (t < T) zt[tl * C + c] = (float)zb[(size_t)t * C + c];
+      __syncthreads();
+      float g = 0.f;
+      if (t < T) {
+        for (int kk = 0; kk < C; ++kk) g = fmaf(w0t[kk * (C + 1) + c], zt[tl * C + kk], g);
+        if (pass == 0) part += g;
+        else if (pass == 1) { const float d = g - mean; part = fmaf(d, d, part); }
+      }
+      if (pass == 2) {
+        float v = 0.f;
+        if (t < T) {
+          v = (g - mean) * rstd;
+          v = v >= 0.f ? v : 0.2f * v;
+          v *= seg_w[c];
+        }
+        red[tid] = v;
+        __syncthreads();
+        if (tid < TL) {                         // s_t for the TL rows of this step
+          float s = 0.f;
+          for (int cc = 0; cc < C; ++cc) s += red[tid * C + cc];
+          if (tb + tid < T) { s += seg_b[0]; smax = fmaxf(smax, s); ssum += s; }
+        }
+      }
+      __syncthreads();
+    }
+    if (pass < 2) {
+      red[tid] = part;
+      __syncthreads();
+      if (tid < C) {
+        float tot = 0.f;
+        for (int i = 0; i < TL; ++i) tot += red[i * C + tid];
+        if (pass == 0) stat[tid] = tot / (float)T;
+        else stat[C + tid] = 1.f / sqrtf(tot / (float)T + kLnEps);
+      }
+      __syncthreads();
+      if (pass == 0) mean = stat[c]; else rstd = stat[C + c];
+      __syncthreads();
+    }
+  }
+  (void)acc1; (void)sbuf;
+  if (tid < TL) { red[tid] = smax; red[32 + tid] = ssum; }
+  __syncthreads();
+  if (tid == 0) {
+    float mx = -INFINITY, sm_ = 0.f;
+    for (int i = 0; i < TL; ++i) { mx = fmaxf(mx, red[i]); sm_ += red[32 + i]; }
+    out[b] = cls_w[0] * mx + cls_w[1] * (sm_ / (float)T) + cls_b[0];
+  }
+}
+
+static int grid_for(long long work_items, int per_cta, int sms) {
+  long long want = (work_items + per_cta - 1) / per_cta;
+  long long cap = (long long)sms * 8;
+  if (want > cap) want = cap;
+  return (int)(want < 1 ? 1 : want);
+}
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+
+}  // namespace avdf
+
+using namespace avdf;
+
+extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) {
+  AVDF_CHECK_ARG(a != nullptr, "args is null");
+  AVDF_CHECK_ARG(a->channels == kC, "channels must be 256");
+  AVDF_CHECK_ARG(a->stride == 1 || a->stride == 2, "stride must be 1 or 2");
+  AVDF_CHECK_ARG(a->n_streams >= 1 && a->n_streams <= 3, "n_streams out of range");
+  AVDF_CHECK_ARG(a->batch >= 0 && a->t_src > 0 && a->t_virt > 0 && a->t_virt % a->stride == 0, "bad sizes");
+  AVDF_CHECK_ARG(a->shift > -16 && a->shift < 16, "shift out of range");
+  AVDF_CHECK_ARG(a->shift >= 0 ? (((a->t_virt - 1) >> a->shift) < a->t_src) : (((a->t_virt - 1) << -a->shift) < a->t_src),
+                 "virtual length maps outside the source");
+  AVDF_CHECK_ARG(a->out_dtype == AVDF_DTYPE_F32 || a->out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_ARG(a->src != nullptr, "src is null");
+  AVDF_CHECK_ARG(a->skip_out == nullptr || (a->stride == 2 && a->shift == 0), "skip_out needs stride 2 and no resampling");
+  LdlParams p{};
+  p.src = a->src; p.mask_out = a->mask_out; p.skip_out = a->skip_out;
+  for (int s = 0; s < a->n_streams; ++s) {
+    AVDF_CHECK_ARG(a->ln_in_w[s] && a->ln_in_b[s] && a->dw_w[s] && a->ln_out_w[s] && a->ln_out_b[s] && a->out[s], "null stream parameter");
+    p.ln_in_w[s] = a->ln_in_w[s]; p.ln_in_b[s] = a->ln_in_b[s]; p.dw_w[s] = a->dw_w[s];
+    p.ln_out_w[s] = a->ln_out_w[s]; p.ln_out_b[s] = a->ln_out_b[s]; p.out[s] = a->out[s];
+  }
+  p.B = a->batch; p.t_src = a->t_src; p.t_virt = a->t_virt; p.shift = a->shift; p.t_out = a->t_virt / a->stride;
+  p.n_streams = a->n_streams;
+  if (a->batch == 0) return AVDF_OK;
+  const long long tiles = (long long)a->batch * ((p.t_out + LDL_ROWS - 1) / LDL_ROWS);
+  const int grid = grid_for(tiles, LDL_WARPS, sm_count());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool bf = a->out_dtype == AVDF_DTYPE_BF16;
+  if (a->stride == 1) {
+    if (bf) ln_dwconv_ln_kernel<__nv_bfloat16, 1><<<grid, LDL_WARPS * 32, 0, st>>>(p);
+    else ln_dwconv_ln_kernel<float, 1><<<grid, LDL_WARPS * 32, 0, st>>>(p);
+  } else {
+    if (bf) ln_dwconv_ln_kernel<__nv_bfloat16, 2><<<grid, LDL_WARPS * 32, 0, st>>>(p);
+    else ln_dwconv_ln_kernel<float, 2><<<grid, LDL_WARPS * 32, 0, st>>>(p);
+  }
+  return check_launch("ln_dwconv_ln_kernel");
+}
+
+extern "C" int avdf_attention(const void* q, const void* k, const void* v, const uint8_t* kv_mask, void* out,
+                              int32_t in_dtype, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels,
+                              int32_t n_head, int32_t window, void* stream) {
+  AVDF_CHECK_ARG(q && k && v && out, "null pointer");
+  AVDF_CHECK_ARG(channels == kC && n_head == 4, "attention supports 4 heads x 64 channels");
+  AVDF_CHECK_ARG(batch >= 0 && t > 0, "bad sizes");
+  AVDF_CHECK_ARG(window <= 1 || (window & 1), "window must be odd (or <= 1 for global attention)");
+  if (batch == 0) return AVDF_OK;
+  const long long tiles = (long long)batch * ((t + ATT_ROWS - 1) / ATT_ROWS);
+  const int grid = grid_for(tiles, ATT_WARPS, sm_count());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  typedef __nv_bfloat16 bf;
+  if (in_dtype == AVDF_DTYPE_F32 && out_dtype == AVDF_DTYPE_F32)
+    attention_kernel<float, float><<<grid, ATT_WARPS * 32, 0, st>>>((const float*)q, (const float*)k, (const float*)v, kv_mask, (float*)out, batch, t, window);
+  else if (in_dtype == AVDF_DTYPE_F32 && out_dtype == AVDF_DTYPE_BF16)
+    attention_kernel<float, bf><<<grid, ATT_WARPS * 32, 0, st>>>((const float*)q, (const float*)k, (const float*)v, kv_mask, (bf*)out, batch, t, window);
+  else if (in_dtype == AVDF_DTYPE_BF16 && out_dtype == AVDF_DTYPE_BF16)
+    attention_kernel<bf, bf><<<grid, ATT_WARPS * 32, 0, st>>>((const bf*)q, (const bf*)k, (const bf*)v, kv_mask, (bf*)out, batch, t, window);
+  else if (in_dtype == AVDF_DTYPE_BF16 && out_dtype == AVDF_DTYPE_F32)
+    attention_kernel<bf, float><<<grid, ATT_WARPS * 32, 0, st>>>((const bf*)q, (const bf*)k, (const bf*)v, kv_mask, (float*)out, batch, t, window);
+  else { set_error("avdf_attention: bad dtype"); return AVDF_ERR_INVALID; }
+  return check_launch("attention_kernel");
+}
+
+extern "C" int avdf_ln_rows(const float* x, const float* w, const float* b, void* out, int32_t out_dtype, int64_t rows,
+                            int32_t channels, void* stream) {
+  AVDF_CHECK_ARG(x && w && b && out, "null pointer");
+  AVDF_CHECK_ARG(channels == 256 || channels == 512 || channels == 1024, "channels must be 256, 512 or 1024");
+  AVDF_CHECK_ARG(rows >= 0, "rows < 0");
+  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  if (rows == 0) return AVDF_OK;
+  const int grid = grid_for(rows, 8, sm_count());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  typedef __nv_bfloat16 bf;
+#define AVDF_LN_CASE(NCH)                                                                          \
+  if (out_dtype == AVDF_DTYPE_BF16) ln_rows_kernel<bf, NCH><<<grid, 256, 0, st>>>(x, w, b, (bf*)out, rows); \
+  else ln_rows_kernel<float, NCH><<<grid, 256, 0, st>>>(x, w, b, (float*)out, rows)
+  if (channels == 256) { AVDF_LN_CASE(1); } else if (channels == 512) { AVDF_LN_CASE(2); } else { AVDF_LN_CASE(4); }
+#undef AVDF_LN_CASE
+  return check_launch("ln_rows_kernel");
+}
+
+extern "C" int avdf_instnorm_lrelu(const float* x, void* out, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels,
+                                   float slope, void* stream) {
+  AVDF_CHECK_ARG(x && out, "null pointer");
+  AVDF_CHECK_ARG(batch >= 0 && t > 0 && channels > 0 && channels % 32 == 0, "channels must be a multiple of 32");
+  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_ARG(batch <= 65535, "batch too large for one launch");
+  if (batch == 0) return AVDF_OK;
+  dim3 grid(channels / 32, batch), block(32, IN_TY);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == AVDF_DTYPE_BF16) instnorm_lrelu_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, (__nv_bfloat16*)out, t, channels, slope);
+  else instnorm_lrelu_kernel<float><<<grid, block, 0, st>>>(x, (float*)out, t, channels, slope);
+  return check_launch("instnorm_lrelu_kernel");
+}
+
+static int fill_levels(int n_levels, const int32_t* level_len, int* off, int* len) {
+  int P = 0;
+  for (int l = 0; l < n_levels; ++l) { off[l] = P; len[l] = level_len[l]; P += level_len[l]; }
+  return P;
+}
+
+extern "C" int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float* dw_w, const float* ln_w, const float* ln_b,
+                             void* out, int32_t out_dtype, int32_t batch, int32_t channels, int32_t n_levels,
+                             const int32_t* level_len, void* stream) {
+  AVDF_CHECK_ARG(lat && dw_w && out && level_len, "null pointer");
+  AVDF_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "ln_w / ln_b must come together");
+  AVDF_CHECK_ARG(channels == kC, "channels must be 256");
+  AVDF_CHECK_ARG(n_levels >= 1 && n_levels <= AVDF_MAX_LEVELS, "n_levels out of range");
+  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  for (int l = 0; l + 1 < n_levels; ++l) AVDF_CHECK_ARG(level_len[l] == 2 * level_len[l + 1], "levels must halve");
+  FpnParams p{};
+  p.lat = lat; p.mask = mask; p.dw_w = dw_w; p.ln_w = ln_w; p.ln_b = ln_b; p.out = out; p.B = batch; p.n_levels = n_levels;
+  p.P = fill_levels(n_levels, level_len, p.lvl_off, p.lvl_len);
+  if (batch == 0) return AVDF_OK;
+  const int grid = grid_for((long long)batch * p.P, 8, sm_count());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == AVDF_DTYPE_BF16) fpn_fuse_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  else fpn_fuse_kernel<float><<<grid, 256, 0, st>>>(p);
+  return check_launch("fpn_fuse_kernel");
+}
+
+extern "C" int avdf_head_final(const void* cls_feat, const void* reg_feat, int32_t dtype, const uint8_t* mask,
+                               const float* cls_w, const float* cls_b, const float* reg_w, const float* reg_b,
+                               const float* level_scale, float* logits, float* offsets, int32_t batch, int32_t channels,
+                               int32_t n_levels, const int32_t* level_len, void* stream) {
+  AVDF_CHECK_ARG(cls_feat && reg_feat && cls_w && cls_b && reg_w && reg_b && level_scale && logits && offsets && level_len, "null pointer");
+  AVDF_CHECK_ARG(channels == kC, "channels must be 256");
+  AVDF_CHECK_ARG(n_levels >= 1 && n_levels <= AVDF_MAX_LEVELS, "n_levels out of range");
+  HeadParams p{};
+  p.cls_feat = cls_feat; p.reg_feat = reg_feat; p.mask = mask; p.cls_w = cls_w; p.cls_b = cls_b; p.reg_w = reg_w; p.reg_b = reg_b;
+  p.logits = logits; p.offsets = offsets; p.B = batch; p.n_levels = n_levels;
+  p.P = fill_levels(n_levels, level_len, p.lvl_off, p.lvl_len);
+  for (int l = 0; l < n_levels; ++l) p.lvl_scale[l] = level_scale[l];
+  if (batch == 0) return AVDF_OK;
+  const int grid = grid_for((long long)batch * p.P, 8, sm_count());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == AVDF_DTYPE_BF16) head_final_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  else if (dtype == AVDF_DTYPE_F32) head_final_kernel<float><<<grid, 256, 0, st>>>(p);
+  else { set_error("avdf_head_final: bad dtype"); return AVDF_ERR_INVALID; }
+  return check_launch("head_final_kernel");
+}
+
+extern "C" int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_w, const float* lin1_w, const float* ln_w,
+                               const float* ln_b, const float* lin2_w, const float* lin2_b, float* out, int32_t batch,
+                               int32_t t, int32_t channels, void* stream) {
+  AVDF_CHECK_ARG(z && conv0_w && lin1_w && ln_w && ln_b && lin2_w && lin2_b && out, "null pointer");
+  AVDF_CHECK_ARG(channels == kC, "channels must be 256");
+  AVDF_CHECK_ARG(t > 0 && t <= VC12_MAXT, "t out of range (1..64)");
+  if (batch == 0) return AVDF_OK;
+  const size_t smem = ((size_t)t * kC + 3 * kC) * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == AVDF_DTYPE_BF16) {
+    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp12_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vcls_exp12_kernel<__nv_bfloat16><<<batch, 256, smem, st>>>((const __nv_bfloat16*)z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, t);
+  } else if (dtype == AVDF_DTYPE_F32) {
+    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp12_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vcls_exp12_kernel<float><<<batch, 256, smem, st>>>((const float*)z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, t);
+  } else { set_error("avdf_vcls_exp12: bad dtype"); return AVDF_ERR_INVALID; }
+  return check_launch("vcls_exp12_kernel");
+}
+
+extern "C" int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_w, const float* seg_w, const float* seg_b,
+                               const float* cls_w, const float* cls_b, float* out, int32_t batch, int32_t t,
+                               int32_t channels, void* stream) {
+  AVDF_CHECK_ARG(z && conv0_w && seg_w && seg_b && cls_w && cls_b && out, "null pointer");
+  AVDF_CHECK_ARG(channels == 32 || channels == 64 || channels == 128, "channels must be 32, 64 or 128");
+  AVDF_CHECK_ARG(t > 0, "t must be positive");
+  if (batch == 0) return AVDF_OK;
+  const int C = channels;
+  const size_t smem = ((size_t)C * (C + 1) + (256 / C) * C + 256 + 2 * C + 64) * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == AVDF_DTYPE_BF16) {
+    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp13_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vcls_exp13_kernel<__nv_bfloat16><<<batch, 256, smem, st>>>((const __nv_bfloat16*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t, C);
+  } else if (dtype == AVDF_DTYPE_F32) {
+    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp13_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vcls_exp13_kernel<float><<<batch, 256, smem, st>>>((const float*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t, C);
+  } else { set_error("avdf_vcls_exp13: bad dtype"); return AVDF_ERR_INVALID; }
+  return check_launch("vcls_exp13_kernel");
+}

@@ -62,9 +62,43 @@ __global__ void __launch_bounds__(256) interp_concat_kernel(const InterpParams p
   }
 }
 
+// preprocessing (libs/modeling/av_fd_no_recon.py:431-479): one video's feats [C, T] fp32 (the dataset item
+// layout) -> token-major [L, C] rows of the batch buffer, zero-padded from T to L. 32x32 smem tile transpose:
+// reads coalesced along T, writes coalesced along C.
+template <typename OutT>
+__global__ void __launch_bounds__(256) pack_feats_kernel(const float* __restrict__ in, int C, int T, int L, OutT* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? in[(size_t)c * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < L && c < C) {
+      const float v = tile[threadIdx.x][i];
+      if (sizeof(OutT) == 2) reinterpret_cast<__nv_bfloat16*>(out)[(size_t)t * C + c] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(out)[(size_t)t * C + c] = v;
+    }
+  }
+}
+
 }  // namespace avdf
 
 using namespace avdf;
+
+extern "C" int avdf_pack_feats(const float* feats_ct, int32_t channels, int32_t t, int32_t t_padded, void* out,
+                               int32_t out_dtype, void* stream) {
+  AVDF_CHECK_ARG(feats_ct && out, "null pointer");
+  AVDF_CHECK_ARG(channels > 0 && t > 0 && t_padded >= t, "bad sizes");
+  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  dim3 grid((t_padded + 31) / 32, (channels + 31) / 32), block(32, 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == AVDF_DTYPE_BF16) pack_feats_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(feats_ct, channels, t, t_padded, reinterpret_cast<__nv_bfloat16*>(out));
+  else pack_feats_kernel<float><<<grid, block, 0, st>>>(feats_ct, channels, t, t_padded, reinterpret_cast<float*>(out));
+  return check_launch("pack_feats_kernel");
+}
 
 extern "C" int avdf_interp_concat(const float* video, const float* byola, const float* emo,
                                   const int32_t* video_off, const int32_t* byola_off, const int32_t* emo_off,

@@ -1,0 +1,444 @@
+"""Device-side execution plan of the localization-inference path.
+
+`LocalizationEngine` owns the packed weights and the static activation buffers
+(token-major [B, T, C], sized once for `max_batch`) and issues the kernel
+sequence of one forward pass through `ops` (= the C-ABI). Nothing is computed
+in PyTorch here: torch provides device memory and the stream, every arithmetic
+step is a libavdf_sm100 kernel. Static buffers + a fixed launch sequence make
+the whole pass CUDA-graph capturable.
+
+Kernel sequence per batch (reference lines each step replaces):
+  video-level branch  Contraction / Extract DownBlocks (blocks.py:1495-1516, 1544-1565, 1640-1661)
+                      = conv_gemm(k3, stride 2|1, +bias, mask) -> instnorm_lrelu, x5; tail vcls_exp12 / vcls_exp13
+  embedding           backbones.py:437-465 = 2 x conv_gemm(k3, mask, LN, ReLU [, +PE]); evaluated ONCE (the
+                      reference runs it three times on identical inputs)
+  18 blocks           blocks.py:783-876 / 1227-1317 = ln_dwconv_ln -> 3 x conv_gemm(1x1 q,k,v) -> attention ->
+                      conv_gemm(proj, mask, residual, gamma) -> ln_rows -> conv_gemm(1x1, GELU) ->
+                      conv_gemm(1x1, mask, residual, gamma); up/down-sampling between scales is an index map
+                      inside ln_dwconv_ln (backbones.py:487,490); hh_branch[last] is dead and skipped
+  neck                necks.py:62-93 = 6 x conv_gemm(1x1 lateral) into one pyramid buffer -> fpn_fuse
+  heads               av_fd_no_recon.py:75-89,144-159 = 2 x 2 x conv_gemm(k3 over all 6 levels in one launch, LN, ReLU)
+                      -> head_final
+  postprocess         av_fd_no_recon.py:760-876 + libs/utils/nms.py = avdf_postprocess (one CTA per video)
+"""
+import math
+
+import numpy as np
+import torch
+
+from ... import ops
+from ...native import AvdfError
+from .spec import EXP13, state_dict_spec
+
+
+def sinusoid_table(n_pos, d):
+    """blocks.py:116-127: fp64 table -> fp32, returned token-major [n_pos, d]."""
+    pos = np.arange(n_pos, dtype=np.float64)[:, None]
+    j = np.arange(d)[None, :]
+    ang = pos / np.power(10000.0, 2.0 * (j // 2) / d)
+    tab = np.empty_like(ang)
+    tab[:, 0::2] = np.sin(ang[:, 0::2])
+    tab[:, 1::2] = np.cos(ang[:, 1::2])
+    return tab.astype(np.float32)
+
+
+class PackedWeights:
+    """Reference state_dict -> device tensors in the kernels' layouts.
+
+    dense conv / linear [co, ci, k] -> [co, k*ci] (tap-major rows) in the GEMM operand dtype;
+    LN / AffineDropPath / bias vectors -> flat fp32; depthwise [C,1,3] -> [C,3] fp32.
+    """
+
+    def __init__(self, sd, device, gemm_dtype):
+        self.sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+        self.device = device
+        self.gemm_dtype = gemm_dtype
+        self._cache = {}
+
+    def has(self, key):
+        return key in self.sd
+
+    def vec(self, key):
+        """flat fp32 vector (LN weight/bias [1,C,1], conv bias, scales)."""
+        ck = ("v", key)
+        if ck not in self._cache:
+            self._cache[ck] = self.sd[key].detach().to(torch.float32).reshape(-1).contiguous().to(self.device)
+        return self._cache[ck]
+
+    def ln(self, prefix):
+        return (self.vec(prefix + ".weight"), self.vec(prefix + ".bias"))
+
+    def dense(self, key, f32=False):
+        """[co, ci, k] or [co, ci] -> [co, k*ci] in the GEMM dtype (or fp32)."""
+        ck = ("d", key, f32)
+        if ck not in self._cache:
+            w = self.sd[key].detach().to(torch.float32)
+            if w.dim() == 3:
+                w = w.permute(0, 2, 1).reshape(w.shape[0], -1)
+            w = w.contiguous().to(self.device)
+            self._cache[ck] = w if f32 else w.to(self.gemm_dtype).contiguous()
+        return self._cache[ck]
+
+    def dw(self, key):
+        ck = ("w", key)
+        if ck not in self._cache:
+            w = self.sd[key].detach().to(torch.float32)
+            self._cache[ck] = w.reshape(w.shape[0], 3).contiguous().to(self.device)
+        return self._cache[ck]
+
+
+class LocalizationEngine:
+    def __init__(self, model_cfg, model_name, state_dict, device, precision="bf16", max_batch=32):
+        if not torch.cuda.is_available():
+            raise AvdfError("LocalizationEngine needs a CUDA device: the path has no CPU fallback")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        c = model_cfg
+        self.cfg = c
+        self.name = model_name
+        self.exp13 = model_name == EXP13
+        self.device = torch.device(device)
+        self.precision = precision
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.max_batch = int(max_batch)
+        self.C = c["embd_dim"]
+        self.n_head = c["n_head"]
+        self.c_in = c["video_input_dim"] + c["audio_input_dim"]
+        self.arch = tuple(c["backbone_arch"])
+        if c["backbone_type"] != "convHRLRFullResSelfAttTransformerRevised":
+            raise AvdfError("only the convHRLRFullResSelfAttTransformerRevised backbone is on the accelerated path")
+        if c["fpn_type"] != "fpn":
+            raise AvdfError("only fpn_type 'fpn' is on the accelerated path")
+        if self.C != 256 or c["fpn_dim"] != 256 or c["head_dim"] != 256 or self.n_head != 4:
+            raise AvdfError("kernels are specialised for embd/fpn/head dim 256 with 4 heads")
+        if c["scale_factor"] != 2 or c["embd_kernel_size"] != 3 or c["head_kernel_size"] != 3 or c["fpn_start_level"] != 0:
+            raise AvdfError("unsupported scale_factor / kernel size / fpn_start_level")
+        if c.get("use_rel_pe", False):
+            raise AvdfError("use_rel_pe is not supported")
+        nwin = c["n_mha_win_size"]
+        self.win = [nwin] * (1 + self.arch[2]) if isinstance(nwin, int) else list(nwin)
+        self.n_levels = self.arch[2] + 1
+        self.max_seq_len = c["max_seq_len"]
+        self.strides = [2 ** i for i in range(self.n_levels)]
+        mdf = 1
+        for s, w in zip(self.strides, self.win):       # av_fd_no_recon.py:217-224
+            st = s * (w // 2) * 2 if w > 1 else s
+            assert self.max_seq_len % st == 0, "max_seq_len must be divisible by fpn stride and window size"
+            mdf = max(mdf, st)
+        self.max_div_factor = mdf
+        self.test_cfg = dict(c["test_cfg"])
+        self.num_classes = c["num_classes"]
+        if self.num_classes != 1:
+            raise AvdfError("the fused postprocess handles num_classes == 1 (the shipped configs)")
+        missing = [k for k in state_dict_spec(c, model_name) if (k not in state_dict and "module." + k not in state_dict)
+                   and not k.startswith("interpolator.expansion.") and not k.startswith("segmentandCls.bn1")]
+        if missing:
+            raise KeyError("state_dict is missing %d tensors, e.g. %s" % (len(missing), missing[:3]))
+        self.w = PackedWeights(state_dict, self.device, self.adt)
+        self._bufs = {}
+        self._mask_cache = {}
+        self._pe_cache = {}
+        self._ws = None
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, name, shape, dtype):
+        """Static buffer sized for max_batch; returns the [B, ...] prefix view."""
+        B = shape[0]
+        key = (name, tuple(shape[1:]), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty((self.max_batch,) + tuple(shape[1:]), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t[:B]
+
+    def workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def padded_len(self, t):
+        """av_fd_no_recon.py:458-466."""
+        if t <= self.max_seq_len:
+            return self.max_seq_len
+        s = self.max_div_factor
+        return (t + s - 1) // s * s
+
+    def level_lens(self, L):
+        return [L // s for s in self.strides]
+
+    def masks(self, valid, L):
+        """Per-level row masks [B, T_l] and the pyramid mask [B, P] (uint8) for valid lengths
+        `valid` (host ints). mask_l[b, t] = (t * 2^l < valid[b]) (nearest down-sampling, blocks.py:51-55)."""
+        key = (tuple(int(v) for v in valid), L)
+        m = self._mask_cache.get(key)
+        if m is None:
+            lens = self.level_lens(L)
+            v = np.asarray(key[0], dtype=np.int64)[:, None]
+            lv = [((np.arange(n)[None, :] * s) < v).astype(np.uint8) for n, s in zip(lens, self.strides)]
+            pyr = np.concatenate(lv, axis=1)
+            flat = np.concatenate([pyr.reshape(-1)] + [a.reshape(-1) for a in lv])
+            dev = torch.from_numpy(flat).to(self.device)
+            B, P = len(valid), sum(lens)
+            out = {"pyr": dev[: B * P].view(B, P)}
+            off = B * P
+            for l, n in enumerate(lens):
+                out[l] = dev[off: off + B * n].view(B, n)
+                off += B * n
+            if len(self._mask_cache) > 64:
+                self._mask_cache.clear()
+            self._mask_cache[key] = out
+            m = out
+        return m
+
+    def pe(self, L):
+        """[L, C] fp32 table / sqrt(C) (backbones.py:336-338); for L > max_seq_len the reference
+        linearly re-interpolates the constant table (backbones.py:456-461) - done once on the host."""
+        t = self._pe_cache.get(L)
+        if t is None:
+            tab = torch.from_numpy(sinusoid_table(self.max_seq_len, self.C)) / math.sqrt(self.C)
+            if L >= self.max_seq_len and L != self.max_seq_len:
+                tab = torch.nn.functional.interpolate(tab.t().unsqueeze(0), L, mode="linear", align_corners=False)[0].t()
+            t = tab[:L].contiguous().to(self.device)
+            self._pe_cache[L] = t
+        return t
+
+    # ------------------------------------------------------------------ building blocks
+    def _gemm(self, a, wkey, *, B, taps=1, stride=1, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
+              act=ops.ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_act=None):
+        w = self.w.dense(wkey)
+        n_out, k = w.shape
+        c_in = k // taps
+        out_bf16 = None
+        if out_act is not None:
+            if self.adt == torch.float32:
+                assert out_f32 is None
+                out_f32 = out_act
+            else:
+                out_bf16 = out_act
+        ws = None
+        if self.adt == torch.float32:
+            ws = self.workspace(B * o_rows * n_out * 4)
+        ops.conv_gemm(a, w, taps=taps, stride=stride, batch=B, c_in=c_in, n_out=n_out, segs=segs, a_rows=a_rows,
+                      o_rows=o_rows, bias=bias, row_mask=row_mask, ln=ln, act=act, pe=pe, residual=residual, gamma=gamma,
+                      out_f32=out_f32, out_bf16=out_bf16, workspace=ws)
+
+    def _attn_and_mlp(self, pre, B, T, mask, skip, window, out_name, want_act_copy):
+        """Shared tail of TransformerBlock / MutilModelTransformerBlock after the dwconv+LN stage:
+        q,k,v 1x1 -> attention -> proj(+skip) -> LN2 -> MLP(+residual). Returns (out_f32, out_act|None)."""
+        C, w = self.C, self.w
+        seg = [(T, 0, 0)]
+        qn, kn, vn = (self.buf(n, (B, T, C), self.adt) for n in ("qn", "kn", "vn"))
+        qp, kp, vp = (self.buf(n, (B, T, C), torch.float32) for n in ("qp", "kp", "vp"))
+        for src, dst, nm in ((qn, qp, "query"), (kn, kp, "key"), (vn, vp, "value")):
+            self._gemm(src, f"{pre}.attn.{nm}.weight", B=B, segs=seg, a_rows=T, o_rows=T,
+                       bias=w.vec(f"{pre}.attn.{nm}.bias"), out_f32=dst)
+        att = self.buf("att", (B, T, C), self.adt)
+        ops.attention(qp, kp, vp, mask, att, batch=B, t=T, n_head=self.n_head, window=window)
+        y = self.buf("y", (B, T, C), torch.float32)
+        ga = w.vec(pre + ".drop_path_attn.scale") if w.has(pre + ".drop_path_attn.scale") else None
+        gm = w.vec(pre + ".drop_path_mlp.scale") if w.has(pre + ".drop_path_mlp.scale") else None
+        self._gemm(att, f"{pre}.attn.proj.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.attn.proj.bias"),
+                   row_mask=mask, residual=skip, gamma=ga, out_f32=y)
+        l2 = self.buf("ln2", (B, T, C), self.adt)
+        ops.ln_rows(y, *w.ln(pre + ".ln2"), l2, B * T)
+        h = self.buf("mlp_h", (B, T, 4 * C), self.adt)
+        self._gemm(l2, f"{pre}.mlp.0.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.mlp.0.bias"),
+                   act=ops.ACT_GELU, out_act=h)
+        out = self.buf(out_name, (B, T, C), torch.float32)
+        out_act = None
+        if want_act_copy and self.adt != torch.float32:
+            out_act = self.buf(out_name + "_act", (B, T, C), self.adt)
+        # the residual y is already zero on masked rows (blocks.py:1311-1313)
+        w2 = self.w.dense(f"{pre}.mlp.3.weight")
+        ws = self.workspace(B * T * C * 4) if self.adt == torch.float32 else None
+        ops.conv_gemm(h, w2, taps=1, stride=1, batch=B, c_in=4 * C, n_out=C, segs=seg, a_rows=T, o_rows=T,
+                      bias=w.vec(f"{pre}.mlp.3.bias"), row_mask=mask, residual=y, gamma=gm, out_f32=out, out_bf16=out_act,
+                      workspace=ws)
+        return out, (out if self.adt == torch.float32 else out_act)
+
+    def transformer_block(self, pre, x, B, T, masks, level, stride, window, out_name, want_act_copy=False):
+        """TransformerBlock.forward (blocks.py:1307-1317); x fp32 [B, T, C] at pyramid level `level`."""
+        C, w = self.C, self.w
+        To = T // stride
+        lvl_out = level + (1 if stride == 2 else 0)
+        mask = masks[lvl_out]
+        outs = [self.buf(n, (B, To, C), self.adt) for n in ("qn", "kn", "vn")]
+        skip = self.buf("skip", (B, To, C), torch.float32) if stride == 2 else x
+        ln1 = w.ln(pre + ".ln1")
+        ops.ln_dwconv_ln(x, batch=B, t_src=T, t_virt=T, shift=0, stride=stride, mask_out=mask, ln_in=[ln1] * 3,
+                         dw=[w.dw(f"{pre}.attn.{n}_conv.conv.weight") for n in ("query", "key", "value")],
+                         ln_out=[w.ln(f"{pre}.attn.{n}_norm") for n in ("query", "key", "value")], outs=outs,
+                         skip_out=skip if stride == 2 else None)
+        return self._attn_and_mlp(pre, B, To, mask, skip, window, out_name, want_act_copy)
+
+    def mm_block(self, pre, xq, kv, B, Tq, Tkv, masks, level, window, out_name, want_act_copy=False):
+        """MutilModelTransformerBlock.forward (blocks.py:866-876): q from xq [B,Tq,C]; k,v from kv [B,Tkv,C]
+        nearest-resampled to Tq (backbones.py:487,490)."""
+        C, w = self.C, self.w
+        mask = masks[level]
+        qn, kn, vn = (self.buf(n, (B, Tq, C), self.adt) for n in ("qn", "kn", "vn"))
+        names = ("query", "key", "value")
+        dws = [w.dw(f"{pre}.attn.{n}_conv.conv.weight") for n in names]
+        lno = [w.ln(f"{pre}.attn.{n}_norm") for n in names]
+        lni = [w.ln(pre + ".lnq"), w.ln(pre + ".lnk"), w.ln(pre + ".lnv")]
+        if kv is xq:
+            ops.ln_dwconv_ln(xq, batch=B, t_src=Tq, t_virt=Tq, shift=0, stride=1, mask_out=mask, ln_in=lni, dw=dws,
+                             ln_out=lno, outs=[qn, kn, vn])
+        else:
+            ops.ln_dwconv_ln(xq, batch=B, t_src=Tq, t_virt=Tq, shift=0, stride=1, mask_out=mask, ln_in=lni[:1],
+                             dw=dws[:1], ln_out=lno[:1], outs=[qn])
+            if Tq >= Tkv:
+                shift = int(round(math.log2(Tq // Tkv)))
+            else:
+                shift = -int(round(math.log2(Tkv // Tq)))
+            ops.ln_dwconv_ln(kv, batch=B, t_src=Tkv, t_virt=Tq, shift=shift, stride=1, mask_out=mask, ln_in=lni[1:],
+                             dw=dws[1:], ln_out=lno[1:], outs=[kn, vn])
+        return self._attn_and_mlp(pre, B, Tq, mask, xq, window, out_name, want_act_copy)
+
+    # ------------------------------------------------------------------ the pass
+    def video_cls(self, x_act, B, L, masks):
+        w, adt = self.w, self.adt
+        vcls = self.buf("vcls", (B,), torch.float32)
+        if self.exp13:
+            pre, stride, dims = "segmentandCls", 1, [self.c_in, 1024, 512, 256, 128, 64]
+        else:
+            C = self.C
+            pre, stride, dims = "interpolator", 2, [self.c_in, C, 2 * C, 4 * C, 8 * C, C]
+        z, T, level = x_act, L, 0
+        for i in range(5):
+            To = T // stride
+            level_o = level + (1 if stride == 2 else 0)
+            raw = self.buf("vc_raw", (B, To * dims[i + 1]), torch.float32)
+            self._gemm(z, f"{pre}.contraction.down_{i + 1}.conv_block.conv.weight", B=B, taps=3, stride=stride,
+                       segs=[(To, 0, 0)], a_rows=T, o_rows=To,
+                       bias=w.vec(f"{pre}.contraction.down_{i + 1}.conv_block.conv.bias"), row_mask=masks[level_o], out_f32=raw)
+            z = self.buf("vc_z%d" % (i & 1), (B, To * dims[i + 1]), adt)
+            ops.instnorm_lrelu(raw.view(B, To, dims[i + 1]), z.view(B, To, dims[i + 1]), batch=B, t=To, channels=dims[i + 1])
+            z = z.view(B, To, dims[i + 1])
+            T, level = To, level_o
+        if self.exp13:
+            ops.vcls_exp13(z, w.dense("segmentandCls.conv0.0.weight", f32=True), w.vec("segmentandCls.seg_linear.weight"),
+                           w.vec("segmentandCls.seg_linear.bias"), w.vec("segmentandCls.cls_linear1.weight"),
+                           w.vec("segmentandCls.cls_linear1.bias"), vcls, batch=B, t=T)
+        else:
+            ops.vcls_exp12(z, w.dense("interpolator.conv0.0.weight", f32=True), w.dense("interpolator.conv1.weight", f32=True),
+                           *w.ln("interpolator.bn1"), w.vec("interpolator.conv2.weight"), w.vec("interpolator.conv2.bias"),
+                           vcls, batch=B, t=T)
+        return vcls
+
+    def forward_dense(self, x_act, valid):
+        """x_act: [B, L, c_in] in the GEMM operand dtype (token-major), valid: host list of valid lengths.
+        Returns (logits [B,P] f32, offsets [B,P,2] f32, vcls [B] f32, masks, level_lens)."""
+        B, L, cin = x_act.shape
+        assert cin == self.c_in and B <= self.max_batch and x_act.dtype == self.adt
+        assert L % self.max_div_factor == 0 or L == self.max_seq_len
+        C, w, adt = self.C, self.w, self.adt
+        lens = self.level_lens(L)
+        P = sum(lens)
+        offs = [sum(lens[:l]) for l in range(self.n_levels)]
+        masks = self.masks(valid, L)
+        vcls = self.video_cls(x_act, B, L, masks)
+        # ---- embedding (backbones.py:437-465), once
+        h = x_act
+        n_embd = self.arch[0]
+        x = None
+        for i in range(n_embd):
+            last = i == n_embd - 1
+            ln = w.ln(f"backbone.embd_norm.{i}") if w.has(f"backbone.embd_norm.{i}.weight") else None
+            bias = w.vec(f"backbone.embd.{i}.conv.bias") if w.has(f"backbone.embd.{i}.conv.bias") else None
+            kw = dict(B=B, taps=3, segs=[(L, 0, 0)], a_rows=L, o_rows=L, bias=bias, row_mask=masks[0], ln=ln, act=ops.ACT_RELU)
+            if last:
+                x = self.buf("x_embd", (B, L, C), torch.float32)
+                self._gemm(h, f"backbone.embd.{i}.conv.weight", pe=self.pe(L) if self.cfg["use_abs_pe"] else None, out_f32=x, **kw)
+            else:
+                e = self.buf("embd%d" % i, (B, L, C), adt)
+                self._gemm(h, f"backbone.embd.{i}.conv.weight", out_act=e, **kw)
+                h = e
+        # ---- backbone (backbones.py:467-495)
+        w0 = self.win[0]
+        x, _ = self.mm_block("backbone.resselfattention", x, x, B, L, L, masks, 0, w0, "x_res")
+        for i in range(self.arch[1]):
+            x, _ = self.transformer_block(f"backbone.stem.{i}", x, B, L, masks, 0, 1, w0, "x_stem%d" % i)
+        lh, lh_act = x, None
+        feats_act = [None] * self.n_levels
+        T = L
+        nb = self.arch[2]
+        for i in range(nb):
+            x, x_act_copy = self.transformer_block(f"backbone.branch.{i}", x, B, T, masks, i, 2, self.win[1 + i],
+                                                   "feat%d" % (i + 1), want_act_copy=True)
+            T //= 2
+            feats_act[i + 1] = x_act_copy
+            lh, lh_act = self.mm_block(f"backbone.lh_branch.{i}", lh, x, B, L, T, masks, 0, w0, "lh%d" % (i & 1),
+                                       want_act_copy=(i == nb - 1))
+            if i + 1 < nb:            # hh_branch[last] is never consumed (backbones.py:485-495)
+                x, _ = self.mm_block(f"backbone.hh_branch.{i}", x, lh, B, T, L, masks, i + 1, w0, "hh%d" % i)
+        feats_act[0] = lh_act
+        # ---- neck (necks.py:62-93)
+        lat = self.buf("lat", (B, P, C), torch.float32)
+        for l in range(self.n_levels):
+            bias = w.vec(f"neck.lateral_convs.{l}.conv.bias") if w.has(f"neck.lateral_convs.{l}.conv.bias") else None
+            self._gemm(feats_act[l], f"neck.lateral_convs.{l}.conv.weight", B=B, segs=[(lens[l], 0, offs[l])], a_rows=lens[l],
+                       o_rows=P, bias=bias, row_mask=masks["pyr"], out_f32=lat)
+        fpn = self.buf("fpn", (B, P, C), adt)
+        if not hasattr(self, "_fpn_params"):
+            dw = torch.stack([w.dw(f"neck.fpn_convs.{l}.conv.weight") for l in range(self.n_levels)]).contiguous()
+            if w.has("neck.fpn_norms.0.weight"):
+                lw = torch.stack([w.vec(f"neck.fpn_norms.{l}.weight") for l in range(self.n_levels)]).contiguous()
+                lb = torch.stack([w.vec(f"neck.fpn_norms.{l}.bias") for l in range(self.n_levels)]).contiguous()
+            else:
+                raise AvdfError("fpn_with_ln=False is not on the accelerated path")
+            self._fpn_params = (dw, lw, lb)
+        ops.fpn_fuse(lat, masks["pyr"], *self._fpn_params, fpn, batch=B, level_len=lens)
+        # ---- heads (av_fd_no_recon.py:75-89, 144-159): all levels in one launch per layer
+        segs = [(lens[l], offs[l], offs[l]) for l in range(self.n_levels)]
+        towers = {}
+        nl = self.cfg["head_num_layers"] - 1
+        for head in ("cls_head", "reg_head"):
+            f = fpn
+            for i in range(nl):
+                ln = w.ln(f"{head}.norm.{i}") if w.has(f"{head}.norm.{i}.weight") else None
+                bias = w.vec(f"{head}.head.{i}.conv.bias") if w.has(f"{head}.head.{i}.conv.bias") else None
+                kw = dict(B=B, taps=3, segs=segs, a_rows=P, o_rows=P, bias=bias, row_mask=masks["pyr"], ln=ln, act=ops.ACT_RELU)
+                if i == nl - 1:       # the last tower layer stays fp32: it feeds the fp32 logit / offset conv
+                    o = self.buf(head + "_tower", (B, P, C), torch.float32)
+                    self._gemm(f, f"{head}.head.{i}.conv.weight", out_f32=o, **kw)
+                else:
+                    o = self.buf("%s_t%d" % (head, i), (B, P, C), adt)
+                    self._gemm(f, f"{head}.head.{i}.conv.weight", out_act=o, **kw)
+                f = o
+            towers[head] = f
+        logits = self.buf("logits", (B, P), torch.float32)
+        offsets = self.buf("offsets", (B, P, 2), torch.float32)
+        if not hasattr(self, "_scales"):
+            self._scales = [float(self.w.sd[f"reg_head.scale.{l}.scale"]) for l in range(self.n_levels)]
+        ops.head_final(towers["cls_head"], towers["reg_head"], masks["pyr"], w.dense("cls_head.cls_head.conv.weight", f32=True),
+                       w.vec("cls_head.cls_head.conv.bias"), w.dense("reg_head.offset_head.conv.weight", f32=True),
+                       w.vec("reg_head.offset_head.conv.bias"), self._scales, logits, offsets, batch=B, level_len=lens)
+        return logits, offsets, vcls, masks, lens
+
+    def postprocess(self, logits, offsets, masks, lens, meta, nms_method=None):
+        """meta: device fp32 [4, B] rows = feat_stride, 0.5*feat_num_frames, fps, duration (or None)."""
+        tc = self.test_cfg
+        B, P = logits.shape
+        K = int(tc["max_seg_num"])
+        method = nms_method or tc["nms_method"]
+        if method not in ("hard", "soft"):
+            raise AvdfError("nms_method %r is not on the accelerated path" % (method,))
+        if tc["multiclass_nms"] and self.num_classes > 1:
+            raise AvdfError("multiclass NMS with more than one class is not on the accelerated path")
+        cs = self.buf("cand_segs", (B, P, 2), torch.float32)
+        cc = self.buf("cand_scores", (B, P), torch.float32)
+        cn = self.buf("cand_count", (B,), torch.int32)
+        osg = self.buf("out_segs", (B, K, 2), torch.float32)
+        osc = self.buf("out_scores", (B, K), torch.float32)
+        ocn = self.buf("out_count", (B,), torch.int32)
+        # multiclass with a single class == class-agnostic without voting (nms.py:123-156)
+        voting = 0.0 if tc["multiclass_nms"] else tc["voting_thresh"]
+        ops.postprocess(B, logits=logits, offsets=offsets, mask=masks["pyr"], level_len=lens,
+                        level_stride=[float(s) for s in self.strides], pre_nms_thresh=tc["pre_nms_thresh"],
+                        pre_nms_topk=tc["pre_nms_topk"], duration_thresh=tc["duration_thresh"], cand_segs=cs, cand_scores=cc,
+                        cand_count=cn, iou_threshold=tc["iou_threshold"], min_score=tc["min_score"], sigma=tc["nms_sigma"],
+                        voting_thresh=voting, max_seg_num=K, use_soft_nms=(method == "soft"),
+                        vid_meta=None if meta is None else [meta[0], meta[1], meta[2], meta[3]],
+                        out_segs=osg, out_scores=osc, out_count=ocn)
+        return osg, osc, ocn

@@ -1,0 +1,265 @@
+"""Tensor-level wrappers of the C-ABI entry points (include/avdf.h).
+
+Each function takes CUDA torch tensors (device memory + current stream are all
+torch provides), checks shapes/dtypes, and calls straight into
+libavdf_sm100.so through `native`. No arithmetic happens in Python.
+Layout: activations are token-major [B, T, C]; conv weights are packed
+[c_out, taps * c_in] with the tap index outermost inside a row.
+"""
+import ctypes
+from ctypes import c_float, c_int32, c_void_p
+
+import torch
+
+from . import native as nv
+from .native import DTYPE_BF16, DTYPE_F32, ACT_NONE, ACT_RELU, ACT_GELU  # noqa: F401
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _chk(t, dtype=None, name="tensor"):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise nv.AvdfError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if not t.is_contiguous():
+        raise nv.AvdfError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def _levels(level_len):
+    arr = (c_int32 * len(level_len))(*[int(v) for v in level_len])
+    return arr
+
+
+# ---------------------------------------------------------------------------- K1
+def interp_concat(streams, offsets, t_out, out):
+    """streams: (video|None, byola|None, emo|None) packed [sum_T, C_s] fp32;
+    offsets: matching int32 [B+1] row prefix tensors; out [B, t_out, C_total]."""
+    L = nv.lib()
+    ptrs, offs, cs = [], [], []
+    batch = None
+    for s, o in zip(streams, offsets):
+        if s is None:
+            ptrs.append(None); offs.append(None); cs.append(0)
+            continue
+        _chk(s, torch.float32, "stream"); _chk(o, torch.int32, "offsets")
+        ptrs.append(nv.ptr(s)); offs.append(nv.ptr(o)); cs.append(s.shape[1])
+        batch = o.numel() - 1
+    _chk(out, None, "out")
+    assert out.shape == (batch, t_out, sum(cs)), (out.shape, batch, t_out, cs)
+    nv.check(L.avdf_interp_concat(ptrs[0], ptrs[1], ptrs[2], offs[0], offs[1], offs[2], batch, cs[0], cs[1], cs[2],
+                                  t_out, nv.ptr(out), _dt(out), nv.stream_ptr()), "avdf_interp_concat")
+    nv.count()
+    return out
+
+
+def pack_feats(feats_ct, out):
+    """feats_ct [C, T] fp32 (device) -> out [L, C] token-major, zero-padded rows T..L."""
+    L = nv.lib()
+    _chk(feats_ct, torch.float32, "feats"); _chk(out, None, "out")
+    C, T = feats_ct.shape
+    assert out.shape[1] == C and out.shape[0] >= T
+    nv.check(L.avdf_pack_feats(nv.ptr(feats_ct), C, T, out.shape[0], nv.ptr(out), _dt(out), nv.stream_ptr()), "avdf_pack_feats")
+    nv.count()
+
+
+# ---------------------------------------------------------------------------- NMS
+def nms_hard(segs, scores, iou_threshold, max_num=0):
+    """nms_1d_cpu.nms on device tensors -> kept indices (int64, device)."""
+    L = nv.lib()
+    _chk(segs, torch.float32, "segs"); _chk(scores, torch.float32, "scores")
+    n = scores.numel()
+    out_idx = torch.empty(max(n, 1), dtype=torch.int64, device=scores.device)
+    out_count = torch.zeros(1, dtype=torch.int32, device=scores.device)
+    wsb = L.avdf_nms_workspace_bytes(n)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=scores.device)
+    nv.check(L.avdf_nms_hard(nv.ptr(segs), nv.ptr(scores), n, float(iou_threshold), int(max_num), nv.ptr(out_idx),
+                             nv.ptr(out_count), nv.ptr(ws), wsb, nv.stream_ptr()), "avdf_nms_hard")
+    nv.count()
+    return out_idx[: int(out_count.item())]
+
+
+def nms_soft(segs, scores, dets, iou_threshold, sigma, min_score, method, max_num=0):
+    """nms_1d_cpu.softnms on device tensors: writes dets[:K] in place, returns indices."""
+    L = nv.lib()
+    _chk(segs, torch.float32, "segs"); _chk(scores, torch.float32, "scores"); _chk(dets, torch.float32, "dets")
+    n = scores.numel()
+    out_idx = torch.empty(max(n, 1), dtype=torch.int64, device=scores.device)
+    out_count = torch.zeros(1, dtype=torch.int32, device=scores.device)
+    wsb = L.avdf_nms_workspace_bytes(n)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=scores.device)
+    nv.check(L.avdf_nms_soft(nv.ptr(segs), nv.ptr(scores), n, nv.ptr(dets), float(iou_threshold), float(sigma),
+                             float(min_score), int(method), int(max_num), nv.ptr(out_idx), nv.ptr(out_count),
+                             nv.ptr(ws), wsb, nv.stream_ptr()), "avdf_nms_soft")
+    nv.count()
+    return out_idx[: int(out_count.item())]
+
+
+def postprocess(batch, *, logits=None, offsets=None, mask=None, level_len=(), level_stride=(), pre_nms_thresh=0.001,
+                pre_nms_topk=2000, duration_thresh=0.001, cand_segs, cand_scores, cand_count, iou_threshold, min_score,
+                sigma, voting_thresh, max_seg_num, use_soft_nms, soft_method=2, vid_meta=None, out_segs, out_scores,
+                out_count, workspace=None):
+    """Fused decode + batched_nms (class-agnostic) + seconds conversion; one CTA per video."""
+    L = nv.lib()
+    a = nv.PostprocessArgs()
+    a.batch = batch
+    if logits is not None:
+        _chk(logits, torch.float32, "logits"); _chk(offsets, torch.float32, "offsets"); _chk(mask, torch.uint8, "mask")
+        a.logits, a.offsets, a.mask = logits.data_ptr(), offsets.data_ptr(), mask.data_ptr()
+        a.n_levels = len(level_len)
+        for i, (n, s) in enumerate(zip(level_len, level_stride)):
+            a.level_len[i] = int(n); a.level_stride[i] = float(s)
+    a.pre_nms_thresh, a.pre_nms_topk, a.duration_thresh = float(pre_nms_thresh), int(pre_nms_topk), float(duration_thresh)
+    _chk(cand_segs, torch.float32, "cand_segs"); _chk(cand_scores, torch.float32, "cand_scores"); _chk(cand_count, torch.int32, "cand_count")
+    a.cand_segs, a.cand_scores, a.cand_count = cand_segs.data_ptr(), cand_scores.data_ptr(), cand_count.data_ptr()
+    a.cand_cap = cand_scores.shape[1]
+    a.iou_threshold, a.min_score, a.sigma, a.voting_thresh = float(iou_threshold), float(min_score), float(sigma), float(voting_thresh)
+    a.max_seg_num, a.use_soft_nms, a.soft_method = int(max_seg_num), int(bool(use_soft_nms)), int(soft_method)
+    if vid_meta is not None:
+        for t in vid_meta:
+            _chk(t, torch.float32, "vid_meta")
+        a.vid_feat_stride, a.vid_half_nframes, a.vid_fps, a.vid_duration = [t.data_ptr() for t in vid_meta]
+    _chk(out_segs, torch.float32, "out_segs"); _chk(out_scores, torch.float32, "out_scores"); _chk(out_count, torch.int32, "out_count")
+    a.out_segs, a.out_scores, a.out_count = out_segs.data_ptr(), out_scores.data_ptr(), out_count.data_ptr()
+    need = L.avdf_postprocess_workspace_bytes(batch, a.cand_cap)
+    if need:
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=out_segs.device)
+        a.workspace, a.workspace_bytes = workspace.data_ptr(), need
+    nv.check(L.avdf_postprocess(ctypes.byref(a), nv.stream_ptr()), "avdf_postprocess")
+    nv.count()
+
+
+def postprocess_workspace_bytes(batch, cand_cap):
+    return nv.lib().avdf_postprocess_workspace_bytes(batch, cand_cap)
+
+
+# ---------------------------------------------------------------------------- conv GEMM
+def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
+              act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_bf16=None, workspace=None):
+    """segs: list of (t_out, a_row, o_row) per level. a: [batch, a_rows, c_in]; w: [n_out, taps*c_in]
+    (same dtype as a). Outputs [batch, o_rows, n_out]."""
+    L = nv.lib()
+    _chk(a, None, "a"); _chk(w, a.dtype, "w")
+    g = nv.ConvGemmArgs()
+    g.batch, g.n_out, g.c_in, g.taps, g.stride, g.n_seg = batch, n_out, c_in, taps, stride, len(segs)
+    for i, (t, ar, orow) in enumerate(segs):
+        g.seg_t_out[i], g.seg_a_row[i], g.seg_o_row[i] = int(t), int(ar), int(orow)
+    g.a_rows_per_video, g.o_rows_per_video = int(a_rows), int(o_rows)
+    g.a, g.w, g.dtype = a.data_ptr(), w.data_ptr(), _dt(a)
+    for name, t in (("bias", bias), ("pe", pe), ("residual", residual), ("gamma", gamma)):
+        _chk(t, torch.float32, name)
+    _chk(row_mask, torch.uint8, "row_mask")
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.row_mask = row_mask.data_ptr() if row_mask is not None else None
+    if ln is not None:
+        _chk(ln[0], torch.float32, "ln_w"); _chk(ln[1], torch.float32, "ln_b")
+        g.ln_w, g.ln_b = ln[0].data_ptr(), ln[1].data_ptr()
+    g.act = act
+    g.pe = pe.data_ptr() if pe is not None else None
+    g.residual = residual.data_ptr() if residual is not None else None
+    g.gamma = gamma.data_ptr() if gamma is not None else None
+    _chk(out_f32, torch.float32, "out_f32"); _chk(out_bf16, torch.bfloat16, "out_bf16")
+    g.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    g.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    need = L.avdf_conv_gemm_workspace_bytes(ctypes.byref(g))
+    if need:
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=a.device)
+        g.workspace, g.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    nv.check(L.avdf_conv_gemm(ctypes.byref(g), nv.stream_ptr()), "avdf_conv_gemm")
+    nv.count(2 if g.dtype == DTYPE_F32 else 1)
+
+
+# ---------------------------------------------------------------------------- block kernels
+def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, dw, ln_out, outs, skip_out=None):
+    """ln_in / ln_out: lists of (w, b); dw: list of [C,3]; outs: list of [batch, t_virt/stride, C] tensors."""
+    L = nv.lib()
+    _chk(src, torch.float32, "src"); _chk(mask_out, torch.uint8, "mask_out"); _chk(skip_out, torch.float32, "skip_out")
+    n = len(outs)
+    a = nv.LnDwconvLnArgs()
+    a.batch, a.channels, a.t_src, a.t_virt, a.shift, a.stride, a.n_streams = batch, src.shape[-1], t_src, t_virt, shift, stride, n
+    a.src = src.data_ptr()
+    a.mask_out = mask_out.data_ptr() if mask_out is not None else None
+    for i in range(n):
+        for t in (ln_in[i][0], ln_in[i][1], dw[i], ln_out[i][0], ln_out[i][1]):
+            _chk(t, torch.float32, "param")
+        _chk(outs[i], outs[0].dtype, "out")
+        a.ln_in_w[i], a.ln_in_b[i] = ln_in[i][0].data_ptr(), ln_in[i][1].data_ptr()
+        a.dw_w[i] = dw[i].data_ptr()
+        a.ln_out_w[i], a.ln_out_b[i] = ln_out[i][0].data_ptr(), ln_out[i][1].data_ptr()
+        a.out[i] = outs[i].data_ptr()
+    a.out_dtype = _dt(outs[0])
+    a.skip_out = skip_out.data_ptr() if skip_out is not None else None
+    nv.check(L.avdf_ln_dwconv_ln(ctypes.byref(a), nv.stream_ptr()), "avdf_ln_dwconv_ln")
+    nv.count()
+
+
+def attention(q, k, v, kv_mask, out, *, batch, t, n_head, window):
+    L = nv.lib()
+    _chk(q, None, "q"); _chk(k, q.dtype, "k"); _chk(v, q.dtype, "v"); _chk(out, None, "out"); _chk(kv_mask, torch.uint8, "kv_mask")
+    nv.check(L.avdf_attention(nv.ptr(q), nv.ptr(k), nv.ptr(v), nv.ptr(kv_mask), nv.ptr(out), _dt(q), _dt(out), batch, t,
+                              q.shape[-1], n_head, window, nv.stream_ptr()), "avdf_attention")
+    nv.count()
+
+
+def ln_rows(x, w, b, out, rows):
+    L = nv.lib()
+    _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b"); _chk(out, None, "out")
+    nv.check(L.avdf_ln_rows(nv.ptr(x), nv.ptr(w), nv.ptr(b), nv.ptr(out), _dt(out), rows, x.shape[-1], nv.stream_ptr()), "avdf_ln_rows")
+    nv.count()
+
+
+def instnorm_lrelu(x, out, *, batch, t, channels, slope=0.2):
+    L = nv.lib()
+    _chk(x, torch.float32, "x"); _chk(out, None, "out")
+    nv.check(L.avdf_instnorm_lrelu(nv.ptr(x), nv.ptr(out), _dt(out), batch, t, channels, float(slope), nv.stream_ptr()), "avdf_instnorm_lrelu")
+    nv.count()
+
+
+def fpn_fuse(lat, mask, dw_w, ln_w, ln_b, out, *, batch, level_len):
+    L = nv.lib()
+    _chk(lat, torch.float32, "lat"); _chk(mask, torch.uint8, "mask"); _chk(dw_w, torch.float32, "dw_w"); _chk(out, None, "out")
+    nv.check(L.avdf_fpn_fuse(nv.ptr(lat), nv.ptr(mask), nv.ptr(dw_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(out), _dt(out), batch,
+                             lat.shape[-1], len(level_len), _levels(level_len), nv.stream_ptr()), "avdf_fpn_fuse")
+    nv.count()
+
+
+def head_final(cls_feat, reg_feat, mask, cls_w, cls_b, reg_w, reg_b, level_scale, logits, offsets, *, batch, level_len):
+    L = nv.lib()
+    _chk(cls_feat, None, "cls_feat"); _chk(reg_feat, cls_feat.dtype, "reg_feat"); _chk(mask, torch.uint8, "mask")
+    for t in (cls_w, cls_b, reg_w, reg_b, logits, offsets):
+        _chk(t, torch.float32, "head tensor")
+    sc = (c_float * len(level_scale))(*[float(s) for s in level_scale])
+    nv.check(L.avdf_head_final(nv.ptr(cls_feat), nv.ptr(reg_feat), _dt(cls_feat), nv.ptr(mask), nv.ptr(cls_w), nv.ptr(cls_b),
+                               nv.ptr(reg_w), nv.ptr(reg_b), sc, nv.ptr(logits), nv.ptr(offsets), batch, cls_feat.shape[-1],
+                               len(level_len), _levels(level_len), nv.stream_ptr()), "avdf_head_final")
+    nv.count()
+
+
+def vcls_exp12(z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, *, batch, t):
+    L = nv.lib()
+    _chk(z, None, "z")
+    for x in (conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out):
+        _chk(x, torch.float32, "vcls tensor")
+    nv.check(L.avdf_vcls_exp12(nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(lin1_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(lin2_w),
+                               nv.ptr(lin2_b), nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr()), "avdf_vcls_exp12")
+    nv.count()
+
+
+def vcls_exp13(z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, *, batch, t):
+    L = nv.lib()
+    _chk(z, None, "z")
+    for x in (conv0_w, seg_w, seg_b, cls_w, cls_b, out):
+        _chk(x, torch.float32, "vcls tensor")
+    nv.check(L.avdf_vcls_exp13(nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(seg_w), nv.ptr(seg_b), nv.ptr(cls_w), nv.ptr(cls_b),
+                               nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr()), "avdf_vcls_exp13")
+    nv.count()

@@ -20,6 +20,7 @@
  *                                   postprocessing) + libs/utils/nms.py:8-190 (NMSop, SoftNMSop,
  *                                   seg_voting, batched_nms)
  *   avdf_interp_concat              libs/datasets/deepfake_video_audio.py:513-547 (F.interpolate x3 + cat)
+ *   avdf_pack_feats                 preprocessing, libs/modeling/av_fd_no_recon.py:431-479 (pad + batch layout)
  *   avdf_conv_gemm                  MaskedConv1D (libs/modeling/blocks.py:13-63) as used by the
  *                                   embedding (backbones.py:437-445), the 1x1 projections and MLP of the
  *                                   transformer blocks (blocks.py:1169-1171,1223,1291-1297), FPN laterals
@@ -46,6 +47,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define AVDF_API __attribute__((visibility("default")))
+#else
+#define AVDF_API
+#endif
+
 #define AVDF_ABI_VERSION 1
 #define AVDF_MAX_LEVELS 8
 #define AVDF_MAX_SEGS 1024
@@ -55,28 +62,33 @@ enum { AVDF_DTYPE_F32 = 0, AVDF_DTYPE_BF16 = 1 };
 enum { AVDF_ACT_NONE = 0, AVDF_ACT_RELU = 1, AVDF_ACT_GELU = 2 };
 
 /* ---- runtime ---- */
-int avdf_abi_version(void);
-const char* avdf_last_error(void);
+AVDF_API int avdf_abi_version(void);
+AVDF_API const char* avdf_last_error(void);
 /* fills SM count and compute capability of the current device */
-int avdf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+AVDF_API int avdf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 
 /* ---- K1: per-stream linear resize to t_out + channel concat (video | byola | emo) ----
  * Streams are packed row-major [sum_b T_s(b), C_s] fp32 with per-stream prefix offsets [batch+1]
  * (rows). A stream with C_s == 0 is absent. out: [batch, t_out, c_video+c_byola+c_emo]. */
-int avdf_interp_concat(const float* video, const float* byola, const float* emo,
+AVDF_API int avdf_interp_concat(const float* video, const float* byola, const float* emo,
                        const int32_t* video_off, const int32_t* byola_off, const int32_t* emo_off,
                        int32_t batch, int32_t c_video, int32_t c_byola, int32_t c_emo, int32_t t_out,
                        void* out, int32_t out_dtype, void* stream);
+
+/* ---- preprocessing (av_fd_no_recon.py:431-479): one video's feats [channels, t] fp32 (dataset item layout)
+ * -> token-major rows out[t_padded, channels], zero-padded from t to t_padded. */
+AVDF_API int avdf_pack_feats(const float* feats_ct, int32_t channels, int32_t t, int32_t t_padded, void* out,
+                    int32_t out_dtype, void* stream);
 
 /* ---- NMS: same contracts as nms_1d_cpu.nms / nms_1d_cpu.softnms, on device memory ----
  * segs [n,2], scores [n]; out_idx [n] int64 (kept input indices, descending score / pick order);
  * out_count [1]. max_num <= 0: run to completion (the reference's behaviour); max_num > 0: stop after
  * that many picks (the wrappers consume no more, nms.py:29-30,56-63). dets [n,3] is written in place
  * for the picks, like the reference. */
-size_t avdf_nms_workspace_bytes(int32_t n);
-int avdf_nms_hard(const float* segs, const float* scores, int32_t n, float iou_threshold, int32_t max_num,
+AVDF_API size_t avdf_nms_workspace_bytes(int32_t n);
+AVDF_API int avdf_nms_hard(const float* segs, const float* scores, int32_t n, float iou_threshold, int32_t max_num,
                   int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
-int avdf_nms_soft(const float* segs, const float* scores, int32_t n, float* dets, float iou_threshold,
+AVDF_API int avdf_nms_soft(const float* segs, const float* scores, int32_t n, float* dets, float iou_threshold,
                   float sigma, float min_score, int32_t method, int32_t max_num, int64_t* out_idx,
                   int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -110,8 +122,8 @@ typedef struct avdf_postprocess_args {
   int32_t* out_count;            /* [batch]                 */
   void* workspace; size_t workspace_bytes;
 } avdf_postprocess_args;          /* host struct */
-size_t avdf_postprocess_workspace_bytes(int32_t batch, int32_t cand_cap);
-int avdf_postprocess(const avdf_postprocess_args* args, void* stream);
+AVDF_API size_t avdf_postprocess_workspace_bytes(int32_t batch, int32_t cand_cap);
+AVDF_API int avdf_postprocess(const avdf_postprocess_args* args, void* stream);
 
 /* ---- conv-as-GEMM with fused epilogue ----
  * out[b, seg_o_row + t, n] = epi( sum_{j<taps} sum_{c<c_in} W[n, j*c_in + c] * A[b, seg_a_row + stride*t + j - taps/2, c] )
@@ -133,8 +145,8 @@ typedef struct avdf_conv_gemm_args {
   float* out_f32; void* out_bf16;   /* [batch, o_rows_per_video, n_out] */
   void* workspace; size_t workspace_bytes;
 } avdf_conv_gemm_args;            /* host struct */
-size_t avdf_conv_gemm_workspace_bytes(const avdf_conv_gemm_args* args);
-int avdf_conv_gemm(const avdf_conv_gemm_args* args, void* stream);
+AVDF_API size_t avdf_conv_gemm_workspace_bytes(const avdf_conv_gemm_args* args);
+AVDF_API int avdf_conv_gemm(const avdf_conv_gemm_args* args, void* stream);
 
 /* ---- LN -> depthwise conv k3 (stride 1|2) * mask -> LN, for up to 3 streams sharing one source ----
  * src [batch, t_src, C] fp32. Virtual input position p in [0, t_virt) reads source row
@@ -153,33 +165,33 @@ typedef struct avdf_ln_dwconv_ln_args {
   int32_t out_dtype;
   float* skip_out;               /* [batch, t_virt / stride, C] fp32 or NULL */
 } avdf_ln_dwconv_ln_args;
-int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* args, void* stream);
+AVDF_API int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* args, void* stream);
 
 /* ---- multi-head attention over q,k,v [batch, t, C]; window > 1: band |i-j| <= window/2 with additive
  * -1e4 on masked keys and zeroed masked query rows (blocks.py:1152-1224); window <= 1: global with
  * -inf on masked keys (blocks.py:274-313). out [batch, t, C]. */
-int avdf_attention(const void* q, const void* k, const void* v, const uint8_t* kv_mask, void* out,
-                   int32_t dtype, int32_t batch, int32_t t, int32_t channels, int32_t n_head, int32_t window,
-                   void* stream);
+AVDF_API int avdf_attention(const void* q, const void* k, const void* v, const uint8_t* kv_mask, void* out,
+                   int32_t in_dtype, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels, int32_t n_head,
+                   int32_t window, void* stream);
 
 /* ---- LayerNorm over channels of fp32 rows -> fp32 or bf16 ---- */
-int avdf_ln_rows(const float* x, const float* w, const float* b, void* out, int32_t out_dtype, int64_t rows,
+AVDF_API int avdf_ln_rows(const float* x, const float* w, const float* b, void* out, int32_t out_dtype, int64_t rows,
                  int32_t channels, void* stream);
 
 /* ---- InstanceNorm1d over T (per video, channel; eps 1e-5, biased) + LeakyReLU(slope) ---- */
-int avdf_instnorm_lrelu(const float* x, void* out, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels,
+AVDF_API int avdf_instnorm_lrelu(const float* x, void* out, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels,
                         float slope, void* stream);
 
 /* ---- FPN top-down fuse: L_l[t] = sum_{j>=l} lat_j[t >> (j-l)]; F_l = LN_l(dwconv3_l(L_l) * mask) ----
  * lat / out are pyramids [batch, P, C] with levels concatenated per video. dw_w [n_levels, C, 3],
  * ln_w / ln_b [n_levels, C]. */
-int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float* dw_w, const float* ln_w, const float* ln_b,
+AVDF_API int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float* dw_w, const float* ln_w, const float* ln_b,
                   void* out, int32_t out_dtype, int32_t batch, int32_t channels, int32_t n_levels,
                   const int32_t* level_len /* host */, void* stream);
 
 /* ---- last conv (k3) of both heads: logits [batch,P] = cls_w . x_cls + cls_b (* mask);
  * offsets [batch,P,2] = relu((reg_w . x_reg + reg_b) * mask * scale_l). Towers are pyramids [batch,P,C]. */
-int avdf_head_final(const void* cls_feat, const void* reg_feat, int32_t dtype, const uint8_t* mask,
+AVDF_API int avdf_head_final(const void* cls_feat, const void* reg_feat, int32_t dtype, const uint8_t* mask,
                     const float* cls_w /* [1,3*C] */, const float* cls_b, const float* reg_w /* [2,3*C] */,
                     const float* reg_b, const float* level_scale /* host [n_levels] */, float* logits,
                     float* offsets, int32_t batch, int32_t channels, int32_t n_levels,
@@ -187,11 +199,11 @@ int avdf_head_final(const void* cls_feat, const void* reg_feat, int32_t dtype, c
 
 /* ---- video-level classifier tails ---- */
 /* exp12 (blocks.py:1608-1626): z [batch, t, C] (after the last DownBlock) -> logit [batch] */
-int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* lin1_w /* [C,2C] */,
+AVDF_API int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* lin1_w /* [C,2C] */,
                     const float* ln_w, const float* ln_b, const float* lin2_w /* [C] */, const float* lin2_b,
                     float* out, int32_t batch, int32_t t, int32_t channels, void* stream);
 /* exp13 (blocks.py:1682-1700): z [batch, t, C] -> logit [batch] */
-int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* seg_w /* [C] */,
+AVDF_API int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* seg_w /* [C] */,
                     const float* seg_b, const float* cls_w /* [2] */, const float* cls_b, float* out,
                     int32_t batch, int32_t t, int32_t channels, void* stream);
 
