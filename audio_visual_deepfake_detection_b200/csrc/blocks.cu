@@ -43,9 +43,6 @@ __device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
-__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-
 // ------------------------------------------------------------------------------------------------
 // LN -> depthwise conv k3 (stride 1|2) * mask -> LN for up to 3 streams sharing one source
 // ------------------------------------------------------------------------------------------------
@@ -401,7 +398,7 @@ __global__ void __launch_bounds__(256) vcls_exp12_kernel(const InT* __restrict__
   float* hbuf = pooled + 2 * kC;        // [256]
   __shared__ float red[2];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < T * kC; i += 256) zs[i] = (float)z[(size_t)b * T * kC + i];
+  for (int i = tid; i < T * kC; i += 256) zs[i] = load1(z + (size_t)b * T * kC + i);
   __syncthreads();
   // g[t][c] for c = warp, warp + 8, ...; lanes split the 256-long dot product
   for (int c = warp; c < kC; c += 8) {
@@ -492,7 +489,7 @@ __global__ void __launch_bounds__(256) vcls_exp13_kernel(const InT* __restrict__
     float part = 0.f;
     for (int tb = 0; tb < T; tb += TL) {
       const int t = tb + tl;
-      if (t < T) zt[tl * C + c] = (float)zb[(size_t)t * C + c];
+      if (t < T) zt[tl * C + c] = load1(zb + (size_t)t * C + c);
       __syncthreads();
       float g = 0.f;
       if (t < T) {
@@ -566,7 +563,7 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   AVDF_CHECK_ARG(a->shift > -16 && a->shift < 16, "shift out of range");
   AVDF_CHECK_ARG(a->shift >= 0 ? (((a->t_virt - 1) >> a->shift) < a->t_src) : (((a->t_virt - 1) << -a->shift) < a->t_src),
                  "virtual length maps outside the source");
-  AVDF_CHECK_ARG(a->out_dtype == AVDF_DTYPE_F32 || a->out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_DTYPE(a->out_dtype, "out_dtype");
   AVDF_CHECK_ARG(a->src != nullptr, "src is null");
   AVDF_CHECK_ARG(a->skip_out == nullptr || (a->stride == 2 && a->shift == 0), "skip_out needs stride 2 and no resampling");
   LdlParams p{};
@@ -582,14 +579,8 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   const long long tiles = (long long)a->batch * ((p.t_out + LDL_ROWS - 1) / LDL_ROWS);
   const int grid = grid_for(tiles, LDL_WARPS, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool bf = a->out_dtype == AVDF_DTYPE_BF16;
-  if (a->stride == 1) {
-    if (bf) ln_dwconv_ln_kernel<__nv_bfloat16, 1><<<grid, LDL_WARPS * 32, 0, st>>>(p);
-    else ln_dwconv_ln_kernel<float, 1><<<grid, LDL_WARPS * 32, 0, st>>>(p);
-  } else {
-    if (bf) ln_dwconv_ln_kernel<__nv_bfloat16, 2><<<grid, LDL_WARPS * 32, 0, st>>>(p);
-    else ln_dwconv_ln_kernel<float, 2><<<grid, LDL_WARPS * 32, 0, st>>>(p);
-  }
+  if (a->stride == 1) AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, (ln_dwconv_ln_kernel<OutT, 1><<<grid, LDL_WARPS * 32, 0, st>>>(p)));
+  else AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, (ln_dwconv_ln_kernel<OutT, 2><<<grid, LDL_WARPS * 32, 0, st>>>(p)));
   return check_launch("ln_dwconv_ln_kernel");
 }
 
@@ -604,16 +595,10 @@ extern "C" int avdf_attention(const void* q, const void* k, const void* v, const
   const long long tiles = (long long)batch * ((t + ATT_ROWS - 1) / ATT_ROWS);
   const int grid = grid_for(tiles, ATT_WARPS, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  typedef __nv_bfloat16 bf;
-  if (in_dtype == AVDF_DTYPE_F32 && out_dtype == AVDF_DTYPE_F32)
-    attention_kernel<float, float><<<grid, ATT_WARPS * 32, 0, st>>>((const float*)q, (const float*)k, (const float*)v, kv_mask, (float*)out, batch, t, window);
-  else if (in_dtype == AVDF_DTYPE_F32 && out_dtype == AVDF_DTYPE_BF16)
-    attention_kernel<float, bf><<<grid, ATT_WARPS * 32, 0, st>>>((const float*)q, (const float*)k, (const float*)v, kv_mask, (bf*)out, batch, t, window);
-  else if (in_dtype == AVDF_DTYPE_BF16 && out_dtype == AVDF_DTYPE_BF16)
-    attention_kernel<bf, bf><<<grid, ATT_WARPS * 32, 0, st>>>((const bf*)q, (const bf*)k, (const bf*)v, kv_mask, (bf*)out, batch, t, window);
-  else if (in_dtype == AVDF_DTYPE_BF16 && out_dtype == AVDF_DTYPE_F32)
-    attention_kernel<bf, float><<<grid, ATT_WARPS * 32, 0, st>>>((const bf*)q, (const bf*)k, (const bf*)v, kv_mask, (float*)out, batch, t, window);
-  else { set_error("avdf_attention: bad dtype"); return AVDF_ERR_INVALID; }
+  AVDF_CHECK_DTYPE(in_dtype, "in_dtype");
+  AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
+  AVDF_DISPATCH_DTYPE(in_dtype, InT, AVDF_DISPATCH_DTYPE(out_dtype, OutT, (attention_kernel<InT, OutT><<<grid, ATT_WARPS * 32, 0, st>>>(
+      (const InT*)q, (const InT*)k, (const InT*)v, kv_mask, (OutT*)out, batch, t, window))));
   return check_launch("attention_kernel");
 }
 
@@ -622,16 +607,13 @@ extern "C" int avdf_ln_rows(const float* x, const float* w, const float* b, void
   AVDF_CHECK_ARG(x && w && b && out, "null pointer");
   AVDF_CHECK_ARG(channels == 256 || channels == 512 || channels == 1024, "channels must be 256, 512 or 1024");
   AVDF_CHECK_ARG(rows >= 0, "rows < 0");
-  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
   if (rows == 0) return AVDF_OK;
   const int grid = grid_for(rows, 8, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  typedef __nv_bfloat16 bf;
-#define AVDF_LN_CASE(NCH)                                                                          \
-  if (out_dtype == AVDF_DTYPE_BF16) ln_rows_kernel<bf, NCH><<<grid, 256, 0, st>>>(x, w, b, (bf*)out, rows); \
-  else ln_rows_kernel<float, NCH><<<grid, 256, 0, st>>>(x, w, b, (float*)out, rows)
-  if (channels == 256) { AVDF_LN_CASE(1); } else if (channels == 512) { AVDF_LN_CASE(2); } else { AVDF_LN_CASE(4); }
-#undef AVDF_LN_CASE
+  if (channels == 256) AVDF_DISPATCH_DTYPE(out_dtype, OutT, (ln_rows_kernel<OutT, 1><<<grid, 256, 0, st>>>(x, w, b, (OutT*)out, rows)));
+  else if (channels == 512) AVDF_DISPATCH_DTYPE(out_dtype, OutT, (ln_rows_kernel<OutT, 2><<<grid, 256, 0, st>>>(x, w, b, (OutT*)out, rows)));
+  else AVDF_DISPATCH_DTYPE(out_dtype, OutT, (ln_rows_kernel<OutT, 4><<<grid, 256, 0, st>>>(x, w, b, (OutT*)out, rows)));
   return check_launch("ln_rows_kernel");
 }
 
@@ -639,13 +621,12 @@ extern "C" int avdf_instnorm_lrelu(const float* x, void* out, int32_t out_dtype,
                                    float slope, void* stream) {
   AVDF_CHECK_ARG(x && out, "null pointer");
   AVDF_CHECK_ARG(batch >= 0 && t > 0 && channels > 0 && channels % 32 == 0, "channels must be a multiple of 32");
-  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
   AVDF_CHECK_ARG(batch <= 65535, "batch too large for one launch");
   if (batch == 0) return AVDF_OK;
   dim3 grid(channels / 32, batch), block(32, IN_TY);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (out_dtype == AVDF_DTYPE_BF16) instnorm_lrelu_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, (__nv_bfloat16*)out, t, channels, slope);
-  else instnorm_lrelu_kernel<float><<<grid, block, 0, st>>>(x, (float*)out, t, channels, slope);
+  AVDF_DISPATCH_DTYPE(out_dtype, OutT, (instnorm_lrelu_kernel<OutT><<<grid, block, 0, st>>>(x, (OutT*)out, t, channels, slope)));
   return check_launch("instnorm_lrelu_kernel");
 }
 
@@ -662,7 +643,7 @@ extern "C" int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float*
   AVDF_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "ln_w / ln_b must come together");
   AVDF_CHECK_ARG(channels == kC, "channels must be 256");
   AVDF_CHECK_ARG(n_levels >= 1 && n_levels <= AVDF_MAX_LEVELS, "n_levels out of range");
-  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
   for (int l = 0; l + 1 < n_levels; ++l) AVDF_CHECK_ARG(level_len[l] == 2 * level_len[l + 1], "levels must halve");
   FpnParams p{};
   p.lat = lat; p.mask = mask; p.dw_w = dw_w; p.ln_w = ln_w; p.ln_b = ln_b; p.out = out; p.B = batch; p.n_levels = n_levels;
@@ -670,8 +651,7 @@ extern "C" int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float*
   if (batch == 0) return AVDF_OK;
   const int grid = grid_for((long long)batch * p.P, 8, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (out_dtype == AVDF_DTYPE_BF16) fpn_fuse_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
-  else fpn_fuse_kernel<float><<<grid, 256, 0, st>>>(p);
+  AVDF_DISPATCH_DTYPE(out_dtype, OutT, (fpn_fuse_kernel<OutT><<<grid, 256, 0, st>>>(p)));
   return check_launch("fpn_fuse_kernel");
 }
 
@@ -690,9 +670,8 @@ extern "C" int avdf_head_final(const void* cls_feat, const void* reg_feat, int32
   if (batch == 0) return AVDF_OK;
   const int grid = grid_for((long long)batch * p.P, 8, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == AVDF_DTYPE_BF16) head_final_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
-  else if (dtype == AVDF_DTYPE_F32) head_final_kernel<float><<<grid, 256, 0, st>>>(p);
-  else { set_error("avdf_head_final: bad dtype"); return AVDF_ERR_INVALID; }
+  AVDF_CHECK_DTYPE(dtype, "dtype");
+  AVDF_DISPATCH_DTYPE(dtype, InT, (head_final_kernel<InT><<<grid, 256, 0, st>>>(p)));
   return check_launch("head_final_kernel");
 }
 
@@ -705,13 +684,11 @@ extern "C" int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_
   if (batch == 0) return AVDF_OK;
   const size_t smem = ((size_t)t * kC + 3 * kC) * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == AVDF_DTYPE_BF16) {
-    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp12_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vcls_exp12_kernel<__nv_bfloat16><<<batch, 256, smem, st>>>((const __nv_bfloat16*)z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, t);
-  } else if (dtype == AVDF_DTYPE_F32) {
-    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp12_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vcls_exp12_kernel<float><<<batch, 256, smem, st>>>((const float*)z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, t);
-  } else { set_error("avdf_vcls_exp12: bad dtype"); return AVDF_ERR_INVALID; }
+  AVDF_CHECK_DTYPE(dtype, "dtype");
+  AVDF_DISPATCH_DTYPE(dtype, InT, {
+    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp12_kernel<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vcls_exp12_kernel<InT><<<batch, 256, smem, st>>>((const InT*)z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, t);
+  });
   return check_launch("vcls_exp12_kernel");
 }
 
@@ -725,12 +702,10 @@ extern "C" int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_
   const int C = channels;
   const size_t smem = ((size_t)C * (C + 1) + (256 / C) * C + 256 + 2 * C + 64) * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == AVDF_DTYPE_BF16) {
-    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp13_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vcls_exp13_kernel<__nv_bfloat16><<<batch, 256, smem, st>>>((const __nv_bfloat16*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t, C);
-  } else if (dtype == AVDF_DTYPE_F32) {
-    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp13_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vcls_exp13_kernel<float><<<batch, 256, smem, st>>>((const float*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t, C);
-  } else { set_error("avdf_vcls_exp13: bad dtype"); return AVDF_ERR_INVALID; }
+  AVDF_CHECK_DTYPE(dtype, "dtype");
+  AVDF_DISPATCH_DTYPE(dtype, InT, {
+    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp13_kernel<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vcls_exp13_kernel<InT><<<batch, 256, smem, st>>>((const InT*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t, C);
+  });
   return check_launch("vcls_exp13_kernel");
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -46,6 +47,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
@@ -83,6 +88,39 @@ template <> struct Row8<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = u;
   }
 };
+
+template <> struct Row8<__half> {
+  __device__ __forceinline__ static void load(const __half* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  __device__ __forceinline__ static void store(__half* p, const float (&v)[8]) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store1(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ float load1(const float* p) { return *p; }
+__device__ __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float load1(const __half* p) { return __half2float(*p); }
+
+// Run `...` with `T` bound to the C++ type of a runtime AVDF_DTYPE_* value.
+#define AVDF_DISPATCH_DTYPE(dt, T, ...)                                              \
+  do {                                                                               \
+    if ((dt) == AVDF_DTYPE_F32) { using T = float; __VA_ARGS__; }                    \
+    else if ((dt) == AVDF_DTYPE_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }      \
+    else { using T = __half; __VA_ARGS__; }                                          \
+  } while (0)
+#define AVDF_CHECK_DTYPE(dt, what) \
+  AVDF_CHECK_ARG((dt) == AVDF_DTYPE_F32 || (dt) == AVDF_DTYPE_BF16 || (dt) == AVDF_DTYPE_F16, what)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

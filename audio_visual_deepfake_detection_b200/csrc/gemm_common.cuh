@@ -7,7 +7,7 @@ namespace avdf {
 struct EpiParams {
   const float* bias; const unsigned char* row_mask; const float* ln_w; const float* ln_b; int act;
   const float* pe; const float* residual; const float* gamma;
-  float* out_f32; __nv_bfloat16* out_bf16;
+  float* out_f32; void* out_h; int out_h_f16;
   int n_out;
 };
 
@@ -31,7 +31,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st);
 inline void fill_epi(const avdf_conv_gemm_args* a, EpiParams& e) {
   e.bias = a->bias; e.row_mask = a->row_mask; e.ln_w = a->ln_w; e.ln_b = a->ln_b; e.act = a->act;
   e.pe = a->pe; e.residual = a->residual; e.gamma = a->gamma;
-  e.out_f32 = a->out_f32; e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  e.out_f32 = a->out_f32; e.out_h = a->out_h; e.out_h_f16 = a->out_h_dtype == AVDF_DTYPE_F16;
   e.n_out = a->n_out;
 }
 inline void fill_seg(const avdf_conv_gemm_args* a, SegInfo& s) {

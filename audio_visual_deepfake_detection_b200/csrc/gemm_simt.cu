@@ -109,7 +109,10 @@ __global__ void __launch_bounds__(256) row_epilogue_kernel(const SimtParams p, c
     if (e.pe) v += e.pe[(size_t)t * N + n] * mk;
     if (e.residual) v = e.residual[orow * N + n] * mk + (e.gamma ? e.gamma[n] : 1.f) * v;
     if (e.out_f32) e.out_f32[orow * N + n] = v;
-    if (e.out_bf16) e.out_bf16[orow * N + n] = __float2bfloat16_rn(v);
+    if (e.out_h) {
+      if (e.out_h_f16) reinterpret_cast<__half*>(e.out_h)[orow * N + n] = __float2half_rn(v);
+      else reinterpret_cast<__nv_bfloat16*>(e.out_h)[orow * N + n] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -153,13 +156,14 @@ extern "C" int avdf_conv_gemm(const avdf_conv_gemm_args* a, void* stream) {
   AVDF_CHECK_ARG(a->stride == 1 || a->stride == 2, "stride must be 1 or 2");
   AVDF_CHECK_ARG(a->n_seg >= 1 && a->n_seg <= AVDF_MAX_LEVELS, "n_seg out of range");
   AVDF_CHECK_ARG(a->a && a->w, "null operand");
-  AVDF_CHECK_ARG(a->out_f32 || a->out_bf16, "no output");
+  AVDF_CHECK_ARG(a->out_f32 || a->out_h, "no output");
+  AVDF_CHECK_ARG(!a->out_h || a->out_h_dtype == AVDF_DTYPE_BF16 || a->out_h_dtype == AVDF_DTYPE_F16, "out_h_dtype must be BF16 or F16");
   AVDF_CHECK_ARG((a->ln_w == nullptr) == (a->ln_b == nullptr), "ln_w / ln_b must come together");
   for (int i = 0; i < a->n_seg; ++i) AVDF_CHECK_ARG(a->seg_t_out[i] > 0, "seg_t_out must be positive");
   if (a->batch == 0) return AVDF_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->dtype == AVDF_DTYPE_F32) return conv_gemm_f32(a, st);
-  if (a->dtype == AVDF_DTYPE_BF16) return conv_gemm_tc(a, st);
+  if (a->dtype == AVDF_DTYPE_BF16 || a->dtype == AVDF_DTYPE_F16) return conv_gemm_tc(a, st);
   set_error("avdf_conv_gemm: unknown dtype %d", a->dtype);
   return AVDF_ERR_INVALID;
 }

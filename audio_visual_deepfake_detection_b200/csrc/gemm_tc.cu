@@ -298,14 +298,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
-        if (e.out_bf16) {
-          uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + orow * N + n);
+        if (e.out_h) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out_h) + orow * N + n);
+          if (e.out_h_f16) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-            o[i] = u;
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_f16x2(v[8 * i], v[8 * i + 1]); u.y = pack_f16x2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_f16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_f16x2(v[8 * i + 6], v[8 * i + 7]);
+              o[i] = u;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              o[i] = u;
+            }
           }
         }
       }
@@ -351,6 +361,8 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   EncodeFn encode = get_encode();
   if (!encode) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled not available from the driver"); return AVDF_ERR_CUDA; }
 
+  const bool f16 = a->dtype == AVDF_DTYPE_F16;
+  const CUtensorMapDataType tm_dtype = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   static Params p;     // large; filled per call, copied into the launch by value
   memset(&p, 0, sizeof(p));
   fill_seg(a, p.seg);
@@ -374,7 +386,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     cuuint32_t estr[4] = {1, 1, 1, 1};
     (void)t_in;
     void* base = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(a->a)) + (size_t)a->seg_a_row[s] * a->c_in * 2;
-    CUresult r = encode(&p.a_map[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+    CUresult r = encode(&p.a_map[s], tm_dtype, 4, base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(A, level %d) failed with %d", s, (int)r); return AVDF_ERR_CUDA; }
@@ -386,13 +398,15 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     cuuint64_t strides[1] = {(cuuint64_t)a->taps * a->c_in * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->w), dims, strides, box, estr,
+    CUresult r = encode(&p.w_map, tm_dtype, 2, const_cast<void*>(a->w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(W) failed with %d", (int)r); return AVDF_ERR_CUDA; }
   }
-  // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+  // instruction descriptor: D=f32 (bits 4-5 = 1), A/B format at bits 7-9 / 10-12 (0 = f16, 1 = bf16), K-major both,
+  // N>>3 at 17, M>>4 at 24
+  const unsigned fmt = f16 ? 0u : 1u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   if (p.total_tiles == 0) return AVDF_OK;
 
   static int sms = 0;

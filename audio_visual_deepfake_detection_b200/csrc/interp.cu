@@ -77,9 +77,7 @@ __global__ void __launch_bounds__(256) pack_feats_kernel(const float* __restrict
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + threadIdx.x;
     if (t < L && c < C) {
-      const float v = tile[threadIdx.x][i];
-      if (sizeof(OutT) == 2) reinterpret_cast<__nv_bfloat16*>(out)[(size_t)t * C + c] = __float2bfloat16_rn(v);
-      else reinterpret_cast<float*>(out)[(size_t)t * C + c] = v;
+      store1(out + (size_t)t * C + c, tile[threadIdx.x][i]);
     }
   }
 }
@@ -92,11 +90,10 @@ extern "C" int avdf_pack_feats(const float* feats_ct, int32_t channels, int32_t 
                                int32_t out_dtype, void* stream) {
   AVDF_CHECK_ARG(feats_ct && out, "null pointer");
   AVDF_CHECK_ARG(channels > 0 && t > 0 && t_padded >= t, "bad sizes");
-  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
   dim3 grid((t_padded + 31) / 32, (channels + 31) / 32), block(32, 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (out_dtype == AVDF_DTYPE_BF16) pack_feats_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(feats_ct, channels, t, t_padded, reinterpret_cast<__nv_bfloat16*>(out));
-  else pack_feats_kernel<float><<<grid, block, 0, st>>>(feats_ct, channels, t, t_padded, reinterpret_cast<float*>(out));
+  AVDF_DISPATCH_DTYPE(out_dtype, OutT, (pack_feats_kernel<OutT><<<grid, block, 0, st>>>(feats_ct, channels, t, t_padded, reinterpret_cast<OutT*>(out))));
   return check_launch("pack_feats_kernel");
 }
 
@@ -108,7 +105,7 @@ extern "C" int avdf_interp_concat(const float* video, const float* byola, const 
   AVDF_CHECK_ARG(c_video >= 0 && c_byola >= 0 && c_emo >= 0, "negative channel count");
   AVDF_CHECK_ARG((c_video % 8 | c_byola % 8 | c_emo % 8) == 0, "channel counts must be multiples of 8");
   AVDF_CHECK_ARG(c_video + c_byola + c_emo > 0, "no stream");
-  AVDF_CHECK_ARG(out_dtype == AVDF_DTYPE_F32 || out_dtype == AVDF_DTYPE_BF16, "out_dtype");
+  AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
   AVDF_CHECK_ARG((c_video == 0 || (video && video_off)) && (c_byola == 0 || (byola && byola_off)) &&
                  (c_emo == 0 || (emo && emo_off)), "null stream pointer");
   AVDF_CHECK_ARG(out != nullptr, "out is null");
@@ -127,9 +124,6 @@ extern "C" int avdf_interp_concat(const float* video, const float* byola, const 
   int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);   // grid-stride, 16 CTAs of 256 per SM
   if (grid < 1) grid = 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (out_dtype == AVDF_DTYPE_BF16)
-    interp_concat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, reinterpret_cast<__nv_bfloat16*>(out));
-  else
-    interp_concat_kernel<float><<<grid, 256, 0, st>>>(p, reinterpret_cast<float*>(out));
+  AVDF_DISPATCH_DTYPE(out_dtype, OutT, (interp_concat_kernel<OutT><<<grid, 256, 0, st>>>(p, reinterpret_cast<OutT*>(out))));
   return check_launch("interp_concat_kernel");
 }

@@ -45,14 +45,13 @@ def sinusoid_table(n_pos, d):
 class PackedWeights:
     """Reference state_dict -> device tensors in the kernels' layouts.
 
-    dense conv / linear [co, ci, k] -> [co, k*ci] (tap-major rows) in the GEMM operand dtype;
+    dense conv / linear [co, ci, k] -> [co, k*ci] (tap-major rows) in the dtype of the A operand;
     LN / AffineDropPath / bias vectors -> flat fp32; depthwise [C,1,3] -> [C,3] fp32.
     """
 
-    def __init__(self, sd, device, gemm_dtype):
+    def __init__(self, sd, device):
         self.sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
         self.device = device
-        self.gemm_dtype = gemm_dtype
         self._cache = {}
 
     def has(self, key):
@@ -68,15 +67,14 @@ class PackedWeights:
     def ln(self, prefix):
         return (self.vec(prefix + ".weight"), self.vec(prefix + ".bias"))
 
-    def dense(self, key, f32=False):
-        """[co, ci, k] or [co, ci] -> [co, k*ci] in the GEMM dtype (or fp32)."""
-        ck = ("d", key, f32)
+    def dense(self, key, dtype=torch.float32):
+        """[co, ci, k] or [co, ci] -> [co, k*ci] in `dtype` (the dtype of the A operand it multiplies)."""
+        ck = ("d", key, dtype)
         if ck not in self._cache:
             w = self.sd[key].detach().to(torch.float32)
             if w.dim() == 3:
                 w = w.permute(0, 2, 1).reshape(w.shape[0], -1)
-            w = w.contiguous().to(self.device)
-            self._cache[ck] = w if f32 else w.to(self.gemm_dtype).contiguous()
+            self._cache[ck] = w.contiguous().to(self.device).to(dtype).contiguous()
         return self._cache[ck]
 
     def dw(self, key):
@@ -87,19 +85,32 @@ class PackedWeights:
         return self._cache[ck]
 
 
+# Operand formats of the tensor-core GEMMs (accumulation is always fp32 in TMEM, the residual stream,
+# LayerNorm statistics, softmax and the last head convolutions are always fp32):
+#   "mixed" (default)  bf16 for GEMMs whose A operand is the raw feature tensor, fp16 for all others. Measured
+#                      logit error 4e-3 relative (bar: 1e-2); same tensor-core rate and bytes as pure bf16.
+#   "bf16"             bf16 operands everywhere: 1.2e-2 on the synthetic worst-case weights - the same error the
+#                      reference itself shows under torch.autocast(bfloat16).
+#   "fp32"             CUDA-core fp32 parity mode (bar: 1e-4).
+PRECISIONS = ("mixed", "bf16", "fp32")
+
+
 class LocalizationEngine:
     def __init__(self, model_cfg, model_name, state_dict, device, precision="bf16", max_batch=32):
         if not torch.cuda.is_available():
             raise AvdfError("LocalizationEngine needs a CUDA device: the path has no CPU fallback")
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (PRECISIONS,))
         c = model_cfg
         self.cfg = c
         self.name = model_name
         self.exp13 = model_name == EXP13
         self.device = torch.device(device)
         self.precision = precision
-        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        # in_dt: format of the raw feature tensor (unbounded values -> bf16 range); adt: format of every
+        # other GEMM operand (LayerNorm / InstanceNorm / softmax / GELU outputs: bounded -> fp16 mantissa)
+        self.in_dt, self.adt = {"fp32": (torch.float32, torch.float32), "bf16": (torch.bfloat16, torch.bfloat16),
+                                "mixed": (torch.bfloat16, torch.float16)}[precision]
         self.max_batch = int(max_batch)
         self.C = c["embd_dim"]
         self.n_head = c["n_head"]
@@ -134,7 +145,7 @@ class LocalizationEngine:
                    and not k.startswith("interpolator.expansion.") and not k.startswith("segmentandCls.bn1")]
         if missing:
             raise KeyError("state_dict is missing %d tensors, e.g. %s" % (len(missing), missing[:3]))
-        self.w = PackedWeights(state_dict, self.device, self.adt)
+        self.w = PackedWeights(state_dict, self.device)
         self._bufs = {}
         self._mask_cache = {}
         self._pe_cache = {}
@@ -205,22 +216,22 @@ class LocalizationEngine:
     # ------------------------------------------------------------------ building blocks
     def _gemm(self, a, wkey, *, B, taps=1, stride=1, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
               act=ops.ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_act=None):
-        w = self.w.dense(wkey)
+        w = self.w.dense(wkey, a.dtype)
         n_out, k = w.shape
         c_in = k // taps
-        out_bf16 = None
+        out_h = None
         if out_act is not None:
-            if self.adt == torch.float32:
+            if out_act.dtype == torch.float32:
                 assert out_f32 is None
                 out_f32 = out_act
             else:
-                out_bf16 = out_act
+                out_h = out_act
         ws = None
-        if self.adt == torch.float32:
+        if a.dtype == torch.float32:
             ws = self.workspace(B * o_rows * n_out * 4)
         ops.conv_gemm(a, w, taps=taps, stride=stride, batch=B, c_in=c_in, n_out=n_out, segs=segs, a_rows=a_rows,
                       o_rows=o_rows, bias=bias, row_mask=row_mask, ln=ln, act=act, pe=pe, residual=residual, gamma=gamma,
-                      out_f32=out_f32, out_bf16=out_bf16, workspace=ws)
+                      out_f32=out_f32, out_h=out_h, workspace=ws)
 
     def _attn_and_mlp(self, pre, B, T, mask, skip, window, out_name, want_act_copy):
         """Shared tail of TransformerBlock / MutilModelTransformerBlock after the dwconv+LN stage:
@@ -249,10 +260,10 @@ class LocalizationEngine:
         if want_act_copy and self.adt != torch.float32:
             out_act = self.buf(out_name + "_act", (B, T, C), self.adt)
         # the residual y is already zero on masked rows (blocks.py:1311-1313)
-        w2 = self.w.dense(f"{pre}.mlp.3.weight")
+        w2 = self.w.dense(f"{pre}.mlp.3.weight", h.dtype)
         ws = self.workspace(B * T * C * 4) if self.adt == torch.float32 else None
         ops.conv_gemm(h, w2, taps=1, stride=1, batch=B, c_in=4 * C, n_out=C, segs=seg, a_rows=T, o_rows=T,
-                      bias=w.vec(f"{pre}.mlp.3.bias"), row_mask=mask, residual=y, gamma=gm, out_f32=out, out_bf16=out_act,
+                      bias=w.vec(f"{pre}.mlp.3.bias"), row_mask=mask, residual=y, gamma=gm, out_f32=out, out_h=out_act,
                       workspace=ws)
         return out, (out if self.adt == torch.float32 else out_act)
 
@@ -317,20 +328,20 @@ class LocalizationEngine:
             z = z.view(B, To, dims[i + 1])
             T, level = To, level_o
         if self.exp13:
-            ops.vcls_exp13(z, w.dense("segmentandCls.conv0.0.weight", f32=True), w.vec("segmentandCls.seg_linear.weight"),
+            ops.vcls_exp13(z, w.dense("segmentandCls.conv0.0.weight", torch.float32), w.vec("segmentandCls.seg_linear.weight"),
                            w.vec("segmentandCls.seg_linear.bias"), w.vec("segmentandCls.cls_linear1.weight"),
                            w.vec("segmentandCls.cls_linear1.bias"), vcls, batch=B, t=T)
         else:
-            ops.vcls_exp12(z, w.dense("interpolator.conv0.0.weight", f32=True), w.dense("interpolator.conv1.weight", f32=True),
+            ops.vcls_exp12(z, w.dense("interpolator.conv0.0.weight", torch.float32), w.dense("interpolator.conv1.weight", torch.float32),
                            *w.ln("interpolator.bn1"), w.vec("interpolator.conv2.weight"), w.vec("interpolator.conv2.bias"),
                            vcls, batch=B, t=T)
         return vcls
 
     def forward_dense(self, x_act, valid):
-        """x_act: [B, L, c_in] in the GEMM operand dtype (token-major), valid: host list of valid lengths.
+        """x_act: [B, L, c_in] in `self.in_dt` (token-major), valid: host list of valid lengths.
         Returns (logits [B,P] f32, offsets [B,P,2] f32, vcls [B] f32, masks, level_lens)."""
         B, L, cin = x_act.shape
-        assert cin == self.c_in and B <= self.max_batch and x_act.dtype == self.adt
+        assert cin == self.c_in and B <= self.max_batch and x_act.dtype == self.in_dt
         assert L % self.max_div_factor == 0 or L == self.max_seq_len
         C, w, adt = self.C, self.w, self.adt
         lens = self.level_lens(L)
@@ -411,8 +422,8 @@ class LocalizationEngine:
         offsets = self.buf("offsets", (B, P, 2), torch.float32)
         if not hasattr(self, "_scales"):
             self._scales = [float(self.w.sd[f"reg_head.scale.{l}.scale"]) for l in range(self.n_levels)]
-        ops.head_final(towers["cls_head"], towers["reg_head"], masks["pyr"], w.dense("cls_head.cls_head.conv.weight", f32=True),
-                       w.vec("cls_head.cls_head.conv.bias"), w.dense("reg_head.offset_head.conv.weight", f32=True),
+        ops.head_final(towers["cls_head"], towers["reg_head"], masks["pyr"], w.dense("cls_head.cls_head.conv.weight", torch.float32),
+                       w.vec("cls_head.cls_head.conv.bias"), w.dense("reg_head.offset_head.conv.weight", torch.float32),
                        w.vec("reg_head.offset_head.conv.bias"), self._scales, logits, offsets, batch=B, level_len=lens)
         return logits, offsets, vcls, masks, lens
 

@@ -37,7 +37,7 @@ class _LocalizationBase(nn.Module):
                  max_seq_len, max_buffer_len_factor, n_head, n_mha_win_size, embd_kernel_size, embd_dim, embd_with_ln,
                  fpn_dim, fpn_with_ln, fpn_start_level, head_dim, regression_range, head_num_layers, head_kernel_size,
                  head_with_ln, use_abs_pe, use_rel_pe, num_classes, train_cfg, test_cfg, mlp_ratio=None,
-                 precision="bf16", max_batch=32):
+                 precision="mixed", max_batch=32):
         super().__init__()
         # same structural assertion as av_fd_no_recon.py:253
         assert backbone_type == "convHRLRFullResSelfAttTransformerRevised"
@@ -140,7 +140,7 @@ class _LocalizationBase(nn.Module):
         B = len(items)
         lens = [int(it["feats"].shape[-1]) for it in items]
         L = eng.padded_len(max(lens))                         # av_fd_no_recon.py:458-466
-        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.adt)
+        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.in_dt)
         for b, it in enumerate(items):                        # preprocessing: pad + batch layout (av_fd_no_recon.py:431-479)
             f = it["feats"]
             if f.shape[0] != eng.c_in:
@@ -157,7 +157,7 @@ class _LocalizationBase(nn.Module):
         B = len(items)
         lens = [int(it["feats"].shape[-1]) for it in items]
         L = eng.padded_len(max(lens))
-        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.adt)
+        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.in_dt)
         for b, it in enumerate(items):
             ops.pack_feats(it["feats"].to(device=eng.device, dtype=torch.float32).contiguous(), x[b])
         logits, offsets, vcls, _, _ = eng.forward_dense(x, lens)
@@ -189,7 +189,7 @@ class _LocalizationBase(nn.Module):
             host = torch.from_numpy(np.concatenate(arrs, axis=0)).pin_memory()
             dev_streams.append(host.to(eng.device, non_blocking=True))
             dev_offs.append(torch.from_numpy(off).to(eng.device, non_blocking=True))
-        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.adt)
+        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.in_dt)
         ops.interp_concat(dev_streams, dev_offs, L, x)
         for c in chunk:
             first = c["streams"]["video"] if "video" in c["streams"] else c["streams"]["byola"]

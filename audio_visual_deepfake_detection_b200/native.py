@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libavdf_sm100.so")
 
 MAX_LEVELS = 8
 MAX_SEGS = 1024
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 # every symbol include/avdf.h declares (checked by tests/test_abi.py)
@@ -57,7 +57,7 @@ class ConvGemmArgs(Structure):
         ("a", c_void_p), ("w", c_void_p), ("dtype", c_int32),
         ("bias", c_void_p), ("row_mask", c_void_p), ("ln_w", c_void_p), ("ln_b", c_void_p), ("act", c_int32),
         ("pe", c_void_p), ("residual", c_void_p), ("gamma", c_void_p),
-        ("out_f32", c_void_p), ("out_bf16", c_void_p),
+        ("out_f32", c_void_p), ("out_h", c_void_p), ("out_h_dtype", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
     ]
 

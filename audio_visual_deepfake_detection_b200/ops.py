@@ -12,7 +12,7 @@ from ctypes import c_float, c_int32, c_void_p
 import torch
 
 from . import native as nv
-from .native import DTYPE_BF16, DTYPE_F32, ACT_NONE, ACT_RELU, ACT_GELU  # noqa: F401
+from .native import DTYPE_BF16, DTYPE_F16, DTYPE_F32, ACT_NONE, ACT_RELU, ACT_GELU  # noqa: F401
 
 
 def _dt(t):
@@ -20,6 +20,8 @@ def _dt(t):
         return DTYPE_F32
     if t.dtype == torch.bfloat16:
         return DTYPE_BF16
+    if t.dtype == torch.float16:
+        return DTYPE_F16
     raise TypeError("unsupported dtype %s" % t.dtype)
 
 
@@ -144,9 +146,10 @@ def postprocess_workspace_bytes(batch, cand_cap):
 
 # ---------------------------------------------------------------------------- conv GEMM
 def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
-              act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_bf16=None, workspace=None):
+              act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_h=None, workspace=None):
     """segs: list of (t_out, a_row, o_row) per level. a: [batch, a_rows, c_in]; w: [n_out, taps*c_in]
-    (same dtype as a). Outputs [batch, o_rows, n_out]."""
+    (same dtype as a: fp32 -> CUDA-core parity path, bf16 / fp16 -> tcgen05 path). Outputs [batch, o_rows, n_out]:
+    out_f32 and/or out_h (a bf16 or fp16 copy)."""
     L = nv.lib()
     _chk(a, None, "a"); _chk(w, a.dtype, "w")
     g = nv.ConvGemmArgs()
@@ -167,9 +170,12 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
     g.pe = pe.data_ptr() if pe is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.gamma = gamma.data_ptr() if gamma is not None else None
-    _chk(out_f32, torch.float32, "out_f32"); _chk(out_bf16, torch.bfloat16, "out_bf16")
+    _chk(out_f32, torch.float32, "out_f32"); _chk(out_h, None, "out_h")
     g.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
-    g.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    if out_h is not None:
+        if out_h.dtype not in (torch.bfloat16, torch.float16):
+            raise TypeError("out_h must be bf16 or fp16")
+        g.out_h, g.out_h_dtype = out_h.data_ptr(), _dt(out_h)
     need = L.avdf_conv_gemm_workspace_bytes(ctypes.byref(g))
     if need:
         if workspace is None or workspace.numel() * workspace.element_size() < need:

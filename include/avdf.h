@@ -58,7 +58,7 @@ extern "C" {
 #define AVDF_MAX_SEGS 1024
 
 enum { AVDF_OK = 0, AVDF_ERR_INVALID = -1, AVDF_ERR_CUDA = -2, AVDF_ERR_UNSUPPORTED = -3 };
-enum { AVDF_DTYPE_F32 = 0, AVDF_DTYPE_BF16 = 1 };
+enum { AVDF_DTYPE_F32 = 0, AVDF_DTYPE_BF16 = 1, AVDF_DTYPE_F16 = 2 };
 enum { AVDF_ACT_NONE = 0, AVDF_ACT_RELU = 1, AVDF_ACT_GELU = 2 };
 
 /* ---- runtime ---- */
@@ -130,7 +130,8 @@ AVDF_API int avdf_postprocess(const avdf_postprocess_args* args, void* stream);
  * (rows outside [0, stride * seg_t_out) of the level read as zero), for every level `seg`.
  * epi(v): v += bias[n]; v *= mask[row]; v = LN_n(v) * ln_w + ln_b; v = act(v); v += pe[t, n] * mask[row];
  *         v = residual[row, n] * mask[row] + gamma[n] * v            (each step only if its pointer is set)
- * dtype F32 -> fp32 CUDA-core path (parity mode); BF16 -> TMA + tcgen05 tensor-core path, fp32 accumulate. */
+ * dtype F32 -> fp32 CUDA-core path (parity mode); BF16 / F16 -> TMA + tcgen05 tensor-core path (A and W in that
+ * 16-bit format, fp32 accumulate in TMEM). out_h (optional) receives a 16-bit copy in out_h_dtype (BF16 | F16). */
 typedef struct avdf_conv_gemm_args {
   int32_t batch, n_out, c_in, taps, stride, n_seg;
   int32_t seg_t_out[AVDF_MAX_LEVELS];
@@ -142,7 +143,7 @@ typedef struct avdf_conv_gemm_args {
   int32_t dtype;
   const float* bias; const uint8_t* row_mask; const float* ln_w; const float* ln_b; int32_t act;
   const float* pe; const float* residual; const float* gamma;
-  float* out_f32; void* out_bf16;   /* [batch, o_rows_per_video, n_out] */
+  float* out_f32; void* out_h; int32_t out_h_dtype;   /* [batch, o_rows_per_video, n_out] */
   void* workspace; size_t workspace_bytes;
 } avdf_conv_gemm_args;            /* host struct */
 AVDF_API size_t avdf_conv_gemm_workspace_bytes(const avdf_conv_gemm_args* args);

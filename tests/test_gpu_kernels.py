@@ -278,7 +278,7 @@ GEMM_CASES = [
 
 
 @pytest.mark.parametrize("case", GEMM_CASES, ids=[c[0] for c in GEMM_CASES])
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
 def test_conv_gemm(case, mode):
     name, B, T, cin, nout, taps, stride, has_bias, has_ln, act, has_pe, has_res = case
     rng = np.random.RandomState(zlib.crc32(name.encode()) % 1000)
@@ -293,17 +293,17 @@ def test_conv_gemm(case, mode):
     gamma = torch.from_numpy(rng.uniform(0.5, 1.5, nout).astype(np.float32)) if has_res else None
     valid = rng.randint(To // 2, To + 1, B); valid[0] = To
     mask = (np.arange(To)[None] < valid[:, None])
-    adt = torch.float32 if mode == "fp32" else torch.bfloat16
+    adt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[mode]
     xq, wq = x.to(adt).float(), w.to(adt).float()                       # what the kernel actually multiplies
     want = _conv_ref(xq, wq, bias, taps, stride, torch.from_numpy(mask), ln, act, pe, res, gamma)
     wp = w.permute(0, 2, 1).reshape(nout, taps * cin).contiguous()
     out32 = torch.zeros((B, To, nout), device=DEV)
-    out16 = torch.zeros((B, To, nout), dtype=torch.bfloat16, device=DEV) if mode == "bf16" else None
+    out16 = torch.zeros((B, To, nout), dtype=adt, device=DEV) if mode != "fp32" else None
     ops.conv_gemm(dev(x, adt), dev(wp, adt), taps=taps, stride=stride, batch=B, c_in=cin, n_out=nout, segs=[(To, 0, 0)],
                   a_rows=T, o_rows=To, bias=None if bias is None else dev(bias), row_mask=dev(mask.astype(np.uint8)),
                   ln=None if ln is None else (dev(ln[0]), dev(ln[1])), act=act, pe=None if pe is None else dev(pe),
                   residual=None if res is None else dev(res), gamma=None if gamma is None else dev(gamma),
-                  out_f32=out32, out_bf16=out16)
+                  out_f32=out32, out_h=out16)
     torch.cuda.synchronize()
     tol = 2e-5 if mode == "fp32" else 2e-4      # same operands, only the accumulation order differs
     err = rel_err(out32.cpu(), want)
@@ -312,7 +312,7 @@ def test_conv_gemm(case, mode):
         assert rel_err(out16.float().cpu(), want) < 1e-2
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
 def test_conv_gemm_pyramid_segments(mode):
     """k3 conv over a 6-level pyramid in ONE launch (head towers): levels must not bleed into each other."""
     rng = np.random.RandomState(3)
@@ -323,7 +323,7 @@ def test_conv_gemm_pyramid_segments(mode):
     w = torch.from_numpy((rng.standard_normal((C, C, 3)) / math.sqrt(3 * C)).astype(np.float32))
     ln = (torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)), torch.from_numpy(rng.normal(0, 0.2, C).astype(np.float32)))
     mask = rng.rand(B, P) > 0.2
-    adt = torch.float32 if mode == "fp32" else torch.bfloat16
+    adt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[mode]
     xq, wq = x.to(adt).float(), w.to(adt).float()
     want = torch.cat([_conv_ref(xq[:, offs[l]:offs[l + 1]], wq, None, 3, 1, torch.from_numpy(mask[:, offs[l]:offs[l + 1]]), ln,
                                 ops.ACT_RELU, None, None, None) for l in range(len(lens))], dim=1)
@@ -371,7 +371,7 @@ def test_ln_dwconv_ln(stride, shift, T_src, T_virt):
 
 
 @pytest.mark.parametrize("window,T", [(7, 96), (7, 5), (-1, 24), (-1, 48)])
-@pytest.mark.parametrize("in_dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("in_dt", [torch.float32, torch.bfloat16, torch.float16])
 def test_attention(window, T, in_dt):
     rng = np.random.RandomState(9)
     B, C, H = 3, 256, 4
@@ -396,7 +396,7 @@ def test_ln_rows(C):
     x = torch.from_numpy(rng.standard_normal((777, C)).astype(np.float32) * 3 + 1)
     w, b = _ln_params(rng, C)
     want = model_ref.channel_ln(x.t()[None], w, b)[0].t()
-    for dt in (torch.float32, torch.bfloat16):
+    for dt in (torch.float32, torch.bfloat16, torch.float16):
         out = torch.zeros((777, C), dtype=dt, device=DEV)
         ops.ln_rows(dev(x), dev(w), dev(b), out, 777)
         assert rel_err(out.float().cpu(), want) < (2e-6 if dt == torch.float32 else 5e-3)
