@@ -174,51 +174,89 @@ class _LocalizationBase(nn.Module):
         return out
 
     def _forward_streams_chunk(self, chunk):
-        eng = self.engine()
-        B, L = len(chunk), eng.max_seq_len
-        names = ("video", "byola", "emo")
-        dev_streams, dev_offs, items = [], [], []
-        for n in names:
+        return self.fetch(self.run_staged(self.stage(self.pack_streams(chunk))))
+
+    # The raw-stream path in four explicit stages, so that a serving loop (and bench.py) can overlap them:
+    #   pack_streams  host:  ragged per-video arrays -> one pinned buffer per stream + row offsets + per-video meta
+    #   stage         H2D:   async copies on the current stream
+    #   run_staged    GPU:   interp_concat -> forward -> decode/NMS; returns DEVICE tensors, no host sync
+    #   fetch         D2H:   results -> the reference's list of dicts
+    def pack_streams(self, chunk, feat_stride=1, num_frames=1):
+        L = self.max_seq_len
+        B = len(chunk)
+        packed = {"ids": [c["video_id"] for c in chunk], "streams": [], "offs": [], "B": B}
+        for n in ("video", "byola", "emo"):
             if n not in chunk[0]["streams"]:
-                dev_streams.append(None); dev_offs.append(None)
+                packed["streams"].append(None); packed["offs"].append(None)
                 continue
-            arrs = [np.ascontiguousarray(c["streams"][n], dtype=np.float32) if not torch.is_tensor(c["streams"][n])
-                    else c["streams"][n].numpy() for c in chunk]
+            arrs = [c["streams"][n].numpy() if torch.is_tensor(c["streams"][n]) else np.asarray(c["streams"][n], dtype=np.float32)
+                    for c in chunk]
             off = np.zeros(B + 1, np.int32)
             off[1:] = np.cumsum([a.shape[0] for a in arrs])
-            host = torch.from_numpy(np.concatenate(arrs, axis=0)).pin_memory()
-            dev_streams.append(host.to(eng.device, non_blocking=True))
-            dev_offs.append(torch.from_numpy(off).to(eng.device, non_blocking=True))
-        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.in_dt)
-        ops.interp_concat(dev_streams, dev_offs, L, x)
-        for c in chunk:
+            host = torch.empty((int(off[-1]), arrs[0].shape[1]), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+            np.concatenate(arrs, axis=0, out=host.numpy())
+            packed["streams"].append(host)
+            packed["offs"].append(torch.from_numpy(off))
+        meta = np.empty((4, B), np.float32)
+        for b, c in enumerate(chunk):
             first = c["streams"]["video"] if "video" in c["streams"] else c["streams"]["byola"]
             t_first = first.shape[0]
-            fs = float((t_first - 1) * 1 + 1) / L             # deepfake_video_audio.py:495-497 (feat_stride = num_frames = 1)
-            items.append({"video_id": c["video_id"], "fps": t_first / c["duration"], "duration": c["duration"],
-                          "feat_stride": fs, "feat_num_frames": fs})
-        return self._run(eng, x, [L] * B, items)
+            fs = float((t_first - 1) * feat_stride + num_frames) / L      # deepfake_video_audio.py:495-497
+            # av_fd_no_recon.py:860-865: python-float scalars enter the fp32 tensor expression
+            meta[:, b] = (np.float32(fs), np.float32(0.5 * fs), np.float32(t_first / c["duration"]), np.float32(c["duration"]))
+        packed["meta"] = torch.from_numpy(meta)
+        return packed
+
+    def stage(self, packed):
+        dev = self.engine().device
+        staged = dict(packed)
+        staged["streams"] = [None if t is None else t.to(dev, non_blocking=True) for t in packed["streams"]]
+        staged["offs"] = [None if t is None else t.to(dev, non_blocking=True) for t in packed["offs"]]
+        staged["meta"] = packed["meta"].to(dev, non_blocking=True)
+        return staged
+
+    @staticmethod
+    def h2d_bytes(packed):
+        n = packed["meta"].numel() * 4
+        for t in packed["streams"] + packed["offs"]:
+            if t is not None:
+                n += t.numel() * t.element_size()
+        return n
+
+    @torch.no_grad()
+    def run_staged(self, staged):
+        eng = self.engine()
+        B, L = staged["B"], eng.max_seq_len
+        x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.in_dt)
+        ops.interp_concat(staged["streams"], staged["offs"], L, x)
+        logits, offsets, vcls, masks, lens = eng.forward_dense(x, [L] * B)
+        osg, osc, ocn = eng.postprocess(logits, offsets, masks, lens, staged["meta"], nms_method=self.test_nms_method)
+        return {"ids": staged["ids"], "segs": osg, "scores": osc, "counts": ocn, "vcls": vcls}
+
+    @staticmethod
+    def fetch(res):
+        segs, scores, counts, vc = res["segs"].cpu(), res["scores"].cpu(), res["counts"].cpu(), res["vcls"].cpu()
+        out = []
+        for b, vid in enumerate(res["ids"]):
+            n = int(counts[b])
+            out.append({"video_id": vid, "segments": segs[b, :n].clone(), "scores": scores[b, :n].clone(),
+                        "labels": torch.zeros(n, dtype=torch.long), "video_cls": vc[b:b + 1].clone()})
+        return out
+
+    @staticmethod
+    def d2h_bytes(res):
+        return sum(res[k].numel() * res[k].element_size() for k in ("segs", "scores", "counts", "vcls"))
 
     def _run(self, eng, x, valid, items):
         B = x.shape[0]
         logits, offsets, vcls, masks, lens = eng.forward_dense(x, valid)
-        if self.test_nms_method == "none":
-            raise AvdfError("nms_method 'none' is not on the accelerated path")
         meta = np.empty((4, B), np.float32)
         for b, it in enumerate(items):                        # av_fd_no_recon.py:860-865 (python-float scalars -> fp32)
-            meta[0, b] = np.float32(it["feat_stride"])
-            meta[1, b] = np.float32(0.5 * it["feat_num_frames"])
-            meta[2, b] = np.float32(it["fps"])
-            meta[3, b] = np.float32(it["duration"])
+            meta[:, b] = (np.float32(it["feat_stride"]), np.float32(0.5 * it["feat_num_frames"]), np.float32(it["fps"]),
+                          np.float32(it["duration"]))
         meta_d = torch.from_numpy(meta).to(eng.device, non_blocking=True)
         osg, osc, ocn = eng.postprocess(logits, offsets, masks, lens, meta_d, nms_method=self.test_nms_method)
-        segs, scores, counts, vc = osg.cpu(), osc.cpu(), ocn.cpu(), vcls.cpu()       # device -> host boundary (:841-846)
-        results = []
-        for b, it in enumerate(items):
-            n = int(counts[b])
-            results.append({"video_id": it["video_id"], "segments": segs[b, :n].clone(), "scores": scores[b, :n].clone(),
-                            "labels": torch.zeros(n, dtype=torch.long), "video_cls": vc[b:b + 1].clone()})
-        return results
+        return self.fetch({"ids": [it["video_id"] for it in items], "segs": osg, "scores": osc, "counts": ocn, "vcls": vcls})
 
 
 @register_meta_arch(EXP12)

@@ -36,6 +36,29 @@ def _chk(t, dtype=None, name="tensor"):
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
 
 
+class Profile:
+    """Optional per-launch CUDA-event timing (bench.py's roofline leg). Off by default: zero overhead."""
+    on = False
+    records = []          # (entry point, work dict, start event, end event)
+
+
+def _call(name, fn, args, launches=1, work=None):
+    if Profile.on:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        Profile.records.append((name, work or {}, e0, e1))
+    else:
+        rc = fn(*args)
+    nv.check(rc, name)
+    nv.count(launches)
+
+
+def _nbytes(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
 def _levels(level_len):
     arr = (c_int32 * len(level_len))(*[int(v) for v in level_len])
     return arr
@@ -57,9 +80,8 @@ def interp_concat(streams, offsets, t_out, out):
         batch = o.numel() - 1
     _chk(out, None, "out")
     assert out.shape == (batch, t_out, sum(cs)), (out.shape, batch, t_out, cs)
-    nv.check(L.avdf_interp_concat(ptrs[0], ptrs[1], ptrs[2], offs[0], offs[1], offs[2], batch, cs[0], cs[1], cs[2],
-                                  t_out, nv.ptr(out), _dt(out), nv.stream_ptr()), "avdf_interp_concat")
-    nv.count()
+    _call("avdf_interp_concat", L.avdf_interp_concat, (ptrs[0], ptrs[1], ptrs[2], offs[0], offs[1], offs[2], batch, cs[0], cs[1], cs[2],
+                                  t_out, nv.ptr(out), _dt(out), nv.stream_ptr(),), launches=1, work={"bytes": _nbytes(*[t for t in streams if t is not None]) + _nbytes(out)})
     return out
 
 
@@ -69,8 +91,7 @@ def pack_feats(feats_ct, out):
     _chk(feats_ct, torch.float32, "feats"); _chk(out, None, "out")
     C, T = feats_ct.shape
     assert out.shape[1] == C and out.shape[0] >= T
-    nv.check(L.avdf_pack_feats(nv.ptr(feats_ct), C, T, out.shape[0], nv.ptr(out), _dt(out), nv.stream_ptr()), "avdf_pack_feats")
-    nv.count()
+    _call("avdf_pack_feats", L.avdf_pack_feats, (nv.ptr(feats_ct), C, T, out.shape[0], nv.ptr(out), _dt(out), nv.stream_ptr(),), launches=1, work=None)
 
 
 # ---------------------------------------------------------------------------- NMS
@@ -83,9 +104,8 @@ def nms_hard(segs, scores, iou_threshold, max_num=0):
     out_count = torch.zeros(1, dtype=torch.int32, device=scores.device)
     wsb = L.avdf_nms_workspace_bytes(n)
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=scores.device)
-    nv.check(L.avdf_nms_hard(nv.ptr(segs), nv.ptr(scores), n, float(iou_threshold), int(max_num), nv.ptr(out_idx),
-                             nv.ptr(out_count), nv.ptr(ws), wsb, nv.stream_ptr()), "avdf_nms_hard")
-    nv.count()
+    _call("avdf_nms_hard", L.avdf_nms_hard, (nv.ptr(segs), nv.ptr(scores), n, float(iou_threshold), int(max_num), nv.ptr(out_idx),
+                             nv.ptr(out_count), nv.ptr(ws), wsb, nv.stream_ptr(),), launches=1, work=None)
     return out_idx[: int(out_count.item())]
 
 
@@ -98,10 +118,9 @@ def nms_soft(segs, scores, dets, iou_threshold, sigma, min_score, method, max_nu
     out_count = torch.zeros(1, dtype=torch.int32, device=scores.device)
     wsb = L.avdf_nms_workspace_bytes(n)
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=scores.device)
-    nv.check(L.avdf_nms_soft(nv.ptr(segs), nv.ptr(scores), n, nv.ptr(dets), float(iou_threshold), float(sigma),
+    _call("avdf_nms_soft", L.avdf_nms_soft, (nv.ptr(segs), nv.ptr(scores), n, nv.ptr(dets), float(iou_threshold), float(sigma),
                              float(min_score), int(method), int(max_num), nv.ptr(out_idx), nv.ptr(out_count),
-                             nv.ptr(ws), wsb, nv.stream_ptr()), "avdf_nms_soft")
-    nv.count()
+                             nv.ptr(ws), wsb, nv.stream_ptr(),), launches=1, work=None)
     return out_idx[: int(out_count.item())]
 
 
@@ -136,8 +155,7 @@ def postprocess(batch, *, logits=None, offsets=None, mask=None, level_len=(), le
         if workspace is None or workspace.numel() * workspace.element_size() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=out_segs.device)
         a.workspace, a.workspace_bytes = workspace.data_ptr(), need
-    nv.check(L.avdf_postprocess(ctypes.byref(a), nv.stream_ptr()), "avdf_postprocess")
-    nv.count()
+    _call("avdf_postprocess", L.avdf_postprocess, (ctypes.byref(a), nv.stream_ptr(),), launches=1, work=None)
 
 
 def postprocess_workspace_bytes(batch, cand_cap):
@@ -181,8 +199,8 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
         if workspace is None or workspace.numel() * workspace.element_size() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=a.device)
         g.workspace, g.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
-    nv.check(L.avdf_conv_gemm(ctypes.byref(g), nv.stream_ptr()), "avdf_conv_gemm")
-    nv.count(2 if g.dtype == DTYPE_F32 else 1)
+    _call("avdf_conv_gemm", L.avdf_conv_gemm, (ctypes.byref(g), nv.stream_ptr(),), launches=2 if g.dtype == DTYPE_F32 else 1, work={"flops": 2.0 * batch * sum(t for t, _, _ in segs) * n_out * taps * c_in, "m": batch * sum(t for t, _, _ in segs), "n": n_out, "k": taps * c_in,
+                "bytes": _nbytes(a, w, out_f32, out_h, residual)})
 
 
 # ---------------------------------------------------------------------------- block kernels
@@ -205,38 +223,33 @@ def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, d
         a.out[i] = outs[i].data_ptr()
     a.out_dtype = _dt(outs[0])
     a.skip_out = skip_out.data_ptr() if skip_out is not None else None
-    nv.check(L.avdf_ln_dwconv_ln(ctypes.byref(a), nv.stream_ptr()), "avdf_ln_dwconv_ln")
-    nv.count()
+    _call("avdf_ln_dwconv_ln", L.avdf_ln_dwconv_ln, (ctypes.byref(a), nv.stream_ptr(),), launches=1, work={"bytes": batch * t_src * src.shape[-1] * 4 + _nbytes(*[o[:batch] for o in outs]) + (_nbytes(skip_out[:batch]) if skip_out is not None else 0)})
 
 
 def attention(q, k, v, kv_mask, out, *, batch, t, n_head, window):
     L = nv.lib()
     _chk(q, None, "q"); _chk(k, q.dtype, "k"); _chk(v, q.dtype, "v"); _chk(out, None, "out"); _chk(kv_mask, torch.uint8, "kv_mask")
-    nv.check(L.avdf_attention(nv.ptr(q), nv.ptr(k), nv.ptr(v), nv.ptr(kv_mask), nv.ptr(out), _dt(q), _dt(out), batch, t,
-                              q.shape[-1], n_head, window, nv.stream_ptr()), "avdf_attention")
-    nv.count()
+    _call("avdf_attention", L.avdf_attention, (nv.ptr(q), nv.ptr(k), nv.ptr(v), nv.ptr(kv_mask), nv.ptr(out), _dt(q), _dt(out), batch, t,
+                              q.shape[-1], n_head, window, nv.stream_ptr(),), launches=1, work={"bytes": _nbytes(q, k, v, out)})
 
 
 def ln_rows(x, w, b, out, rows):
     L = nv.lib()
     _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b"); _chk(out, None, "out")
-    nv.check(L.avdf_ln_rows(nv.ptr(x), nv.ptr(w), nv.ptr(b), nv.ptr(out), _dt(out), rows, x.shape[-1], nv.stream_ptr()), "avdf_ln_rows")
-    nv.count()
+    _call("avdf_ln_rows", L.avdf_ln_rows, (nv.ptr(x), nv.ptr(w), nv.ptr(b), nv.ptr(out), _dt(out), rows, x.shape[-1], nv.stream_ptr(),), launches=1, work={"bytes": rows * x.shape[-1] * (4 + out.element_size())})
 
 
 def instnorm_lrelu(x, out, *, batch, t, channels, slope=0.2):
     L = nv.lib()
     _chk(x, torch.float32, "x"); _chk(out, None, "out")
-    nv.check(L.avdf_instnorm_lrelu(nv.ptr(x), nv.ptr(out), _dt(out), batch, t, channels, float(slope), nv.stream_ptr()), "avdf_instnorm_lrelu")
-    nv.count()
+    _call("avdf_instnorm_lrelu", L.avdf_instnorm_lrelu, (nv.ptr(x), nv.ptr(out), _dt(out), batch, t, channels, float(slope), nv.stream_ptr(),), launches=1, work={"bytes": batch * t * channels * (4 + out.element_size())})
 
 
 def fpn_fuse(lat, mask, dw_w, ln_w, ln_b, out, *, batch, level_len):
     L = nv.lib()
     _chk(lat, torch.float32, "lat"); _chk(mask, torch.uint8, "mask"); _chk(dw_w, torch.float32, "dw_w"); _chk(out, None, "out")
-    nv.check(L.avdf_fpn_fuse(nv.ptr(lat), nv.ptr(mask), nv.ptr(dw_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(out), _dt(out), batch,
-                             lat.shape[-1], len(level_len), _levels(level_len), nv.stream_ptr()), "avdf_fpn_fuse")
-    nv.count()
+    _call("avdf_fpn_fuse", L.avdf_fpn_fuse, (nv.ptr(lat), nv.ptr(mask), nv.ptr(dw_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(out), _dt(out), batch,
+                             lat.shape[-1], len(level_len), _levels(level_len), nv.stream_ptr(),), launches=1, work={"bytes": _nbytes(lat, out)})
 
 
 def head_final(cls_feat, reg_feat, mask, cls_w, cls_b, reg_w, reg_b, level_scale, logits, offsets, *, batch, level_len):
@@ -245,10 +258,9 @@ def head_final(cls_feat, reg_feat, mask, cls_w, cls_b, reg_w, reg_b, level_scale
     for t in (cls_w, cls_b, reg_w, reg_b, logits, offsets):
         _chk(t, torch.float32, "head tensor")
     sc = (c_float * len(level_scale))(*[float(s) for s in level_scale])
-    nv.check(L.avdf_head_final(nv.ptr(cls_feat), nv.ptr(reg_feat), _dt(cls_feat), nv.ptr(mask), nv.ptr(cls_w), nv.ptr(cls_b),
+    _call("avdf_head_final", L.avdf_head_final, (nv.ptr(cls_feat), nv.ptr(reg_feat), _dt(cls_feat), nv.ptr(mask), nv.ptr(cls_w), nv.ptr(cls_b),
                                nv.ptr(reg_w), nv.ptr(reg_b), sc, nv.ptr(logits), nv.ptr(offsets), batch, cls_feat.shape[-1],
-                               len(level_len), _levels(level_len), nv.stream_ptr()), "avdf_head_final")
-    nv.count()
+                               len(level_len), _levels(level_len), nv.stream_ptr(),), launches=1, work=None)
 
 
 def vcls_exp12(z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, *, batch, t):
@@ -256,9 +268,8 @@ def vcls_exp12(z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, *, batch, t)
     _chk(z, None, "z")
     for x in (conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out):
         _chk(x, torch.float32, "vcls tensor")
-    nv.check(L.avdf_vcls_exp12(nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(lin1_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(lin2_w),
-                               nv.ptr(lin2_b), nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr()), "avdf_vcls_exp12")
-    nv.count()
+    _call("avdf_vcls_exp12", L.avdf_vcls_exp12, (nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(lin1_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(lin2_w),
+                               nv.ptr(lin2_b), nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr(),), launches=1, work=None)
 
 
 def vcls_exp13(z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, *, batch, t):
@@ -266,6 +277,5 @@ def vcls_exp13(z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, *, batch, t):
     _chk(z, None, "z")
     for x in (conv0_w, seg_w, seg_b, cls_w, cls_b, out):
         _chk(x, torch.float32, "vcls tensor")
-    nv.check(L.avdf_vcls_exp13(nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(seg_w), nv.ptr(seg_b), nv.ptr(cls_w), nv.ptr(cls_b),
-                               nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr()), "avdf_vcls_exp13")
-    nv.count()
+    _call("avdf_vcls_exp13", L.avdf_vcls_exp13, (nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(seg_w), nv.ptr(seg_b), nv.ptr(cls_w), nv.ptr(cls_b),
+                               nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr(),), launches=1, work=None)
