@@ -279,6 +279,9 @@ def run_ours(args):
             d = agg.setdefault(nm, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
             d["ms"] += a.elapsed_time(b); d["n"] += 1
             d["flops"] += work.get("flops", 0.0); d["bytes"] += work.get("bytes", 0.0)
+        if args.dump_launches:
+            rows = [{"call": nm, "us": 1000.0 * a.elapsed_time(b), **{k: v for k, v in work.items()}} for nm, work, a, b in ops.Profile.records]
+            json.dump(rows[-(len(rows) // psteps):], open(args.dump_launches, "w"), indent=0)
         tot = sum(d["ms"] for d in agg.values())
         for nm, d in agg.items():
             kernels[nm] = {"ms_per_step": d["ms"] / psteps, "launches_per_step": d["n"] / psteps, "share": d["ms"] / tot,
@@ -333,6 +336,7 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "fp32"])
     ap.add_argument("--ref-videos", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event timings of one step to this json")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "ours" and args.gpus > 1 and world == 1:
