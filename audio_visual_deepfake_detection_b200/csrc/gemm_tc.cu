@@ -9,9 +9,10 @@
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM),
 //               tcgen05.commit releases smem stages / publishes the accumulator.
 //   warp 2      TMEM allocator (512 columns = two 256-column accumulators, double buffered).
-//   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns), one output row per thread, two passes
-//               over TMEM when LayerNorm is fused (row statistics, then normalise + store).
-// smem ring: 4 stages x (16 KB A + 32 KB W), 128B-swizzled, mbarrier full/empty pairs.
+//   warps 4-11  epilogue: tcgen05.ld (32 lanes x 32 columns, thread = row), two passes over TMEM when LayerNorm
+//               is fused (row statistics, then normalise), 32x32 smem transpose per warp so that every global
+//               access (residual load, fp32 / 16-bit store) is one full 128 B / 64 B line per instruction.
+// smem ring: 3 stages x (16 KB A + 32 KB W), 128B-swizzled, mbarrier full/empty pairs.
 #include <cuda.h>
 #include <string.h>
 #include "gemm_common.cuh"
@@ -19,11 +20,13 @@
 namespace avdf {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, MAX_BN = 256;
+constexpr int BM = 128, BK = 64, STAGES = 3, MAX_BN = 256;
 constexpr int A_STAGE = BM * BK * 2;          // 16384
 constexpr int B_STAGE = MAX_BN * BK * 2;      // 32768
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*barriers*/ + 4 * MAX_BN * 4 /*epilogue vectors*/ + 1024 /*align slack*/;
-constexpr int THREADS = 256;
+constexpr int EPI_VEC_BYTES = 4 * MAX_BN * 4 + 2 * 2 * BM * 2 * 4 + 8 * 32 * 24;   // bias / ln_w / ln_b / gamma + double-buffered LayerNorm partial sums + per-warp row tables
+constexpr int STAGE_TILE_BYTES = 16 * 32 * 32 * 4;               // per epilogue warp: a 32x32 fp32 accumulator tile + a residual tile
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*barriers*/ + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024 /*align slack*/;
+constexpr int THREADS = 384;                                     // 4 control warps + 8 epilogue warps
 
 struct Params {
   CUtensorMap a_map[AVDF_MAX_LEVELS];
@@ -34,9 +37,12 @@ struct Params {
   int n_out, c_in, taps, stride, bn, n_tiles_n, total_tiles;
   unsigned idesc;
   EpiParams epi;
+  unsigned long long* dbg;                   // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
 };
 
 // ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define AVDF_TS(slot) do { if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -126,16 +132,23 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
   return c;
 }
 
+// MODE >= 0 fixes the epilogue variant at compile time (bit 0 LayerNorm, bits 1-2 activation, bit 3 residual,
+// bit 4 positional encoding) so the row loop carries no dead branches; MODE < 0 reads the flags at run time.
+constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (pe ? 16 : 0); }
+
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
-  // 1024 B alignment for the 128B swizzle atoms
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  // 1024 B alignment for the 128B swizzle atoms (an offset into the array keeps the shared address space visible
+  // to the compiler: LDS/STS instead of generic loads)
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + STAGES * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024);   // 4 x MAX_BN floats
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024);
+  float* stage_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024 + EPI_VEC_BYTES);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -143,6 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) AVDF_TS(0);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.seg.n_seg; ++s)
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -162,6 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp == 0) AVDF_TS(1);
 
   const int kb_per_tap = p.c_in / BK;
   const int k_iters = p.taps * kb_per_tap;
@@ -200,129 +215,186 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
+          if (it == 0 && ki == 0) AVDF_TS(2);
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * A_STAGE));
           const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * B_STAGE));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)          // +32 B per K=16 step inside the swizzle atom
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (ki == k_iters - 1) umma_commit(tfull_bar(acc));
+          if (ki == k_iters - 1) { umma_commit(tfull_bar(acc)); if (it == 0) AVDF_TS(3); }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- epilogue (one output row per thread)
+    // ---------------------------------------------------------------- epilogue: 8 warps
+    // warp e = warp - 4: TMEM lane quarter q = warp & 3 (rows 32q .. 32q+31 of the tile), column half h = e >> 2.
+    // tcgen05.ld hands every thread one ROW (32 consecutive columns per load); global memory wants one row per
+    // WARP (32 lanes x 4 B = one 128 B line). Each 32x32 block therefore goes RAW through a per-warp smem tile
+    // (16-byte XOR swizzle: conflict-free both ways) and the whole epilogue math runs in the transposed domain
+    // (lane = column: per-column vectors are one register each, per-row scalars come from a small row table), so
+    // every global access - residual, fp32 store, 16-bit store - is one full line per instruction.
+    // The row loop is deliberately ROLLED (x4): a fully unrolled epilogue is ~100 KB of straight-line SASS that is
+    // executed once per tile and runs at instruction-fetch speed (measured: 12 us per 128x128 tile).
+    // Residual rows are fetched with cp.async into a second per-warp tile one chunk ahead (first chunk: before the
+    // accumulator wait), so their latency hides behind the MMA mainloop / the previous chunk.
     const EpiParams& e = p.epi;
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
+    const int ew = warp - 4;
+    const int q = warp & 3, h = ew >> 2;
     const int N = p.n_out;
-    const int et = threadIdx.x - 128;            // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 128;            // 0..255 among the epilogue threads
     float* s_bias = epi_smem; float* s_lnw = epi_smem + MAX_BN; float* s_lnb = epi_smem + 2 * MAX_BN; float* s_gam = epi_smem + 3 * MAX_BN;
+    float* s_part_base = epi_smem + 4 * MAX_BN;  // [tile parity][2 halves][128 rows][2] LayerNorm partial sums
+    float* stg = stage_smem + ew * (32 * 32);    // this warp's 32 x 32 fp32 transpose tile (accumulators)
+    float* rsg = stage_smem + (8 + ew) * (32 * 32);   // this warp's 32 x 32 residual tile, row-major [row][column]
+    // per-warp row table: output row offset (or -1), then {mask, mean, rstd, time step} per row
+    long long* w_ro = reinterpret_cast<long long*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2) + ew * 32;
+    float4* w_rw = reinterpret_cast<float4*>(reinterpret_cast<long long*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2) + 8 * 32) + ew * 32;
+    const int chunks = p.bn >> 5;
+    const int c_begin = h == 0 ? 0 : (chunks + 1) / 2, c_end = h == 0 ? (chunks + 1) / 2 : chunks;
+    const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
+    const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
+    const bool has_pe = MODE < 0 ? (e.pe != nullptr) : ((MODE & 16) != 0);
+    const int act = MODE < 0 ? e.act : ((MODE >> 1) & 3);
+    const int g8 = lane & 7, rsub = lane >> 3;   // transposed domain: 16-byte column group, row inside a 4-row step
     int it = 0, loaded_n0 = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = decode_tile(p, tile);
+      if (it == 0 && ew == 0) AVDF_TS(8);
       if (tc_.n0 != loaded_n0) {                 // per-channel epilogue vectors of this n-tile -> smem
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < p.bn; i += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < p.bn; i += 256) {
           s_bias[i] = e.bias ? __ldg(e.bias + tc_.n0 + i) : 0.f;
           s_lnw[i] = e.ln_w ? __ldg(e.ln_w + tc_.n0 + i) : 1.f;
           s_lnb[i] = e.ln_b ? __ldg(e.ln_b + tc_.n0 + i) : 0.f;
           s_gam[i] = e.gamma ? __ldg(e.gamma + tc_.n0 + i) : 1.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         loaded_n0 = tc_.n0;
       }
+      if (it == 0 && ew == 0) AVDF_TS(9);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      float* s_part = s_part_base + acc * (2 * BM * 2);
+      // my row in the TMEM domain (thread = row)
+      const int r = q * 32 + lane;
       const int b = tc_.b0 + r / tc_.tt;
       const int t = tc_.t0 + (r & (tc_.tt - 1));
       const bool valid = b < p.seg.batch;
-      const size_t orow = valid ? ((size_t)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t) : 0;
+      const long long orow = valid ? ((long long)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t) : -1;
       const float mk = (valid && e.row_mask) ? (e.row_mask[orow] ? 1.f : 0.f) : 1.f;
+      __syncwarp();                               // previous tile's reads of the row table are done
+      w_ro[lane] = orow;
+      __syncwarp();
+      auto fetch_residual = [&](int ch) {         // 32 rows x 128 B of the residual -> rsg, asynchronously
+        const float* src = e.residual + tc_.n0 + ch * 32 + g8 * 4;
+        const uint32_t dst = smem_u32(rsg + rsub * 32 + g8 * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long ro = w_ro[i * 4 + rsub];
+          if (ro >= 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + ro * N) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (has_res && c_begin < c_end) fetch_residual(c_begin);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
+      if (it == 0 && ew == 0) AVDF_TS(4);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
-      const int chunks = p.bn >> 5;
       float mean = 0.f, rstd = 1.f;
-      if (e.ln_w) {
+      if (has_ln) {                               // row statistics over all bn columns: each half sums its chunks
         float s = 0.f, ss = 0.f;
-        for (int ch = 0; ch < chunks; ++ch) {
+        for (int ch = c_begin; ch < c_end; ++ch) {
           float v[32];
           tmem_ld32(taddr + ch * 32, v);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + ch * 32);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (v[i] + s_bias[ch * 32 + i]) * mk;
-            s += x; ss = fmaf(x, x, ss);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i];
+            const float x0 = (v[4 * i] + bb.x) * mk, x1 = (v[4 * i + 1] + bb.y) * mk, x2 = (v[4 * i + 2] + bb.z) * mk, x3 = (v[4 * i + 3] + bb.w) * mk;
+            s += (x0 + x1) + (x2 + x3);
+            ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
           }
         }
+        s_part[(h * 128 + r) * 2] = s; s_part[(h * 128 + r) * 2 + 1] = ss;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        s += s_part[((h ^ 1) * 128 + r) * 2]; ss += s_part[((h ^ 1) * 128 + r) * 2 + 1];
         mean = s / (float)p.bn;
         const float var = fmaxf(ss / (float)p.bn - mean * mean, 0.f);
         rstd = rsqrtf(var + 1e-5f);
       }
-      for (int ch = 0; ch < chunks; ++ch) {
-        float v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        if (ch == chunks - 1) {                   // all TMEM reads of this accumulator are done
-          tcgen05_fence_before();
-          mbar_arrive(tempty_bar(acc));
-        }
-        if (!valid) continue;
-        const int n = tc_.n0 + ch * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = (v[i] + s_bias[ch * 32 + i]) * mk;
-          if (e.ln_w) x = (x - mean) * rstd * s_lnw[ch * 32 + i] + s_lnb[ch * 32 + i];
-          v[i] = apply_act(x, e.act);
-        }
-        if (e.pe) {
-          const float4* pe = reinterpret_cast<const float4*>(e.pe + (size_t)t * N + n);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 f = __ldg(pe + i);
-            v[4 * i] += f.x * mk; v[4 * i + 1] += f.y * mk; v[4 * i + 2] += f.z * mk; v[4 * i + 3] += f.w * mk;
+      w_rw[lane] = make_float4(mk, mean, rstd, __int_as_float(t));
+      if (c_begin == c_end) {                     // narrow tiles: this half owns no columns
+        tcgen05_fence_before();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        {
+          float v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(10);
+          if (ch == c_end - 1) {                  // this warp's TMEM reads of the accumulator are done
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
-        }
-        if (e.residual) {
-          const float4* rs = reinterpret_cast<const float4*>(e.residual + orow * N + n);
+          __syncwarp();                           // previous chunk's reads of the staging tile are done
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 f = __ldg(rs + i);
-            const float* g = s_gam + ch * 32 + 4 * i;
-            v[4 * i] = f.x * mk + g[0] * v[4 * i]; v[4 * i + 1] = f.y * mk + g[1] * v[4 * i + 1];
-            v[4 * i + 2] = f.z * mk + g[2] * v[4 * i + 2]; v[4 * i + 3] = f.w * mk + g[3] * v[4 * i + 3];
-          }
+          for (int j = 0; j < 8; ++j)             // row `lane`, 16-byte group j -> swizzled slot j ^ (lane & 7)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        if (e.out_f32) {
-          float4* o = reinterpret_cast<float4*>(e.out_f32 + orow * N + n);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (e.out_h) {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out_h) + orow * N + n);
-          if (e.out_h_f16) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = pack_f16x2(v[8 * i], v[8 * i + 1]); u.y = pack_f16x2(v[8 * i + 2], v[8 * i + 3]);
-              u.z = pack_f16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_f16x2(v[8 * i + 6], v[8 * i + 7]);
-              o[i] = u;
+        if (has_res) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(11);
+        const int cl = ch * 32 + g8 * 4;          // my 4 columns in the transposed domain
+        const int n = tc_.n0 + cl;
+        const float4 bias4 = *reinterpret_cast<const float4*>(s_bias + cl);
+        const float4 lnw4 = *reinterpret_cast<const float4*>(s_lnw + cl), lnb4 = *reinterpret_cast<const float4*>(s_lnb + cl);
+        const float4 gam4 = *reinterpret_cast<const float4*>(s_gam + cl);
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rsub;
+          const long long ro = w_ro[rr];
+          if (ro >= 0) {
+            const float4 rw = w_rw[rr];           // {mask, mean, rstd, t}
+            float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((g8 ^ (rr & 7)) << 2));
+            x.x = (x.x + bias4.x) * rw.x; x.y = (x.y + bias4.y) * rw.x; x.z = (x.z + bias4.z) * rw.x; x.w = (x.w + bias4.w) * rw.x;
+            if (has_ln) {
+              x.x = fmaf((x.x - rw.y) * rw.z, lnw4.x, lnb4.x); x.y = fmaf((x.y - rw.y) * rw.z, lnw4.y, lnb4.y);
+              x.z = fmaf((x.z - rw.y) * rw.z, lnw4.z, lnb4.z); x.w = fmaf((x.w - rw.y) * rw.z, lnw4.w, lnb4.w);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              o[i] = u;
+            x.x = apply_act(x.x, act); x.y = apply_act(x.y, act); x.z = apply_act(x.z, act); x.w = apply_act(x.w, act);
+            if (has_pe) {
+              const float4 pv = __ldg(reinterpret_cast<const float4*>(e.pe + (size_t)__float_as_int(rw.w) * N + n));
+              x.x = fmaf(pv.x, rw.x, x.x); x.y = fmaf(pv.y, rw.x, x.y); x.z = fmaf(pv.z, rw.x, x.z); x.w = fmaf(pv.w, rw.x, x.w);
+            }
+            if (has_res) {
+              const float4 rv = *reinterpret_cast<const float4*>(rsg + rr * 32 + g8 * 4);
+              x.x = fmaf(gam4.x, x.x, rv.x * rw.x); x.y = fmaf(gam4.y, x.y, rv.y * rw.x);
+              x.z = fmaf(gam4.z, x.z, rv.z * rw.x); x.w = fmaf(gam4.w, x.w, rv.w * rw.x);
+            }
+            if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + ro * N + n) = x;
+            if (e.out_h) {
+              uint2 u;
+              if (e.out_h_f16) { u.x = pack_f16x2(x.x, x.y); u.y = pack_f16x2(x.z, x.w); }
+              else { u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); }
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.out_h) + ro * N + n) = u;
             }
           }
+        }
+        if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(12);
+        if (has_res && ch + 1 < c_end) {          // next chunk's residual (all lanes are done reading rsg)
+          __syncwarp();
+          fetch_residual(ch + 1);
         }
       }
     }
   }
+  if (warp == 4) AVDF_TS(5);
   tcgen05_fence_before();
   __syncthreads();
+  if (warp == 0) AVDF_TS(6);
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -348,11 +420,15 @@ static EncodeFn get_encode() {
 
 }  // namespace tc
 
+static unsigned long long* g_dbg = nullptr;
+
 int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   using namespace tc;
   AVDF_CHECK_ARG(a->c_in % BK == 0, "bf16 path: c_in must be a multiple of 64");
   AVDF_CHECK_ARG(a->n_out % 32 == 0, "bf16 path: n_out must be a multiple of 32");
-  const int bn = a->n_out >= MAX_BN ? MAX_BN : a->n_out;
+  // N tile: 256 (LayerNorm needs the whole row in one CTA; wide outputs), 128 for plain 256-wide outputs so that
+  // 24576-row problems give 384 tiles (2.6 waves on 148 SMs instead of 1.3)
+  const int bn = a->n_out > MAX_BN ? MAX_BN : (a->n_out == MAX_BN ? (a->ln_w ? MAX_BN : 128) : a->n_out);
   AVDF_CHECK_ARG(a->n_out % bn == 0, "bf16 path: n_out must be <= 256 or a multiple of 256");
   AVDF_CHECK_ARG(bn % 16 == 0 && bn >= 32, "bf16 path: unsupported n_out");
   AVDF_CHECK_ARG(!a->ln_w || a->n_out == bn, "bf16 path: fused LayerNorm needs n_out <= 256");
@@ -367,6 +443,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   fill_seg(a, p.seg);
   fill_epi(a, p.epi);
+  p.dbg = g_dbg;
   p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.bn = bn;
   p.n_tiles_n = a->n_out / bn;
   int tiles = 0;
@@ -414,11 +491,35 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     int dev = 0;
     AVDF_CUDA(cudaGetDevice(&dev));
     AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#define AVDF_SET_SMEM(M) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))
+    AVDF_SET_SMEM(-1);
+    AVDF_SET_SMEM(mode_of(false, AVDF_ACT_NONE, false, false));
+    AVDF_SET_SMEM(mode_of(false, AVDF_ACT_NONE, true, false));
+    AVDF_SET_SMEM(mode_of(false, AVDF_ACT_GELU, false, false));
+    AVDF_SET_SMEM(mode_of(true, AVDF_ACT_RELU, false, false));
+    AVDF_SET_SMEM(mode_of(true, AVDF_ACT_RELU, false, true));
+#undef AVDF_SET_SMEM
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  conv_gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr);
+#define AVDF_LAUNCH(M) conv_gemm_tc_kernel<M><<<grid, THREADS, SMEM_BYTES, st>>>(p)
+  switch (mode) {
+    case mode_of(false, AVDF_ACT_NONE, false, false): AVDF_LAUNCH(mode_of(false, AVDF_ACT_NONE, false, false)); break;
+    case mode_of(false, AVDF_ACT_NONE, true, false): AVDF_LAUNCH(mode_of(false, AVDF_ACT_NONE, true, false)); break;
+    case mode_of(false, AVDF_ACT_GELU, false, false): AVDF_LAUNCH(mode_of(false, AVDF_ACT_GELU, false, false)); break;
+    case mode_of(true, AVDF_ACT_RELU, false, false): AVDF_LAUNCH(mode_of(true, AVDF_ACT_RELU, false, false)); break;
+    case mode_of(true, AVDF_ACT_RELU, false, true): AVDF_LAUNCH(mode_of(true, AVDF_ACT_RELU, false, true)); break;
+    default: AVDF_LAUNCH(-1); break;
+  }
+#undef AVDF_LAUNCH
   return check_launch("conv_gemm_tc_kernel");
 }
 
 }  // namespace avdf
+
+// Debug hook (not part of the C-ABI contract in include/avdf.h's operator list): device buffer of 8 uint64 per CTA
+// that receives globaltimer stamps of the kernel phases; NULL switches it off.
+extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_timeline(unsigned long long* dev_buf) {
+  avdf::g_dbg = dev_buf;
+  return 0;
+}

@@ -233,6 +233,21 @@ class _LocalizationBase(nn.Module):
         osg, osc, ocn = eng.postprocess(logits, offsets, masks, lens, staged["meta"], nms_method=self.test_nms_method)
         return {"ids": staged["ids"], "segs": osg, "scores": osc, "counts": ocn, "vcls": vcls}
 
+    def capture(self, staged):
+        """Record the whole pass over a staged (device-resident) batch into a CUDA graph: ~190 kernel launches
+        become one cudaGraphLaunch, which removes the host launch cost that otherwise bounds the step
+        (measured: 25 us of Python + driver time per launch vs 7-40 us of GPU time per kernel). The graph reads
+        the staged tensors and writes the engine's static buffers, so `staged` must stay alive and unchanged in
+        place; replay() returns the same device-side result dict as run_staged()."""
+        from ... import native
+        self.run_staged(staged)                     # allocates every static buffer / cache outside the capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = native.LAUNCHES["n"]
+        with torch.cuda.graph(graph):
+            res = self.run_staged(staged)
+        return GraphedPass(graph, res, native.LAUNCHES["n"] - n0, staged)
+
     @staticmethod
     def fetch(res):
         segs, scores, counts, vc = res["segs"].cpu(), res["scores"].cpu(), res["counts"].cpu(), res["vcls"].cpu()
@@ -257,6 +272,19 @@ class _LocalizationBase(nn.Module):
         meta_d = torch.from_numpy(meta).to(eng.device, non_blocking=True)
         osg, osc, ocn = eng.postprocess(logits, offsets, masks, lens, meta_d, nms_method=self.test_nms_method)
         return self.fetch({"ids": [it["video_id"] for it in items], "segs": osg, "scores": osc, "counts": ocn, "vcls": vcls})
+
+
+class GraphedPass:
+    """A captured pass (see _LocalizationBase.capture)."""
+
+    def __init__(self, graph, result, n_launches, staged):
+        self.graph, self.result, self.n_launches, self.staged = graph, result, n_launches, staged
+
+    def replay(self):
+        from ... import native
+        self.graph.replay()
+        native.count(self.n_launches)
+        return self.result
 
 
 @register_meta_arch(EXP12)
