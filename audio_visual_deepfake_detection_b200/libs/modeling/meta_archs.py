@@ -167,14 +167,25 @@ class _LocalizationBase(nn.Module):
     def forward_streams(self, batch):
         """batch: list of dicts {video_id, duration, streams: {'video'?: [T_v,256], 'byola': [T_b,2048],
         'emo': [T_e,768]} fp32 numpy/torch, time-major like the `.npy` files}. Runs the dataset's resampling to
-        max_seq_len + concat (deepfake_video_audio.py:513-547) on the GPU, then the model."""
+        max_seq_len + concat (deepfake_video_audio.py:513-547) on the GPU, then the model; returns the same list
+        of dicts as forward(). Host buffers in, host tensors out (pinned staging + CUDA graph inside)."""
+        runner = self.runner()
         out = []
         for i in range(0, len(batch), self.max_batch):
-            out.extend(self._forward_streams_chunk(batch[i:i + self.max_batch]))
+            out.extend(runner.run(batch[i:i + self.max_batch]))
         return out
 
-    def _forward_streams_chunk(self, chunk):
-        return self.fetch(self.run_staged(self.stage(self.pack_streams(chunk))))
+    @torch.no_grad()
+    def stream(self, batches):
+        """Pipelined variant for serving loops: `for results in model.stream(iterable_of_batches)` overlaps the
+        host-side packing of batch i+1 with the copies and GPU work of batch i (two pinned staging slots)."""
+        yield from self.runner().stream(batches)
+
+    def runner(self):
+        if getattr(self, "_runner", None) is None or self._runner.eng is not self.engine():
+            from .streaming import StreamRunner
+            self._runner = StreamRunner(self)
+        return self._runner
 
     # The raw-stream path in four explicit stages, so that a serving loop (and bench.py) can overlap them:
     #   pack_streams  host:  ragged per-video arrays -> one pinned buffer per stream + row offsets + per-video meta

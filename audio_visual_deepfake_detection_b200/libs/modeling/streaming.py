@@ -1,0 +1,162 @@
+"""Host <-> device pipeline of the raw-stream entry point (`model.forward_streams`, `model.stream`).
+
+Per batch of <= max_batch videos:
+  pack   (host threads)  every video's [T_s, C_s] fp32 arrays are copied into ONE pinned buffer per stream
+                         (row offsets + per-video metadata alongside)
+  H2D    (copy engine)   pinned -> static device staging buffers, asynchronous on the compute stream
+  GPU                    the whole pass (interp/concat -> model -> decode -> NMS) replayed as ONE CUDA graph
+  D2H                    fixed-size results -> pinned host, then an event
+Two slots alternate, so packing batch i+1 overlaps the GPU work and the copies of batch i. This replaces the
+reference's DataLoader workers (which run F.interpolate on the CPU, libs/datasets/deepfake_video_audio.py:513-547)
+plus the per-video `.to(device)` / `.cpu()` of libs/modeling/av_fd_no_recon.py:476-477, 841-846.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+STREAMS = ("video", "byola", "emo")
+
+
+class _Slot:
+    def __init__(self, runner, index):
+        self.runner, self.index = runner, index
+        self.cap = [0, 0, 0]              # rows
+        self.host = [None, None, None]
+        self.dev = [None, None, None]
+        self.graphs = {}                  # batch size -> GraphedPass
+        self.done = torch.cuda.Event()
+        self.ids, self.B, self.busy = None, 0, False
+
+    def ensure(self, rows, chans, max_batch, K, device):
+        grown = False
+        for s in range(3):
+            if chans[s] == 0:
+                continue
+            if self.host[s] is None or rows[s] > self.cap[s]:
+                self.cap[s] = int(rows[s] * 1.25) + 64
+                self.host[s] = torch.empty((self.cap[s], chans[s]), dtype=torch.float32, pin_memory=True)
+                self.dev[s] = torch.empty((self.cap[s], chans[s]), dtype=torch.float32, device=device)
+                grown = True
+        if not hasattr(self, "h_off"):
+            self.h_off = torch.zeros((3, max_batch + 1), dtype=torch.int32, pin_memory=True)
+            self.d_off = torch.zeros((3, max_batch + 1), dtype=torch.int32, device=device)
+            self.h_meta = torch.zeros((4, max_batch), dtype=torch.float32, pin_memory=True)
+            self.d_meta = torch.zeros((4, max_batch), dtype=torch.float32, device=device)
+            self.h_segs = torch.zeros((max_batch, K, 2), dtype=torch.float32, pin_memory=True)
+            self.h_scores = torch.zeros((max_batch, K), dtype=torch.float32, pin_memory=True)
+            self.h_counts = torch.zeros((max_batch,), dtype=torch.int32, pin_memory=True)
+            self.h_vcls = torch.zeros((max_batch,), dtype=torch.float32, pin_memory=True)
+        if grown:
+            self.graphs.clear()           # captured kernels hold the old staging pointers
+
+
+class StreamRunner:
+    def __init__(self, model, n_slots=2, n_threads=None):
+        self.model = model
+        self.eng = model.engine()
+        self.slots = [_Slot(self, i) for i in range(n_slots)]
+        self.next = 0
+        self.pool = ThreadPoolExecutor(max_workers=n_threads or min(16, os.cpu_count() or 4))
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.use_graph = True
+
+    # ---------------------------------------------------------------- stages
+    def _pack(self, slot, chunk, feat_stride=1, num_frames=1):
+        eng, L = self.eng, self.eng.max_seq_len
+        B = len(chunk)
+        present = [n in chunk[0]["streams"] for n in STREAMS]
+        arrs = [[np.asarray(c["streams"][n].numpy() if torch.is_tensor(c["streams"][n]) else c["streams"][n]) for c in chunk]
+                if p else None for n, p in zip(STREAMS, present)]
+        rows = [sum(a.shape[0] for a in al) if al else 0 for al in arrs]
+        chans = [al[0].shape[1] if al else 0 for al in arrs]
+        if sum(chans) != eng.c_in:
+            raise ValueError("streams carry %d channels, the model expects %d" % (sum(chans), eng.c_in))
+        K = int(eng.test_cfg["max_seg_num"])
+        slot.ensure(rows, chans, eng.max_batch, K, eng.device)
+        off = slot.h_off.numpy()
+        jobs = []
+        for s in range(3):
+            if arrs[s] is None:
+                continue
+            off[s, 0] = 0
+            off[s, 1:B + 1] = np.cumsum([a.shape[0] for a in arrs[s]])
+            dst = slot.host[s].numpy()
+            for b, a in enumerate(arrs[s]):
+                jobs.append((dst[off[s, b]:off[s, b + 1]], a))
+        list(self.pool.map(lambda j: np.copyto(j[0], j[1]), jobs))         # numpy releases the GIL while copying
+        meta = slot.h_meta.numpy()
+        for b, c in enumerate(chunk):
+            first = c["streams"]["video"] if present[0] else c["streams"]["byola"]
+            t_first = first.shape[0]
+            fs = float((t_first - 1) * feat_stride + num_frames) / L        # deepfake_video_audio.py:495-497
+            # av_fd_no_recon.py:860-865: python-float scalars enter an fp32 tensor expression
+            meta[:, b] = (np.float32(fs), np.float32(0.5 * fs), np.float32(t_first / c["duration"]), np.float32(c["duration"]))
+        slot.rows, slot.chans, slot.B, slot.ids = rows, chans, B, [c["video_id"] for c in chunk]
+
+    def _launch(self, slot):
+        eng, B = self.eng, slot.B
+        nbytes = 0
+        for s in range(3):
+            if slot.chans[s]:
+                slot.dev[s][:slot.rows[s]].copy_(slot.host[s][:slot.rows[s]], non_blocking=True)
+                nbytes += slot.rows[s] * slot.chans[s] * 4
+        slot.d_off.copy_(slot.h_off, non_blocking=True)
+        slot.d_meta.copy_(slot.h_meta, non_blocking=True)
+        self.h2d_bytes += nbytes + slot.h_off.numel() * 4 + slot.h_meta.numel() * 4
+        staged = {"ids": slot.ids, "B": B, "meta": slot.d_meta[:, :B] if B == eng.max_batch else slot.d_meta[:, :B].contiguous(),
+                  "streams": [slot.dev[s] if slot.chans[s] else None for s in range(3)],
+                  "offs": [slot.d_off[s, :B + 1] if slot.chans[s] else None for s in range(3)]}
+        if self.use_graph and B == eng.max_batch:
+            g = slot.graphs.get(B)
+            if g is None:
+                g = self.model.capture(staged)
+                slot.graphs[B] = g
+            res = g.replay()
+        else:
+            res = self.model.run_staged(staged)
+        slot.h_segs[:B].copy_(res["segs"], non_blocking=True)
+        slot.h_scores[:B].copy_(res["scores"], non_blocking=True)
+        slot.h_counts[:B].copy_(res["counts"], non_blocking=True)
+        slot.h_vcls[:B].copy_(res["vcls"], non_blocking=True)
+        self.d2h_bytes += B * (slot.h_segs.shape[1] * 3 + 2) * 4
+        slot.done.record()
+        slot.busy = True
+
+    def _collect(self, slot):
+        slot.done.synchronize()
+        slot.busy = False
+        out = []
+        counts = slot.h_counts.numpy()
+        for b, vid in enumerate(slot.ids):
+            n = int(counts[b])
+            out.append({"video_id": vid, "segments": slot.h_segs[b, :n].clone(), "scores": slot.h_scores[b, :n].clone(),
+                        "labels": torch.zeros(n, dtype=torch.long), "video_cls": slot.h_vcls[b:b + 1].clone()})
+        return out
+
+    # ---------------------------------------------------------------- public
+    def run(self, chunk):
+        """One batch, synchronously."""
+        slot = self.slots[0]
+        if slot.busy:
+            self._collect(slot)
+        self._pack(slot, chunk)
+        self._launch(slot)
+        return self._collect(slot)
+
+    def stream(self, batches):
+        """Generator over an iterable of batches (each <= max_batch videos): yields every batch's results in order,
+        one batch behind the submission so that host packing overlaps GPU work."""
+        pending = []
+        for chunk in batches:
+            slot = self.slots[self.next]
+            self.next = (self.next + 1) % len(self.slots)
+            if slot.busy:
+                yield self._collect(pending.pop(0))
+            self._pack(slot, chunk)
+            self._launch(slot)
+            pending.append(slot)
+        while pending:
+            yield self._collect(pending.pop(0))
