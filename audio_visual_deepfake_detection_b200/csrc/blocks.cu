@@ -51,20 +51,28 @@ struct LdlParams {
   const float* ln_in_w[3]; const float* ln_in_b[3]; const float* dw_w[3];
   const float* ln_out_w[3]; const float* ln_out_b[3];
   void* out[3]; float* skip_out;
-  int B, t_src, t_virt, shift, t_out, n_streams;
+  int B, t_src, t_virt, shift, t_out, n_streams, out_rows;
 };
 constexpr int LDL_ROWS = 8;            // output rows per warp
 constexpr int LDL_WARPS = 8;
 
+// With u = xhat * w_in + b_in (xhat = the normalised source row, shared by all streams) the depthwise conv is
+//   acc[c] = sum_j dw[c][j] * u_j[c] = sum_j (dw[c][j] w_in[c]) * xhat_j[c] + b_in[c] * sum_j dw[c][j]
+// so the per-stream constants A_j = dw_j * w_in, Bj = dw_j * b_in, Bsum = sum_j Bj are folded once per CTA into shared
+// memory and an interior output row costs 3 FFMA per channel and stream (edge rows, where a tap falls outside
+// [0, t_virt), use the per-tap Bj instead of Bsum).
 template <typename OutT, int STRIDE>
-__global__ void __launch_bounds__(LDL_WARPS * 32) ln_dwconv_ln_kernel(const LdlParams p) {
-  // per stream: ln_in_w, ln_in_b, dw tap0, tap1, tap2, ln_out_w, ln_out_b  (7 x 256 floats)
-  __shared__ __align__(16) float sp[3][7][kC];
+__global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const LdlParams p) {
+  // per stream: A0, A1, A2, Bsum, B0, B1, B2, ln_out_w, ln_out_b  (9 x 256 floats)
+  __shared__ __align__(16) float sp[3][9][kC];
   for (int i = threadIdx.x; i < p.n_streams * kC; i += blockDim.x) {
     const int s = i / kC, c = i - s * kC;
-    sp[s][0][c] = p.ln_in_w[s][c]; sp[s][1][c] = p.ln_in_b[s][c];
-    sp[s][2][c] = p.dw_w[s][3 * c]; sp[s][3][c] = p.dw_w[s][3 * c + 1]; sp[s][4][c] = p.dw_w[s][3 * c + 2];
-    sp[s][5][c] = p.ln_out_w[s][c]; sp[s][6][c] = p.ln_out_b[s][c];
+    const float w = p.ln_in_w[s][c], bb = p.ln_in_b[s][c];
+    const float d0 = p.dw_w[s][3 * c], d1 = p.dw_w[s][3 * c + 1], d2 = p.dw_w[s][3 * c + 2];
+    sp[s][0][c] = d0 * w; sp[s][1][c] = d1 * w; sp[s][2][c] = d2 * w;
+    sp[s][4][c] = d0 * bb; sp[s][5][c] = d1 * bb; sp[s][6][c] = d2 * bb;
+    sp[s][3][c] = d0 * bb + d1 * bb + d2 * bb;
+    sp[s][7][c] = p.ln_out_w[s][c]; sp[s][8][c] = p.ln_out_b[s][c];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,60 +84,84 @@ __global__ void __launch_bounds__(LDL_WARPS * 32) ln_dwconv_ln_kernel(const LdlP
     const int t0 = (int)(tile - (long long)b * tiles_per_video) * LDL_ROWS;
     const int t1 = min(t0 + LDL_ROWS, p.t_out);
     const float* src_b = p.src + (size_t)b * p.t_src * kC;
-    float raw[3][8]; float mean[3], rstd[3]; bool ok[3];
+    float xh[3][8];                 // normalised rows of the 3-position window
+    float rw[STRIDE == 2 ? 3 : 1][8];   // raw rows (only the stride-2 MaxPool skip needs them)
+    bool ok[3] = {false, false, false};
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { ok[j] = false; mean[j] = 0.f; rstd[j] = 0.f;
+    for (int j = 0; j < 3; ++j)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) raw[j][k] = 0.f; }
-    for (int pos = STRIDE * t0 - 1; pos <= STRIDE * (t1 - 1) + 1; ++pos) {
-      // slide the 3-position window
+      for (int k = 0; k < 8; ++k) xh[j][k] = 0.f;
+    // software pipeline: the source row of position pos + 1 is in flight while position pos is processed
+    const int pos_first = STRIDE * t0 - 1, pos_last = STRIDE * (t1 - 1) + 1;
+    float nxt[8];
+    auto fetch = [&](int pos) {
+      if (pos >= 0 && pos < p.t_virt && pos <= pos_last) {
+        const int r = p.shift >= 0 ? (pos >> p.shift) : (pos << (-p.shift));
+        Row8<float>::load(src_b + (size_t)r * kC + c0, nxt);
+      }
+    };
+    fetch(pos_first);
+    for (int pos = pos_first; pos <= pos_last; ++pos) {
+      // slide the window, normalise the new row
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { raw[0][k] = raw[1][k]; raw[1][k] = raw[2][k]; }
-      mean[0] = mean[1]; mean[1] = mean[2]; rstd[0] = rstd[1]; rstd[1] = rstd[2]; ok[0] = ok[1]; ok[1] = ok[2];
+      for (int k = 0; k < 8; ++k) { xh[0][k] = xh[1][k]; xh[1][k] = xh[2][k]; }
+      if (STRIDE == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { rw[0][k] = rw[STRIDE == 2 ? 1 : 0][k]; rw[STRIDE == 2 ? 1 : 0][k] = rw[STRIDE == 2 ? 2 : 0][k]; rw[STRIDE == 2 ? 2 : 0][k] = nxt[k]; }
+      }
+      ok[0] = ok[1]; ok[1] = ok[2];
       ok[2] = pos >= 0 && pos < p.t_virt;
       if (ok[2]) {
-        const int r = p.shift >= 0 ? (pos >> p.shift) : (pos << (-p.shift));
-        Row8<float>::load(src_b + (size_t)r * kC + c0, raw[2]);
-        row_stats(raw[2], mean[2], rstd[2]);
+        float mean, rstd;
+        row_stats(nxt, mean, rstd);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xh[2][k] = (nxt[k] - mean) * rstd;
       }
+      fetch(pos + 1);
       const int rel = pos - (STRIDE * t0 + 1);
       if (rel < 0 || (rel % STRIDE) != 0) continue;
       const int t = t0 + rel / STRIDE;          // output row whose taps are window[0..2]
-      const size_t orow = (size_t)b * p.t_out + t;
-      const float mk = p.mask_out ? (p.mask_out[orow] ? 1.f : 0.f) : 1.f;
+      const size_t orow = (size_t)b * p.t_out + t;              // dense row: mask / skip
+      const size_t srow = (size_t)b * p.out_rows + t;           // row in the (possibly interleaved) output buffers
+      const bool keep = p.mask_out ? (p.mask_out[orow] != 0) : true;
+      const bool interior = ok[0] && ok[2];                      // ok[1] always holds for an output row
       for (int s = 0; s < p.n_streams; ++s) {
-        float w[8], bb[8], acc[8];
-        lds8(&sp[s][0][c0], w); lds8(&sp[s][1][c0], bb);
+        float acc[8];
+        if (!keep) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        } else if (interior) {
+          float a0[8], a1[8], a2[8];
+          lds8(&sp[s][3][c0], acc); lds8(&sp[s][0][c0], a0); lds8(&sp[s][1][c0], a1); lds8(&sp[s][2][c0], a2);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          float d[8];
-          lds8(&sp[s][2 + j][c0], d);
-          if (ok[j]) {
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(a2[k], xh[2][k], fmaf(a1[k], xh[1][k], fmaf(a0[k], xh[0][k], acc[k])));
+        } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float u = fmaf((raw[j][k] - mean[j]) * rstd[j], w[k], bb[k]);
-              acc[k] = fmaf(d[k], u, acc[k]);
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (ok[j]) {
+              float a[8], bj[8];
+              lds8(&sp[s][j][c0], a); lds8(&sp[s][4 + j][c0], bj);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] += fmaf(a[k], xh[j][k], bj[k]);
             }
           }
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] *= mk;
-        float m2, r2;
+        float m2, r2, w[8], bb[8];
         row_stats(acc, m2, r2);
-        lds8(&sp[s][5][c0], w); lds8(&sp[s][6][c0], bb);
+        lds8(&sp[s][7][c0], w); lds8(&sp[s][8][c0], bb);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m2) * r2, w[k], bb[k]);
-        Row8<OutT>::store(reinterpret_cast<OutT*>(p.out[s]) + orow * kC + c0, acc);
+        Row8<OutT>::store(reinterpret_cast<OutT*>(p.out[s]) + srow * kC + c0, acc);
       }
       if (STRIDE == 2 && p.skip_out) {           // MaxPool1d(3, 2, 1) of the raw rows, -inf padding
         float mx[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float m = raw[1][k];
-          if (ok[0]) m = fmaxf(m, raw[0][k]);
-          if (ok[2]) m = fmaxf(m, raw[2][k]);
+          float m = rw[STRIDE == 2 ? 1 : 0][k];
+          if (ok[0]) m = fmaxf(m, rw[0][k]);
+          if (ok[2]) m = fmaxf(m, rw[STRIDE == 2 ? 2 : 0][k]);
           mx[k] = m;
         }
         Row8<float>::store(p.skip_out + orow * kC + c0, mx);
@@ -146,7 +178,7 @@ constexpr int ATT_ROWS = 4, ATT_WARPS = 8;
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const InT* __restrict__ q, const InT* __restrict__ k,
                                                                   const InT* __restrict__ v, const unsigned char* __restrict__ kv_mask,
-                                                                  OutT* __restrict__ out, int B, int T, int window) {
+                                                                  OutT* __restrict__ out, int B, int T, int RPV, int window) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = lane * 8;
   const int tiles_per_video = (T + ATT_ROWS - 1) / ATT_ROWS;
@@ -156,10 +188,11 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const InT* __
   for (long long tile = (long long)blockIdx.x * ATT_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * ATT_WARPS) {
     const int b = (int)(tile / tiles_per_video);
     const int t0 = (int)(tile - (long long)b * tiles_per_video) * ATT_ROWS;
-    const size_t base = (size_t)b * T;
+    const size_t base = (size_t)b * T;          // mask / output rows
+    const size_t qb = (size_t)b * RPV;          // q / k / v rows
     for (int i = t0; i < min(t0 + ATT_ROWS, T); ++i) {
       float qv[8];
-      Row8<InT>::load(q + (base + i) * kC + c0, qv);
+      Row8<InT>::load(q + (qb + i) * kC + c0, qv);
 #pragma unroll
       for (int d = 0; d < 8; ++d) qv[d] *= scale;
       const int lo = window > 1 ? max(0, i - half) : 0;
@@ -171,8 +204,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const InT* __
         const bool mk = kv_mask ? (kv_mask[base + j] != 0) : true;
         if (window <= 1 && !mk) continue;                 // global: masked keys are -inf
         float kv[8], vv[8];
-        Row8<InT>::load(k + (base + j) * kC + c0, kv);
-        Row8<InT>::load(v + (base + j) * kC + c0, vv);
+        Row8<InT>::load(k + (qb + j) * kC + c0, kv);
+        Row8<InT>::load(v + (qb + j) * kC + c0, vv);
         float s = 0.f;
 #pragma unroll
         for (int d = 0; d < 8; ++d) s = fmaf(qv[d], kv[d], s);
@@ -194,6 +227,100 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const InT* __
       for (int d = 0; d < 8; ++d) acc[d] *= inv;
       Row8<OutT>::store(out + (base + i) * kC + c0, acc);
     }
+  }
+}
+
+
+// Banded attention with the K / V rows of a query tile staged in shared memory: a CTA owns ATB_ROWS consecutive
+// query rows of one video and cp.async-loads rows [t0 - HALF, t0 + ATB_ROWS + HALF) of K and V once (each K/V row is
+// otherwise re-read from L1/L2 by 2*HALF+1 different queries). One warp per query row, 8 lanes per head; the
+// 2*HALF+1 scores of a row are computed first (independent dot products), then a two-pass softmax in base 2
+// (log2(e) folded into the query scale, ex2.approx), then the weighted sum of V.
+constexpr int ATB_ROWS = 32, ATB_WARPS = 8;
+
+template <typename InT, typename OutT, int HALF>
+__global__ void __launch_bounds__(ATB_WARPS * 32) attention_banded_kernel(const InT* __restrict__ q, const InT* __restrict__ k,
+                                                                         const InT* __restrict__ v, const unsigned char* __restrict__ kv_mask,
+                                                                         OutT* __restrict__ out, int B, int T, int RPV) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  constexpr int ROWB = kC * (int)sizeof(InT);                  // bytes per K or V row
+  constexpr int NROW = ATB_ROWS + 2 * HALF, W = 2 * HALF + 1;
+  InT* ks = reinterpret_cast<InT*>(att_smem);
+  InT* vs = reinterpret_cast<InT*>(att_smem + (size_t)NROW * ROWB);
+  __shared__ unsigned char s_mask[NROW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_per_video = (T + ATB_ROWS - 1) / ATB_ROWS;
+  const int b = blockIdx.x / tiles_per_video;
+  const int t0 = (blockIdx.x - b * tiles_per_video) * ATB_ROWS;
+  const int t1 = min(t0 + ATB_ROWS, T);
+  const int lo = t0 - HALF;                                    // smem row r holds key row lo + r (if inside [0, T))
+  const size_t qb = (size_t)b * RPV, base = (size_t)b * T;
+  constexpr int CH = ROWB / 16;                                // 16-byte chunks per row
+  for (int i = threadIdx.x; i < NROW * CH; i += blockDim.x) {
+    const int r = i / CH, c = i - r * CH;
+    const int j = lo + r;
+    if (j < 0 || j >= T || j >= t1 + HALF) continue;
+    const size_t g = ((qb + j) * kC) * sizeof(InT) + (size_t)c * 16;
+    const unsigned sk = (unsigned)__cvta_generic_to_shared(reinterpret_cast<unsigned char*>(ks) + (size_t)r * ROWB + c * 16);
+    const unsigned sv = (unsigned)__cvta_generic_to_shared(reinterpret_cast<unsigned char*>(vs) + (size_t)r * ROWB + c * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sk), "l"(reinterpret_cast<const unsigned char*>(k) + g) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sv), "l"(reinterpret_cast<const unsigned char*>(v) + g) : "memory");
+  }
+  for (int i = threadIdx.x; i < NROW; i += blockDim.x) {
+    const int j = lo + i;
+    s_mask[i] = (j >= 0 && j < T) ? (kv_mask ? kv_mask[base + j] : 1) : 0;
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int c0 = lane * 8;
+  const float scale = 0.125f * 1.4426950408889634f;           // 1/sqrt(64) * log2(e)
+  for (int i = t0 + warp; i < t1; i += ATB_WARPS) {
+    float qv[8];
+    Row8<InT>::load(q + (qb + i) * kC + c0, qv);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) qv[d] *= scale;
+    const int r0 = i - HALF - lo;                               // smem row of key i - HALF (= i - t0 >= 0)
+    float sc[W];
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int j = i - HALF + w;
+      float s = 0.f;
+      if (j >= 0 && j < T) {                                    // warp-uniform
+        float kv[8];
+        Row8<InT>::load(ks + (size_t)(r0 + w) * kC + c0, kv);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) s = fmaf(qv[d], kv[d], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (j < 0 || j >= T) s = -INFINITY;                       // outside the sequence
+      else if (!s_mask[r0 + w]) s += -1e4f * 1.4426950408889634f;   // blocks.py:1194-1195 (additive, base-2 domain)
+      sc[w] = s;
+      m = fmaxf(m, s);
+    }
+    float l = 0.f, acc[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int j = i - HALF + w;
+      if (j >= 0 && j < T) {
+        float pj;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pj) : "f"(sc[w] - m));
+        l += pj;
+        float vv[8];
+        Row8<InT>::load(vs + (size_t)(r0 + w) * kC + c0, vv);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[d] = fmaf(pj, vv[d], acc[d]);
+      }
+    }
+    const float inv = (s_mask[i - lo] && l > 0.f) ? 1.f / l : 0.f;   // blocks.py:1208-1209
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] *= inv;
+    Row8<OutT>::store(out + (base + i) * kC + c0, acc);
   }
 }
 
@@ -574,6 +701,8 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
     p.ln_out_w[s] = a->ln_out_w[s]; p.ln_out_b[s] = a->ln_out_b[s]; p.out[s] = a->out[s];
   }
   p.B = a->batch; p.t_src = a->t_src; p.t_virt = a->t_virt; p.shift = a->shift; p.t_out = a->t_virt / a->stride;
+  p.out_rows = a->out_rows_per_video > 0 ? a->out_rows_per_video : p.t_out;
+  AVDF_CHECK_ARG(p.out_rows >= p.t_out, "out_rows_per_video smaller than the output length");
   p.n_streams = a->n_streams;
   if (a->batch == 0) return AVDF_OK;
   const long long tiles = (long long)a->batch * ((p.t_out + LDL_ROWS - 1) / LDL_ROWS);
@@ -585,20 +714,37 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
 }
 
 extern "C" int avdf_attention(const void* q, const void* k, const void* v, const uint8_t* kv_mask, void* out,
-                              int32_t in_dtype, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels,
-                              int32_t n_head, int32_t window, void* stream) {
+                              int32_t in_dtype, int32_t out_dtype, int32_t batch, int32_t t, int32_t qkv_rows_per_video,
+                              int32_t channels, int32_t n_head, int32_t window, void* stream) {
   AVDF_CHECK_ARG(q && k && v && out, "null pointer");
   AVDF_CHECK_ARG(channels == kC && n_head == 4, "attention supports 4 heads x 64 channels");
   AVDF_CHECK_ARG(batch >= 0 && t > 0, "bad sizes");
   AVDF_CHECK_ARG(window <= 1 || (window & 1), "window must be odd (or <= 1 for global attention)");
-  if (batch == 0) return AVDF_OK;
-  const long long tiles = (long long)batch * ((t + ATT_ROWS - 1) / ATT_ROWS);
-  const int grid = grid_for(tiles, ATT_WARPS, sm_count());
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   AVDF_CHECK_DTYPE(in_dtype, "in_dtype");
   AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
+  const int rpv = qkv_rows_per_video > 0 ? qkv_rows_per_video : t;
+  AVDF_CHECK_ARG(rpv >= t, "qkv_rows_per_video smaller than t");
+  if (batch == 0) return AVDF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (window == 7) {                            // the window every shipped config uses: smem-tiled specialisation
+    constexpr int HALF = 3;
+    const int grid = batch * ((t + ATB_ROWS - 1) / ATB_ROWS);
+    AVDF_DISPATCH_DTYPE(in_dtype, InT, AVDF_DISPATCH_DTYPE(out_dtype, OutT, {
+      const size_t smem = 2 * (size_t)(ATB_ROWS + 2 * HALF) * kC * sizeof(InT);
+      static bool attr_done = false;
+      if (!attr_done) {
+        AVDF_CUDA(cudaFuncSetAttribute(attention_banded_kernel<InT, OutT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+      }
+      attention_banded_kernel<InT, OutT, HALF><<<grid, ATB_WARPS * 32, smem, st>>>((const InT*)q, (const InT*)k, (const InT*)v, kv_mask,
+                                                                                  (OutT*)out, batch, t, rpv);
+    }));
+    return check_launch("attention_banded_kernel");
+  }
+  const long long tiles = (long long)batch * ((t + ATT_ROWS - 1) / ATT_ROWS);
+  const int grid = grid_for(tiles, ATT_WARPS, sm_count());
   AVDF_DISPATCH_DTYPE(in_dtype, InT, AVDF_DISPATCH_DTYPE(out_dtype, OutT, (attention_kernel<InT, OutT><<<grid, ATT_WARPS * 32, 0, st>>>(
-      (const InT*)q, (const InT*)k, (const InT*)v, kv_mask, (OutT*)out, batch, t, window))));
+      (const InT*)q, (const InT*)k, (const InT*)v, kv_mask, (OutT*)out, batch, t, rpv, window))));
   return check_launch("attention_kernel");
 }
 

@@ -16,6 +16,7 @@ struct SegInfo {
   int t_out[AVDF_MAX_LEVELS];
   int a_row[AVDF_MAX_LEVELS];
   int o_row[AVDF_MAX_LEVELS];
+  int w_row[AVDF_MAX_LEVELS];
   long long a_rows, o_rows;     // rows per video in A / out
 };
 
@@ -36,7 +37,7 @@ inline void fill_epi(const avdf_conv_gemm_args* a, EpiParams& e) {
 }
 inline void fill_seg(const avdf_conv_gemm_args* a, SegInfo& s) {
   s.n_seg = a->n_seg; s.batch = a->batch;
-  for (int i = 0; i < a->n_seg; ++i) { s.t_out[i] = a->seg_t_out[i]; s.a_row[i] = a->seg_a_row[i]; s.o_row[i] = a->seg_o_row[i]; }
+  for (int i = 0; i < a->n_seg; ++i) { s.t_out[i] = a->seg_t_out[i]; s.a_row[i] = a->seg_a_row[i]; s.o_row[i] = a->seg_o_row[i]; s.w_row[i] = a->seg_w_row[i]; }
   s.a_rows = a->a_rows_per_video; s.o_rows = a->o_rows_per_video;
 }
 

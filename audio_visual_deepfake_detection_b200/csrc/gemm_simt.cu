@@ -116,7 +116,30 @@ __global__ void __launch_bounds__(256) row_epilogue_kernel(const SimtParams p, c
   }
 }
 
+static int conv_gemm_f32_one(const avdf_conv_gemm_args* a, cudaStream_t st);
+
+// Segments with their own weight block (seg_w_row != 0) run as one launch per segment with the weight / vector
+// pointers advanced on the host; the shared-weight case (pyramid levels) is a single launch.
 int conv_gemm_f32(const avdf_conv_gemm_args* a, cudaStream_t st) {
+  bool shared = true;
+  for (int i = 0; i < a->n_seg; ++i) shared = shared && a->seg_w_row[i] == 0;
+  if (shared) return conv_gemm_f32_one(a, st);
+  for (int i = 0; i < a->n_seg; ++i) {
+    avdf_conv_gemm_args b = *a;
+    const int wo = a->seg_w_row[i];
+    b.n_seg = 1;
+    b.seg_t_out[0] = a->seg_t_out[i]; b.seg_a_row[0] = a->seg_a_row[i]; b.seg_o_row[0] = a->seg_o_row[i]; b.seg_w_row[0] = 0;
+    b.w = reinterpret_cast<const float*>(a->w) + (size_t)wo * a->taps * a->c_in;
+    if (a->bias) b.bias = a->bias + wo;
+    if (a->ln_w) { b.ln_w = a->ln_w + wo; b.ln_b = a->ln_b + wo; }
+    if (a->gamma) b.gamma = a->gamma + wo;
+    int rc = conv_gemm_f32_one(&b, st);
+    if (rc) return rc;
+  }
+  return AVDF_OK;
+}
+
+static int conv_gemm_f32_one(const avdf_conv_gemm_args* a, cudaStream_t st) {
   SimtParams p{};
   fill_seg(a, p.seg);
   int m = 0;
@@ -160,6 +183,8 @@ extern "C" int avdf_conv_gemm(const avdf_conv_gemm_args* a, void* stream) {
   AVDF_CHECK_ARG(!a->out_h || a->out_h_dtype == AVDF_DTYPE_BF16 || a->out_h_dtype == AVDF_DTYPE_F16, "out_h_dtype must be BF16 or F16");
   AVDF_CHECK_ARG((a->ln_w == nullptr) == (a->ln_b == nullptr), "ln_w / ln_b must come together");
   for (int i = 0; i < a->n_seg; ++i) AVDF_CHECK_ARG(a->seg_t_out[i] > 0, "seg_t_out must be positive");
+  for (int i = 0; i < a->n_seg; ++i)
+    AVDF_CHECK_ARG(a->seg_w_row[i] >= 0 && a->seg_w_row[i] + a->n_out <= (a->n_w_rows > 0 ? a->n_w_rows : a->n_out), "seg_w_row out of range");
   if (a->batch == 0) return AVDF_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->dtype == AVDF_DTYPE_F32) return conv_gemm_f32(a, st);

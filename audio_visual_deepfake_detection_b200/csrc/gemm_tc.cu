@@ -34,7 +34,7 @@ struct Params {
   SegInfo seg;
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
   int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
-  int n_out, c_in, taps, stride, bn, n_tiles_n, total_tiles;
+  int n_out, c_in, taps, stride, bn, n_tiles_n, n_tiles_m, total_tiles;
   unsigned idesc;
   EpiParams epi;
   unsigned long long* dbg;                   // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
@@ -115,11 +115,38 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// exact-erf GELU (blocks.py:1239) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the 16-bit
+// output rounding of this path; rcp/ex2 are the 2-ulp MUFU approximations): 2 MUFU + 9 FMA-class ops instead of
+// erff's ~35 instructions -
+// the 256->1024 MLP GEMM epilogue is ALU-bound on this function.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e2;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(-1.4426950408889634f * z * z));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_z = poly * t * e2;                                      // 1 - erf(z), z >= 0
+  const float half_x = 0.5f * x;
+  // 0.5 x (1 + erf(x/sqrt2)) = x - 0.5 x erfc(z) for x >= 0, 0.5 x erfc(z) for x < 0
+  return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
+}
+__device__ __forceinline__ float act_tc(float v, int act) {
+  if (act == AVDF_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == AVDF_ACT_GELU) return gelu_fast(v);
+  return v;
+}
+
 struct TileCoord { int seg, b0, t0, tt, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
   TileCoord c;
-  const int mt = tile / p.n_tiles_n;
-  c.n0 = (tile - mt * p.n_tiles_n) * p.bn;
+  // m fastest: consecutive tiles of a persistent CTA (tile, tile + grid, ...) mostly share the weight tile and the
+  // per-channel epilogue vectors
+  const int nt = tile / p.n_tiles_m;
+  const int mt = tile - nt * p.n_tiles_m;
+  c.n0 = nt * p.bn;
   int s = 0;
   while (s + 1 < p.seg.n_seg && mt >= p.seg_tile_start[s + 1]) ++s;
   c.seg = s;
@@ -196,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
             tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), kb * BK, par, tc_.t0 + dt, tc_.b0);
-            tma_load_2d(smem_u32(smem_b + stage * B_STAGE), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0);
+            tma_load_2d(smem_u32(smem_b + stage * B_STAGE), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -262,16 +289,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = decode_tile(p, tile);
       if (it == 0 && ew == 0) AVDF_TS(8);
-      if (tc_.n0 != loaded_n0) {                 // per-channel epilogue vectors of this n-tile -> smem
+      const int vec0 = tc_.n0 + p.seg.w_row[tc_.seg];   // first entry of this tile's per-channel vectors
+      if (vec0 != loaded_n0) {                   // per-channel epilogue vectors of this n-tile -> smem
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = et; i < p.bn; i += 256) {
-          s_bias[i] = e.bias ? __ldg(e.bias + tc_.n0 + i) : 0.f;
-          s_lnw[i] = e.ln_w ? __ldg(e.ln_w + tc_.n0 + i) : 1.f;
-          s_lnb[i] = e.ln_b ? __ldg(e.ln_b + tc_.n0 + i) : 0.f;
-          s_gam[i] = e.gamma ? __ldg(e.gamma + tc_.n0 + i) : 1.f;
+          s_bias[i] = e.bias ? __ldg(e.bias + vec0 + i) : 0.f;
+          s_lnw[i] = e.ln_w ? __ldg(e.ln_w + vec0 + i) : 1.f;
+          s_lnb[i] = e.ln_b ? __ldg(e.ln_b + vec0 + i) : 0.f;
+          s_gam[i] = e.gamma ? __ldg(e.gamma + vec0 + i) : 1.f;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        loaded_n0 = tc_.n0;
+        loaded_n0 = vec0;
       }
       if (it == 0 && ew == 0) AVDF_TS(9);
       const int acc = it & 1;
@@ -352,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         const float4 bias4 = *reinterpret_cast<const float4*>(s_bias + cl);
         const float4 lnw4 = *reinterpret_cast<const float4*>(s_lnw + cl), lnb4 = *reinterpret_cast<const float4*>(s_lnb + cl);
         const float4 gam4 = *reinterpret_cast<const float4*>(s_gam + cl);
-#pragma unroll 2
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + rsub;
           const long long ro = w_ro[rr];
@@ -364,7 +392,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
               x.x = fmaf((x.x - rw.y) * rw.z, lnw4.x, lnb4.x); x.y = fmaf((x.y - rw.y) * rw.z, lnw4.y, lnb4.y);
               x.z = fmaf((x.z - rw.y) * rw.z, lnw4.z, lnb4.z); x.w = fmaf((x.w - rw.y) * rw.z, lnw4.w, lnb4.w);
             }
-            x.x = apply_act(x.x, act); x.y = apply_act(x.y, act); x.z = apply_act(x.z, act); x.w = apply_act(x.w, act);
+            x.x = act_tc(x.x, act); x.y = act_tc(x.y, act); x.z = act_tc(x.z, act); x.w = act_tc(x.w, act);
             if (has_pe) {
               const float4 pv = __ldg(reinterpret_cast<const float4*>(e.pe + (size_t)__float_as_int(rw.w) * N + n));
               x.x = fmaf(pv.x, rw.x, x.x); x.y = fmaf(pv.y, rw.x, x.y); x.z = fmaf(pv.z, rw.x, x.z); x.w = fmaf(pv.w, rw.x, x.w);
@@ -469,9 +497,10 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     if (r != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(A, level %d) failed with %d", s, (int)r); return AVDF_ERR_CUDA; }
   }
   p.seg_tile_start[a->n_seg] = tiles;
+  p.n_tiles_m = tiles;
   p.total_tiles = tiles * p.n_tiles_n;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)a->taps * a->c_in, (cuuint64_t)a->n_out};
+    cuuint64_t dims[2] = {(cuuint64_t)a->taps * a->c_in, (cuuint64_t)(a->n_w_rows > 0 ? a->n_w_rows : a->n_out)};
     cuuint64_t strides[1] = {(cuuint64_t)a->taps * a->c_in * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};

@@ -77,6 +77,19 @@ class PackedWeights:
             self._cache[ck] = w.contiguous().to(self.device).to(dtype).contiguous()
         return self._cache[ck]
 
+    def stack_dense(self, keys, dtype):
+        """Several [co, ci(, k)] weights stacked along co (one GEMM launch with per-segment weight blocks)."""
+        ck = ("sd", tuple(keys), dtype)
+        if ck not in self._cache:
+            self._cache[ck] = torch.cat([self.dense(k, dtype) for k in keys], dim=0).contiguous()
+        return self._cache[ck]
+
+    def stack_vec(self, keys):
+        ck = ("sv", tuple(keys))
+        if ck not in self._cache:
+            self._cache[ck] = torch.cat([self.vec(k) for k in keys]).contiguous()
+        return self._cache[ck]
+
     def dw(self, key):
         ck = ("w", key)
         if ck not in self._cache:
@@ -216,8 +229,10 @@ class LocalizationEngine:
     # ------------------------------------------------------------------ building blocks
     def _gemm(self, a, wkey, *, B, taps=1, stride=1, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
               act=ops.ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_act=None):
-        w = self.w.dense(wkey, a.dtype)
+        w = self.w.dense(wkey, a.dtype) if isinstance(wkey, str) else self.w.stack_dense(wkey, a.dtype)
         n_out, k = w.shape
+        if not isinstance(wkey, str):
+            n_out //= len(wkey)
         c_in = k // taps
         out_h = None
         if out_act is not None:
@@ -238,13 +253,15 @@ class LocalizationEngine:
         q,k,v 1x1 -> attention -> proj(+skip) -> LN2 -> MLP(+residual). Returns (out_f32, out_act|None)."""
         C, w = self.C, self.w
         seg = [(T, 0, 0)]
-        qn, kn, vn = (self.buf(n, (B, T, C), self.adt) for n in ("qn", "kn", "vn"))
-        qp, kp, vp = (self.buf(n, (B, T, C), torch.float32) for n in ("qp", "kp", "vp"))
-        for src, dst, nm in ((qn, qp, "query"), (kn, kp, "key"), (vn, vp, "value")):
-            self._gemm(src, f"{pre}.attn.{nm}.weight", B=B, segs=seg, a_rows=T, o_rows=T,
-                       bias=w.vec(f"{pre}.attn.{nm}.bias"), out_f32=dst)
+        # q, k, v projections as ONE launch: the dwconv+LN stage wrote a video's q/k/v rows stacked ([B, 3T, C]);
+        # three segments with their own 256-row weight block each (blocks.py:1169-1171)
+        qkvn = self.buf("qkvn", (B, 3 * T, C), self.adt)
+        qkvp = self.buf("qkvp", (B, 3 * T, C), self.adt)
+        names = ("query", "key", "value")
+        self._gemm(qkvn, [f"{pre}.attn.{nm}.weight" for nm in names], B=B, segs=[(T, i * T, i * T, i * C) for i in range(3)],
+                   a_rows=3 * T, o_rows=3 * T, bias=w.stack_vec([f"{pre}.attn.{nm}.bias" for nm in names]), out_act=qkvp)
         att = self.buf("att", (B, T, C), self.adt)
-        ops.attention(qp, kp, vp, mask, att, batch=B, t=T, n_head=self.n_head, window=window)
+        ops.attention(None, None, None, mask, att, batch=B, t=T, n_head=self.n_head, window=window, qkv=qkvp)
         y = self.buf("y", (B, T, C), torch.float32)
         ga = w.vec(pre + ".drop_path_attn.scale") if w.has(pre + ".drop_path_attn.scale") else None
         gm = w.vec(pre + ".drop_path_mlp.scale") if w.has(pre + ".drop_path_mlp.scale") else None
@@ -273,13 +290,13 @@ class LocalizationEngine:
         To = T // stride
         lvl_out = level + (1 if stride == 2 else 0)
         mask = masks[lvl_out]
-        outs = [self.buf(n, (B, To, C), self.adt) for n in ("qn", "kn", "vn")]
+        qkvn = self.buf("qkvn", (B, 3 * To, C), self.adt)
         skip = self.buf("skip", (B, To, C), torch.float32) if stride == 2 else x
         ln1 = w.ln(pre + ".ln1")
         ops.ln_dwconv_ln(x, batch=B, t_src=T, t_virt=T, shift=0, stride=stride, mask_out=mask, ln_in=[ln1] * 3,
                          dw=[w.dw(f"{pre}.attn.{n}_conv.conv.weight") for n in ("query", "key", "value")],
-                         ln_out=[w.ln(f"{pre}.attn.{n}_norm") for n in ("query", "key", "value")], outs=outs,
-                         skip_out=skip if stride == 2 else None)
+                         ln_out=[w.ln(f"{pre}.attn.{n}_norm") for n in ("query", "key", "value")], outs=[qkvn] * 3,
+                         out_rows=3 * To, out_row_offsets=[0, To, 2 * To], skip_out=skip if stride == 2 else None)
         return self._attn_and_mlp(pre, B, To, mask, skip, window, out_name, want_act_copy)
 
     def mm_block(self, pre, xq, kv, B, Tq, Tkv, masks, level, window, out_name, want_act_copy=False):
@@ -287,23 +304,23 @@ class LocalizationEngine:
         nearest-resampled to Tq (backbones.py:487,490)."""
         C, w = self.C, self.w
         mask = masks[level]
-        qn, kn, vn = (self.buf(n, (B, Tq, C), self.adt) for n in ("qn", "kn", "vn"))
+        qkvn = self.buf("qkvn", (B, 3 * Tq, C), self.adt)
         names = ("query", "key", "value")
         dws = [w.dw(f"{pre}.attn.{n}_conv.conv.weight") for n in names]
         lno = [w.ln(f"{pre}.attn.{n}_norm") for n in names]
         lni = [w.ln(pre + ".lnq"), w.ln(pre + ".lnk"), w.ln(pre + ".lnv")]
         if kv is xq:
             ops.ln_dwconv_ln(xq, batch=B, t_src=Tq, t_virt=Tq, shift=0, stride=1, mask_out=mask, ln_in=lni, dw=dws,
-                             ln_out=lno, outs=[qn, kn, vn])
+                             ln_out=lno, outs=[qkvn] * 3, out_rows=3 * Tq, out_row_offsets=[0, Tq, 2 * Tq])
         else:
             ops.ln_dwconv_ln(xq, batch=B, t_src=Tq, t_virt=Tq, shift=0, stride=1, mask_out=mask, ln_in=lni[:1],
-                             dw=dws[:1], ln_out=lno[:1], outs=[qn])
+                             dw=dws[:1], ln_out=lno[:1], outs=[qkvn], out_rows=3 * Tq, out_row_offsets=[0])
             if Tq >= Tkv:
                 shift = int(round(math.log2(Tq // Tkv)))
             else:
                 shift = -int(round(math.log2(Tkv // Tq)))
             ops.ln_dwconv_ln(kv, batch=B, t_src=Tkv, t_virt=Tq, shift=shift, stride=1, mask_out=mask, ln_in=lni[1:],
-                             dw=dws[1:], ln_out=lno[1:], outs=[kn, vn])
+                             dw=dws[1:], ln_out=lno[1:], outs=[qkvn] * 2, out_rows=3 * Tq, out_row_offsets=[Tq, 2 * Tq])
         return self._attn_and_mlp(pre, B, Tq, mask, xq, window, out_name, want_act_copy)
 
     # ------------------------------------------------------------------ the pass

@@ -53,6 +53,7 @@ class ConvGemmArgs(Structure):
     _fields_ = [
         ("batch", c_int32), ("n_out", c_int32), ("c_in", c_int32), ("taps", c_int32), ("stride", c_int32), ("n_seg", c_int32),
         ("seg_t_out", c_int32 * MAX_LEVELS), ("seg_a_row", c_int32 * MAX_LEVELS), ("seg_o_row", c_int32 * MAX_LEVELS),
+        ("seg_w_row", c_int32 * MAX_LEVELS), ("n_w_rows", c_int32),
         ("a_rows_per_video", c_int64), ("o_rows_per_video", c_int64),
         ("a", c_void_p), ("w", c_void_p), ("dtype", c_int32),
         ("bias", c_void_p), ("row_mask", c_void_p), ("ln_w", c_void_p), ("ln_b", c_void_p), ("act", c_int32),
@@ -69,7 +70,7 @@ class LnDwconvLnArgs(Structure):
         ("src", c_void_p), ("mask_out", c_void_p),
         ("ln_in_w", c_void_p * 3), ("ln_in_b", c_void_p * 3), ("dw_w", c_void_p * 3),
         ("ln_out_w", c_void_p * 3), ("ln_out_b", c_void_p * 3),
-        ("out", c_void_p * 3), ("out_dtype", c_int32), ("skip_out", c_void_p),
+        ("out", c_void_p * 3), ("out_dtype", c_int32), ("out_rows_per_video", c_int32), ("skip_out", c_void_p),
     ]
 
 
@@ -103,7 +104,7 @@ def lib():
     L.avdf_conv_gemm_workspace_bytes.argtypes = [POINTER(ConvGemmArgs)]
     L.avdf_conv_gemm.argtypes = [POINTER(ConvGemmArgs), c_void_p]
     L.avdf_ln_dwconv_ln.argtypes = [POINTER(LnDwconvLnArgs), c_void_p]
-    L.avdf_attention.argtypes = [c_void_p] * 5 + [c_int32] * 7 + [c_void_p]
+    L.avdf_attention.argtypes = [c_void_p] * 5 + [c_int32] * 8 + [c_void_p]
     L.avdf_ln_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p]
     L.avdf_instnorm_lrelu.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]
     L.avdf_fpn_fuse.argtypes = [c_void_p] * 6 + [c_int32] * 4 + [POINTER(c_int32), c_void_p]

@@ -165,15 +165,17 @@ def postprocess_workspace_bytes(batch, cand_cap):
 # ---------------------------------------------------------------------------- conv GEMM
 def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
               act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_h=None, workspace=None):
-    """segs: list of (t_out, a_row, o_row) per level. a: [batch, a_rows, c_in]; w: [n_out, taps*c_in]
+    """segs: list of (t_out, a_row, o_row[, w_row]) per segment. a: [batch, a_rows, c_in]; w: [n_w_rows, taps*c_in]
     (same dtype as a: fp32 -> CUDA-core parity path, bf16 / fp16 -> tcgen05 path). Outputs [batch, o_rows, n_out]:
     out_f32 and/or out_h (a bf16 or fp16 copy)."""
     L = nv.lib()
     _chk(a, None, "a"); _chk(w, a.dtype, "w")
     g = nv.ConvGemmArgs()
     g.batch, g.n_out, g.c_in, g.taps, g.stride, g.n_seg = batch, n_out, c_in, taps, stride, len(segs)
-    for i, (t, ar, orow) in enumerate(segs):
-        g.seg_t_out[i], g.seg_a_row[i], g.seg_o_row[i] = int(t), int(ar), int(orow)
+    for i, sg in enumerate(segs):
+        g.seg_t_out[i], g.seg_a_row[i], g.seg_o_row[i] = int(sg[0]), int(sg[1]), int(sg[2])
+        g.seg_w_row[i] = int(sg[3]) if len(sg) > 3 else 0
+    g.n_w_rows = w.shape[0]
     g.a_rows_per_video, g.o_rows_per_video = int(a_rows), int(o_rows)
     g.a, g.w, g.dtype = a.data_ptr(), w.data_ptr(), _dt(a)
     for name, t in (("bias", bias), ("pe", pe), ("residual", residual), ("gamma", gamma)):
@@ -199,13 +201,16 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
         if workspace is None or workspace.numel() * workspace.element_size() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=a.device)
         g.workspace, g.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
-    _call("avdf_conv_gemm", L.avdf_conv_gemm, (ctypes.byref(g), nv.stream_ptr(),), launches=2 if g.dtype == DTYPE_F32 else 1, work={"flops": 2.0 * batch * sum(t for t, _, _ in segs) * n_out * taps * c_in, "m": batch * sum(t for t, _, _ in segs), "n": n_out, "k": taps * c_in,
+    _call("avdf_conv_gemm", L.avdf_conv_gemm, (ctypes.byref(g), nv.stream_ptr(),), launches=2 if g.dtype == DTYPE_F32 else 1, work={"flops": 2.0 * batch * sum(sg[0] for sg in segs) * n_out * taps * c_in, "m": batch * sum(sg[0] for sg in segs), "n": n_out, "k": taps * c_in,
                 "bytes": _nbytes(a, w, out_f32, out_h, residual)})
 
 
 # ---------------------------------------------------------------------------- block kernels
-def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, dw, ln_out, outs, skip_out=None):
-    """ln_in / ln_out: lists of (w, b); dw: list of [C,3]; outs: list of [batch, t_virt/stride, C] tensors."""
+def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, dw, ln_out, outs, skip_out=None, out_rows=0,
+                 out_row_offsets=None):
+    """ln_in / ln_out: lists of (w, b); dw: list of [C,3]; outs: list of output tensors. Dense: each
+    [batch, t_virt/stride, C]. Interleaved: every entry is the SAME base tensor [batch, out_rows, C] and
+    out_row_offsets[i] is the first row of stream i inside a video's block."""
     L = nv.lib()
     _chk(src, torch.float32, "src"); _chk(mask_out, torch.uint8, "mask_out"); _chk(skip_out, torch.float32, "skip_out")
     n = len(outs)
@@ -220,17 +225,29 @@ def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, d
         a.ln_in_w[i], a.ln_in_b[i] = ln_in[i][0].data_ptr(), ln_in[i][1].data_ptr()
         a.dw_w[i] = dw[i].data_ptr()
         a.ln_out_w[i], a.ln_out_b[i] = ln_out[i][0].data_ptr(), ln_out[i][1].data_ptr()
-        a.out[i] = outs[i].data_ptr()
+        a.out[i] = outs[i].data_ptr() + (out_row_offsets[i] * src.shape[-1] * outs[i].element_size() if out_row_offsets else 0)
     a.out_dtype = _dt(outs[0])
+    a.out_rows_per_video = int(out_rows)
     a.skip_out = skip_out.data_ptr() if skip_out is not None else None
     _call("avdf_ln_dwconv_ln", L.avdf_ln_dwconv_ln, (ctypes.byref(a), nv.stream_ptr(),), launches=1, work={"bytes": batch * t_src * src.shape[-1] * 4 + _nbytes(*[o[:batch] for o in outs]) + (_nbytes(skip_out[:batch]) if skip_out is not None else 0)})
 
 
-def attention(q, k, v, kv_mask, out, *, batch, t, n_head, window):
+def attention(q, k, v, kv_mask, out, *, batch, t, n_head, window, qkv=None):
+    """q, k, v: [batch, t, C] each, or `qkv` = one [batch, 3t, C] tensor holding a video's q rows, k rows, v rows."""
     L = nv.lib()
-    _chk(q, None, "q"); _chk(k, q.dtype, "k"); _chk(v, q.dtype, "v"); _chk(out, None, "out"); _chk(kv_mask, torch.uint8, "kv_mask")
-    _call("avdf_attention", L.avdf_attention, (nv.ptr(q), nv.ptr(k), nv.ptr(v), nv.ptr(kv_mask), nv.ptr(out), _dt(q), _dt(out), batch, t,
-                              q.shape[-1], n_head, window, nv.stream_ptr(),), launches=1, work={"bytes": _nbytes(q, k, v, out)})
+    rpv = 0
+    if qkv is not None:
+        _chk(qkv, None, "qkv")
+        C, es = qkv.shape[-1], qkv.element_size()
+        base = qkv.data_ptr()
+        qp, kp, vp = (c_void_p(base + i * t * C * es) for i in range(3))
+        q, rpv = qkv, 3 * t
+    else:
+        _chk(q, None, "q"); _chk(k, q.dtype, "k"); _chk(v, q.dtype, "v")
+        qp, kp, vp = nv.ptr(q), nv.ptr(k), nv.ptr(v)
+    _chk(out, None, "out"); _chk(kv_mask, torch.uint8, "kv_mask")
+    _call("avdf_attention", L.avdf_attention, (qp, kp, vp, nv.ptr(kv_mask), nv.ptr(out), _dt(q), _dt(out), batch, t, rpv,
+                              q.shape[-1], n_head, window, nv.stream_ptr(),), launches=1, work={"bytes": (_nbytes(qkv) if qkv is not None else _nbytes(q, k, v)) + _nbytes(out)})
 
 
 def ln_rows(x, w, b, out, rows):

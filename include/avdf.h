@@ -127,7 +127,9 @@ AVDF_API int avdf_postprocess(const avdf_postprocess_args* args, void* stream);
 
 /* ---- conv-as-GEMM with fused epilogue ----
  * out[b, seg_o_row + t, n] = epi( sum_{j<taps} sum_{c<c_in} W[n, j*c_in + c] * A[b, seg_a_row + stride*t + j - taps/2, c] )
- * (rows outside [0, stride * seg_t_out) of the level read as zero), for every level `seg`.
+ * (rows outside [0, stride * seg_t_out) of the level read as zero), for every segment `seg`. Segments are levels of a
+ * pyramid (shared weights) or independent problems stacked along the rows with their own weight block (seg_w_row):
+ * e.g. the q, k, v projections of one attention block in a single launch.
  * epi(v): v += bias[n]; v *= mask[row]; v = LN_n(v) * ln_w + ln_b; v = act(v); v += pe[t, n] * mask[row];
  *         v = residual[row, n] * mask[row] + gamma[n] * v            (each step only if its pointer is set)
  * dtype F32 -> fp32 CUDA-core path (parity mode); BF16 / F16 -> TMA + tcgen05 tensor-core path (A and W in that
@@ -137,6 +139,9 @@ typedef struct avdf_conv_gemm_args {
   int32_t seg_t_out[AVDF_MAX_LEVELS];
   int32_t seg_a_row[AVDF_MAX_LEVELS];
   int32_t seg_o_row[AVDF_MAX_LEVELS];
+  int32_t seg_w_row[AVDF_MAX_LEVELS];  /* row offset into w / bias / ln_* / gamma for this segment (0: shared weights);
+                                        * w then holds n_w_rows >= seg_w_row + n_out rows (0 means n_out) */
+  int32_t n_w_rows;
   int64_t a_rows_per_video, o_rows_per_video;
   const void* a;                 /* [batch, a_rows_per_video, c_in] */
   const void* w;                 /* [n_out, taps * c_in] */
@@ -162,18 +167,20 @@ typedef struct avdf_ln_dwconv_ln_args {
   const float* ln_in_w[3]; const float* ln_in_b[3];
   const float* dw_w[3];          /* [C, 3] */
   const float* ln_out_w[3]; const float* ln_out_b[3];
-  void* out[3];                  /* [batch, t_virt / stride, C] */
+  void* out[3];                  /* [batch, out_rows_per_video, C], row t' of video b at b * out_rows_per_video + t' */
   int32_t out_dtype;
+  int32_t out_rows_per_video;    /* 0: t_virt / stride (dense). Larger: several streams interleaved per video */
   float* skip_out;               /* [batch, t_virt / stride, C] fp32 or NULL */
 } avdf_ln_dwconv_ln_args;
 AVDF_API int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* args, void* stream);
 
 /* ---- multi-head attention over q,k,v [batch, t, C]; window > 1: band |i-j| <= window/2 with additive
  * -1e4 on masked keys and zeroed masked query rows (blocks.py:1152-1224); window <= 1: global with
- * -inf on masked keys (blocks.py:274-313). out [batch, t, C]. */
+ * -inf on masked keys (blocks.py:274-313). Row i of video b of q/k/v is at (b * qkv_rows_per_video + i) * C from the
+ * respective pointer (qkv_rows_per_video 0 = t; 3t when q,k,v of a video are stacked in one buffer). out [batch, t, C]. */
 AVDF_API int avdf_attention(const void* q, const void* k, const void* v, const uint8_t* kv_mask, void* out,
-                   int32_t in_dtype, int32_t out_dtype, int32_t batch, int32_t t, int32_t channels, int32_t n_head,
-                   int32_t window, void* stream);
+                   int32_t in_dtype, int32_t out_dtype, int32_t batch, int32_t t, int32_t qkv_rows_per_video,
+                   int32_t channels, int32_t n_head, int32_t window, void* stream);
 
 /* ---- LayerNorm over channels of fp32 rows -> fp32 or bf16 ---- */
 AVDF_API int avdf_ln_rows(const float* x, const float* w, const float* b, void* out, int32_t out_dtype, int64_t rows,

@@ -8,13 +8,13 @@ dev = "cuda"
 L = nv.lib()
 L.avdf_debug_gemm_timeline.argtypes = [ctypes.c_void_p]
 
-def run(B, T, K, N, residual, ln=False, reps=20, dt=torch.float16):
+def run(B, T, K, N, residual, ln=False, reps=20, dt=torch.float16, act=0, half_out=False):
     a = torch.randn(B, T, K, device=dev).to(dt); w = (torch.randn(N, K, device=dev) / K ** 0.5).to(dt)
-    out = torch.empty(B, T, N, device=dev); res = torch.randn(B, T, N, device=dev) if residual else None
+    out = None if half_out else torch.empty(B, T, N, device=dev); outh = torch.empty(B, T, N, device=dev, dtype=dt) if half_out else None; res = torch.randn(B, T, N, device=dev) if residual else None
     bias = torch.zeros(N, device=dev); mask = torch.ones(B, T, dtype=torch.uint8, device=dev)
     lnp = (torch.ones(N, device=dev), torch.zeros(N, device=dev)) if ln else None
     call = lambda: ops.conv_gemm(a, w, taps=1, batch=B, c_in=K, n_out=N, segs=[(T, 0, 0)], a_rows=T, o_rows=T, bias=bias,
-                                 row_mask=mask, residual=res, ln=lnp, out_f32=out)
+                                 row_mask=None if half_out else mask, residual=res, ln=lnp, act=act, out_f32=out, out_h=outh)
     dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     L.avdf_debug_gemm_timeline(ctypes.c_void_p(dbg.data_ptr()))
     call(); torch.cuda.synchronize(); dbg.zero_(); call(); torch.cuda.synchronize()
@@ -22,7 +22,7 @@ def run(B, T, K, N, residual, ln=False, reps=20, dt=torch.float16):
     L.avdf_debug_gemm_timeline(None)
     t0 = d[0, 0].item()
     names = ["start", "setup done", "first TMA landed", "last MMA committed", "epilogue got acc", "epilogue done", "after final sync", "-", "epi enter", "epi vectors loaded", "first tmem_ld", "first staged", "first chunk stored"]
-    print(f"--- M={B*T} N={N} K={K} residual={residual} ln={ln}: CTA0 phases (ns from start):", {n: int(d[0, i].item() - t0) for i, n in enumerate(names)})
+    print(f"--- M={B*T} N={N} K={K} residual={residual} ln={ln} act={act} half_out={half_out}: CTA0 phases (ns from start):", {n: int(d[0, i].item() - t0) for i, n in enumerate(names)})
     ends = d[:, 6]; used = ends > 0
     print("    all CTAs: start spread %d ns, end-start max %d ns" % (int((d[used, 0].max() - d[used, 0].min()).item()), int((ends[used].max() - d[used, 0].min()).item())))
     # GPU-only cost: graph of `reps` launches
@@ -39,10 +39,8 @@ def run(B, T, K, N, residual, ln=False, reps=20, dt=torch.float16):
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     print("    graph replay: %.2f us per launch" % (1000 * e0.elapsed_time(e1) / reps))
 
-for (B, T) in ((1, 768), (32, 768)):
-    run(B, T, 256, 256, False)
-    run(B, T, 256, 256, True)
-run(32, 768, 256, 1024, False)
+run(32, 768, 256, 1024, False, act=2, half_out=True)
+run(32, 768, 256, 1024, False, act=0, half_out=True)
+run(32, 768, 256, 1024, False, act=0, half_out=False)
+run(32, 2304, 256, 256, False, act=0, half_out=True)
 run(32, 768, 1024, 256, True)
-run(32, 768, 768, 256, False, ln=True)
-run(32, 768, 8448, 256, False, ln=True, dt=torch.bfloat16)

@@ -474,3 +474,49 @@ def test_vcls_tails():
     out = torch.zeros(B, device=DEV)
     ops.vcls_exp13(dev(z), dev(w0), dev(sw), dev(sb), dev(cw), dev(cb), out, batch=B, t=T)
     assert rel_err(out.cpu(), want) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_conv_gemm_stacked_weight_blocks(mode):
+    """q, k, v projections in one launch: three row segments per video, each with its own 256-row weight block."""
+    rng = np.random.RandomState(8)
+    B, T, C = 5, 48, 256
+    adt = torch.float32 if mode == "fp32" else torch.float16
+    a = torch.from_numpy(rng.standard_normal((B, 3 * T, C)).astype(np.float32))
+    ws = [torch.from_numpy((rng.standard_normal((C, C)) / 16).astype(np.float32)) for _ in range(3)]
+    bs = [torch.from_numpy(rng.normal(0, 0.3, C).astype(np.float32)) for _ in range(3)]
+    out = torch.zeros((B, 3 * T, C), device=DEV)
+    out_h = torch.zeros((B, 3 * T, C), dtype=torch.float16, device=DEV) if mode != "fp32" else None
+    ops.conv_gemm(dev(a, adt), dev(torch.cat(ws), adt), taps=1, batch=B, c_in=C, n_out=C,
+                  segs=[(T, i * T, i * T, i * C) for i in range(3)], a_rows=3 * T, o_rows=3 * T, bias=dev(torch.cat(bs)),
+                  out_f32=out, out_h=out_h)
+    aq = a.to(adt).float()
+    for i in range(3):
+        want = aq[:, i * T:(i + 1) * T] @ ws[i].to(adt).float().t() + bs[i]
+        assert rel_err(out[:, i * T:(i + 1) * T].cpu(), want) < (2e-5 if mode == "fp32" else 2e-4), i
+        if out_h is not None:
+            assert rel_err(out_h[:, i * T:(i + 1) * T].float().cpu(), want) < 2e-3
+
+
+def test_attention_stacked_qkv_and_interleaved_dwconv():
+    rng = np.random.RandomState(10)
+    B, T, C = 3, 80, 256
+    qkv = torch.from_numpy(rng.standard_normal((B, 3 * T, C)).astype(np.float32)).to(torch.float16)
+    mask = torch.from_numpy(np.arange(T)[None] < np.array([T, 50, T - 1])[:, None])
+    out_a = torch.zeros((B, T, C), device=DEV); out_b = torch.zeros((B, T, C), device=DEV)
+    ops.attention(None, None, None, dev(mask.to(torch.uint8)), out_a, batch=B, t=T, n_head=4, window=7, qkv=dev(qkv))
+    q, k, v = (dev(qkv[:, i * T:(i + 1) * T].contiguous()) for i in range(3))
+    ops.attention(q, k, v, dev(mask.to(torch.uint8)), out_b, batch=B, t=T, n_head=4, window=7)
+    assert torch.equal(out_a, out_b)
+    # ln_dwconv_ln writing three streams interleaved into one [B, 3T, C] buffer == three dense outputs
+    x = torch.from_numpy(rng.standard_normal((B, T, C)).astype(np.float32))
+    lni = [_ln_params(rng) for _ in range(3)]; lno = [_ln_params(rng) for _ in range(3)]
+    dws = [torch.from_numpy(rng.normal(0, 0.6, (C, 3)).astype(np.float32)) for _ in range(3)]
+    kw = dict(batch=B, t_src=T, t_virt=T, shift=0, stride=1, mask_out=dev(mask.to(torch.uint8)),
+              ln_in=[(dev(a), dev(b)) for a, b in lni], dw=[dev(d) for d in dws], ln_out=[(dev(a), dev(b)) for a, b in lno])
+    dense = [torch.zeros((B, T, C), device=DEV) for _ in range(3)]
+    ops.ln_dwconv_ln(dev(x), outs=dense, **kw)
+    inter = torch.zeros((B, 3 * T, C), device=DEV)
+    ops.ln_dwconv_ln(dev(x), outs=[inter] * 3, out_rows=3 * T, out_row_offsets=[0, T, 2 * T], **kw)
+    for i in range(3):
+        assert torch.equal(inter[:, i * T:(i + 1) * T], dense[i])
