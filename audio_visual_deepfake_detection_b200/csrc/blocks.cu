@@ -55,16 +55,21 @@ struct LdlParams {
 };
 constexpr int LDL_ROWS = 8;            // output rows per warp
 constexpr int LDL_WARPS = 8;
+constexpr int LDL_DEPTH = 4;           // source rows in flight per warp (cp.async ring): 24 warps x 3 KB per SM keeps HBM busy
 
 // With u = xhat * w_in + b_in (xhat = the normalised source row, shared by all streams) the depthwise conv is
 //   acc[c] = sum_j dw[c][j] * u_j[c] = sum_j (dw[c][j] w_in[c]) * xhat_j[c] + b_in[c] * sum_j dw[c][j]
 // so the per-stream constants A_j = dw_j * w_in, Bj = dw_j * b_in, Bsum = sum_j Bj are folded once per CTA into shared
 // memory and an interior output row costs 3 FFMA per channel and stream (edge rows, where a tap falls outside
 // [0, t_virt), use the per-tap Bj instead of Bsum).
-template <typename OutT, int STRIDE>
+// The NS streams of an output row are computed together so that their LayerNorm reductions (sum and sum of squares,
+// single pass) travel through the same 5 shuffle steps: one dependent chain per row instead of 2 per stream.
+template <typename OutT, int STRIDE, int NS>
 __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const LdlParams p) {
   // per stream: A0, A1, A2, Bsum, B0, B1, B2, ln_out_w, ln_out_b  (9 x 256 floats)
-  __shared__ __align__(16) float sp[3][9][kC];
+  extern __shared__ __align__(16) float ldl_smem[];
+  float (*sp)[9][kC] = reinterpret_cast<float (*)[9][kC]>(ldl_smem);                                   // [NS][9][256]
+  float (*ring)[LDL_DEPTH][kC] = reinterpret_cast<float (*)[LDL_DEPTH][kC]>(ldl_smem + NS * 9 * kC);   // [warps][depth][256]
   for (int i = threadIdx.x; i < p.n_streams * kC; i += blockDim.x) {
     const int s = i / kC, c = i - s * kC;
     const float w = p.ln_in_w[s][c], bb = p.ln_in_b[s][c];
@@ -91,33 +96,42 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int k = 0; k < 8; ++k) xh[j][k] = 0.f;
-    // software pipeline: the source row of position pos + 1 is in flight while position pos is processed
+    // software pipeline: the source rows of positions pos + 1 .. pos + LDL_DEPTH - 1 are in flight (cp.async into a
+    // per-warp smem ring; every lane copies and later reads its own 32 bytes, so no cross-lane synchronisation)
     const int pos_first = STRIDE * t0 - 1, pos_last = STRIDE * (t1 - 1) + 1;
-    float nxt[8];
-    auto fetch = [&](int pos) {
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[warp][0][c0]);
+    auto issue = [&](int pos) {
       if (pos >= 0 && pos < p.t_virt && pos <= pos_last) {
         const int r = p.shift >= 0 ? (pos >> p.shift) : (pos << (-p.shift));
-        Row8<float>::load(src_b + (size_t)r * kC + c0, nxt);
+        const float* g = src_b + (size_t)r * kC + c0;
+        const unsigned d = ring_base + (unsigned)(((pos - pos_first) % LDL_DEPTH) * kC * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(g + 4) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch(pos_first);
+#pragma unroll
+    for (int d = 0; d < LDL_DEPTH; ++d) issue(pos_first + d);
+    float nxt[8];
     for (int pos = pos_first; pos <= pos_last; ++pos) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(LDL_DEPTH - 1) : "memory");
       // slide the window, normalise the new row
 #pragma unroll
       for (int k = 0; k < 8; ++k) { xh[0][k] = xh[1][k]; xh[1][k] = xh[2][k]; }
+      ok[0] = ok[1]; ok[1] = ok[2];
+      ok[2] = pos >= 0 && pos < p.t_virt;
+      if (ok[2]) lds8(&ring[warp][(pos - pos_first) % LDL_DEPTH][c0], nxt);
       if (STRIDE == 2) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { rw[0][k] = rw[STRIDE == 2 ? 1 : 0][k]; rw[STRIDE == 2 ? 1 : 0][k] = rw[STRIDE == 2 ? 2 : 0][k]; rw[STRIDE == 2 ? 2 : 0][k] = nxt[k]; }
       }
-      ok[0] = ok[1]; ok[1] = ok[2];
-      ok[2] = pos >= 0 && pos < p.t_virt;
       if (ok[2]) {
         float mean, rstd;
         row_stats(nxt, mean, rstd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) xh[2][k] = (nxt[k] - mean) * rstd;
       }
-      fetch(pos + 1);
+      issue(pos + LDL_DEPTH);                    // refill the slot just consumed
       const int rel = pos - (STRIDE * t0 + 1);
       if (rel < 0 || (rel % STRIDE) != 0) continue;
       const int t = t0 + rel / STRIDE;          // output row whose taps are window[0..2]
@@ -125,35 +139,55 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
       const size_t srow = (size_t)b * p.out_rows + t;           // row in the (possibly interleaved) output buffers
       const bool keep = p.mask_out ? (p.mask_out[orow] != 0) : true;
       const bool interior = ok[0] && ok[2];                      // ok[1] always holds for an output row
-      for (int s = 0; s < p.n_streams; ++s) {
-        float acc[8];
+      float acc[NS][8];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
         if (!keep) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+          for (int k = 0; k < 8; ++k) acc[s][k] = 0.f;
         } else if (interior) {
           float a0[8], a1[8], a2[8];
-          lds8(&sp[s][3][c0], acc); lds8(&sp[s][0][c0], a0); lds8(&sp[s][1][c0], a1); lds8(&sp[s][2][c0], a2);
+          lds8(&sp[s][3][c0], acc[s]); lds8(&sp[s][0][c0], a0); lds8(&sp[s][1][c0], a1); lds8(&sp[s][2][c0], a2);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(a2[k], xh[2][k], fmaf(a1[k], xh[1][k], fmaf(a0[k], xh[0][k], acc[k])));
+          for (int k = 0; k < 8; ++k) acc[s][k] = fmaf(a2[k], xh[2][k], fmaf(a1[k], xh[1][k], fmaf(a0[k], xh[0][k], acc[s][k])));
         } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+          for (int k = 0; k < 8; ++k) acc[s][k] = 0.f;
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             if (ok[j]) {
               float a[8], bj[8];
               lds8(&sp[s][j][c0], a); lds8(&sp[s][4 + j][c0], bj);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) acc[k] += fmaf(a[k], xh[j][k], bj[k]);
+              for (int k = 0; k < 8; ++k) acc[s][k] += fmaf(a[k], xh[j][k], bj[k]);
             }
           }
         }
-        float m2, r2, w[8], bb[8];
-        row_stats(acc, m2, r2);
+      }
+      float su[NS], sq[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        su[s] = 0.f; sq[s] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { su[s] += acc[s][k]; sq[s] = fmaf(acc[s][k], acc[s][k], sq[s]); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          su[s] += __shfl_xor_sync(0xffffffffu, su[s], o);
+          sq[s] += __shfl_xor_sync(0xffffffffu, sq[s], o);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float m2 = su[s] * (1.f / kC);
+        const float r2 = 1.f / sqrtf(fmaxf(sq[s] * (1.f / kC) - m2 * m2, 0.f) + kLnEps);
+        float w[8], bb[8];
         lds8(&sp[s][7][c0], w); lds8(&sp[s][8][c0], bb);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m2) * r2, w[k], bb[k]);
-        Row8<OutT>::store(reinterpret_cast<OutT*>(p.out[s]) + srow * kC + c0, acc);
+        for (int k = 0; k < 8; ++k) acc[s][k] = fmaf((acc[s][k] - m2) * r2, w[k], bb[k]);
+        Row8<OutT>::store(reinterpret_cast<OutT*>(p.out[s]) + srow * kC + c0, acc[s]);
       }
       if (STRIDE == 2 && p.skip_out) {           // MaxPool1d(3, 2, 1) of the raw rows, -inf padding
         float mx[8];
@@ -167,6 +201,7 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
         Row8<float>::store(p.skip_out + orow * kC + c0, mx);
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 }
 
@@ -708,8 +743,19 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   const long long tiles = (long long)a->batch * ((p.t_out + LDL_ROWS - 1) / LDL_ROWS);
   const int grid = grid_for(tiles, LDL_WARPS, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->stride == 1) AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, (ln_dwconv_ln_kernel<OutT, 1><<<grid, LDL_WARPS * 32, 0, st>>>(p)));
-  else AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, (ln_dwconv_ln_kernel<OutT, 2><<<grid, LDL_WARPS * 32, 0, st>>>(p)));
+#define AVDF_LDL(S, NS)                                                                                              \
+  AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, {                                                                          \
+    const size_t smem = (size_t)(NS * 9 + LDL_WARPS * LDL_DEPTH) * kC * sizeof(float);                               \
+    static bool attr_done = false;                                                                                   \
+    if (!attr_done) {                                                                                                \
+      AVDF_CUDA(cudaFuncSetAttribute(ln_dwconv_ln_kernel<OutT, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_done = true;                                                                                              \
+    }                                                                                                                \
+    ln_dwconv_ln_kernel<OutT, S, NS><<<grid, LDL_WARPS * 32, smem, st>>>(p);                                         \
+  })
+  if (a->stride == 1) { if (a->n_streams == 1) AVDF_LDL(1, 1); else if (a->n_streams == 2) AVDF_LDL(1, 2); else AVDF_LDL(1, 3); }
+  else { if (a->n_streams == 1) AVDF_LDL(2, 1); else if (a->n_streams == 2) AVDF_LDL(2, 2); else AVDF_LDL(2, 3); }
+#undef AVDF_LDL
   return check_launch("ln_dwconv_ln_kernel");
 }
 

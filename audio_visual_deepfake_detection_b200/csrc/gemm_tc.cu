@@ -108,6 +108,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// asynchronous variant: the registers may be read only after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
 // start address >> 4, LBO unused (0), SBO = 1024 B >> 4, descriptor version 1 (sm_100), layout SWIZZLE_128B (2).
@@ -357,20 +370,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         tcgen05_fence_before();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
+      float* const o32 = e.out_f32;
+      uint16_t* const o16 = reinterpret_cast<uint16_t*>(e.out_h);
+      const bool o16_f16 = e.out_h_f16 != 0;
+      uint32_t v[32];                             // accumulator block of the current chunk (raw bits)
+      if (c_begin < c_end) tmem_ld32_issue(taddr + c_begin * 32, v);
       for (int ch = c_begin; ch < c_end; ++ch) {
-        {
-          float v[32];
-          tmem_ld32(taddr + ch * 32, v);
-          if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(10);
-          if (ch == c_end - 1) {                  // this warp's TMEM reads of the accumulator are done
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-          }
-          __syncwarp();                           // previous chunk's reads of the staging tile are done
+        tmem_ld_wait();
+        if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(10);
+        __syncwarp();                             // previous chunk's reads of the staging tile are done
 #pragma unroll
-          for (int j = 0; j < 8; ++j)             // row `lane`, 16-byte group j -> swizzled slot j ^ (lane & 7)
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j)               // row `lane`, 16-byte group j -> swizzled slot j ^ (lane & 7)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (ch + 1 < c_end) {
+          tmem_ld32_issue(taddr + (ch + 1) * 32, v);   // next block's TMEM read overlaps this block's row loop
+        } else {                                  // this warp's TMEM reads of the accumulator are issued: after they
+          tmem_ld_wait();                         // complete the MMA warp may overwrite it
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         if (has_res) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -380,35 +398,38 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         const float4 bias4 = *reinterpret_cast<const float4*>(s_bias + cl);
         const float4 lnw4 = *reinterpret_cast<const float4*>(s_lnw + cl), lnb4 = *reinterpret_cast<const float4*>(s_lnb + cl);
         const float4 gam4 = *reinterpret_cast<const float4*>(s_gam + cl);
+        // branch-free body (only the global accesses are predicated on the row being valid) so that the 8 unrolled
+        // iterations interleave: the row table / staging loads of all of them are in flight together
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + rsub;
           const long long ro = w_ro[rr];
-          if (ro >= 0) {
-            const float4 rw = w_rw[rr];           // {mask, mean, rstd, t}
-            float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((g8 ^ (rr & 7)) << 2));
-            x.x = (x.x + bias4.x) * rw.x; x.y = (x.y + bias4.y) * rw.x; x.z = (x.z + bias4.z) * rw.x; x.w = (x.w + bias4.w) * rw.x;
-            if (has_ln) {
-              x.x = fmaf((x.x - rw.y) * rw.z, lnw4.x, lnb4.x); x.y = fmaf((x.y - rw.y) * rw.z, lnw4.y, lnb4.y);
-              x.z = fmaf((x.z - rw.y) * rw.z, lnw4.z, lnb4.z); x.w = fmaf((x.w - rw.y) * rw.z, lnw4.w, lnb4.w);
-            }
-            x.x = act_tc(x.x, act); x.y = act_tc(x.y, act); x.z = act_tc(x.z, act); x.w = act_tc(x.w, act);
-            if (has_pe) {
-              const float4 pv = __ldg(reinterpret_cast<const float4*>(e.pe + (size_t)__float_as_int(rw.w) * N + n));
-              x.x = fmaf(pv.x, rw.x, x.x); x.y = fmaf(pv.y, rw.x, x.y); x.z = fmaf(pv.z, rw.x, x.z); x.w = fmaf(pv.w, rw.x, x.w);
-            }
-            if (has_res) {
-              const float4 rv = *reinterpret_cast<const float4*>(rsg + rr * 32 + g8 * 4);
-              x.x = fmaf(gam4.x, x.x, rv.x * rw.x); x.y = fmaf(gam4.y, x.y, rv.y * rw.x);
-              x.z = fmaf(gam4.z, x.z, rv.z * rw.x); x.w = fmaf(gam4.w, x.w, rv.w * rw.x);
-            }
-            if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + ro * N + n) = x;
-            if (e.out_h) {
-              uint2 u;
-              if (e.out_h_f16) { u.x = pack_f16x2(x.x, x.y); u.y = pack_f16x2(x.z, x.w); }
-              else { u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); }
-              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.out_h) + ro * N + n) = u;
-            }
+          const bool rv_ok = ro >= 0;
+          const float4 rw = w_rw[rr];             // {mask, mean, rstd, t}
+          float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((g8 ^ (rr & 7)) << 2));
+          x.x = (x.x + bias4.x) * rw.x; x.y = (x.y + bias4.y) * rw.x; x.z = (x.z + bias4.z) * rw.x; x.w = (x.w + bias4.w) * rw.x;
+          if (has_ln) {
+            x.x = fmaf((x.x - rw.y) * rw.z, lnw4.x, lnb4.x); x.y = fmaf((x.y - rw.y) * rw.z, lnw4.y, lnb4.y);
+            x.z = fmaf((x.z - rw.y) * rw.z, lnw4.z, lnb4.z); x.w = fmaf((x.w - rw.y) * rw.z, lnw4.w, lnb4.w);
+          }
+          x.x = act_tc(x.x, act); x.y = act_tc(x.y, act); x.z = act_tc(x.z, act); x.w = act_tc(x.w, act);
+          if (has_pe) {
+            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rv_ok) pv = __ldg(reinterpret_cast<const float4*>(e.pe + (size_t)__float_as_int(rw.w) * N + n));
+            x.x = fmaf(pv.x, rw.x, x.x); x.y = fmaf(pv.y, rw.x, x.y); x.z = fmaf(pv.z, rw.x, x.z); x.w = fmaf(pv.w, rw.x, x.w);
+          }
+          if (has_res) {
+            const float4 rv = *reinterpret_cast<const float4*>(rsg + rr * 32 + g8 * 4);
+            x.x = fmaf(gam4.x, x.x, rv.x * rw.x); x.y = fmaf(gam4.y, x.y, rv.y * rw.x);
+            x.z = fmaf(gam4.z, x.z, rv.z * rw.x); x.w = fmaf(gam4.w, x.w, rv.w * rw.x);
+          }
+          const long long off = ro * N + n;
+          if (o32 && rv_ok) *reinterpret_cast<float4*>(o32 + off) = x;
+          if (o16 && rv_ok) {
+            uint2 u;
+            if (o16_f16) { u.x = pack_f16x2(x.x, x.y); u.y = pack_f16x2(x.z, x.w); }
+            else { u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); }
+            *reinterpret_cast<uint2*>(o16 + off) = u;
           }
         }
         if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(12);
