@@ -160,6 +160,7 @@ class LocalizationEngine:
             raise KeyError("state_dict is missing %d tensors, e.g. %s" % (len(missing), missing[:3]))
         self.w = PackedWeights(state_dict, self.device)
         self._bufs = {}
+        self.lane = 0                 # buffer set in use: independent batches in flight on different streams use different lanes
         self._mask_cache = {}
         self._pe_cache = {}
         self._ws = None
@@ -168,7 +169,7 @@ class LocalizationEngine:
     def buf(self, name, shape, dtype):
         """Static buffer sized for max_batch; returns the [B, ...] prefix view."""
         B = shape[0]
-        key = (name, tuple(shape[1:]), dtype)
+        key = (self.lane, name, tuple(shape[1:]), dtype)
         t = self._bufs.get(key)
         if t is None:
             t = torch.empty((self.max_batch,) + tuple(shape[1:]), dtype=dtype, device=self.device)
@@ -176,9 +177,13 @@ class LocalizationEngine:
         return t[:B]
 
     def workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._ws
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(self.lane)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[self.lane] = ws
+        return ws
 
     def padded_len(self, t):
         """av_fd_no_recon.py:458-466."""

@@ -235,28 +235,32 @@ class _LocalizationBase(nn.Module):
         return n
 
     @torch.no_grad()
-    def run_staged(self, staged):
+    def run_staged(self, staged, lane=0):
+        """lane selects the engine's buffer set: batches that are in flight at the same time (different CUDA
+        streams) must use different lanes."""
         eng = self.engine()
+        eng.lane = lane
         B, L = staged["B"], eng.max_seq_len
         x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.in_dt)
         ops.interp_concat(staged["streams"], staged["offs"], L, x)
         logits, offsets, vcls, masks, lens = eng.forward_dense(x, [L] * B)
         osg, osc, ocn = eng.postprocess(logits, offsets, masks, lens, staged["meta"], nms_method=self.test_nms_method)
+        eng.lane = 0
         return {"ids": staged["ids"], "segs": osg, "scores": osc, "counts": ocn, "vcls": vcls}
 
-    def capture(self, staged):
+    def capture(self, staged, lane=0):
         """Record the whole pass over a staged (device-resident) batch into a CUDA graph: ~190 kernel launches
         become one cudaGraphLaunch, which removes the host launch cost that otherwise bounds the step
         (measured: 25 us of Python + driver time per launch vs 7-40 us of GPU time per kernel). The graph reads
         the staged tensors and writes the engine's static buffers, so `staged` must stay alive and unchanged in
         place; replay() returns the same device-side result dict as run_staged()."""
         from ... import native
-        self.run_staged(staged)                     # allocates every static buffer / cache outside the capture
+        self.run_staged(staged, lane)               # allocates every static buffer / cache outside the capture
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         n0 = native.LAUNCHES["n"]
         with torch.cuda.graph(graph):
-            res = self.run_staged(staged)
+            res = self.run_staged(staged, lane)
         return GraphedPass(graph, res, native.LAUNCHES["n"] - n0, staged)
 
     @staticmethod

@@ -27,6 +27,7 @@ class _Slot:
         self.dev = [None, None, None]
         self.graphs = {}                  # batch size -> GraphedPass
         self.done = torch.cuda.Event()
+        self.stream = torch.cuda.Stream()     # slots run on their own streams: copies and kernels of consecutive batches overlap
         self.ids, self.B, self.busy = None, 0, False
 
     def ensure(self, rows, chans, max_batch, K, device):
@@ -86,7 +87,15 @@ class StreamRunner:
             dst = slot.host[s].numpy()
             for b, a in enumerate(arrs[s]):
                 jobs.append((dst[off[s, b]:off[s, b + 1]], a))
-        list(self.pool.map(lambda j: np.copyto(j[0], j[1]), jobs))         # numpy releases the GIL while copying
+        # one task per worker (a ThreadPoolExecutor task costs ~30 us of Python): largest copies first, round-robin
+        jobs.sort(key=lambda j: -j[1].nbytes)
+        nw = self.pool._max_workers
+        groups = [jobs[i::nw] for i in range(nw)]
+
+        def copy_group(g):
+            for dst_, src_ in g:
+                np.copyto(dst_, src_)                                        # numpy releases the GIL while copying
+        list(self.pool.map(copy_group, [g for g in groups if g]))
         meta = slot.h_meta.numpy()
         for b, c in enumerate(chunk):
             first = c["streams"]["video"] if present[0] else c["streams"]["byola"]
@@ -97,6 +106,11 @@ class StreamRunner:
         slot.rows, slot.chans, slot.B, slot.ids = rows, chans, B, [c["video_id"] for c in chunk]
 
     def _launch(self, slot):
+        slot.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(slot.stream):
+            self._launch_on_stream(slot)
+
+    def _launch_on_stream(self, slot):
         eng, B = self.eng, slot.B
         nbytes = 0
         for s in range(3):
@@ -112,11 +126,11 @@ class StreamRunner:
         if self.use_graph and B == eng.max_batch:
             g = slot.graphs.get(B)
             if g is None:
-                g = self.model.capture(staged)
+                g = self.model.capture(staged, lane=slot.index)
                 slot.graphs[B] = g
             res = g.replay()
         else:
-            res = self.model.run_staged(staged)
+            res = self.model.run_staged(staged, lane=slot.index)
         slot.h_segs[:B].copy_(res["segs"], non_blocking=True)
         slot.h_scores[:B].copy_(res["scores"], non_blocking=True)
         slot.h_counts[:B].copy_(res["counts"], non_blocking=True)

@@ -89,7 +89,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -224,25 +224,38 @@ def run_ours(args):
         return allrec
 
     # ---------------- device-resident throughput ----------------
+    # n_lanes batches are in flight at once, each on its own stream and buffer set: while one batch is in the
+    # small pyramid levels (6..48 CTAs on 148 SMs) the other fills the idle SMs
+    n_lanes = max(1, args.lanes)
     if args.no_graph:
         class _Eager:
-            def __init__(self, st): self.st = st
-            def replay(self): return model.run_staged(self.st)
-        passes = [_Eager(s_) for s_ in staged]
+            def __init__(self, st, lane): self.st, self.lane = st, lane
+            def replay(self): return model.run_staged(self.st, self.lane)
+        passes = [_Eager(s_, i % n_lanes) for i, s_ in enumerate(staged)]
     else:
-        passes = [model.capture(s_) for s_ in staged]      # one CUDA graph per resident input batch
-    for i in range(args.warmup):
-        res = passes[i % N_POOL].replay()
-    gather([record(res, 0)])
+        # one CUDA graph per resident input batch; batch i runs on lane (buffer set) i % n_lanes
+        passes = [model.capture(s_, lane=i % n_lanes) for i, s_ in enumerate(staged)]
+    lanes = [torch.cuda.Stream() for _ in range(n_lanes)]
+    def run_steps(n, base):
+        main = torch.cuda.current_stream()
+        out = []
+        for s_ in lanes:
+            s_.wait_stream(main)
+        for i in range(n):
+            with torch.cuda.stream(lanes[i % n_lanes]):
+                res_ = passes[i % N_POOL].replay()
+                out.append(record(res_, base + i * BATCH))
+        for s_ in lanes:
+            main.wait_stream(s_)
+        return out
+
+    gather(run_steps(max(args.warmup, N_POOL), 0))
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     native.LAUNCHES["n"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    recs = []
     e0.record()
-    for i in range(args.steps):
-        res = passes[i % N_POOL].replay()
-        recs.append(record(res, (rank * args.steps + i) * BATCH))
+    recs = run_steps(args.steps, rank * args.steps * BATCH)
     allrec = gather(recs)
     e1.record()
     barrier()
@@ -324,7 +337,7 @@ def run_ours(args):
                 "config": {"workload": desc, "videos_per_step_per_gpu": BATCH, "t": cfg["model"]["max_seq_len"], "nms": "soft",
                            "precision": args.precision + (" (bf16 raw-feature operands, fp16 bounded activations, fp32 accumulate/stream)" if args.precision == "mixed" else ""),
                            "l2": "inputs rotate over %d distinct resident batches (%.0f MB total > 126 MB L2)" % (N_POOL, N_POOL * h2d / 1e6),
-                           "launch": "eager (one Python call per kernel)" if args.no_graph else "CUDA graph per resident batch (one cudaGraphLaunch per step)",
+                           "lanes": n_lanes, "launch": "eager (one Python call per kernel)" if args.no_graph else "CUDA graph per resident batch (one cudaGraphLaunch per step)",
                            "parallelism": "videos sharded over %d rank(s); one all-gather of result records per run" % world,
                            "gflop_per_video": flops_per_video(cfg["model"], name.endswith("THE")) / 1e9},
                 "e2e": {"value": e2e_value, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -343,13 +356,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=120)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="audio", choices=list(WORKLOADS))
     ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "fp32"])
     ap.add_argument("--ref-videos", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3, help="batches in flight at once (each on its own stream and buffer set)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event timings of one step to this json")
     args = ap.parse_args()
