@@ -15,6 +15,7 @@
 // smem ring: 3 stages x (16 KB A + 32 KB W), 128B-swizzled, mbarrier full/empty pairs.
 #include <cuda.h>
 #include <string.h>
+#include <type_traits>
 #include "gemm_common.cuh"
 
 namespace avdf {
@@ -42,7 +43,11 @@ struct Params {
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef AVDF_GEMM_TIMELINE
 #define AVDF_TS(slot) do { if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+#else
+#define AVDF_TS(slot) do { } while (0)
+#endif
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -176,7 +181,8 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
 // bit 4 positional encoding) so the row loop carries no dead branches; MODE < 0 reads the flags at run time.
 constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (pe ? 16 : 0); }
 
-template <int MODE>
+// OUTK >= 0 fixes which outputs exist: bit 0 fp32, bit 1 16-bit copy, bit 2 the 16-bit copy is fp16 (else bf16).
+template <int MODE, int OUTK>
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024 B alignment for the 128B swizzle atoms (an offset into the array keeps the shared address space visible
@@ -289,8 +295,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     float* stg = stage_smem + ew * (32 * 32);    // this warp's 32 x 32 fp32 transpose tile (accumulators)
     float* rsg = stage_smem + (8 + ew) * (32 * 32);   // this warp's 32 x 32 residual tile, row-major [row][column]
     // per-warp row table: output row offset (or -1), then {mask, mean, rstd, time step} per row
-    long long* w_ro = reinterpret_cast<long long*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2) + ew * 32;
-    float4* w_rw = reinterpret_cast<float4*>(reinterpret_cast<long long*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2) + 8 * 32) + ew * 32;
+    int* w_ro = reinterpret_cast<int*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2) + ew * 32;     // row start (elements) or -1
+    float4* w_rw = reinterpret_cast<float4*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2 + 8 * 32) + ew * 32;
     const int chunks = p.bn >> 5;
     const int c_begin = h == 0 ? 0 : (chunks + 1) / 2, c_end = h == 0 ? (chunks + 1) / 2 : chunks;
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
@@ -326,15 +332,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
       const long long orow = valid ? ((long long)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t) : -1;
       const float mk = (valid && e.row_mask) ? (e.row_mask[orow] ? 1.f : 0.f) : 1.f;
       __syncwarp();                               // previous tile's reads of the row table are done
-      w_ro[lane] = orow;
+      w_ro[lane] = valid ? (int)(orow * N) : -1;
+      const bool tile_all_valid = __all_sync(0xffffffffu, valid);
       __syncwarp();
       auto fetch_residual = [&](int ch) {         // 32 rows x 128 B of the residual -> rsg, asynchronously
         const float* src = e.residual + tc_.n0 + ch * 32 + g8 * 4;
         const uint32_t dst = smem_u32(rsg + rsub * 32 + g8 * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const long long ro = w_ro[i * 4 + rsub];
-          if (ro >= 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + ro * N) : "memory");
+          const int ro = w_ro[i * 4 + rsub];
+          if (ro >= 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + ro) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
@@ -370,9 +377,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         tcgen05_fence_before();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      float* const o32 = e.out_f32;
-      uint16_t* const o16 = reinterpret_cast<uint16_t*>(e.out_h);
-      const bool o16_f16 = e.out_h_f16 != 0;
+      const bool has32 = OUTK < 0 ? (e.out_f32 != nullptr) : ((OUTK & 1) != 0);
+      const bool has16 = OUTK < 0 ? (e.out_h != nullptr) : ((OUTK & 2) != 0);
+      const bool o16_f16 = OUTK < 0 ? (e.out_h_f16 != 0) : ((OUTK & 4) != 0);
       uint32_t v[32];                             // accumulator block of the current chunk (raw bits)
       if (c_begin < c_end) tmem_ld32_issue(taddr + c_begin * 32, v);
       for (int ch = c_begin; ch < c_end; ++ch) {
@@ -398,40 +405,46 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         const float4 bias4 = *reinterpret_cast<const float4*>(s_bias + cl);
         const float4 lnw4 = *reinterpret_cast<const float4*>(s_lnw + cl), lnb4 = *reinterpret_cast<const float4*>(s_lnb + cl);
         const float4 gam4 = *reinterpret_cast<const float4*>(s_gam + cl);
-        // branch-free body (only the global accesses are predicated on the row being valid) so that the 8 unrolled
-        // iterations interleave: the row table / staging loads of all of them are in flight together
+        float* const o32 = e.out_f32 + n;          // column-adjusted bases; the row table holds 32-bit row starts
+        uint16_t* const o16 = reinterpret_cast<uint16_t*>(e.out_h) + n;
+        // branch-free body so that the 8 unrolled iterations interleave (row table / staging loads of all of them in
+        // flight together). Tiles whose 32 rows are all inside the batch (every tile except a ragged batch tail) take
+        // the variant without per-row predicates.
+        auto rows = [&](auto all_valid_tag) {
+          constexpr bool ALLV = decltype(all_valid_tag)::value;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rsub;
-          const long long ro = w_ro[rr];
-          const bool rv_ok = ro >= 0;
-          const float4 rw = w_rw[rr];             // {mask, mean, rstd, t}
-          float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((g8 ^ (rr & 7)) << 2));
-          x.x = (x.x + bias4.x) * rw.x; x.y = (x.y + bias4.y) * rw.x; x.z = (x.z + bias4.z) * rw.x; x.w = (x.w + bias4.w) * rw.x;
-          if (has_ln) {
-            x.x = fmaf((x.x - rw.y) * rw.z, lnw4.x, lnb4.x); x.y = fmaf((x.y - rw.y) * rw.z, lnw4.y, lnb4.y);
-            x.z = fmaf((x.z - rw.y) * rw.z, lnw4.z, lnb4.z); x.w = fmaf((x.w - rw.y) * rw.z, lnw4.w, lnb4.w);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            const int ro = w_ro[rr];
+            const bool rv_ok = ALLV || ro >= 0;
+            const float4 rw = w_rw[rr];             // {mask, mean, rstd, t}
+            float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((g8 ^ (rr & 7)) << 2));
+            x.x = (x.x + bias4.x) * rw.x; x.y = (x.y + bias4.y) * rw.x; x.z = (x.z + bias4.z) * rw.x; x.w = (x.w + bias4.w) * rw.x;
+            if (has_ln) {
+              x.x = fmaf((x.x - rw.y) * rw.z, lnw4.x, lnb4.x); x.y = fmaf((x.y - rw.y) * rw.z, lnw4.y, lnb4.y);
+              x.z = fmaf((x.z - rw.y) * rw.z, lnw4.z, lnb4.z); x.w = fmaf((x.w - rw.y) * rw.z, lnw4.w, lnb4.w);
+            }
+            x.x = act_tc(x.x, act); x.y = act_tc(x.y, act); x.z = act_tc(x.z, act); x.w = act_tc(x.w, act);
+            if (has_pe) {
+              float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rv_ok) pv = __ldg(reinterpret_cast<const float4*>(e.pe + (size_t)__float_as_int(rw.w) * N + n));
+              x.x = fmaf(pv.x, rw.x, x.x); x.y = fmaf(pv.y, rw.x, x.y); x.z = fmaf(pv.z, rw.x, x.z); x.w = fmaf(pv.w, rw.x, x.w);
+            }
+            if (has_res) {
+              const float4 rv = *reinterpret_cast<const float4*>(rsg + rr * 32 + g8 * 4);
+              x.x = fmaf(gam4.x, x.x, rv.x * rw.x); x.y = fmaf(gam4.y, x.y, rv.y * rw.x);
+              x.z = fmaf(gam4.z, x.z, rv.z * rw.x); x.w = fmaf(gam4.w, x.w, rv.w * rw.x);
+            }
+            if (has32 && rv_ok) *reinterpret_cast<float4*>(o32 + ro) = x;
+            if (has16 && rv_ok) {
+              uint2 u;
+              if (o16_f16) { u.x = pack_f16x2(x.x, x.y); u.y = pack_f16x2(x.z, x.w); }
+              else { u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); }
+              *reinterpret_cast<uint2*>(o16 + ro) = u;
+            }
           }
-          x.x = act_tc(x.x, act); x.y = act_tc(x.y, act); x.z = act_tc(x.z, act); x.w = act_tc(x.w, act);
-          if (has_pe) {
-            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rv_ok) pv = __ldg(reinterpret_cast<const float4*>(e.pe + (size_t)__float_as_int(rw.w) * N + n));
-            x.x = fmaf(pv.x, rw.x, x.x); x.y = fmaf(pv.y, rw.x, x.y); x.z = fmaf(pv.z, rw.x, x.z); x.w = fmaf(pv.w, rw.x, x.w);
-          }
-          if (has_res) {
-            const float4 rv = *reinterpret_cast<const float4*>(rsg + rr * 32 + g8 * 4);
-            x.x = fmaf(gam4.x, x.x, rv.x * rw.x); x.y = fmaf(gam4.y, x.y, rv.y * rw.x);
-            x.z = fmaf(gam4.z, x.z, rv.z * rw.x); x.w = fmaf(gam4.w, x.w, rv.w * rw.x);
-          }
-          const long long off = ro * N + n;
-          if (o32 && rv_ok) *reinterpret_cast<float4*>(o32 + off) = x;
-          if (o16 && rv_ok) {
-            uint2 u;
-            if (o16_f16) { u.x = pack_f16x2(x.x, x.y); u.y = pack_f16x2(x.z, x.w); }
-            else { u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); }
-            *reinterpret_cast<uint2*>(o16 + off) = u;
-          }
-        }
+        };
+        if (tile_all_valid) rows(std::true_type{}); else rows(std::false_type{});
         if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(12);
         if (has_res && ch + 1 < c_end) {          // next chunk's residual (all lanes are done reading rsg)
           __syncwarp();
@@ -541,27 +554,28 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     int dev = 0;
     AVDF_CUDA(cudaGetDevice(&dev));
     AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-#define AVDF_SET_SMEM(M) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))
-    AVDF_SET_SMEM(-1);
-    AVDF_SET_SMEM(mode_of(false, AVDF_ACT_NONE, false, false));
-    AVDF_SET_SMEM(mode_of(false, AVDF_ACT_NONE, true, false));
-    AVDF_SET_SMEM(mode_of(false, AVDF_ACT_GELU, false, false));
-    AVDF_SET_SMEM(mode_of(true, AVDF_ACT_RELU, false, false));
-    AVDF_SET_SMEM(mode_of(true, AVDF_ACT_RELU, false, true));
+    // (mode, output kind) pairs the inference path uses get their own instantiation; anything else runs the generic one
+#define AVDF_TC_VARIANTS(X)                                                                                   \
+    X(mode_of(false, AVDF_ACT_NONE, false, false), 1) X(mode_of(false, AVDF_ACT_NONE, false, false), 6)           \
+    X(mode_of(false, AVDF_ACT_NONE, false, false), 2) X(mode_of(false, AVDF_ACT_NONE, true, false), 1)            \
+    X(mode_of(false, AVDF_ACT_NONE, true, false), 7) X(mode_of(false, AVDF_ACT_NONE, true, false), 3)             \
+    X(mode_of(false, AVDF_ACT_GELU, false, false), 6) X(mode_of(false, AVDF_ACT_GELU, false, false), 2)           \
+    X(mode_of(true, AVDF_ACT_RELU, false, false), 6) X(mode_of(true, AVDF_ACT_RELU, false, false), 2)             \
+    X(mode_of(true, AVDF_ACT_RELU, false, false), 1) X(mode_of(true, AVDF_ACT_RELU, false, true), 1)
+#define AVDF_SET_SMEM(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AVDF_SET_SMEM(-1, -1)
+    AVDF_TC_VARIANTS(AVDF_SET_SMEM)
 #undef AVDF_SET_SMEM
   }
+  AVDF_CHECK_ARG((long long)a->batch * a->o_rows_per_video * a->n_out < (1ll << 31), "output larger than 2^31 elements");
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr);
-#define AVDF_LAUNCH(M) conv_gemm_tc_kernel<M><<<grid, THREADS, SMEM_BYTES, st>>>(p)
-  switch (mode) {
-    case mode_of(false, AVDF_ACT_NONE, false, false): AVDF_LAUNCH(mode_of(false, AVDF_ACT_NONE, false, false)); break;
-    case mode_of(false, AVDF_ACT_NONE, true, false): AVDF_LAUNCH(mode_of(false, AVDF_ACT_NONE, true, false)); break;
-    case mode_of(false, AVDF_ACT_GELU, false, false): AVDF_LAUNCH(mode_of(false, AVDF_ACT_GELU, false, false)); break;
-    case mode_of(true, AVDF_ACT_RELU, false, false): AVDF_LAUNCH(mode_of(true, AVDF_ACT_RELU, false, false)); break;
-    case mode_of(true, AVDF_ACT_RELU, false, true): AVDF_LAUNCH(mode_of(true, AVDF_ACT_RELU, false, true)); break;
-    default: AVDF_LAUNCH(-1); break;
-  }
+  const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
+  bool launched = false;
+#define AVDF_LAUNCH(M, O) if (!launched && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, SMEM_BYTES, st>>>(p); launched = true; }
+  AVDF_TC_VARIANTS(AVDF_LAUNCH)
 #undef AVDF_LAUNCH
+  if (!launched) conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, SMEM_BYTES, st>>>(p);
   return check_launch("conv_gemm_tc_kernel");
 }
 
