@@ -11,6 +11,8 @@ reference's DataLoader workers (which run F.interpolate on the CPU, libs/dataset
 plus the per-video `.to(device)` / `.cpu()` of libs/modeling/av_fd_no_recon.py:476-477, 841-846.
 """
 import os
+import queue
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -54,7 +56,7 @@ class _Slot:
 
 
 class StreamRunner:
-    def __init__(self, model, n_slots=2, n_threads=None):
+    def __init__(self, model, n_slots=3, n_threads=None):
         self.model = model
         self.eng = model.engine()
         self.slots = [_Slot(self, i) for i in range(n_slots)]
@@ -63,6 +65,7 @@ class StreamRunner:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.use_graph = True
+        self.n_packers = 1           # more packers contend for the GIL and the copy pool (measured: 2 -> 0.56x)
 
     # ---------------------------------------------------------------- stages
     def _pack(self, slot, chunk, feat_stride=1, num_frames=1):
@@ -142,13 +145,13 @@ class StreamRunner:
     def _collect(self, slot):
         slot.done.synchronize()
         slot.busy = False
-        out = []
-        counts = slot.h_counts.numpy()
-        for b, vid in enumerate(slot.ids):
-            n = int(counts[b])
-            out.append({"video_id": vid, "segments": slot.h_segs[b, :n].clone(), "scores": slot.h_scores[b, :n].clone(),
-                        "labels": torch.zeros(n, dtype=torch.long), "video_cls": slot.h_vcls[b:b + 1].clone()})
-        return out
+        B = slot.B
+        # one clone per result array (the pinned buffers are reused by the next batch), then cheap per-video views
+        segs, scores, vcls = slot.h_segs[:B].clone(), slot.h_scores[:B].clone(), slot.h_vcls[:B].clone()
+        counts = slot.h_counts[:B].tolist()
+        empty_labels = torch.zeros(segs.shape[1], dtype=torch.long)
+        return [{"video_id": vid, "segments": segs[b, :n], "scores": scores[b, :n], "labels": empty_labels[:n],
+                 "video_cls": vcls[b:b + 1]} for b, (vid, n) in enumerate(zip(slot.ids, counts))]
 
     # ---------------------------------------------------------------- public
     def run(self, chunk):
@@ -161,16 +164,95 @@ class StreamRunner:
         return self._collect(slot)
 
     def stream(self, batches):
-        """Generator over an iterable of batches (each <= max_batch videos): yields every batch's results in order,
-        one batch behind the submission so that host packing overlaps GPU work."""
-        pending = []
-        for chunk in batches:
-            slot = self.slots[self.next]
-            self.next = (self.next + 1) % len(self.slots)
+        """Generator over an iterable of batches (each <= max_batch videos): yields every batch's results in order.
+        A packer thread fills free staging slots (pinned memcpy on the worker pool, GIL released) while this thread
+        launches slot i (H2D + graph + D2H on the slot's stream) and collects slot i - (n_slots - 1)."""
+        free = queue.Queue()
+        for slot in self.slots:
             if slot.busy:
-                yield self._collect(pending.pop(0))
-            self._pack(slot, chunk)
-            self._launch(slot)
-            pending.append(slot)
-        while pending:
-            yield self._collect(pending.pop(0))
+                self._collect(slot)
+            free.put(slot)
+        err = []
+        it = iter(batches)
+        lock = threading.Lock()
+        cond = threading.Condition()
+        packed = {}                 # sequence number -> slot (None marks the end of the input)
+        state = {"next": 0, "stop": False}
+
+        def packer():
+            try:
+                while True:
+                    slot = free.get()
+                    if slot is None:
+                        return
+                    with lock:      # keep (sequence number, slot order) consistent with the input order
+                        if state["stop"]:
+                            free.put(slot)
+                            return
+                        try:
+                            chunk = next(it)
+                        except StopIteration:
+                            state["stop"] = True
+                            seq = state["next"]
+                            with cond:
+                                packed[seq] = None
+                                cond.notify_all()
+                            free.put(slot)
+                            return
+                        seq = state["next"]
+                        state["next"] += 1
+                    self._pack(slot, chunk)
+                    with cond:
+                        packed[seq] = slot
+                        cond.notify_all()
+            except BaseException as exc:      # surfaced in the consumer
+                err.append(exc)
+                with cond:
+                    packed[-1] = None
+                    cond.notify_all()
+
+        threads = [threading.Thread(target=packer, daemon=True) for _ in range(self.n_packers)]
+        for th in threads:
+            th.start()
+
+        class _Ready:
+            seq = 0
+
+            @staticmethod
+            def get():
+                with cond:
+                    while _Ready.seq not in packed and -1 not in packed:
+                        cond.wait()
+                    if -1 in packed:
+                        return None
+                    slot_ = packed.pop(_Ready.seq)
+                _Ready.seq += 1
+                return slot_
+        ready = _Ready
+        inflight = []
+        try:
+            while True:
+                slot = ready.get()
+                if slot is None:
+                    break
+                self._launch(slot)
+                inflight.append(slot)
+                if len(inflight) >= len(self.slots) - 1:
+                    done = inflight.pop(0)
+                    out = self._collect(done)
+                    free.put(done)
+                    yield out
+            while inflight:
+                done = inflight.pop(0)
+                out = self._collect(done)
+                free.put(done)
+                yield out
+        finally:
+            with lock:
+                state["stop"] = True
+            for _ in threads:
+                free.put(None)
+            for th in threads:
+                th.join(timeout=5)
+        if err:
+            raise err[0]
