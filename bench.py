@@ -321,11 +321,23 @@ def run_ours(args):
         except Exception:
             pass
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_gbs = peaks.get("hbm_gbs", 6650.0)
+        for nm, kv in kernels.items():                 # HBM-roofline fraction of the memory-bound kernels (algorithmic bytes)
+            if kv["gbs"] and nm != "avdf_conv_gemm":
+                kv["hbm_frac"] = kv["gbs"] / peak_gbs
+        traffic = None
+        try:        # DRAM bytes per launch of the GEMM kernel from the committed ncu pass (profiles/), not measured live
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_c_step_traffic.json")))["kernels"]["tc::conv_gemm_tc_kernel"]
+            traffic = (tj["dram_read_bytes_per_step"] + tj["dram_write_bytes_per_step"]) / tj["launches_per_step"]
+        except Exception:
+            pass
         g = agg.get("avdf_conv_gemm")
         if g and args.precision != "fp32":
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None,
+                    "frac": ach / peak_tf, "traffic": traffic,
+                    "traffic_note": "mean DRAM read+write bytes per launch, ncu pass profiles/r1_c_ncu_step_launches.csv (audio workload)",
+                    "algorithmic_bytes_per_launch": g["bytes"] / g["n"],
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     "launches_per_step": g["n"] / psteps, "avg_launch_us": 1000.0 * g["ms"] / g["n"],
                     "algorithmic_gflop_per_launch": g["flops"] / g["n"] / 1e9}
