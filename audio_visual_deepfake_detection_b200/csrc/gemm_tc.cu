@@ -24,14 +24,17 @@ namespace tc {
 constexpr int BM = 128, BK = 64, STAGES = 3, MAX_BN = 256;
 constexpr int A_STAGE = BM * BK * 2;          // 16384
 constexpr int B_STAGE = MAX_BN * BK * 2;      // 32768
-constexpr int EPI_VEC_BYTES = 4 * MAX_BN * 4 + 2 * 2 * BM * 2 * 4 + 8 * 32 * 24;   // bias / ln_w / ln_b / gamma + double-buffered LayerNorm partial sums + per-warp row tables
-constexpr int STAGE_TILE_BYTES = 16 * 32 * 32 * 4;               // per epilogue warp: a 32x32 fp32 accumulator tile + a residual tile
+constexpr int EPI_VEC_BYTES = 4 * MAX_BN * 4 + 2 * 2 * BM * 2 * 4;   // bias / ln_w / ln_b / gamma + double-buffered LayerNorm partial sums (8 KB)
+constexpr int STAGE_TILE_BYTES = 16 * 32 * 32 * 4;               // per epilogue warp: a 32x32 fp32 result tile + a residual tile (TMA, 128B swizzle)
 constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*barriers*/ + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024 /*align slack*/;
 constexpr int THREADS = 384;                                     // 4 control warps + 8 epilogue warps
 
 struct Params {
   CUtensorMap a_map[AVDF_MAX_LEVELS];
   CUtensorMap w_map;
+  CUtensorMap o32_map[AVDF_MAX_LEVELS];      // fp32 output, 3-D (n, t, video) per segment, box = one epilogue warp's 32 rows x 32 columns
+  CUtensorMap o16_map[AVDF_MAX_LEVELS];      // 16-bit output copy
+  CUtensorMap res_map[AVDF_MAX_LEVELS];      // residual (same geometry as the fp32 output)
   SegInfo seg;
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
   int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
@@ -81,6 +84,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -276,15 +291,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: 8 warps
     // warp e = warp - 4: TMEM lane quarter q = warp & 3 (rows 32q .. 32q+31 of the tile), column half h = e >> 2.
-    // tcgen05.ld hands every thread one ROW (32 consecutive columns per load); global memory wants one row per
-    // WARP (32 lanes x 4 B = one 128 B line). Each 32x32 block therefore goes RAW through a per-warp smem tile
-    // (16-byte XOR swizzle: conflict-free both ways) and the whole epilogue math runs in the transposed domain
-    // (lane = column: per-column vectors are one register each, per-row scalars come from a small row table), so
-    // every global access - residual, fp32 store, 16-bit store - is one full line per instruction.
-    // The row loop is deliberately ROLLED (x4): a fully unrolled epilogue is ~100 KB of straight-line SASS that is
-    // executed once per tile and runs at instruction-fetch speed (measured: 12 us per 128x128 tile).
-    // Residual rows are fetched with cp.async into a second per-warp tile one chunk ahead (first chunk: before the
-    // accumulator wait), so their latency hides behind the MMA mainloop / the previous chunk.
+    // The math runs in the layout tcgen05.ld delivers (thread = output row, 32 consecutive columns in registers):
+    // per-row quantities (mask, LayerNorm mean / rstd) are plain registers, per-column vectors are broadcast
+    // LDS.128. Global memory is touched only by TMA: the residual block of the next chunk is prefetched into a
+    // 128B-swizzled smem tile (mbarrier), results are written to swizzled smem tiles and leave with
+    // cp.async.bulk.tensor stores (3-D box = this warp's 32 rows x 32 columns; rows beyond the batch are clipped by
+    // the tensor map). No per-row address arithmetic, no transposition, no per-lane global accesses.
     const EpiParams& e = p.epi;
     const int ew = warp - 4;
     const int q = warp & 3, h = ew >> 2;
@@ -292,22 +304,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     const int et = threadIdx.x - 128;            // 0..255 among the epilogue threads
     float* s_bias = epi_smem; float* s_lnw = epi_smem + MAX_BN; float* s_lnb = epi_smem + 2 * MAX_BN; float* s_gam = epi_smem + 3 * MAX_BN;
     float* s_part_base = epi_smem + 4 * MAX_BN;  // [tile parity][2 halves][128 rows][2] LayerNorm partial sums
-    float* stg = stage_smem + ew * (32 * 32);    // this warp's 32 x 32 fp32 transpose tile (accumulators)
-    float* rsg = stage_smem + (8 + ew) * (32 * 32);   // this warp's 32 x 32 residual tile, row-major [row][column]
-    // per-warp row table: output row offset (or -1), then {mask, mean, rstd, time step} per row
-    int* w_ro = reinterpret_cast<int*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2) + ew * 32;     // row start (elements) or -1
-    float4* w_rw = reinterpret_cast<float4*>(epi_smem + 4 * MAX_BN + 2 * 2 * BM * 2 + 8 * 32) + ew * 32;
+    unsigned char* t32 = reinterpret_cast<unsigned char*>(stage_smem) + ew * 4096;          // fp32 result tile (swizzle 128B)
+    unsigned char* trs = reinterpret_cast<unsigned char*>(stage_smem) + (8 + ew) * 4096;    // residual tile (swizzle 128B)
+    const uint32_t res_bar = bar_base + 8u * (2 * STAGES + 4 + 1 + ew);                     // after the TMEM pointer slot
     const int chunks = p.bn >> 5;
     const int c_begin = h == 0 ? 0 : (chunks + 1) / 2, c_end = h == 0 ? (chunks + 1) / 2 : chunks;
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
     const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
     const bool has_pe = MODE < 0 ? (e.pe != nullptr) : ((MODE & 16) != 0);
     const int act = MODE < 0 ? e.act : ((MODE >> 1) & 3);
-    const int g8 = lane & 7, rsub = lane >> 3;   // transposed domain: 16-byte column group, row inside a 4-row step
+    const bool has32 = OUTK < 0 ? (e.out_f32 != nullptr) : ((OUTK & 1) != 0);
+    const bool has16 = OUTK < 0 ? (e.out_h != nullptr) : ((OUTK & 2) != 0);
+    const bool o16_f16 = OUTK < 0 ? (e.out_h_f16 != 0) : ((OUTK & 4) != 0);
+    // 16-bit result tile (swizzle 64B): shares the fp32 tile when there is no fp32 output, else the residual tile
+    unsigned char* t16 = has32 ? trs : t32;
+    const int sw7 = lane & 7;                    // 128B swizzle: 16-byte chunk j of row `lane` lives in slot j ^ (lane & 7)
+    const int sw3 = (lane >> 1) & 3;             // 64B swizzle: chunk j of row `lane` lives in slot j ^ ((lane >> 1) & 3)
+    if (lane == 0) mbar_init(res_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t res_phase = 0;
     int it = 0, loaded_n0 = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = decode_tile(p, tile);
-      if (it == 0 && ew == 0) AVDF_TS(8);
       const int vec0 = tc_.n0 + p.seg.w_row[tc_.seg];   // first entry of this tile's per-channel vectors
       if (vec0 != loaded_n0) {                   // per-channel epilogue vectors of this n-tile -> smem
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -320,35 +339,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         asm volatile("bar.sync 1, 256;" ::: "memory");
         loaded_n0 = vec0;
       }
-      if (it == 0 && ew == 0) AVDF_TS(9);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       float* s_part = s_part_base + acc * (2 * BM * 2);
-      // my row in the TMEM domain (thread = row)
+      // my row (thread = row) and this warp's box origin inside the segment
       const int r = q * 32 + lane;
       const int b = tc_.b0 + r / tc_.tt;
       const int t = tc_.t0 + (r & (tc_.tt - 1));
       const bool valid = b < p.seg.batch;
-      const long long orow = valid ? ((long long)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t) : -1;
-      const float mk = (valid && e.row_mask) ? (e.row_mask[orow] ? 1.f : 0.f) : 1.f;
-      __syncwarp();                               // previous tile's reads of the row table are done
-      w_ro[lane] = valid ? (int)(orow * N) : -1;
-      const bool tile_all_valid = __all_sync(0xffffffffu, valid);
-      __syncwarp();
-      auto fetch_residual = [&](int ch) {         // 32 rows x 128 B of the residual -> rsg, asynchronously
-        const float* src = e.residual + tc_.n0 + ch * 32 + g8 * 4;
-        const uint32_t dst = smem_u32(rsg + rsub * 32 + g8 * 4);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ro = w_ro[i * 4 + rsub];
-          if (ro >= 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + ro) : "memory");
+      const int wb = tc_.b0 + (q * 32) / tc_.tt, wt = tc_.t0 + ((q * 32) & (tc_.tt - 1));   // box origin (video, time)
+      float mk = 1.f;
+      if (valid && e.row_mask) mk = e.row_mask[(size_t)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t] ? 1.f : 0.f;
+      auto fetch_residual = [&](int ch) {         // 32 rows x 128 B of the residual -> trs (TMA, swizzle 128B)
+        if (lane == 0) {
+          mbar_arrive_expect_tx(res_bar, 4096);
+          tma_load_3d(smem_u32(trs), &p.res_map[tc_.seg], res_bar, tc_.n0 + ch * 32, wt, wb);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
       };
       if (has_res && c_begin < c_end) fetch_residual(c_begin);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      if (it == 0 && ew == 0) AVDF_TS(4);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
       float mean = 0.f, rstd = 1.f;
       if (has_ln) {                               // row statistics over all bn columns: each half sums its chunks
@@ -372,86 +382,109 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         const float var = fmaxf(ss / (float)p.bn - mean * mean, 0.f);
         rstd = rsqrtf(var + 1e-5f);
       }
-      w_rw[lane] = make_float4(mk, mean, rstd, __int_as_float(t));
       if (c_begin == c_end) {                     // narrow tiles: this half owns no columns
         tcgen05_fence_before();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      const bool has32 = OUTK < 0 ? (e.out_f32 != nullptr) : ((OUTK & 1) != 0);
-      const bool has16 = OUTK < 0 ? (e.out_h != nullptr) : ((OUTK & 2) != 0);
-      const bool o16_f16 = OUTK < 0 ? (e.out_h_f16 != 0) : ((OUTK & 4) != 0);
-      uint32_t v[32];                             // accumulator block of the current chunk (raw bits)
-      if (c_begin < c_end) tmem_ld32_issue(taddr + c_begin * 32, v);
+      uint32_t vr[32];                            // accumulator block of the current chunk (raw bits)
+      if (c_begin < c_end) tmem_ld32_issue(taddr + c_begin * 32, vr);
       for (int ch = c_begin; ch < c_end; ++ch) {
         tmem_ld_wait();
-        if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(10);
-        __syncwarp();                             // previous chunk's reads of the staging tile are done
+        float x[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)               // row `lane`, 16-byte group j -> swizzled slot j ^ (lane & 7)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vr[i]);
         if (ch + 1 < c_end) {
-          tmem_ld32_issue(taddr + (ch + 1) * 32, v);   // next block's TMEM read overlaps this block's row loop
-        } else {                                  // this warp's TMEM reads of the accumulator are issued: after they
-          tmem_ld_wait();                         // complete the MMA warp may overwrite it
+          tmem_ld32_issue(taddr + (ch + 1) * 32, vr);   // next block's TMEM read overlaps this block's math
+        } else {                                  // all TMEM reads of this warp are issued: once they complete the
+          tmem_ld_wait();                         // MMA warp may overwrite the accumulator
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (has_res) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(11);
-        const int cl = ch * 32 + g8 * 4;          // my 4 columns in the transposed domain
-        const int n = tc_.n0 + cl;
-        const float4 bias4 = *reinterpret_cast<const float4*>(s_bias + cl);
-        const float4 lnw4 = *reinterpret_cast<const float4*>(s_lnw + cl), lnb4 = *reinterpret_cast<const float4*>(s_lnb + cl);
-        const float4 gam4 = *reinterpret_cast<const float4*>(s_gam + cl);
-        float* const o32 = e.out_f32 + n;          // column-adjusted bases; the row table holds 32-bit row starts
-        uint16_t* const o16 = reinterpret_cast<uint16_t*>(e.out_h) + n;
-        // branch-free body so that the 8 unrolled iterations interleave (row table / staging loads of all of them in
-        // flight together). Tiles whose 32 rows are all inside the batch (every tile except a ragged batch tail) take
-        // the variant without per-row predicates.
-        auto rows = [&](auto all_valid_tag) {
-          constexpr bool ALLV = decltype(all_valid_tag)::value;
+        const int cl = ch * 32;
+        {                                         // (acc + bias) * mask -> LayerNorm -> activation
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + cl);
+          const float4* w4 = reinterpret_cast<const float4*>(s_lnw + cl);
+          const float4* l4 = reinterpret_cast<const float4*>(s_lnb + cl);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub;
-            const int ro = w_ro[rr];
-            const bool rv_ok = ALLV || ro >= 0;
-            const float4 rw = w_rw[rr];             // {mask, mean, rstd, t}
-            float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((g8 ^ (rr & 7)) << 2));
-            x.x = (x.x + bias4.x) * rw.x; x.y = (x.y + bias4.y) * rw.x; x.z = (x.z + bias4.z) * rw.x; x.w = (x.w + bias4.w) * rw.x;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            x[4 * j] = (x[4 * j] + bb.x) * mk; x[4 * j + 1] = (x[4 * j + 1] + bb.y) * mk;
+            x[4 * j + 2] = (x[4 * j + 2] + bb.z) * mk; x[4 * j + 3] = (x[4 * j + 3] + bb.w) * mk;
             if (has_ln) {
-              x.x = fmaf((x.x - rw.y) * rw.z, lnw4.x, lnb4.x); x.y = fmaf((x.y - rw.y) * rw.z, lnw4.y, lnb4.y);
-              x.z = fmaf((x.z - rw.y) * rw.z, lnw4.z, lnb4.z); x.w = fmaf((x.w - rw.y) * rw.z, lnw4.w, lnb4.w);
+              const float4 ww = w4[j], ll = l4[j];
+              x[4 * j] = fmaf((x[4 * j] - mean) * rstd, ww.x, ll.x); x[4 * j + 1] = fmaf((x[4 * j + 1] - mean) * rstd, ww.y, ll.y);
+              x[4 * j + 2] = fmaf((x[4 * j + 2] - mean) * rstd, ww.z, ll.z); x[4 * j + 3] = fmaf((x[4 * j + 3] - mean) * rstd, ww.w, ll.w);
             }
-            x.x = act_tc(x.x, act); x.y = act_tc(x.y, act); x.z = act_tc(x.z, act); x.w = act_tc(x.w, act);
-            if (has_pe) {
-              float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rv_ok) pv = __ldg(reinterpret_cast<const float4*>(e.pe + (size_t)__float_as_int(rw.w) * N + n));
-              x.x = fmaf(pv.x, rw.x, x.x); x.y = fmaf(pv.y, rw.x, x.y); x.z = fmaf(pv.z, rw.x, x.z); x.w = fmaf(pv.w, rw.x, x.w);
-            }
-            if (has_res) {
-              const float4 rv = *reinterpret_cast<const float4*>(rsg + rr * 32 + g8 * 4);
-              x.x = fmaf(gam4.x, x.x, rv.x * rw.x); x.y = fmaf(gam4.y, x.y, rv.y * rw.x);
-              x.z = fmaf(gam4.z, x.z, rv.z * rw.x); x.w = fmaf(gam4.w, x.w, rv.w * rw.x);
-            }
-            if (has32 && rv_ok) *reinterpret_cast<float4*>(o32 + ro) = x;
-            if (has16 && rv_ok) {
-              uint2 u;
-              if (o16_f16) { u.x = pack_f16x2(x.x, x.y); u.y = pack_f16x2(x.z, x.w); }
-              else { u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); }
-              *reinterpret_cast<uint2*>(o16 + ro) = u;
-            }
+            x[4 * j] = act_tc(x[4 * j], act); x[4 * j + 1] = act_tc(x[4 * j + 1], act);
+            x[4 * j + 2] = act_tc(x[4 * j + 2], act); x[4 * j + 3] = act_tc(x[4 * j + 3], act);
           }
-        };
-        if (tile_all_valid) rows(std::true_type{}); else rows(std::false_type{});
-        if (it == 0 && ew == 0 && ch == c_begin) AVDF_TS(12);
-        if (has_res && ch + 1 < c_end) {          // next chunk's residual (all lanes are done reading rsg)
-          __syncwarp();
+        }
+        if (has_pe && valid) {                    // + PE[t, n] * mask (embedding only: one launch per pass)
+          const float4* pe4 = reinterpret_cast<const float4*>(e.pe + (size_t)t * N + tc_.n0 + cl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 pv = __ldg(pe4 + j);
+            x[4 * j] = fmaf(pv.x, mk, x[4 * j]); x[4 * j + 1] = fmaf(pv.y, mk, x[4 * j + 1]);
+            x[4 * j + 2] = fmaf(pv.z, mk, x[4 * j + 2]); x[4 * j + 3] = fmaf(pv.w, mk, x[4 * j + 3]);
+          }
+        }
+        if (has_res) {                            // residual * mask + gamma * x
+          mbar_wait(res_bar, res_phase);
+          res_phase ^= 1;
+          const float4* g4 = reinterpret_cast<const float4*>(s_gam + cl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 rv = *reinterpret_cast<const float4*>(trs + lane * 128 + ((j ^ sw7) << 4));
+            const float4 gg = g4[j];
+            x[4 * j] = fmaf(gg.x, x[4 * j], rv.x * mk); x[4 * j + 1] = fmaf(gg.y, x[4 * j + 1], rv.y * mk);
+            x[4 * j + 2] = fmaf(gg.z, x[4 * j + 2], rv.z * mk); x[4 * j + 3] = fmaf(gg.w, x[4 * j + 3], rv.w * mk);
+          }
+          __syncwarp();                           // every lane has read the residual tile
+        }
+        // the previous chunk's TMA stores must have finished READING the tiles before they are overwritten
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (has32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(t32 + lane * 128 + ((j ^ sw7) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+        if (has16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            if (o16_f16) {
+              u.x = pack_f16x2(x[8 * j], x[8 * j + 1]); u.y = pack_f16x2(x[8 * j + 2], x[8 * j + 3]);
+              u.z = pack_f16x2(x[8 * j + 4], x[8 * j + 5]); u.w = pack_f16x2(x[8 * j + 6], x[8 * j + 7]);
+            } else {
+              u.x = pack_bf16x2(x[8 * j], x[8 * j + 1]); u.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+              u.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]); u.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+            }
+            *reinterpret_cast<uint4*>(t16 + lane * 64 + ((j ^ sw3) << 4)) = u;
+          }
+        }
+        fence_async_smem();                       // generic-proxy smem writes -> visible to the async proxy (TMA)
+        __syncwarp();
+        if (lane == 0) {
+          if (has32) tma_store_3d(&p.o32_map[tc_.seg], smem_u32(t32), tc_.n0 + cl, wt, wb);
+          if (has16) tma_store_3d(&p.o16_map[tc_.seg], smem_u32(t16), tc_.n0 + cl, wt, wb);
+          tma_store_commit();
+        }
+        if (has_res && ch + 1 < c_end) {          // next chunk's residual; if the 16-bit tile aliases the residual
+          if (has16 && has32) {                   // tile, its store must have read it first
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
           fetch_residual(ch + 1);
         }
       }
+      if (has_res && has16 && has32) {            // before the next tile's first residual prefetch
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
   if (warp == 4) AVDF_TS(5);
   tcgen05_fence_before();
@@ -529,6 +562,26 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(A, level %d) failed with %d", s, (int)r); return AVDF_ERR_CUDA; }
+    // epilogue maps of this segment: 3-D (n, t, video); box = 32 columns x the 32 rows one epilogue warp owns
+    {
+      const int tw = tt < 32 ? tt : 32, bw = 32 / tw;
+      struct { CUtensorMap* map; const void* base; CUtensorMapDataType dt; int es; CUtensorMapSwizzle sw; } outs[3] = {
+          {&p.o32_map[s], a->out_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B},
+          {&p.o16_map[s], a->out_h, a->out_h_dtype == AVDF_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_64B},
+          {&p.res_map[s], a->residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B}};
+      for (int o = 0; o < 3; ++o) {
+        if (!outs[o].base) continue;
+        AVDF_CHECK_ARG((reinterpret_cast<uintptr_t>(outs[o].base) & 15) == 0, "outputs / residual must be 16-byte aligned");
+        cuuint64_t odims[3] = {(cuuint64_t)a->n_out, (cuuint64_t)T, (cuuint64_t)a->batch};
+        cuuint64_t ostr[2] = {(cuuint64_t)a->n_out * outs[o].es, (cuuint64_t)a->o_rows_per_video * a->n_out * outs[o].es};
+        cuuint32_t obox[3] = {32u, (cuuint32_t)tw, (cuuint32_t)bw};
+        cuuint32_t oes[3] = {1, 1, 1};
+        void* obase = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(outs[o].base)) + (size_t)a->seg_o_row[s] * a->n_out * outs[o].es;
+        CUresult ro = encode(outs[o].map, outs[o].dt, 3, obase, odims, ostr, obox, oes, CU_TENSOR_MAP_INTERLEAVE_NONE, outs[o].sw,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (ro != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(output %d, level %d) failed with %d", o, s, (int)ro); return AVDF_ERR_CUDA; }
+      }
+    }
   }
   p.seg_tile_start[a->n_seg] = tiles;
   p.n_tiles_m = tiles;
