@@ -22,6 +22,7 @@ namespace avdf {
 namespace tc {
 
 constexpr int BM = 128, BK = 64, STAGES = 3, MAX_BN = 256;
+constexpr int BSTAT_STAGES = 5, MAX_STAGES = 5, BSTAT_SLAB = 65536;   // weight-stationary: 64 KB slab + 5 x 16 KB A stages = the same 144 KB
 constexpr int A_STAGE = BM * BK * 2;          // 16384
 constexpr int B_STAGE = MAX_BN * BK * 2;      // 32768
 constexpr int EPI_VEC_BYTES = 4 * MAX_BN * 4 + 2 * 2 * BM * 2 * 4;   // bias / ln_w / ln_b / gamma + double-buffered LayerNorm partial sums (8 KB)
@@ -39,6 +40,7 @@ struct Params {
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
   int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
   int n_out, c_in, taps, stride, bn, n_tiles_n, n_tiles_m, total_tiles;
+  int bstat;                                 // weight-stationary mode: the whole [bn, K] weight slab stays in smem, only A streams
   unsigned idesc;
   EpiParams epi;
   unsigned long long* dbg;                   // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
@@ -207,14 +209,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   unsigned char* smem_b = smem + STAGES * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
   float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024);
   float* stage_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024 + EPI_VEC_BYTES);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * MAX_STAGES + 4), bempty_bar = bar_base + 8u * (2 * MAX_STAGES + 5);
+  const int n_stages = p.bstat ? BSTAT_STAGES : STAGES;
+  // weight-stationary carve-up of the same 144 KB: [slab 64 KB][A ring 5 x 16 KB]
+  unsigned char* slab = smem;
+  if (p.bstat) smem_a = smem + BSTAT_SLAB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) AVDF_TS(0);
@@ -225,7 +232,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.w_map) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(bfull_bar, 1); mbar_init(bempty_bar, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -247,8 +255,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int cur_slab = -1, slab_loads = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc_ = decode_tile(p, tile);
+        if (p.bstat) {
+          const int slab_id = tc_.n0 + p.seg.w_row[tc_.seg];
+          if (slab_id != cur_slab) {               // (re)load the weight slab: all k-blocks of this n-tile
+            if (slab_loads > 0) mbar_wait(bempty_bar, (slab_loads - 1) & 1);   // MMAs reading the old slab are done
+            mbar_arrive_expect_tx(bfull_bar, (uint32_t)k_iters * p.bn * BK * 2);
+            for (int ki = 0; ki < k_iters; ++ki)
+              tma_load_2d(smem_u32(slab + (size_t)ki * p.bn * BK * 2), &p.w_map, bfull_bar, ki * BK, slab_id);
+            cur_slab = slab_id; ++slab_loads;
+          }
+          for (int ki = 0; ki < k_iters; ++ki) {   // taps == 1 in this mode: A is a plain [rows, K] stream
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_arrive_expect_tx(full_bar(stage), A_STAGE);
+            tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), ki * BK, 0, tc_.t0, tc_.b0);
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int d = tap - (p.taps >> 1);
           int par = 0, dt = d;
@@ -258,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
             mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
             tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), kb * BK, par, tc_.t0 + dt, tc_.b0);
             tma_load_2d(smem_u32(smem_b + stage * B_STAGE), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -267,7 +293,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
+      int cur_slab = -1, slab_seen = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        int slab_id = -1, next_slab = -1;
+        if (p.bstat) {
+          const TileCoord tc_ = decode_tile(p, tile);
+          slab_id = tc_.n0 + p.seg.w_row[tc_.seg];
+          if (tile + (int)gridDim.x < p.total_tiles) {
+            const TileCoord nx = decode_tile(p, tile + gridDim.x);
+            next_slab = nx.n0 + p.seg.w_row[nx.seg];
+          }
+          if (slab_id != cur_slab) { mbar_wait(bfull_bar, slab_seen & 1); ++slab_seen; cur_slab = slab_id; }
+        }
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -278,13 +315,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
           tcgen05_fence_after();
           if (it == 0 && ki == 0) AVDF_TS(2);
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * A_STAGE));
-          const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * B_STAGE));
+          const uint64_t db = make_sw128_desc(p.bstat ? smem_u32(slab + (size_t)ki * p.bn * BK * 2) : smem_u32(smem_b + stage * B_STAGE));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)          // +32 B per K=16 step inside the swizzle atom
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (ki == k_iters - 1) { umma_commit(tfull_bar(acc)); if (it == 0) AVDF_TS(3); }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (ki == k_iters - 1) {
+            umma_commit(tfull_bar(acc));
+            if (p.bstat && next_slab != -1 && next_slab != slab_id) umma_commit(bempty_bar);   // slab free once these MMAs retire
+            if (it == 0) AVDF_TS(3);
+          }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -306,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     float* s_part_base = epi_smem + 4 * MAX_BN;  // [tile parity][2 halves][128 rows][2] LayerNorm partial sums
     unsigned char* t32 = reinterpret_cast<unsigned char*>(stage_smem) + ew * 4096;          // fp32 result tile (swizzle 128B)
     unsigned char* trs = reinterpret_cast<unsigned char*>(stage_smem) + (8 + ew) * 4096;    // residual tile (swizzle 128B)
-    const uint32_t res_bar = bar_base + 8u * (2 * STAGES + 4 + 1 + ew);                     // after the TMEM pointer slot
+    const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 7 + ew);                     // after the TMEM pointer slot
     const int chunks = p.bn >> 5;
     const int c_begin = h == 0 ? 0 : (chunks + 1) / 2, c_end = h == 0 ? (chunks + 1) / 2 : chunks;
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
@@ -323,8 +364,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     if (lane == 0) mbar_init(res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    uint32_t res_phase = 0;
+    uint32_t res_phase = 0, store_seq = 0;
     int it = 0, loaded_n0 = -1;
+    // row mask of a tile's row owned by this thread (a global load: fetched one tile ahead so that its latency is
+    // off the critical path of the tile's epilogue)
+    auto row_mask_of = [&](int tile_) -> float {
+      if (tile_ >= p.total_tiles || !e.row_mask) return 1.f;
+      const TileCoord c = decode_tile(p, tile_);
+      const int r_ = q * 32 + lane;
+      const int b_ = c.b0 + r_ / c.tt, t_ = c.t0 + (r_ & (c.tt - 1));
+      if (b_ >= p.seg.batch) return 1.f;
+      return e.row_mask[(size_t)b_ * p.seg.o_rows + p.seg.o_row[c.seg] + t_] ? 1.f : 0.f;
+    };
+    float mk_next = row_mask_of(blockIdx.x);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = decode_tile(p, tile);
       const int vec0 = tc_.n0 + p.seg.w_row[tc_.seg];   // first entry of this tile's per-channel vectors
@@ -348,8 +400,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
       const int t = tc_.t0 + (r & (tc_.tt - 1));
       const bool valid = b < p.seg.batch;
       const int wb = tc_.b0 + (q * 32) / tc_.tt, wt = tc_.t0 + ((q * 32) & (tc_.tt - 1));   // box origin (video, time)
-      float mk = 1.f;
-      if (valid && e.row_mask) mk = e.row_mask[(size_t)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t] ? 1.f : 0.f;
+      const float mk = mk_next;
+      mk_next = row_mask_of(tile + gridDim.x);    // in flight during this tile's epilogue
       auto fetch_residual = [&](int ch) {         // 32 rows x 128 B of the residual -> trs (TMA, swizzle 128B)
         if (lane == 0) {
           mbar_arrive_expect_tx(res_bar, 4096);
@@ -443,7 +495,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
           __syncwarp();                           // every lane has read the residual tile
         }
         // the previous chunk's TMA stores must have finished READING the tiles before they are overwritten
-        if (lane == 0) tma_store_wait_read();
+        unsigned char* t16c = t16;
+        if (!has32) {                               // 16-bit only: alternate halves, allow one store in flight
+          t16c = t32 + ((store_seq++ & 1) << 11);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        } else {
+          if (lane == 0) tma_store_wait_read();
+        }
         __syncwarp();
         if (has32) {
 #pragma unroll
@@ -461,14 +519,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
               u.x = pack_bf16x2(x[8 * j], x[8 * j + 1]); u.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
               u.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]); u.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
             }
-            *reinterpret_cast<uint4*>(t16 + lane * 64 + ((j ^ sw3) << 4)) = u;
+            *reinterpret_cast<uint4*>(t16c + lane * 64 + ((j ^ sw3) << 4)) = u;
           }
         }
         fence_async_smem();                       // generic-proxy smem writes -> visible to the async proxy (TMA)
         __syncwarp();
         if (lane == 0) {
           if (has32) tma_store_3d(&p.o32_map[tc_.seg], smem_u32(t32), tc_.n0 + cl, wt, wb);
-          if (has16) tma_store_3d(&p.o16_map[tc_.seg], smem_u32(t16), tc_.n0 + cl, wt, wb);
+          if (has16) tma_store_3d(&p.o16_map[tc_.seg], smem_u32(t16c), tc_.n0 + cl, wt, wb);
           tma_store_commit();
         }
         if (has_res && ch + 1 < c_end) {          // next chunk's residual; if the 16-bit tile aliases the residual
@@ -523,7 +581,9 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   AVDF_CHECK_ARG(a->n_out % 32 == 0, "bf16 path: n_out must be a multiple of 32");
   // N tile: 256 (LayerNorm needs the whole row in one CTA; wide outputs), 128 for plain 256-wide outputs so that
   // 24576-row problems give 384 tiles (2.6 waves on 148 SMs instead of 1.3)
-  const int bn = a->n_out > MAX_BN ? MAX_BN : (a->n_out == MAX_BN ? (a->ln_w ? MAX_BN : 128) : a->n_out);
+  // weight-stationary candidates: 1x1 GEMMs whose [128, K] weight slab fits 64 KB (K <= 256: q/k/v, proj, MLP up, FPN laterals)
+  const bool want_bstat = a->taps == 1 && a->stride == 1 && !a->ln_w && a->n_out % 128 == 0 && (long long)a->c_in * 128 * 2 <= BSTAT_SLAB;
+  const int bn = want_bstat ? 128 : (a->n_out > MAX_BN ? MAX_BN : (a->n_out == MAX_BN ? (a->ln_w ? MAX_BN : 128) : a->n_out));
   AVDF_CHECK_ARG(a->n_out % bn == 0, "bf16 path: n_out must be <= 256 or a multiple of 256");
   AVDF_CHECK_ARG(bn % 16 == 0 && bn >= 32, "bf16 path: unsupported n_out");
   AVDF_CHECK_ARG(!a->ln_w || a->n_out == bn, "bf16 path: fused LayerNorm needs n_out <= 256");
@@ -541,6 +601,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   p.dbg = g_dbg;
   p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.bn = bn;
   p.n_tiles_n = a->n_out / bn;
+  p.bstat = (a->taps == 1 && a->stride == 1 && (long long)a->c_in * bn * 2 <= BSTAT_SLAB) ? 1 : 0;
   int tiles = 0;
   for (int s = 0; s < a->n_seg; ++s) {
     const int T = a->seg_t_out[s];
