@@ -32,13 +32,19 @@ class _Slot:
         self.stream = torch.cuda.Stream()     # slots run on their own streams: copies and kernels of consecutive batches overlap
         self.ids, self.B, self.busy = None, 0, False
 
-    def ensure(self, rows, chans, max_batch, K, device):
+    def ensure(self, rows, chans, max_batch, K, device, seconds):
+        """Staging capacity. The captured graph holds the device staging pointers, so growing them forces a
+        re-capture: size them once for a full batch of MAX_SECONDS-long videos at this stream's frame rate (the
+        AV-Deepfake1M test split tops out at 33 s) and grow (x1.5) only if a batch still exceeds that."""
+        MAX_SECONDS = 36.0
         grown = False
         for s in range(3):
             if chans[s] == 0:
                 continue
             if self.host[s] is None or rows[s] > self.cap[s]:
-                self.cap[s] = int(rows[s] * 1.25) + 64
+                rate = rows[s] / max(seconds, 1e-3)                       # rows per second of video for this stream
+                want = int(max_batch * MAX_SECONDS * rate * 1.05) + 64 if self.host[s] is None else 0
+                self.cap[s] = max(want, int(rows[s] * 1.5) + 64)
                 self.host[s] = torch.empty((self.cap[s], chans[s]), dtype=torch.float32, pin_memory=True)
                 self.dev[s] = torch.empty((self.cap[s], chans[s]), dtype=torch.float32, device=device)
                 grown = True
@@ -79,7 +85,7 @@ class StreamRunner:
         if sum(chans) != eng.c_in:
             raise ValueError("streams carry %d channels, the model expects %d" % (sum(chans), eng.c_in))
         K = int(eng.test_cfg["max_seg_num"])
-        slot.ensure(rows, chans, eng.max_batch, K, eng.device)
+        slot.ensure(rows, chans, eng.max_batch, K, eng.device, sum(float(c["duration"]) for c in chunk))
         off = slot.h_off.numpy()
         jobs = []
         for s in range(3):
