@@ -545,157 +545,165 @@ __global__ void __launch_bounds__(256) head_final_kernel(const HeadParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// exp12 video-level tail, one CTA (256 threads) per video:
+// exp12 video-level tail, one CTA (256 threads) per video, thread = output channel:
 //   g = LeakyReLU_.2(IN_T(W0 z)) [T, C]; pooled = [max_t g | mean_t g]; h = ReLU(LN(W1 pooled)); out = w2.h + b2
+// The 1x1 conv is 256 rank-1 updates: thread c reads W0T[k][c] (coalesced) and z[k][0..T) (smem broadcast) and keeps
+// its channel's T values in registers, so the InstanceNorm over T and the pooling need no communication at all.
+// Weights arrive TRANSPOSED ([in, out]) for exactly that access pattern.
 // ------------------------------------------------------------------------------------------------
-constexpr int VC12_MAXT = 64;
+constexpr int VC12_MAXT = 32;
 template <typename InT>
-__global__ void __launch_bounds__(256) vcls_exp12_kernel(const InT* __restrict__ z, const float* __restrict__ w0,
-                                                         const float* __restrict__ w1, const float* __restrict__ ln_w,
+__global__ void __launch_bounds__(256) vcls_exp12_kernel(const InT* __restrict__ z, const float* __restrict__ w0t,
+                                                         const float* __restrict__ w1t, const float* __restrict__ ln_w,
                                                          const float* __restrict__ ln_b, const float* __restrict__ w2,
                                                          const float* __restrict__ b2, float* __restrict__ out, int T) {
-  extern __shared__ __align__(16) float sm[];
-  float* zs = sm;                       // [T][256]
-  float* pooled = zs + (size_t)T * kC;  // [512]
-  float* hbuf = pooled + 2 * kC;        // [256]
-  __shared__ float red[2];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < T * kC; i += 256) zs[i] = load1(z + (size_t)b * T * kC + i);
+  __shared__ __align__(16) float zs[kC][VC12_MAXT];      // z transposed: [k][t]
+  __shared__ float pooled[2 * kC];
+  __shared__ float red[2][8];
+  const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  for (int i = c; i < T * kC; i += 256) { const int t = i / kC, k = i - t * kC; zs[k][t] = load1(z + (size_t)b * T * kC + i); }
+  for (int i = c; i < kC * (VC12_MAXT - T); i += 256) { const int k = i / (VC12_MAXT - T), t = T + i - k * (VC12_MAXT - T); zs[k][t] = 0.f; }
   __syncthreads();
-  // g[t][c] for c = warp, warp + 8, ...; lanes split the 256-long dot product
-  for (int c = warp; c < kC; c += 8) {
-    float w[8];
-    Row8<float>::load(w0 + (size_t)c * kC + lane * 8, w);
-    float mx = -INFINITY, sum_g = 0.f;
-    float g[VC12_MAXT];
-    float s1 = 0.f;
-    for (int t = 0; t < T; ++t) {
-      float x[8];
-      lds8(zs + t * kC + lane * 8, x);
-      float a = 0.f;
+  float g[VC12_MAXT];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a = fmaf(w[k], x[k], a);
-      a = warp_sum(a);
-      g[t % VC12_MAXT] = a; s1 += a;
+  for (int t = 0; t < VC12_MAXT; ++t) g[t] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kC; ++k) {            // unrolled: 8 independent weight loads in flight per thread
+    const float w = __ldg(w0t + (size_t)k * kC + c);
+    const float4* zr = reinterpret_cast<const float4*>(&zs[k][0]);
+#pragma unroll
+    for (int j = 0; j < VC12_MAXT / 4; ++j) {
+      const float4 zz = zr[j];
+      g[4 * j] = fmaf(w, zz.x, g[4 * j]); g[4 * j + 1] = fmaf(w, zz.y, g[4 * j + 1]);
+      g[4 * j + 2] = fmaf(w, zz.z, g[4 * j + 2]); g[4 * j + 3] = fmaf(w, zz.w, g[4 * j + 3]);
     }
-    const float mean = s1 / (float)T;
-    float qv = 0.f;
-    for (int t = 0; t < T; ++t) { const float d = g[t % VC12_MAXT] - mean; qv = fmaf(d, d, qv); }
-    const float rstd = 1.f / sqrtf(qv / (float)T + kLnEps);
-    for (int t = 0; t < T; ++t) {
-      float v = (g[t % VC12_MAXT] - mean) * rstd;
-      v = v >= 0.f ? v : 0.2f * v;
-      mx = fmaxf(mx, v); sum_g += v;
-    }
-    if (lane == 0) { pooled[c] = mx; pooled[kC + c] = sum_g / (float)T; }
   }
+  float s1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < VC12_MAXT; ++t) if (t < T) s1 += g[t];
+  const float mean = s1 / (float)T;
+  float qv = 0.f;
+#pragma unroll
+  for (int t = 0; t < VC12_MAXT; ++t) if (t < T) { const float d = g[t] - mean; qv = fmaf(d, d, qv); }
+  const float rstd = 1.f / sqrtf(qv / (float)T + kLnEps);
+  float mx = -INFINITY, sum_g = 0.f;
+#pragma unroll
+  for (int t = 0; t < VC12_MAXT; ++t) if (t < T) {
+    float v = (g[t] - mean) * rstd;
+    v = v >= 0.f ? v : 0.2f * v;
+    mx = fmaxf(mx, v); sum_g += v;
+  }
+  pooled[c] = mx; pooled[kC + c] = sum_g / (float)T;
   __syncthreads();
-  // h[c] = W1[c, :512] . pooled
-  for (int c = warp; c < kC; c += 8) {
-    float a = 0.f;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float w[8], x[8];
-      Row8<float>::load(w1 + (size_t)c * 2 * kC + h * kC + lane * 8, w);
-      lds8(pooled + h * kC + lane * 8, x);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a = fmaf(w[k], x[k], a);
-    }
-    a = warp_sum(a);
-    if (lane == 0) hbuf[c] = a;
-  }
+  float hc = 0.f;                                        // h[c] = sum_j W1[c][j] pooled[j]
+#pragma unroll 16
+  for (int j = 0; j < 2 * kC; ++j) hc = fmaf(__ldg(w1t + (size_t)j * kC + c), pooled[j], hc);
+  // LayerNorm over the 256 channels (two-pass), ReLU, dot with w2
+  float s = warp_sum(hc);
+  if (lane == 0) red[0][warp] = s;
   __syncthreads();
-  if (warp == 0) {
-    float v[8];
-    lds8(hbuf + lane * 8, v);
-    float m, rs;
-    row_stats(v, m, rs);
-    float a = 0.f;
+  float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = lane * 8 + k;
-      const float y = fmaxf(fmaf((v[k] - m) * rs, ln_w[c], ln_b[c]), 0.f);
-      a = fmaf(w2[c], y, a);
-    }
-    a = warp_sum(a);
-    if (lane == 0) out[b] = a + b2[0];
+  for (int i = 0; i < 8; ++i) tot += red[0][i];
+  const float m = tot / (float)kC;
+  const float d = hc - m;
+  float q2 = warp_sum(d * d);
+  if (lane == 0) red[1][warp] = q2;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[1][i];
+  const float rs = 1.f / sqrtf(tot / (float)kC + kLnEps);
+  const float y = fmaxf(fmaf(d * rs, ln_w[c], ln_b[c]), 0.f);
+  float a = warp_sum(w2[c] * y);
+  __syncthreads();
+  if (lane == 0) red[0][warp] = a;
+  __syncthreads();
+  if (c == 0) {
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += red[0][i];
+    out[b] = r + b2[0];
   }
-  (void)red;
 }
 
 // ------------------------------------------------------------------------------------------------
-// exp13 video-level tail, one CTA per video, C (= 64) channels:
+// exp13 video-level tail, one CTA per video, C (<= 128) channels, thread = (channel c, time lane):
 //   g = LeakyReLU_.2(IN_T(W0 z)) [T, C]; s_t = seg_w . g_t + seg_b; out = cls_w . [max_t s, mean_t s] + cls_b
-// thread = (channel c = tid % C, time lane tid / C); W0 transposed in smem; three passes over z (L2).
+// Each thread keeps row c of W0 in registers; z rows are read once per pass (L1 broadcast across the C threads of a
+// time lane). Pass 1 accumulates sum / sum of squares of g per channel, pass 2 recomputes g, normalises and reduces
+// over channels with one shuffle tree per time step.
 // ------------------------------------------------------------------------------------------------
-template <typename InT>
+template <typename InT, int C>
 __global__ void __launch_bounds__(256) vcls_exp13_kernel(const InT* __restrict__ z, const float* __restrict__ w0,
                                                          const float* __restrict__ seg_w, const float* __restrict__ seg_b,
                                                          const float* __restrict__ cls_w, const float* __restrict__ cls_b,
-                                                         float* __restrict__ out, int T, int C) {
-  extern __shared__ __align__(16) float sm[];
-  float* w0t = sm;                         // [C][C+1]  w0t[k][c] = w0[c][k]
-  float* zt = w0t + C * (C + 1);           // [TL][C]   staged z rows
-  float* red = zt + (256 / C) * C;         // [256]
-  float* stat = red + 256;                 // mean[C], rstd[C]
-  float* sbuf = stat + 2 * C;              // s_t partials: [TL]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int c = tid % C, tl = tid / C, TL = 256 / C;
-  for (int i = tid; i < C * C; i += 256) { const int cc = i / C, kk = i - cc * C; w0t[kk * (C + 1) + cc] = w0[i]; }
-  __syncthreads();
+                                                         float* __restrict__ out, int T) {
+  constexpr int TL = 256 / C;                            // time lanes
+  __shared__ float red[2][256];
+  __shared__ float stat[2][C];
+  __shared__ float zrow[TL][C];
+  __shared__ float spart[TL][C / 32];
+  __shared__ float sfin[2][TL];
+  const int b = blockIdx.x, tid = threadIdx.x, c = tid % C, tl = tid / C, lane = tid & 31;
   const InT* zb = z + (size_t)b * T * C;
-  float acc1 = 0.f;
-  float mean = 0.f, rstd = 0.f;
-  float smax = -INFINITY, ssum = 0.f;
-  for (int pass = 0; pass < 3; ++pass) {
-    float part = 0.f;
-    for (int tb = 0; tb < T; tb += TL) {
-      const int t = tb + tl;
-      if (t < T) zt[tl * C + c] = load1(zb + (size_t)t * C + c);
-      __syncthreads();
+  float w[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) w[k] = __ldg(w0 + (size_t)c * C + k);
+  const int steps = (T + TL - 1) / TL;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < steps; ++i) {
+    const int t = i * TL + tl;
+    __syncthreads();
+    if (t < T) zrow[tl][c] = load1(zb + (size_t)t * C + c);
+    __syncthreads();
+    if (t < T) {
       float g = 0.f;
-      if (t < T) {
-        for (int kk = 0; kk < C; ++kk) g = fmaf(w0t[kk * (C + 1) + c], zt[tl * C + kk], g);
-        if (pass == 0) part += g;
-        else if (pass == 1) { const float d = g - mean; part = fmaf(d, d, part); }
-      }
-      if (pass == 2) {
-        float v = 0.f;
-        if (t < T) {
-          v = (g - mean) * rstd;
-          v = v >= 0.f ? v : 0.2f * v;
-          v *= seg_w[c];
-        }
-        red[tid] = v;
-        __syncthreads();
-        if (tid < TL) {                         // s_t for the TL rows of this step
-          float s = 0.f;
-          for (int cc = 0; cc < C; ++cc) s += red[tid * C + cc];
-          if (tb + tid < T) { s += seg_b[0]; smax = fmaxf(smax, s); ssum += s; }
-        }
-      }
-      __syncthreads();
-    }
-    if (pass < 2) {
-      red[tid] = part;
-      __syncthreads();
-      if (tid < C) {
-        float tot = 0.f;
-        for (int i = 0; i < TL; ++i) tot += red[i * C + tid];
-        if (pass == 0) stat[tid] = tot / (float)T;
-        else stat[C + tid] = 1.f / sqrtf(tot / (float)T + kLnEps);
-      }
-      __syncthreads();
-      if (pass == 0) mean = stat[c]; else rstd = stat[C + c];
-      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < C; ++k) g = fmaf(w[k], zrow[tl][k], g);
+      s1 += g; s2 = fmaf(g, g, s2);
     }
   }
-  (void)acc1; (void)sbuf;
-  if (tid < TL) { red[tid] = smax; red[32 + tid] = ssum; }
+  red[0][tid] = s1; red[1][tid] = s2;
+  __syncthreads();
+  if (tid < C) {
+    float a = 0.f, q = 0.f;
+    for (int j = 0; j < TL; ++j) { a += red[0][j * C + tid]; q += red[1][j * C + tid]; }
+    const float m = a / (float)T;
+    stat[0][tid] = m;
+    stat[1][tid] = 1.f / sqrtf(fmaxf(q / (float)T - m * m, 0.f) + kLnEps);
+  }
+  __syncthreads();
+  const float mean = stat[0][c], rstd = stat[1][c], sw = seg_w[c];
+  float smax = -INFINITY, ssum = 0.f;
+  for (int i = 0; i < steps; ++i) {
+    const int t = i * TL + tl;
+    __syncthreads();
+    if (t < T) zrow[tl][c] = load1(zb + (size_t)t * C + c);
+    __syncthreads();
+    float v = 0.f;
+    if (t < T) {
+      float g = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) g = fmaf(w[k], zrow[tl][k], g);
+      v = (g - mean) * rstd;
+      v = (v >= 0.f ? v : 0.2f * v) * sw;
+    }
+    v = warp_sum(v);                                     // C is a multiple of 32: a warp never straddles time lanes
+    if (lane == 0) spart[tl][(tid % C) / 32] = v;
+    __syncthreads();
+    if (c == 0 && t < T) {
+      float st = seg_b[0];
+#pragma unroll
+      for (int j = 0; j < C / 32; ++j) st += spart[tl][j];
+      smax = fmaxf(smax, st); ssum += st;
+    }
+  }
+  if (c == 0) { sfin[0][tl] = smax; sfin[1][tl] = ssum; }
   __syncthreads();
   if (tid == 0) {
     float mx = -INFINITY, sm_ = 0.f;
-    for (int i = 0; i < TL; ++i) { mx = fmaxf(mx, red[i]); sm_ += red[32 + i]; }
+    for (int j = 0; j < TL; ++j) { mx = fmaxf(mx, sfin[0][j]); sm_ += sfin[1][j]; }
     out[b] = cls_w[0] * mx + cls_w[1] * (sm_ / (float)T) + cls_b[0];
   }
 }
@@ -867,20 +875,16 @@ extern "C" int avdf_head_final(const void* cls_feat, const void* reg_feat, int32
   return check_launch("head_final_kernel");
 }
 
-extern "C" int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_w, const float* lin1_w, const float* ln_w,
+extern "C" int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_wt, const float* lin1_wt, const float* ln_w,
                                const float* ln_b, const float* lin2_w, const float* lin2_b, float* out, int32_t batch,
                                int32_t t, int32_t channels, void* stream) {
-  AVDF_CHECK_ARG(z && conv0_w && lin1_w && ln_w && ln_b && lin2_w && lin2_b && out, "null pointer");
+  AVDF_CHECK_ARG(z && conv0_wt && lin1_wt && ln_w && ln_b && lin2_w && lin2_b && out, "null pointer");
   AVDF_CHECK_ARG(channels == kC, "channels must be 256");
-  AVDF_CHECK_ARG(t > 0 && t <= VC12_MAXT, "t out of range (1..64)");
-  if (batch == 0) return AVDF_OK;
-  const size_t smem = ((size_t)t * kC + 3 * kC) * sizeof(float);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  AVDF_CHECK_ARG(t > 0 && t <= VC12_MAXT, "t out of range (1..32)");
   AVDF_CHECK_DTYPE(dtype, "dtype");
-  AVDF_DISPATCH_DTYPE(dtype, InT, {
-    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp12_kernel<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vcls_exp12_kernel<InT><<<batch, 256, smem, st>>>((const InT*)z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, t);
-  });
+  if (batch == 0) return AVDF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  AVDF_DISPATCH_DTYPE(dtype, InT, (vcls_exp12_kernel<InT><<<batch, 256, 0, st>>>((const InT*)z, conv0_wt, lin1_wt, ln_w, ln_b, lin2_w, lin2_b, out, t)));
   return check_launch("vcls_exp12_kernel");
 }
 
@@ -888,16 +892,12 @@ extern "C" int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_
                                const float* cls_w, const float* cls_b, float* out, int32_t batch, int32_t t,
                                int32_t channels, void* stream) {
   AVDF_CHECK_ARG(z && conv0_w && seg_w && seg_b && cls_w && cls_b && out, "null pointer");
-  AVDF_CHECK_ARG(channels == 32 || channels == 64 || channels == 128, "channels must be 32, 64 or 128");
+  AVDF_CHECK_ARG(channels == 32 || channels == 64, "channels must be 32 or 64");
   AVDF_CHECK_ARG(t > 0, "t must be positive");
-  if (batch == 0) return AVDF_OK;
-  const int C = channels;
-  const size_t smem = ((size_t)C * (C + 1) + (256 / C) * C + 256 + 2 * C + 64) * sizeof(float);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   AVDF_CHECK_DTYPE(dtype, "dtype");
-  AVDF_DISPATCH_DTYPE(dtype, InT, {
-    AVDF_CUDA(cudaFuncSetAttribute(vcls_exp13_kernel<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vcls_exp13_kernel<InT><<<batch, 256, smem, st>>>((const InT*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t, C);
-  });
+  if (batch == 0) return AVDF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (channels == 64) AVDF_DISPATCH_DTYPE(dtype, InT, (vcls_exp13_kernel<InT, 64><<<batch, 256, 0, st>>>((const InT*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t)));
+  else AVDF_DISPATCH_DTYPE(dtype, InT, (vcls_exp13_kernel<InT, 32><<<batch, 256, 0, st>>>((const InT*)z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, t)));
   return check_launch("vcls_exp13_kernel");
 }

@@ -77,6 +77,15 @@ class PackedWeights:
             self._cache[ck] = w.contiguous().to(self.device).to(dtype).contiguous()
         return self._cache[ck]
 
+    def dense_t(self, key):
+        """[co, ci(, 1)] -> transposed fp32 [ci, co] (thread-per-output-channel kernels read it coalesced)."""
+        ck = ("t", key)
+        if ck not in self._cache:
+            w = self.sd[key].detach().to(torch.float32)
+            w = w.reshape(w.shape[0], -1)
+            self._cache[ck] = w.t().contiguous().to(self.device)
+        return self._cache[ck]
+
     def stack_dense(self, keys, dtype):
         """Several [co, ci(, k)] weights stacked along co (one GEMM launch with per-segment weight blocks)."""
         ck = ("sd", tuple(keys), dtype)
@@ -354,7 +363,7 @@ class LocalizationEngine:
                            w.vec("segmentandCls.seg_linear.bias"), w.vec("segmentandCls.cls_linear1.weight"),
                            w.vec("segmentandCls.cls_linear1.bias"), vcls, batch=B, t=T)
         else:
-            ops.vcls_exp12(z, w.dense("interpolator.conv0.0.weight", torch.float32), w.dense("interpolator.conv1.weight", torch.float32),
+            ops.vcls_exp12(z, w.dense_t("interpolator.conv0.0.weight"), w.dense_t("interpolator.conv1.weight"),
                            *w.ln("interpolator.bn1"), w.vec("interpolator.conv2.weight"), w.vec("interpolator.conv2.bias"),
                            vcls, batch=B, t=T)
         return vcls

@@ -206,8 +206,9 @@ AVDF_API int avdf_head_final(const void* cls_feat, const void* reg_feat, int32_t
                     const int32_t* level_len /* host */, void* stream);
 
 /* ---- video-level classifier tails ---- */
-/* exp12 (blocks.py:1608-1626): z [batch, t, C] (after the last DownBlock) -> logit [batch] */
-AVDF_API int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* lin1_w /* [C,2C] */,
+/* exp12 (blocks.py:1608-1626): z [batch, t <= 32, C] (after the last DownBlock) -> logit [batch]. The two dense
+ * weights are passed TRANSPOSED ([in, out]: conv0_wt[k][c] = conv0.weight[c][k], lin1_wt[j][c] = conv1.weight[c][j]). */
+AVDF_API int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_wt /* [C,C] */, const float* lin1_wt /* [2C,C] */,
                     const float* ln_w, const float* ln_b, const float* lin2_w /* [C] */, const float* lin2_b,
                     float* out, int32_t batch, int32_t t, int32_t channels, void* stream);
 /* exp13 (blocks.py:1682-1700): z [batch, t, C] -> logit [batch] */

@@ -461,7 +461,7 @@ def test_vcls_tails():
     h = torch.relu(model_ref.channel_ln((pooled @ w1.t()).unsqueeze(-1), lw, lb).squeeze(-1))
     want = h @ w2 + b2
     out = torch.zeros(B, device=DEV)
-    ops.vcls_exp12(dev(z), dev(w0), dev(w1), dev(lw), dev(lb), dev(w2), dev(b2), out, batch=B, t=T)
+    ops.vcls_exp12(dev(z), dev(w0.t().contiguous()), dev(w1.t().contiguous()), dev(lw), dev(lb), dev(w2), dev(b2), out, batch=B, t=T)
     assert rel_err(out.cpu(), want) < 2e-5
     T, C = 768, 64
     z = torch.from_numpy(rng.standard_normal((B, T, C)).astype(np.float32))
