@@ -35,6 +35,7 @@ struct Params {
   CUtensorMap w_map;
   CUtensorMap o32_map[AVDF_MAX_LEVELS];      // fp32 output, 3-D (n, t, video) per segment, box = one epilogue warp's 32 rows x 32 columns
   CUtensorMap o16_map[AVDF_MAX_LEVELS];      // 16-bit output copy
+  CUtensorMap o16w_map[AVDF_MAX_LEVELS];     // 16-bit output, 64-column box (32 rows x 128 B, swizzle 128B) for the wide epilogue pass
   CUtensorMap res_map[AVDF_MAX_LEVELS];      // residual (same geometry as the fp32 output)
   SegInfo seg;
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
@@ -209,15 +210,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   unsigned char* smem_b = smem + STAGES * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 10);
   float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024);
   float* stage_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024 + EPI_VEC_BYTES);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
-  const uint32_t bfull_bar = bar_base + 8u * (2 * MAX_STAGES + 4), bempty_bar = bar_base + 8u * (2 * MAX_STAGES + 5);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 4 + s); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * MAX_STAGES + 8), bempty_bar = bar_base + 8u * (2 * MAX_STAGES + 9);
+  // accumulator ring in TMEM: 4 x 128 columns for narrow tiles, 2 x 256 otherwise. A deeper ring lets the MMA warp run
+  // further ahead of the epilogue and hides the commit -> mbarrier -> tcgen05.ld hand-off latencies.
+  const int n_acc = p.bn <= 128 ? 4 : 2;
+  const int acc_cols = 512 / n_acc;
   const int n_stages = p.bstat ? BSTAT_STAGES : STAGES;
   // weight-stationary carve-up of the same 144 KB: [slab 64 KB][A ring 5 x 16 KB]
   unsigned char* slab = smem;
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(bfull_bar, 1); mbar_init(bempty_bar, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -305,11 +310,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
           }
           if (slab_id != cur_slab) { mbar_wait(bfull_bar, slab_seen & 1); ++slab_seen; cur_slab = slab_id; }
         }
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = it % n_acc;
+        const uint32_t acc_phase = (it / n_acc) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     float* s_part_base = epi_smem + 4 * MAX_BN;  // [tile parity][2 halves][128 rows][2] LayerNorm partial sums
     unsigned char* t32 = reinterpret_cast<unsigned char*>(stage_smem) + ew * 4096;          // fp32 result tile (swizzle 128B)
     unsigned char* trs = reinterpret_cast<unsigned char*>(stage_smem) + (8 + ew) * 4096;    // residual tile (swizzle 128B)
-    const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 7 + ew);                     // after the TMEM pointer slot
+    const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 11 + ew);                     // after the TMEM pointer slot
     const int chunks = p.bn >> 5;
     const int c_begin = h == 0 ? 0 : (chunks + 1) / 2, c_end = h == 0 ? (chunks + 1) / 2 : chunks;
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
@@ -391,9 +396,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         asm volatile("bar.sync 1, 256;" ::: "memory");
         loaded_n0 = vec0;
       }
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      float* s_part = s_part_base + acc * (2 * BM * 2);
+      const int acc = it % n_acc;
+      const uint32_t acc_phase = (it / n_acc) & 1;
+      float* s_part = s_part_base + (it & 1) * (2 * BM * 2);
       // my row (thread = row) and this warp's box origin inside the segment
       const int r = q * 32 + lane;
       const int b = tc_.b0 + r / tc_.tt;
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
       if (has_res && c_begin < c_end) fetch_residual(c_begin);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
       float mean = 0.f, rstd = 1.f;
       if (has_ln) {                               // row statistics over all bn columns: each half sums its chunks
         float s = 0.f, ss = 0.f;
@@ -437,6 +442,60 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
       if (c_begin == c_end) {                     // narrow tiles: this half owns no columns
         tcgen05_fence_before();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      // ---- wide pass (16-bit output only, no residual / PE): 64 columns per step halve the per-step fixed latencies
+      //      (TMEM wait, proxy fence, warp sync, TMA issue, store-read wait); the two 4 KB tiles alternate
+      constexpr bool WIDE_OK = MODE >= 0 && OUTK >= 0 && (OUTK & 3) == 2 && (MODE & 24) == 0;
+      if (WIDE_OK && ((c_end - c_begin) & 1) == 0 && c_end > c_begin) {
+        for (int ch = c_begin; ch < c_end; ch += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld32_issue(taddr + ch * 32, va);
+          tmem_ld32_issue(taddr + (ch + 1) * 32, vb);
+          tmem_ld_wait();
+          if (ch + 2 >= c_end) {                   // all TMEM reads of this warp done: release the accumulator
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          unsigned char* tw = (store_seq++ & 1) ? trs : t32;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cl = (ch + half) * 32;
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + cl);
+            const float4* w4 = reinterpret_cast<const float4*>(s_lnw + cl);
+            const float4* l4 = reinterpret_cast<const float4*>(s_lnb + cl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {          // 8 columns -> one 16-byte chunk of the 128 B row
+              float y[8];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const float4 bb = b4[2 * j + u];
+                const uint32_t* vv = half == 0 ? va : vb;
+                float x0 = (__uint_as_float(vv[8 * j + 4 * u]) + bb.x) * mk, x1 = (__uint_as_float(vv[8 * j + 4 * u + 1]) + bb.y) * mk;
+                float x2 = (__uint_as_float(vv[8 * j + 4 * u + 2]) + bb.z) * mk, x3 = (__uint_as_float(vv[8 * j + 4 * u + 3]) + bb.w) * mk;
+                if (has_ln) {
+                  const float4 ww = w4[2 * j + u], ll = l4[2 * j + u];
+                  x0 = fmaf((x0 - mean) * rstd, ww.x, ll.x); x1 = fmaf((x1 - mean) * rstd, ww.y, ll.y);
+                  x2 = fmaf((x2 - mean) * rstd, ww.z, ll.z); x3 = fmaf((x3 - mean) * rstd, ww.w, ll.w);
+                }
+                y[4 * u] = act_tc(x0, act); y[4 * u + 1] = act_tc(x1, act); y[4 * u + 2] = act_tc(x2, act); y[4 * u + 3] = act_tc(x3, act);
+              }
+              uint4 uo;
+              if (o16_f16) { uo.x = pack_f16x2(y[0], y[1]); uo.y = pack_f16x2(y[2], y[3]); uo.z = pack_f16x2(y[4], y[5]); uo.w = pack_f16x2(y[6], y[7]); }
+              else { uo.x = pack_bf16x2(y[0], y[1]); uo.y = pack_bf16x2(y[2], y[3]); uo.z = pack_bf16x2(y[4], y[5]); uo.w = pack_bf16x2(y[6], y[7]); }
+              *reinterpret_cast<uint4*>(tw + lane * 128 + (((half * 4 + j) ^ sw7) << 4)) = uo;
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&p.o16w_map[tc_.seg], smem_u32(tw), tc_.n0 + ch * 32, wt, wb);
+            tma_store_commit();
+          }
+        }
+        continue;                                   // next tile
       }
       uint32_t vr[32];                            // accumulator block of the current chunk (raw bits)
       if (c_begin < c_end) tmem_ld32_issue(taddr + c_begin * 32, vr);
@@ -630,6 +689,17 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
           {&p.o32_map[s], a->out_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B},
           {&p.o16_map[s], a->out_h, a->out_h_dtype == AVDF_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_64B},
           {&p.res_map[s], a->residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B}};
+      if (a->out_h && !a->out_f32 && bn % 64 == 0) {     // wide 16-bit box
+        cuuint64_t odims[3] = {(cuuint64_t)a->n_out, (cuuint64_t)T, (cuuint64_t)a->batch};
+        cuuint64_t ostr[2] = {(cuuint64_t)a->n_out * 2, (cuuint64_t)a->o_rows_per_video * a->n_out * 2};
+        cuuint32_t obox[3] = {64u, (cuuint32_t)tw, (cuuint32_t)bw};
+        cuuint32_t oes[3] = {1, 1, 1};
+        void* obase = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(a->out_h)) + (size_t)a->seg_o_row[s] * a->n_out * 2;
+        CUresult ro = encode(&p.o16w_map[s], a->out_h_dtype == AVDF_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                             obase, odims, ostr, obox, oes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (ro != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(wide output, level %d) failed with %d", s, (int)ro); return AVDF_ERR_CUDA; }
+      }
       for (int o = 0; o < 3; ++o) {
         if (!outs[o].base) continue;
         AVDF_CHECK_ARG((reinterpret_cast<uintptr_t>(outs[o].base) & 15) == 0, "outputs / residual must be 16-byte aligned");

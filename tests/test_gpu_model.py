@@ -123,3 +123,37 @@ def test_reference_style_driver(tmp_path):
     rec = json.load(open(tmp_path / "data_left.json"))
     assert [r["video_id"] for r in rec] == [it["video_id"] for it in items]
     assert all(set(r) == {"video_id", "video_cls", "scores", "segments"} for r in rec)
+
+
+def test_api_edge_cases():
+    """Empty list, more videos than max_batch (chunked), hard-NMS config, batched_nms front-end incl. multiclass."""
+    from audio_visual_deepfake_detection_b200.libs.utils import batched_nms
+    import nms_ref
+    from make_golden import sweep_inputs
+    model, use_video = build("exp12", "mixed")            # max_batch = 8
+    assert model([]) == []
+    durs = [4.5 + 0.7 * i for i in range(11)]
+    import interp_ref
+    items = [interp_ref.dataset_item(syn.synthetic_streams(d, 300 + i), d, f"e{i}") for i, d in enumerate(durs)]
+    out = model(items)                                     # 11 > max_batch: two chunks
+    assert [r["video_id"] for r in out] == [it["video_id"] for it in items]
+    solo = model([items[9]])[0]
+    assert torch.equal(solo["scores"], out[9]["scores"]) and torch.equal(solo["segments"], out[9]["segments"])
+    assert all(r["scores"].numel() <= model.test_max_seg_num for r in out)
+    assert all(bool((r["segments"] >= 0).all()) and bool((r["segments"][:, 1] <= d + 1e-4).all()) for r, d in zip(out, durs))
+    # batched_nms with the reference's signature, CPU tensors in / out
+    segs, sc = sweep_inputs(1512, 7000 + 1512)
+    s, p = torch.from_numpy(segs), torch.from_numpy(sc)
+    for soft in (False, True):
+        got = batched_nms(s, p, torch.zeros(1512, dtype=torch.long), 0.1, 0.2, 100, use_soft_nms=soft, multiclass=False,
+                          sigma=0.75, voting_thresh=0.9)
+        want = nms_ref.batched_nms(s, p, torch.zeros(1512, dtype=torch.long), 0.1, 0.2, 100, use_soft_nms=soft,
+                                   multiclass=False, sigma=0.75, voting_thresh=0.9)
+        assert got[0].device.type == "cpu" and got[2].dtype == torch.long
+        assert torch.equal(got[1], want[1])
+        np.testing.assert_allclose(got[0].numpy(), want[0].numpy().reshape(-1, 2), atol=1e-4)
+    labels = torch.from_numpy((np.arange(1512) % 3).astype(np.int64))
+    got = batched_nms(s, p, labels, 0.1, 0.2, 100, use_soft_nms=False, multiclass=True, sigma=0.75, voting_thresh=0.9)
+    want = nms_ref.batched_nms(s, p, labels, 0.1, 0.2, 100, use_soft_nms=False, multiclass=True, sigma=0.75, voting_thresh=0.9)
+    assert torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
+    np.testing.assert_allclose(got[0].numpy(), want[0].numpy().reshape(-1, 2), atol=1e-5)
