@@ -1,19 +1,25 @@
-// bf16 tensor-core path of avdf_conv_gemm for sm_100a: TMA-fed, warp-specialised, persistent
-// implicit-GEMM 1-D convolution on tcgen05 with the accumulator in TMEM and the whole
-// MaskedConv1D -> (+bias) -> mask -> LayerNorm -> activation -> (+PE) -> residual epilogue fused.
+// 16-bit tensor-core path of avdf_conv_gemm for sm_100a: TMA-fed, warp-specialised, persistent implicit-GEMM 1-D
+// convolution on tcgen05 with the accumulator in TMEM and the whole MaskedConv1D -> (+bias) -> mask -> LayerNorm ->
+// activation -> (+PE) -> gamma * x + residual epilogue fused.
 //
-// Tile: 128 output tokens x BN (<=256) output channels, K stepped in 64-channel blocks per tap.
-//   warp 0      TMA producer: A = 4-D box (64 ch, parity, TT steps, BB videos) of the token-major
-//               activation -- conv taps are shifted boxes, zero padding is TMA out-of-bounds fill,
-//               stride 2 is the parity dimension; W = 2-D box (64, BN) of the [N, taps*C] weights.
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM),
-//               tcgen05.commit releases smem stages / publishes the accumulator.
-//   warp 2      TMEM allocator (512 columns = two 256-column accumulators, double buffered).
-//   warps 4-11  epilogue: tcgen05.ld (32 lanes x 32 columns, thread = row), two passes over TMEM when LayerNorm
-//               is fused (row statistics, then normalise), 32x32 smem transpose per warp so that every global
-//               access (residual load, fp32 / 16-bit store) is one full 128 B / 64 B line per instruction.
-// smem ring: 3 stages x (16 KB A + 32 KB W), 128B-swizzled, mbarrier full/empty pairs.
+// Tile: 128 output tokens x BN output channels, K stepped in 64-channel blocks per tap. 256 threads:
+//   warp 0      TMA producer: A = 4-D box (64 ch, parity, TT steps, BB videos) of the token-major activation -- conv taps
+//               are shifted boxes, zero padding is TMA out-of-bounds fill, stride 2 is the parity dimension;
+//               W = 2-D box (64, BN) of the [N, taps*C] weights.
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16, bf16|fp16 -> fp32 in TMEM); tcgen05.commit
+//               releases smem stages / publishes the accumulator.
+//   warp 2      TMEM allocator.   warp 3 idle.
+//   warps 4-7   epilogue, one TMEM lane quarter each (thread = output row): tcgen05.ld -> math in registers ->
+//               swizzled smem tile -> TMA store; residual tiles arrive by TMA load. Global memory is touched by TMA only.
+// Two configurations of the same kernel:
+//   narrow (BN <= 128): 2 stages x (16 KB A + 16 KB W), 2 x 128 TMEM columns, ~103 KB smem, <= 128 registers
+//                       -> TWO CTAs per SM. The K=256 GEMMs that dominate the launch count are latency-bound per tile
+//                       (TMA -> MMA -> commit -> tcgen05.ld -> store is a chain of ~2 us); two independent tile
+//                       pipelines per SM overlap those chains.
+//   wide   (BN = 256):  3 stages x (16 KB A + 32 KB W), 2 x 256 TMEM columns, one CTA per SM (LayerNorm over the row
+//                       needs all 256 channels in one CTA; the big-K embedding GEMMs are MMA-bound).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 #include "gemm_common.cuh"
@@ -21,14 +27,16 @@
 namespace avdf {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, STAGES = 3, MAX_BN = 256;
-constexpr int BSTAT_STAGES = 5, MAX_STAGES = 5, BSTAT_SLAB = 65536;   // weight-stationary: 64 KB slab + 5 x 16 KB A stages = the same 144 KB
+constexpr int BM = 128, BK = 64, MAX_BN = 256, MAX_STAGES = 3;
 constexpr int A_STAGE = BM * BK * 2;          // 16384
-constexpr int B_STAGE = MAX_BN * BK * 2;      // 32768
-constexpr int EPI_VEC_BYTES = 4 * MAX_BN * 4 + 2 * 2 * BM * 2 * 4;   // bias / ln_w / ln_b / gamma + double-buffered LayerNorm partial sums (8 KB)
-constexpr int STAGE_TILE_BYTES = 16 * 32 * 32 * 4;               // per epilogue warp: a 32x32 fp32 result tile + a residual tile (TMA, 128B swizzle)
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*barriers*/ + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024 /*align slack*/;
-constexpr int THREADS = 384;                                     // 4 control warps + 8 epilogue warps
+constexpr int EPI_VEC_BYTES = 4 * MAX_BN * 4; // bias / ln_w / ln_b / gamma of the current n-tile
+constexpr int STAGE_TILE_BYTES = 4 * 2 * 4096;   // per epilogue warp: a 4 KB result tile + a 4 KB residual / second result tile
+constexpr int THREADS = 256;                  // 4 control warps + 4 epilogue warps
+__host__ __device__ constexpr int n_stages_of(int bn) { return bn <= 128 ? 2 : 3; }
+__host__ __device__ constexpr int b_stage_of(int bn) { return (bn <= 128 ? 128 : 256) * BK * 2; }
+__host__ __device__ constexpr int smem_bytes_of(int bn) {
+  return n_stages_of(bn) * (A_STAGE + b_stage_of(bn)) + 1024 /*barriers*/ + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024 /*align slack*/;
+}
 
 struct Params {
   CUtensorMap a_map[AVDF_MAX_LEVELS];
@@ -41,7 +49,6 @@ struct Params {
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
   int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
   int n_out, c_in, taps, stride, bn, n_tiles_n, n_tiles_m, total_tiles;
-  int bstat;                                 // weight-stationary mode: the whole [bn, K] weight slab stays in smem, only A streams
   unsigned idesc;
   EpiParams epi;
   unsigned long long* dbg;                   // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
@@ -196,37 +203,33 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
 }
 
 // MODE >= 0 fixes the epilogue variant at compile time (bit 0 LayerNorm, bits 1-2 activation, bit 3 residual,
-// bit 4 positional encoding) so the row loop carries no dead branches; MODE < 0 reads the flags at run time.
+// bit 4 positional encoding) so the epilogue carries no dead branches; MODE < 0 reads the flags at run time.
 constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (pe ? 16 : 0); }
 
 // OUTK >= 0 fixes which outputs exist: bit 0 fp32, bit 1 16-bit copy, bit 2 the 16-bit copy is fp16 (else bf16).
 template <int MODE, int OUTK>
-__global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024 B alignment for the 128B swizzle atoms (an offset into the array keeps the shared address space visible
   // to the compiler: LDS/STS instead of generic loads)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int n_stages = n_stages_of(p.bn);
+  const int b_stage = b_stage_of(p.bn);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + STAGES * A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
-  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 10);
-  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024);
-  float* stage_smem = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE) + 1024 + EPI_VEC_BYTES);
+  unsigned char* smem_b = smem + n_stages * A_STAGE;
+  unsigned char* after = smem + n_stages * (A_STAGE + b_stage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after);
+  // bars: full[3], empty[3], tmem_full[2], tmem_empty[2], tmem ptr, residual[4]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  float* epi_smem = reinterpret_cast<float*>(after + 1024);
+  unsigned char* stage_smem = after + 1024 + EPI_VEC_BYTES;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 4 + s); };
-  const uint32_t bfull_bar = bar_base + 8u * (2 * MAX_STAGES + 8), bempty_bar = bar_base + 8u * (2 * MAX_STAGES + 9);
-  // accumulator ring in TMEM: 4 x 128 columns for narrow tiles, 2 x 256 otherwise. A deeper ring lets the MMA warp run
-  // further ahead of the epilogue and hides the commit -> mbarrier -> tcgen05.ld hand-off latencies.
-  const int n_acc = p.bn <= 128 ? 4 : 2;
-  const int acc_cols = 512 / n_acc;
-  const int n_stages = p.bstat ? BSTAT_STAGES : STAGES;
-  // weight-stationary carve-up of the same 144 KB: [slab 64 KB][A ring 5 x 16 KB]
-  unsigned char* slab = smem;
-  if (p.bstat) smem_a = smem + BSTAT_SLAB;
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+  const int acc_cols = p.bn <= 128 ? 128 : 256;      // two accumulators: 256 or 512 TMEM columns per CTA
+  const uint32_t tmem_cols = 2u * acc_cols;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) AVDF_TS(0);
@@ -238,12 +241,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(bfull_bar, 1); mbar_init(bempty_bar, 1);
-    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -260,26 +262,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      int cur_slab = -1, slab_loads = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc_ = decode_tile(p, tile);
-        if (p.bstat) {
-          const int slab_id = tc_.n0 + p.seg.w_row[tc_.seg];
-          if (slab_id != cur_slab) {               // (re)load the weight slab: all k-blocks of this n-tile
-            if (slab_loads > 0) mbar_wait(bempty_bar, (slab_loads - 1) & 1);   // MMAs reading the old slab are done
-            mbar_arrive_expect_tx(bfull_bar, (uint32_t)k_iters * p.bn * BK * 2);
-            for (int ki = 0; ki < k_iters; ++ki)
-              tma_load_2d(smem_u32(slab + (size_t)ki * p.bn * BK * 2), &p.w_map, bfull_bar, ki * BK, slab_id);
-            cur_slab = slab_id; ++slab_loads;
-          }
-          for (int ki = 0; ki < k_iters; ++ki) {   // taps == 1 in this mode: A is a plain [rows, K] stream
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_arrive_expect_tx(full_bar(stage), A_STAGE);
-            tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), ki * BK, 0, tc_.t0, tc_.b0);
-            if (++stage == n_stages) { stage = 0; phase ^= 1; }
-          }
-          continue;
-        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int d = tap - (p.taps >> 1);
           int par = 0, dt = d;
@@ -288,7 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
             tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), kb * BK, par, tc_.t0 + dt, tc_.b0);
-            tma_load_2d(smem_u32(smem_b + stage * B_STAGE), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
+            tma_load_2d(smem_u32(smem_b + stage * b_stage), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -298,63 +282,42 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
-      int cur_slab = -1, slab_seen = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        int slab_id = -1, next_slab = -1;
-        if (p.bstat) {
-          const TileCoord tc_ = decode_tile(p, tile);
-          slab_id = tc_.n0 + p.seg.w_row[tc_.seg];
-          if (tile + (int)gridDim.x < p.total_tiles) {
-            const TileCoord nx = decode_tile(p, tile + gridDim.x);
-            next_slab = nx.n0 + p.seg.w_row[nx.seg];
-          }
-          if (slab_id != cur_slab) { mbar_wait(bfull_bar, slab_seen & 1); ++slab_seen; cur_slab = slab_id; }
-        }
-        const int acc = it % n_acc;
-        const uint32_t acc_phase = (it / n_acc) & 1;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
         for (int ki = 0; ki < k_iters; ++ki) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          if (it == 0 && ki == 0) AVDF_TS(2);
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * A_STAGE));
-          const uint64_t db = make_sw128_desc(p.bstat ? smem_u32(slab + (size_t)ki * p.bn * BK * 2) : smem_u32(smem_b + stage * B_STAGE));
+          const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * b_stage));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)          // +32 B per K=16 step inside the swizzle atom
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (ki == k_iters - 1) {
-            umma_commit(tfull_bar(acc));
-            if (p.bstat && next_slab != -1 && next_slab != slab_id) umma_commit(bempty_bar);   // slab free once these MMAs retire
-            if (it == 0) AVDF_TS(3);
-          }
+          if (ki == k_iters - 1) umma_commit(tfull_bar(acc));
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- epilogue: 8 warps
-    // warp e = warp - 4: TMEM lane quarter q = warp & 3 (rows 32q .. 32q+31 of the tile), column half h = e >> 2.
-    // The math runs in the layout tcgen05.ld delivers (thread = output row, 32 consecutive columns in registers):
+    // ---------------------------------------------------------------- epilogue: 4 warps, warp q owns TMEM lanes / tile rows 32q .. 32q+31
+    // The math runs in the layout tcgen05.ld delivers (thread = output row, 32 consecutive columns per load):
     // per-row quantities (mask, LayerNorm mean / rstd) are plain registers, per-column vectors are broadcast
-    // LDS.128. Global memory is touched only by TMA: the residual block of the next chunk is prefetched into a
-    // 128B-swizzled smem tile (mbarrier), results are written to swizzled smem tiles and leave with
-    // cp.async.bulk.tensor stores (3-D box = this warp's 32 rows x 32 columns; rows beyond the batch are clipped by
-    // the tensor map). No per-row address arithmetic, no transposition, no per-lane global accesses.
+    // LDS.128. Results go to 128B/64B-swizzled smem tiles and leave with cp.async.bulk.tensor stores (3-D box =
+    // this warp's 32 rows x 32 or 64 columns; rows beyond the batch are clipped by the tensor map); the residual
+    // block of the next chunk is prefetched by TMA into a swizzled tile (mbarrier).
     const EpiParams& e = p.epi;
-    const int ew = warp - 4;
-    const int q = warp & 3, h = ew >> 2;
+    const int q = warp - 4;
     const int N = p.n_out;
-    const int et = threadIdx.x - 128;            // 0..255 among the epilogue threads
+    const int et = threadIdx.x - 128;            // 0..127 among the epilogue threads
     float* s_bias = epi_smem; float* s_lnw = epi_smem + MAX_BN; float* s_lnb = epi_smem + 2 * MAX_BN; float* s_gam = epi_smem + 3 * MAX_BN;
-    float* s_part_base = epi_smem + 4 * MAX_BN;  // [tile parity][2 halves][128 rows][2] LayerNorm partial sums
-    unsigned char* t32 = reinterpret_cast<unsigned char*>(stage_smem) + ew * 4096;          // fp32 result tile (swizzle 128B)
-    unsigned char* trs = reinterpret_cast<unsigned char*>(stage_smem) + (8 + ew) * 4096;    // residual tile (swizzle 128B)
-    const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 11 + ew);                     // after the TMEM pointer slot
+    unsigned char* t32 = stage_smem + q * 8192;          // result tile (fp32: swizzle 128B)
+    unsigned char* trs = stage_smem + q * 8192 + 4096;   // residual tile / second result tile
+    const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 5 + q);
     const int chunks = p.bn >> 5;
-    const int c_begin = h == 0 ? 0 : (chunks + 1) / 2, c_end = h == 0 ? (chunks + 1) / 2 : chunks;
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
     const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
     const bool has_pe = MODE < 0 ? (e.pe != nullptr) : ((MODE & 16) != 0);
@@ -362,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     const bool has32 = OUTK < 0 ? (e.out_f32 != nullptr) : ((OUTK & 1) != 0);
     const bool has16 = OUTK < 0 ? (e.out_h != nullptr) : ((OUTK & 2) != 0);
     const bool o16_f16 = OUTK < 0 ? (e.out_h_f16 != 0) : ((OUTK & 4) != 0);
-    // 16-bit result tile (swizzle 64B): shares the fp32 tile when there is no fp32 output, else the residual tile
+    // 16-bit result tile (32 columns: swizzle 64B): shares the fp32 tile when there is no fp32 output, else the residual tile
     unsigned char* t16 = has32 ? trs : t32;
     const int sw7 = lane & 7;                    // 128B swizzle: 16-byte chunk j of row `lane` lives in slot j ^ (lane & 7)
     const int sw3 = (lane >> 1) & 3;             // 64B swizzle: chunk j of row `lane` lives in slot j ^ ((lane >> 1) & 3)
@@ -386,19 +349,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
       const TileCoord tc_ = decode_tile(p, tile);
       const int vec0 = tc_.n0 + p.seg.w_row[tc_.seg];   // first entry of this tile's per-channel vectors
       if (vec0 != loaded_n0) {                   // per-channel epilogue vectors of this n-tile -> smem
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = et; i < p.bn; i += 256) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < p.bn; i += 128) {
           s_bias[i] = e.bias ? __ldg(e.bias + vec0 + i) : 0.f;
           s_lnw[i] = e.ln_w ? __ldg(e.ln_w + vec0 + i) : 1.f;
           s_lnb[i] = e.ln_b ? __ldg(e.ln_b + vec0 + i) : 0.f;
           s_gam[i] = e.gamma ? __ldg(e.gamma + vec0 + i) : 1.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         loaded_n0 = vec0;
       }
-      const int acc = it % n_acc;
-      const uint32_t acc_phase = (it / n_acc) & 1;
-      float* s_part = s_part_base + (it & 1) * (2 * BM * 2);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
       // my row (thread = row) and this warp's box origin inside the segment
       const int r = q * 32 + lane;
       const int b = tc_.b0 + r / tc_.tt;
@@ -413,14 +375,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
           tma_load_3d(smem_u32(trs), &p.res_map[tc_.seg], res_bar, tc_.n0 + ch * 32, wt, wb);
         }
       };
-      if (has_res && c_begin < c_end) fetch_residual(c_begin);
+      if (has_res) fetch_residual(0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
       float mean = 0.f, rstd = 1.f;
-      if (has_ln) {                               // row statistics over all bn columns: each half sums its chunks
+      if (has_ln) {                               // row statistics over all bn columns (this thread owns the whole row)
         float s = 0.f, ss = 0.f;
-        for (int ch = c_begin; ch < c_end; ++ch) {
+        for (int ch = 0; ch < chunks; ++ch) {
           float v[32];
           tmem_ld32(taddr + ch * 32, v);
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + ch * 32);
@@ -432,27 +394,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
             ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
           }
         }
-        s_part[(h * 128 + r) * 2] = s; s_part[(h * 128 + r) * 2 + 1] = ss;
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        s += s_part[((h ^ 1) * 128 + r) * 2]; ss += s_part[((h ^ 1) * 128 + r) * 2 + 1];
         mean = s / (float)p.bn;
         const float var = fmaxf(ss / (float)p.bn - mean * mean, 0.f);
         rstd = rsqrtf(var + 1e-5f);
       }
-      if (c_begin == c_end) {                     // narrow tiles: this half owns no columns
-        tcgen05_fence_before();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-      }
       // ---- wide pass (16-bit output only, no residual / PE): 64 columns per step halve the per-step fixed latencies
       //      (TMEM wait, proxy fence, warp sync, TMA issue, store-read wait); the two 4 KB tiles alternate
       constexpr bool WIDE_OK = MODE >= 0 && OUTK >= 0 && (OUTK & 3) == 2 && (MODE & 24) == 0;
-      if (WIDE_OK && ((c_end - c_begin) & 1) == 0 && c_end > c_begin) {
-        for (int ch = c_begin; ch < c_end; ch += 2) {
+      if (WIDE_OK && (chunks & 1) == 0) {
+        for (int ch = 0; ch < chunks; ch += 2) {
           uint32_t va[32], vb[32];
           tmem_ld32_issue(taddr + ch * 32, va);
           tmem_ld32_issue(taddr + (ch + 1) * 32, vb);
           tmem_ld_wait();
-          if (ch + 2 >= c_end) {                   // all TMEM reads of this warp done: release the accumulator
+          if (ch + 2 >= chunks) {                  // all TMEM reads of this warp done: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -498,17 +453,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         continue;                                   // next tile
       }
       uint32_t vr[32];                            // accumulator block of the current chunk (raw bits)
-      if (c_begin < c_end) tmem_ld32_issue(taddr + c_begin * 32, vr);
-      for (int ch = c_begin; ch < c_end; ++ch) {
+      tmem_ld32_issue(taddr, vr);
+      for (int ch = 0; ch < chunks; ++ch) {
         tmem_ld_wait();
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vr[i]);
-        if (ch + 1 < c_end) {
+        if (ch + 1 < chunks) {
           tmem_ld32_issue(taddr + (ch + 1) * 32, vr);   // next block's TMEM read overlaps this block's math
         } else {                                  // all TMEM reads of this warp are issued: once they complete the
-          tmem_ld_wait();                         // MMA warp may overwrite the accumulator
-          tcgen05_fence_before();
+          tcgen05_fence_before();                 // MMA warp may overwrite the accumulator
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
@@ -555,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
         }
         // the previous chunk's TMA stores must have finished READING the tiles before they are overwritten
         unsigned char* t16c = t16;
-        if (!has32) {                               // 16-bit only: alternate halves, allow one store in flight
+        if (!has32) {                               // 16-bit only: alternate halves of the 4 KB tile, one store may stay in flight
           t16c = t32 + ((store_seq++ & 1) << 11);
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         } else {
@@ -588,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
           if (has16) tma_store_3d(&p.o16_map[tc_.seg], smem_u32(t16c), tc_.n0 + cl, wt, wb);
           tma_store_commit();
         }
-        if (has_res && ch + 1 < c_end) {          // next chunk's residual; if the 16-bit tile aliases the residual
+        if (has_res && ch + 1 < chunks) {         // next chunk's residual; if the 16-bit tile aliases the residual
           if (has16 && has32) {                   // tile, its store must have read it first
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -603,13 +557,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_tc_kernel(const __grid_c
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
-  if (warp == 4) AVDF_TS(5);
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) AVDF_TS(6);
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -638,11 +590,10 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   using namespace tc;
   AVDF_CHECK_ARG(a->c_in % BK == 0, "bf16 path: c_in must be a multiple of 64");
   AVDF_CHECK_ARG(a->n_out % 32 == 0, "bf16 path: n_out must be a multiple of 32");
-  // N tile: 256 (LayerNorm needs the whole row in one CTA; wide outputs), 128 for plain 256-wide outputs so that
-  // 24576-row problems give 384 tiles (2.6 waves on 148 SMs instead of 1.3)
-  // weight-stationary candidates: 1x1 GEMMs whose [128, K] weight slab fits 64 KB (K <= 256: q/k/v, proj, MLP up, FPN laterals)
-  const bool want_bstat = a->taps == 1 && a->stride == 1 && !a->ln_w && a->n_out % 128 == 0 && (long long)a->c_in * 128 * 2 <= BSTAT_SLAB;
-  const int bn = want_bstat ? 128 : (a->n_out > MAX_BN ? MAX_BN : (a->n_out == MAX_BN ? (a->ln_w ? MAX_BN : 128) : a->n_out));
+  // N tile: 256 only where LayerNorm needs the whole row in one CTA; everything else uses the narrow configuration
+  // (BN <= 128, two CTAs per SM)
+  // (BN <= 128, two CTAs per SM). (A 256-wide tile for the K = 1024 MLP-down GEMM was measured: 31.4 vs 29.9 us, no gain.)
+  const int bn = a->ln_w ? (a->n_out >= MAX_BN ? MAX_BN : a->n_out) : (a->n_out % 128 == 0 ? 128 : (a->n_out > MAX_BN ? MAX_BN : a->n_out));
   AVDF_CHECK_ARG(a->n_out % bn == 0, "bf16 path: n_out must be <= 256 or a multiple of 256");
   AVDF_CHECK_ARG(bn % 16 == 0 && bn >= 32, "bf16 path: unsupported n_out");
   AVDF_CHECK_ARG(!a->ln_w || a->n_out == bn, "bf16 path: fused LayerNorm needs n_out <= 256");
@@ -660,7 +611,6 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   p.dbg = g_dbg;
   p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.bn = bn;
   p.n_tiles_n = a->n_out / bn;
-  p.bstat = (a->taps == 1 && a->stride == 1 && (long long)a->c_in * bn * 2 <= BSTAT_SLAB) ? 1 : 0;
   int tiles = 0;
   for (int s = 0; s < a->n_seg; ++s) {
     const int T = a->seg_t_out[s];
@@ -746,20 +696,22 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     X(mode_of(false, AVDF_ACT_GELU, false, false), 6) X(mode_of(false, AVDF_ACT_GELU, false, false), 2)           \
     X(mode_of(true, AVDF_ACT_RELU, false, false), 6) X(mode_of(true, AVDF_ACT_RELU, false, false), 2)             \
     X(mode_of(true, AVDF_ACT_RELU, false, false), 1) X(mode_of(true, AVDF_ACT_RELU, false, true), 1)
-#define AVDF_SET_SMEM(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#define AVDF_SET_SMEM(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(MAX_BN)));
     AVDF_SET_SMEM(-1, -1)
     AVDF_TC_VARIANTS(AVDF_SET_SMEM)
 #undef AVDF_SET_SMEM
   }
   AVDF_CHECK_ARG((long long)a->batch * a->o_rows_per_video * a->n_out < (1ll << 31), "output larger than 2^31 elements");
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int ctas_per_sm = bn <= 128 ? 2 : 1;      // narrow tiles: two co-resident CTAs per SM
+  const int grid = p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm;
+  const int smem_bytes = smem_bytes_of(bn);
   const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr);
   const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
   bool launched = false;
-#define AVDF_LAUNCH(M, O) if (!launched && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, SMEM_BYTES, st>>>(p); launched = true; }
+#define AVDF_LAUNCH(M, O) if (!launched && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
   AVDF_TC_VARIANTS(AVDF_LAUNCH)
 #undef AVDF_LAUNCH
-  if (!launched) conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  if (!launched) conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, smem_bytes, st>>>(p);
   return check_launch("conv_gemm_tc_kernel");
 }
 
