@@ -170,7 +170,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "videos/s", "cores": threads, "kind": "port",
                              "sample": "%d videos per step, oracle/model_ref.py + oracle/nms_ref.c, torch CPU fp32" % n},
             "e2e": {"value": v, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -327,7 +327,7 @@ def run_ours(args):
                 kv["hbm_frac"] = kv["gbs"] / peak_gbs
         traffic = None
         try:        # DRAM bytes per launch of the GEMM kernel from the committed ncu pass (profiles/), not measured live
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_c_step_traffic.json")))["kernels"]["tc::conv_gemm_tc_kernel"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_e_step_traffic.json")))["kernels"]["tc::conv_gemm_tc_kernel"]
             traffic = (tj["dram_read_bytes_per_step"] + tj["dram_write_bytes_per_step"]) / tj["launches_per_step"]
         except Exception:
             pass
@@ -336,7 +336,7 @@ def run_ours(args):
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach / peak_tf, "traffic": traffic,
-                    "traffic_note": "mean DRAM read+write bytes per launch, ncu pass profiles/r1_c_ncu_step_launches.csv (audio workload)",
+                    "traffic_note": "mean DRAM read+write bytes per launch, ncu pass profiles/r1_e_ncu_step_launches.csv (audio workload)",
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"],
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     "launches_per_step": g["n"] / psteps, "avg_launch_us": 1000.0 * g["ms"] / g["n"],
@@ -361,10 +361,31 @@ def run_ours(args):
             v, dt_cpu = cpu_reference(args.workload, args.ref_videos, threads)
             line["cpu_baseline"] = {"value": v, "unit": "videos/s", "cores": threads, "kind": "port",
                                     "sample": "%d videos (%.1f s), oracle/model_ref.py + oracle/nms_ref.c, torch CPU fp32, B=1 per call" % (args.ref_videos, dt_cpu)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) is re-routed to stderr; the one JSON line goes
+    to the original stdout through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -377,7 +398,7 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "fp32"])
     ap.add_argument("--ref-videos", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=3, help="batches in flight at once (each on its own stream and buffer set)")
+    ap.add_argument("--lanes", type=int, default=4, help="batches in flight at once (each on its own stream and buffer set)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event timings of one step to this json")
     args = ap.parse_args()
@@ -387,6 +408,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
                "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
