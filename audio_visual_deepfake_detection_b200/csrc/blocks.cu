@@ -98,6 +98,12 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
       for (int k = 0; k < 8; ++k) xh[j][k] = 0.f;
     // software pipeline: the source rows of positions pos + 1 .. pos + LDL_DEPTH - 1 are in flight (cp.async into a
     // per-warp smem ring; every lane copies and later reads its own 32 bytes, so no cross-lane synchronisation)
+    // the tile's mask bytes, one per lane, fetched once (a per-row byte load sat on the critical path of every row)
+    unsigned tile_mask = 0xffffffffu;
+    if (p.mask_out) {
+      const bool mbit = (t0 + lane < t1) ? (p.mask_out[(size_t)b * p.t_out + t0 + lane] != 0) : true;
+      tile_mask = __ballot_sync(0xffffffffu, mbit);
+    }
     const int pos_first = STRIDE * t0 - 1, pos_last = STRIDE * (t1 - 1) + 1;
     const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[warp][0][c0]);
     auto issue = [&](int pos) {
@@ -125,9 +131,16 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
 #pragma unroll
         for (int k = 0; k < 8; ++k) { rw[0][k] = rw[STRIDE == 2 ? 1 : 0][k]; rw[STRIDE == 2 ? 1 : 0][k] = rw[STRIDE == 2 ? 2 : 0][k]; rw[STRIDE == 2 ? 2 : 0][k] = nxt[k]; }
       }
-      if (ok[2]) {
-        float mean, rstd;
-        row_stats(nxt, mean, rstd);
+      if (ok[2]) {                                // input LayerNorm: shifted single pass - sum and sum of squares of
+        const float pivot = __shfl_sync(0xffffffffu, nxt[0], 0);   // (x - pivot) share the 5 shuffle steps
+        float su = 0.f, sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = nxt[k] - pivot; su += d; sq = fmaf(d, d, sq); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { su += __shfl_xor_sync(0xffffffffu, su, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        const float dm = su * (1.f / kC);
+        const float rstd = 1.f / sqrtf(fmaxf(sq * (1.f / kC) - dm * dm, 0.f) + kLnEps);
+        const float mean = pivot + dm;
 #pragma unroll
         for (int k = 0; k < 8; ++k) xh[2][k] = (nxt[k] - mean) * rstd;
       }
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
       const int t = t0 + rel / STRIDE;          // output row whose taps are window[0..2]
       const size_t orow = (size_t)b * p.t_out + t;              // dense row: mask / skip
       const size_t srow = (size_t)b * p.out_rows + t;           // row in the (possibly interleaved) output buffers
-      const bool keep = p.mask_out ? (p.mask_out[orow] != 0) : true;
+      const bool keep = (tile_mask >> (t - t0)) & 1u;
       const bool interior = ok[0] && ok[2];                      // ok[1] always holds for an output row
       float acc[NS][8];
 #pragma unroll

@@ -67,7 +67,9 @@ class StreamRunner:
         self.eng = model.engine()
         self.slots = [_Slot(self, i) for i in range(n_slots)]
         self.next = 0
-        self.pool = ThreadPoolExecutor(max_workers=n_threads or min(16, os.cpu_count() or 4))
+        # copy workers: the host cores are shared by the ranks of a node (torchrun exports LOCAL_WORLD_SIZE)
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        self.pool = ThreadPoolExecutor(max_workers=n_threads or max(4, min(16, (os.cpu_count() or 4) // local_world)))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.use_graph = True
