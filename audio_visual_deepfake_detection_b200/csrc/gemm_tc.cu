@@ -176,6 +176,35 @@ __device__ __forceinline__ float gelu_fast(float x) {
   // 0.5 x (1 + erf(x/sqrt2)) = x - 0.5 x erfc(z) for x >= 0, 0.5 x erfc(z) for x < 0
   return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
 }
+// the same on a packed pair: 11 packed FP ops + 4 MUFU + selects per TWO elements
+__device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
+  const f32x2 ax = x & 0x7fffffff7fffffffull;
+  const f32x2 z = mul2(ax, pk2(0.70710678118654752440f));
+  float d0, d1, t0, t1, e0, e1;
+  upk2(fma2(pk2(0.3275911f), z, pk2(1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  upk2(mul2(mul2(z, z), pk2(-1.4426950408889634f)), d0, d1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(d0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(d1));
+  const f32x2 t = pk2(t0, t1);
+  f32x2 poly = fma2(pk2(1.061405429f), t, pk2(-1.453152027f));
+  poly = fma2(poly, t, pk2(1.421413741f));
+  poly = fma2(poly, t, pk2(-0.284496736f));
+  poly = fma2(poly, t, pk2(0.254829592f));
+  const f32x2 erfc_z = mul2(mul2(poly, t), pk2(e0, e1));
+  const f32x2 hx = mul2(x, pk2(0.5f));
+  const f32x2 neg = mul2(hx, erfc_z);                   // x < 0:  0.5 x erfc(z)
+  const f32x2 pos = add2(x, neg ^ 0x8000000080000000ull);   // x >= 0: x - 0.5 x erfc(z)
+  float x0, x1, p0, p1, n0, n1;
+  upk2(x, x0, x1); upk2(pos, p0, p1); upk2(neg, n0, n1);
+  return pk2(x0 >= 0.f ? p0 : n0, x1 >= 0.f ? p1 : n1);
+}
+__device__ __forceinline__ f32x2 act_tc2(f32x2 v, int act) {
+  if (act == AVDF_ACT_RELU) { float a, b; upk2(v, a, b); return pk2(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
+  if (act == AVDF_ACT_GELU) return gelu_fast2(v);
+  return v;
+}
 __device__ __forceinline__ float act_tc(float v, int act) {
   if (act == AVDF_ACT_RELU) return fmaxf(v, 0.f);
   if (act == AVDF_ACT_GELU) return gelu_fast(v);
@@ -413,6 +442,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
           unsigned char* tw = (store_seq++ & 1) ? trs : t32;
+          const f32x2 mk2 = pk2(mk), nmean2 = pk2(-mean), rstd2 = pk2(rstd);
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -422,24 +452,30 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
             const float4* w4 = reinterpret_cast<const float4*>(s_lnw + cl);
             const float4* l4 = reinterpret_cast<const float4*>(s_lnb + cl);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {          // 8 columns -> one 16-byte chunk of the 128 B row
-              float y[8];
+            for (int j = 0; j < 4; ++j) {          // 8 columns -> one 16-byte chunk of the 128 B row; packed fp32 pairs
+              const uint32_t* vv = half == 0 ? va : vb;
+              f32x2 y[4];
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
                 const float4 bb = b4[2 * j + u];
-                const uint32_t* vv = half == 0 ? va : vb;
-                float x0 = (__uint_as_float(vv[8 * j + 4 * u]) + bb.x) * mk, x1 = (__uint_as_float(vv[8 * j + 4 * u + 1]) + bb.y) * mk;
-                float x2 = (__uint_as_float(vv[8 * j + 4 * u + 2]) + bb.z) * mk, x3 = (__uint_as_float(vv[8 * j + 4 * u + 3]) + bb.w) * mk;
+                f32x2 xa = mul2(add2(pk2(__uint_as_float(vv[8 * j + 4 * u]), __uint_as_float(vv[8 * j + 4 * u + 1])), pk2(bb.x, bb.y)), mk2);
+                f32x2 xb = mul2(add2(pk2(__uint_as_float(vv[8 * j + 4 * u + 2]), __uint_as_float(vv[8 * j + 4 * u + 3])), pk2(bb.z, bb.w)), mk2);
                 if (has_ln) {
                   const float4 ww = w4[2 * j + u], ll = l4[2 * j + u];
-                  x0 = fmaf((x0 - mean) * rstd, ww.x, ll.x); x1 = fmaf((x1 - mean) * rstd, ww.y, ll.y);
-                  x2 = fmaf((x2 - mean) * rstd, ww.z, ll.z); x3 = fmaf((x3 - mean) * rstd, ww.w, ll.w);
+                  xa = fma2(mul2(add2(xa, nmean2), rstd2), pk2(ww.x, ww.y), pk2(ll.x, ll.y));
+                  xb = fma2(mul2(add2(xb, nmean2), rstd2), pk2(ww.z, ww.w), pk2(ll.z, ll.w));
                 }
-                y[4 * u] = act_tc(x0, act); y[4 * u + 1] = act_tc(x1, act); y[4 * u + 2] = act_tc(x2, act); y[4 * u + 3] = act_tc(x3, act);
+                y[2 * u] = act_tc2(xa, act); y[2 * u + 1] = act_tc2(xb, act);
               }
               uint4 uo;
-              if (o16_f16) { uo.x = pack_f16x2(y[0], y[1]); uo.y = pack_f16x2(y[2], y[3]); uo.z = pack_f16x2(y[4], y[5]); uo.w = pack_f16x2(y[6], y[7]); }
-              else { uo.x = pack_bf16x2(y[0], y[1]); uo.y = pack_bf16x2(y[2], y[3]); uo.z = pack_bf16x2(y[4], y[5]); uo.w = pack_bf16x2(y[6], y[7]); }
+              float f0, f1;
+              if (o16_f16) {
+                upk2(y[0], f0, f1); uo.x = pack_f16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_f16x2(f0, f1);
+                upk2(y[2], f0, f1); uo.z = pack_f16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_f16x2(f0, f1);
+              } else {
+                upk2(y[0], f0, f1); uo.x = pack_bf16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_bf16x2(f0, f1);
+                upk2(y[2], f0, f1); uo.z = pack_bf16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_bf16x2(f0, f1);
+              }
               *reinterpret_cast<uint4*>(tw + lane * 128 + (((half * 4 + j) ^ sw7) << 4)) = uo;
             }
           }
