@@ -129,6 +129,9 @@ class _LocalizationBase(nn.Module):
     def forward(self, video_list):
         if self.training:
             raise NotImplementedError("training (losses / label assignment) is outside the accelerated inference path")
+        if len(video_list) and "feats" not in video_list[0] and "streams" in video_list[0]:
+            # items of the inference datasets of this package: raw streams, resampled on the GPU
+            return self.forward_streams(video_list)
         out = []
         for i in range(0, len(video_list), self.max_batch):
             out.extend(self._forward_items(video_list[i:i + self.max_batch]))
