@@ -101,3 +101,39 @@ def test_dataset_to_model_matches_reference_items(tmp_path):
     assert torch.equal(full["feats"], ref_item["feats"])              # bit-exact interpolation
     want = model([ref_item])[0]
     assert torch.equal(got[1]["scores"], want["scores"]) and torch.equal(got[1]["segments"], want["segments"])
+
+
+@pytest.mark.gpu
+def test_inference_cli_end_to_end(tmp_path):
+    """`python inference.py cfg sub_index ckpt --merge` on a synthetic corpus: the reference's CLI contract."""
+    import subprocess
+    import sys
+    import yaml
+    from audio_visual_deepfake_detection_b200.libs.core import load_config_for
+    from audio_visual_deepfake_detection_b200.libs.modeling import EXP12
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    durs = [4.03, 5.5, 7.42, 9.04, 6.2]
+    folders = write_corpus(str(tmp_path / "data"), durs)
+    cfg = yaml.load(open(os.path.join(root, "configs", "deepfake_exp12_test.yaml")), Loader=yaml.FullLoader)
+    cfg["dataset"].update(video_feat_folder=folders["video"], audio_byola_feat_folder=folders["byola"],
+                          audio_emo_feat_folder=folders["emo"], test_folder=folders["lists"])
+    cfg["loader"] = {"batch_size": 1, "num_workers": 0}
+    cfg_path = str(tmp_path / "cfg.yaml")
+    yaml.dump(cfg, open(cfg_path, "w"))
+    full = load_config_for(EXP12)
+    sd = syn.synthetic_state_dict(full["model"], EXP12, seed=0)
+    ckpt = str(tmp_path / "run" / "epoch_010.pth.tar")
+    os.makedirs(os.path.dirname(ckpt))
+    torch.save({"epoch": 10, "state_dict_ema": {"module." + k: v for k, v in sd.items()}}, ckpt)
+    r = subprocess.run([sys.executable, os.path.join(root, "inference.py"), cfg_path, "3", ckpt, "-b", "4", "--merge"],
+                       capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out_dir = tmp_path / "run" / "3"
+    recs = json.load(open(out_dir / "data_left.json"))
+    assert [x["video_id"] for x in recs] == [f"id{i:03d}/clip.mp4" for i in range(5)]
+    pred = json.load(open(out_dir / "prediction.json"))
+    assert set(pred) == {x["video_id"] for x in recs}
+    for x in recs:
+        kept = [[s, seg[0], seg[1]] for s, seg in zip(x["scores"], x["segments"]) if s > 0.2] or [[0, 0, 0]]
+        assert pred[x["video_id"]] == kept
+    assert len(open(out_dir / "prediction.txt").read().splitlines()) == 5
