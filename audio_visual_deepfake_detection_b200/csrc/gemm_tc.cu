@@ -640,7 +640,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
 
   const bool f16 = a->dtype == AVDF_DTYPE_F16;
   const CUtensorMapDataType tm_dtype = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  static Params p;     // large; filled per call, copied into the launch by value
+  static thread_local Params p;     // large (tensor maps); filled per call, copied into the launch by value
   memset(&p, 0, sizeof(p));
   fill_seg(a, p.seg);
   fill_epi(a, p.epi);

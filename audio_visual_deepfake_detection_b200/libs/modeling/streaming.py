@@ -6,7 +6,8 @@ Per batch of <= max_batch videos:
   H2D    (copy engine)   pinned -> static device staging buffers, asynchronous on the compute stream
   GPU                    the whole pass (interp/concat -> model -> decode -> NMS) replayed as ONE CUDA graph
   D2H                    fixed-size results -> pinned host, then an event
-Two slots alternate, so packing batch i+1 overlaps the GPU work and the copies of batch i. This replaces the
+n_slots (default 6, env AVDF_STREAM_SLOTS) staging slots rotate: one is being packed while up to n_slots-1 batches are in flight on the
+GPU, each on its own stream and engine lane (buffer set), so copies and kernels of consecutive batches overlap. This replaces the
 reference's DataLoader workers (which run F.interpolate on the CPU, libs/datasets/deepfake_video_audio.py:513-547)
 plus the per-video `.to(device)` / `.cpu()` of libs/modeling/av_fd_no_recon.py:476-477, 841-846.
 """
@@ -62,7 +63,8 @@ class _Slot:
 
 
 class StreamRunner:
-    def __init__(self, model, n_slots=3, n_threads=None):
+    def __init__(self, model, n_slots=None, n_threads=None):
+        n_slots = n_slots or int(os.environ.get("AVDF_STREAM_SLOTS", "6"))
         self.model = model
         self.eng = model.engine()
         self.slots = [_Slot(self, i) for i in range(n_slots)]

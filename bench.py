@@ -275,7 +275,7 @@ def run_ours(args):
     # memory, copies them H2D, replays the pass and reads the results back D2H - all inside the timed region.
     runner = model.runner()
     runner.use_graph = not args.no_graph
-    for _ in model.stream(raw[i % N_POOL] for i in range(max(args.warmup, 3))):
+    for _ in model.stream(raw[i % N_POOL] for i in range(max(args.warmup, 2 * len(runner.slots)))):   # every slot captures its graph here
         pass
     barrier()
     runner.h2d_bytes = runner.d2h_bytes = 0
