@@ -51,26 +51,52 @@ struct LdlParams {
   const float* ln_in_w[3]; const float* ln_in_b[3]; const float* dw_w[3];
   const float* ln_out_w[3]; const float* ln_out_b[3];
   void* out[3]; float* skip_out;
-  int B, t_src, t_virt, shift, t_out, n_streams, out_rows;
+  int B, t_src, t_virt, shift, t_out, n_streams, out_rows, rows;
 };
-constexpr int LDL_ROWS = 8;            // output rows per warp
+constexpr int LDL_MAX_ROWS = 8;        // output rows per warp tile: 8, 4 or 2 (host picks the largest that still fills the SMs)
 constexpr int LDL_WARPS = 8;
 constexpr int LDL_DEPTH = 4;           // source rows in flight per warp (cp.async ring): 24 warps x 3 KB per SM keeps HBM busy
+
+// A lane owns channels [4 lane, 4 lane + 4) and [128 + 4 lane, 128 + 4 lane + 4): every 16-byte shared-memory access of a
+// warp then covers 512 contiguous bytes (conflict-free LDS.128; 8 contiguous channels per lane put lanes i and i + 4
+// on the same banks and doubled the wavefronts of what ncu showed to be the limiting pipe).
+__device__ __forceinline__ void lds8p(const float* row, int lane, f32x2 (&v)[4]) {       // 8 floats as 4 packed pairs
+  const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(row + 4 * lane);
+  const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(row + 128 + 4 * lane);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ float hsum2(f32x2 v) { float a, b; upk2(v, a, b); return a + b; }
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void store4(__half* p, float a, float b, float c, float d) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16x2(a, b), pack_f16x2(c, d));
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+template <typename OutT> __device__ __forceinline__ void store8p(OutT* row, int lane, const f32x2 (&v)[4]) {
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) upk2(v[k], f[2 * k], f[2 * k + 1]);
+  store4(row + 4 * lane, f[0], f[1], f[2], f[3]);
+  store4(row + 128 + 4 * lane, f[4], f[5], f[6], f[7]);
+}
 
 // With u = xhat * w_in + b_in (xhat = the normalised source row, shared by all streams) the depthwise conv is
 //   acc[c] = sum_j dw[c][j] * u_j[c] = sum_j (dw[c][j] w_in[c]) * xhat_j[c] + b_in[c] * sum_j dw[c][j]
 // so the per-stream constants A_j = dw_j * w_in, Bj = dw_j * b_in, Bsum = sum_j Bj are folded once per CTA into shared
-// memory and an interior output row costs 3 FFMA per channel and stream (edge rows, where a tap falls outside
+// memory and an interior output row costs 3 FMA per channel and stream (edge rows, where a tap falls outside
 // [0, t_virt), use the per-tap Bj instead of Bsum).
-// The NS streams of an output row are computed together so that their LayerNorm reductions (sum and sum of squares,
-// single pass) travel through the same 5 shuffle steps: one dependent chain per row instead of 2 per stream.
+// The kernel is bound by issue slots (ncu: ~600 instructions per output row before this layout), so all the
+// element-wise math runs on packed fp32 pairs (fma.rn.f32x2: two channels per instruction), each LayerNorm carries
+// its (sum, sum of squares) as ONE packed pair through the 5 butterfly steps, and 1/sqrt is the MUFU rsqrt (2 ulp).
+// The NS streams of an output row are computed together so that their reductions overlap.
 template <typename OutT, int STRIDE, int NS>
 __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const LdlParams p) {
   // per stream: A0, A1, A2, Bsum, B0, B1, B2, ln_out_w, ln_out_b  (9 x 256 floats)
   extern __shared__ __align__(16) float ldl_smem[];
   float (*sp)[9][kC] = reinterpret_cast<float (*)[9][kC]>(ldl_smem);                                   // [NS][9][256]
   float (*ring)[LDL_DEPTH][kC] = reinterpret_cast<float (*)[LDL_DEPTH][kC]>(ldl_smem + NS * 9 * kC);   // [warps][depth][256]
-  for (int i = threadIdx.x; i < p.n_streams * kC; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NS * kC; i += blockDim.x) {
     const int s = i / kC, c = i - s * kC;
     const float w = p.ln_in_w[s][c], bb = p.ln_in_b[s][c];
     const float d0 = p.dw_w[s][3 * c], d1 = p.dw_w[s][3 * c + 1], d2 = p.dw_w[s][3 * c + 2];
@@ -81,68 +107,79 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tiles_per_video = (p.t_out + LDL_ROWS - 1) / LDL_ROWS;
+  const int R = p.rows;
+  const int tiles_per_video = (p.t_out + R - 1) / R;
   const long long n_tiles = (long long)p.B * tiles_per_video;
-  const int c0 = lane * 8;
+  const f32x2 zero2 = pk2(0.f);
   for (long long tile = (long long)blockIdx.x * LDL_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * LDL_WARPS) {
     const int b = (int)(tile / tiles_per_video);
-    const int t0 = (int)(tile - (long long)b * tiles_per_video) * LDL_ROWS;
-    const int t1 = min(t0 + LDL_ROWS, p.t_out);
+    const int t0 = (int)(tile - (long long)b * tiles_per_video) * R;
+    const int t1 = min(t0 + R, p.t_out);
     const float* src_b = p.src + (size_t)b * p.t_src * kC;
-    float xh[3][8];                 // normalised rows of the 3-position window
-    float rw[STRIDE == 2 ? 3 : 1][8];   // raw rows (only the stride-2 MaxPool skip needs them)
+    f32x2 xh[3][4];                 // normalised rows of the 3-position window
+    f32x2 rw[STRIDE == 2 ? 3 : 1][4];   // raw rows (only the stride-2 MaxPool skip needs them)
     bool ok[3] = {false, false, false};
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) xh[j][k] = 0.f;
-    // software pipeline: the source rows of positions pos + 1 .. pos + LDL_DEPTH - 1 are in flight (cp.async into a
-    // per-warp smem ring; every lane copies and later reads its own 32 bytes, so no cross-lane synchronisation)
+      for (int k = 0; k < 4; ++k) xh[j][k] = zero2;
     // the tile's mask bytes, one per lane, fetched once (a per-row byte load sat on the critical path of every row)
     unsigned tile_mask = 0xffffffffu;
     if (p.mask_out) {
       const bool mbit = (t0 + lane < t1) ? (p.mask_out[(size_t)b * p.t_out + t0 + lane] != 0) : true;
       tile_mask = __ballot_sync(0xffffffffu, mbit);
     }
+    // software pipeline: the source rows of positions pos + 1 .. pos + LDL_DEPTH - 1 are in flight (cp.async into a
+    // per-warp smem ring; every lane copies and later reads its own 32 bytes, so no cross-lane synchronisation)
     const int pos_first = STRIDE * t0 - 1, pos_last = STRIDE * (t1 - 1) + 1;
-    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[warp][0][c0]);
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[warp][0][4 * lane]);
     auto issue = [&](int pos) {
       if (pos >= 0 && pos < p.t_virt && pos <= pos_last) {
         const int r = p.shift >= 0 ? (pos >> p.shift) : (pos << (-p.shift));
-        const float* g = src_b + (size_t)r * kC + c0;
+        const float* g = src_b + (size_t)r * kC + 4 * lane;
         const unsigned d = ring_base + (unsigned)(((pos - pos_first) % LDL_DEPTH) * kC * 4);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(g + 4) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512), "l"(g + 128) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll
     for (int d = 0; d < LDL_DEPTH; ++d) issue(pos_first + d);
-    float nxt[8];
     for (int pos = pos_first; pos <= pos_last; ++pos) {
       asm volatile("cp.async.wait_group %0;" ::"n"(LDL_DEPTH - 1) : "memory");
       // slide the window, normalise the new row
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { xh[0][k] = xh[1][k]; xh[1][k] = xh[2][k]; }
+      for (int k = 0; k < 4; ++k) { xh[0][k] = xh[1][k]; xh[1][k] = xh[2][k]; }
       ok[0] = ok[1]; ok[1] = ok[2];
       ok[2] = pos >= 0 && pos < p.t_virt;
-      if (ok[2]) lds8(&ring[warp][(pos - pos_first) % LDL_DEPTH][c0], nxt);
+      f32x2 nxt[4];
+      if (ok[2]) lds8p(ring[warp][(pos - pos_first) % LDL_DEPTH], lane, nxt);
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nxt[k] = zero2;
+      }
       if (STRIDE == 2) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { rw[0][k] = rw[STRIDE == 2 ? 1 : 0][k]; rw[STRIDE == 2 ? 1 : 0][k] = rw[STRIDE == 2 ? 2 : 0][k]; rw[STRIDE == 2 ? 2 : 0][k] = nxt[k]; }
+        for (int k = 0; k < 4; ++k) { rw[0][k] = rw[STRIDE == 2 ? 1 : 0][k]; rw[STRIDE == 2 ? 1 : 0][k] = rw[STRIDE == 2 ? 2 : 0][k]; rw[STRIDE == 2 ? 2 : 0][k] = nxt[k]; }
       }
       if (ok[2]) {                                // input LayerNorm: shifted single pass - sum and sum of squares of
-        const float pivot = __shfl_sync(0xffffffffu, nxt[0], 0);   // (x - pivot) share the 5 shuffle steps
-        float su = 0.f, sq = 0.f;
+        float n0, n1;                             // (x - pivot) travel as one packed pair through the 5 shuffle steps
+        upk2(nxt[0], n0, n1);
+        const float pivot = __shfl_sync(0xffffffffu, n0, 0);
+        const f32x2 npiv = pk2(-pivot);
+        f32x2 s2 = zero2, q2 = zero2;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const float d = nxt[k] - pivot; su += d; sq = fmaf(d, d, sq); }
+        for (int k = 0; k < 4; ++k) { const f32x2 d = add2(nxt[k], npiv); s2 = add2(s2, d); q2 = fma2(d, d, q2); }
+        f32x2 st = pk2(hsum2(s2), hsum2(q2));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { su += __shfl_xor_sync(0xffffffffu, su, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        for (int o = 16; o > 0; o >>= 1) st = add2(st, __shfl_xor_sync(0xffffffffu, st, o));
+        float su, sq;
+        upk2(st, su, sq);
         const float dm = su * (1.f / kC);
-        const float rstd = 1.f / sqrtf(fmaxf(sq * (1.f / kC) - dm * dm, 0.f) + kLnEps);
-        const float mean = pivot + dm;
+        const float rstd = rsqrtf(fmaxf(sq * (1.f / kC) - dm * dm, 0.f) + kLnEps);
+        const f32x2 nmean = pk2(-(pivot + dm)), rs2 = pk2(rstd);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) xh[2][k] = (nxt[k] - mean) * rstd;
+        for (int k = 0; k < 4; ++k) xh[2][k] = mul2(add2(nxt[k], nmean), rs2);
       }
       issue(pos + LDL_DEPTH);                    // refill the slot just consumed
       const int rel = pos - (STRIDE * t0 + 1);
@@ -152,66 +189,72 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
       const size_t srow = (size_t)b * p.out_rows + t;           // row in the (possibly interleaved) output buffers
       const bool keep = (tile_mask >> (t - t0)) & 1u;
       const bool interior = ok[0] && ok[2];                      // ok[1] always holds for an output row
-      float acc[NS][8];
+      f32x2 acc[NS][4];
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         if (!keep) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[s][k] = 0.f;
+          for (int k = 0; k < 4; ++k) acc[s][k] = zero2;
         } else if (interior) {
-          float a0[8], a1[8], a2[8];
-          lds8(&sp[s][3][c0], acc[s]); lds8(&sp[s][0][c0], a0); lds8(&sp[s][1][c0], a1); lds8(&sp[s][2][c0], a2);
+          f32x2 a0[4], a1[4], a2[4];
+          lds8p(sp[s][3], lane, acc[s]); lds8p(sp[s][0], lane, a0); lds8p(sp[s][1], lane, a1); lds8p(sp[s][2], lane, a2);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[s][k] = fmaf(a2[k], xh[2][k], fmaf(a1[k], xh[1][k], fmaf(a0[k], xh[0][k], acc[s][k])));
+          for (int k = 0; k < 4; ++k) acc[s][k] = fma2(a2[k], xh[2][k], fma2(a1[k], xh[1][k], fma2(a0[k], xh[0][k], acc[s][k])));
         } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[s][k] = 0.f;
+          for (int k = 0; k < 4; ++k) acc[s][k] = zero2;
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             if (ok[j]) {
-              float a[8], bj[8];
-              lds8(&sp[s][j][c0], a); lds8(&sp[s][4 + j][c0], bj);
+              f32x2 a[4], bj[4];
+              lds8p(sp[s][j], lane, a); lds8p(sp[s][4 + j], lane, bj);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) acc[s][k] += fmaf(a[k], xh[j][k], bj[k]);
+              for (int k = 0; k < 4; ++k) acc[s][k] = add2(acc[s][k], fma2(a[k], xh[j][k], bj[k]));
             }
           }
         }
       }
-      float su[NS], sq[NS];
+      f32x2 st[NS];                               // (sum, sum of squares) per stream
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        su[s] = 0.f; sq[s] = 0.f;
+        const f32x2 s2 = add2(add2(acc[s][0], acc[s][1]), add2(acc[s][2], acc[s][3]));
+        f32x2 q2 = mul2(acc[s][0], acc[s][0]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { su[s] += acc[s][k]; sq[s] = fmaf(acc[s][k], acc[s][k], sq[s]); }
+        for (int k = 1; k < 4; ++k) q2 = fma2(acc[s][k], acc[s][k], q2);
+        st[s] = pk2(hsum2(s2), hsum2(q2));
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          su[s] += __shfl_xor_sync(0xffffffffu, su[s], o);
-          sq[s] += __shfl_xor_sync(0xffffffffu, sq[s], o);
-        }
+        for (int s = 0; s < NS; ++s) st[s] = add2(st[s], __shfl_xor_sync(0xffffffffu, st[s], o));
       }
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        const float m2 = su[s] * (1.f / kC);
-        const float r2 = 1.f / sqrtf(fmaxf(sq[s] * (1.f / kC) - m2 * m2, 0.f) + kLnEps);
-        float w[8], bb[8];
-        lds8(&sp[s][7][c0], w); lds8(&sp[s][8][c0], bb);
+        float su, sq;
+        upk2(st[s], su, sq);
+        const float m2 = su * (1.f / kC);
+        const float r2 = rsqrtf(fmaxf(sq * (1.f / kC) - m2 * m2, 0.f) + kLnEps);
+        const f32x2 rr = pk2(r2), mm = pk2(-m2 * r2);
+        f32x2 w[4], bb[4];
+        lds8p(sp[s][7], lane, w); lds8p(sp[s][8], lane, bb);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[s][k] = fmaf((acc[s][k] - m2) * r2, w[k], bb[k]);
-        Row8<OutT>::store(reinterpret_cast<OutT*>(p.out[s]) + srow * kC + c0, acc[s]);
+        for (int k = 0; k < 4; ++k) acc[s][k] = fma2(fma2(acc[s][k], rr, mm), w[k], bb[k]);
+        store8p(reinterpret_cast<OutT*>(p.out[s]) + srow * kC, lane, acc[s]);
       }
       if (STRIDE == 2 && p.skip_out) {           // MaxPool1d(3, 2, 1) of the raw rows, -inf padding
         float mx[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float m = rw[STRIDE == 2 ? 1 : 0][k];
-          if (ok[0]) m = fmaxf(m, rw[0][k]);
-          if (ok[2]) m = fmaxf(m, rw[STRIDE == 2 ? 2 : 0][k]);
-          mx[k] = m;
+        for (int k = 0; k < 4; ++k) {
+          float m0, m1, l0, l1, h0, h1;
+          upk2(rw[STRIDE == 2 ? 1 : 0][k], m0, m1);
+          upk2(rw[0][k], l0, l1);
+          upk2(rw[STRIDE == 2 ? 2 : 0][k], h0, h1);
+          if (ok[0]) { m0 = fmaxf(m0, l0); m1 = fmaxf(m1, l1); }
+          if (ok[2]) { m0 = fmaxf(m0, h0); m1 = fmaxf(m1, h1); }
+          mx[2 * k] = m0; mx[2 * k + 1] = m1;
         }
-        Row8<float>::store(p.skip_out + orow * kC + c0, mx);
+        store4(p.skip_out + orow * kC + 4 * lane, mx[0], mx[1], mx[2], mx[3]);
+        store4(p.skip_out + orow * kC + 128 + 4 * lane, mx[4], mx[5], mx[6], mx[7]);
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -761,7 +804,17 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   AVDF_CHECK_ARG(p.out_rows >= p.t_out, "out_rows_per_video smaller than the output length");
   p.n_streams = a->n_streams;
   if (a->batch == 0) return AVDF_OK;
-  const long long tiles = (long long)a->batch * ((p.t_out + LDL_ROWS - 1) / LDL_ROWS);
+  AVDF_CHECK_ARG(a->tile_rows == 0 || a->tile_rows == 2 || a->tile_rows == 4 || a->tile_rows == 8, "tile_rows must be 0 (auto), 2, 4 or 8");
+  // rows per warp tile: the largest of 8 / 4 / 2 that still gives (almost) every resident warp a tile - shorter tiles
+  // re-normalise 2 halo rows per tile but shorten the serial per-warp chain of the small pyramid levels
+  const long long warp_slots = (long long)sm_count() * 3 * LDL_WARPS;
+  int rows = a->tile_rows;
+  if (rows == 0) {
+    rows = LDL_MAX_ROWS;
+    while (rows > 2 && (long long)a->batch * ((p.t_out + rows - 1) / rows) * 4 < warp_slots * 3) rows /= 2;
+  }
+  p.rows = rows;
+  const long long tiles = (long long)a->batch * ((p.t_out + rows - 1) / rows);
   const int grid = grid_for(tiles, LDL_WARPS, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define AVDF_LDL(S, NS)                                                                                              \

@@ -71,6 +71,7 @@ class LnDwconvLnArgs(Structure):
         ("ln_in_w", c_void_p * 3), ("ln_in_b", c_void_p * 3), ("dw_w", c_void_p * 3),
         ("ln_out_w", c_void_p * 3), ("ln_out_b", c_void_p * 3),
         ("out", c_void_p * 3), ("out_dtype", c_int32), ("out_rows_per_video", c_int32), ("skip_out", c_void_p),
+        ("tile_rows", c_int32),
     ]
 
 

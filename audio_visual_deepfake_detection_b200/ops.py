@@ -207,7 +207,7 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
 
 # ---------------------------------------------------------------------------- block kernels
 def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, dw, ln_out, outs, skip_out=None, out_rows=0,
-                 out_row_offsets=None):
+                 out_row_offsets=None, tile_rows=0):
     """ln_in / ln_out: lists of (w, b); dw: list of [C,3]; outs: list of output tensors. Dense: each
     [batch, t_virt/stride, C]. Interleaved: every entry is the SAME base tensor [batch, out_rows, C] and
     out_row_offsets[i] is the first row of stream i inside a video's block."""
@@ -229,7 +229,10 @@ def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, d
     a.out_dtype = _dt(outs[0])
     a.out_rows_per_video = int(out_rows)
     a.skip_out = skip_out.data_ptr() if skip_out is not None else None
-    _call("avdf_ln_dwconv_ln", L.avdf_ln_dwconv_ln, (ctypes.byref(a), nv.stream_ptr(),), launches=1, work={"bytes": batch * t_src * src.shape[-1] * 4 + _nbytes(*[o[:batch] for o in outs]) + (_nbytes(skip_out[:batch]) if skip_out is not None else 0)})
+    a.tile_rows = int(tile_rows)
+    C, t_out = src.shape[-1], t_virt // stride
+    nbytes = batch * min(t_src, t_virt) * C * 4 + n * batch * t_out * C * outs[0].element_size() + (batch * t_out * C * 4 if skip_out is not None else 0)
+    _call("avdf_ln_dwconv_ln", L.avdf_ln_dwconv_ln, (ctypes.byref(a), nv.stream_ptr(),), launches=1, work={"bytes": nbytes})
 
 
 def attention(q, k, v, kv_mask, out, *, batch, t, n_head, window, qkv=None):

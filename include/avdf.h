@@ -171,6 +171,7 @@ typedef struct avdf_ln_dwconv_ln_args {
   int32_t out_dtype;
   int32_t out_rows_per_video;    /* 0: t_virt / stride (dense). Larger: several streams interleaved per video */
   float* skip_out;               /* [batch, t_virt / stride, C] fp32 or NULL */
+  int32_t tile_rows;             /* output rows per warp tile: 0 = chosen from the problem size, or 2 / 4 / 8 */
 } avdf_ln_dwconv_ln_args;
 AVDF_API int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* args, void* stream);
 

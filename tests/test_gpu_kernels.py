@@ -339,8 +339,9 @@ def _ln_params(rng, C=256):
     return (torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)), torch.from_numpy(rng.normal(0, 0.2, C).astype(np.float32)))
 
 
+@pytest.mark.parametrize("tile_rows", [0, 2, 4, 8])
 @pytest.mark.parametrize("stride,shift,T_src,T_virt", [(1, 0, 96, 96), (2, 0, 96, 96), (1, 2, 24, 96), (1, -3, 192, 24), (1, 0, 20, 20)])
-def test_ln_dwconv_ln(stride, shift, T_src, T_virt):
+def test_ln_dwconv_ln(stride, shift, T_src, T_virt, tile_rows):
     rng = np.random.RandomState(7)
     B, C = 3, 256
     To = T_virt // stride
@@ -354,7 +355,7 @@ def test_ln_dwconv_ln(stride, shift, T_src, T_virt):
     skip = torch.zeros((B, To, C), device=DEV) if (stride == 2) else None
     ops.ln_dwconv_ln(dev(x), batch=B, t_src=T_src, t_virt=T_virt, shift=shift, stride=stride, mask_out=dev(mask.astype(np.uint8)),
                      ln_in=[(dev(a), dev(b)) for a, b in lni], dw=[dev(d) for d in dws],
-                     ln_out=[(dev(a), dev(b)) for a, b in lno], outs=outs, skip_out=skip)
+                     ln_out=[(dev(a), dev(b)) for a, b in lno], outs=outs, skip_out=skip, tile_rows=tile_rows)
     xc = x.permute(0, 2, 1)
     idx = (torch.arange(T_virt) >> shift) if shift >= 0 else (torch.arange(T_virt) << -shift)
     xv = xc[..., idx]                                                  # nearest resample (backbones.py:487,490)
