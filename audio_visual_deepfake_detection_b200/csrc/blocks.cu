@@ -327,18 +327,19 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const InT* __
 // otherwise re-read from L1/L2 by 2*HALF+1 different queries). One warp per query row, 8 lanes per head; the
 // 2*HALF+1 scores of a row are computed first (independent dot products), then a two-pass softmax in base 2
 // (log2(e) folded into the query scale, ex2.approx), then the weighted sum of V.
-constexpr int ATB_ROWS = 32, ATB_WARPS = 8;
+constexpr int ATB_MAX_ROWS = 64, ATB_WARPS = 8;   // query rows per CTA are a launch parameter (<= ATB_MAX_ROWS)
 
 template <typename InT, typename OutT, int HALF>
 __global__ void __launch_bounds__(ATB_WARPS * 32) attention_banded_kernel(const InT* __restrict__ q, const InT* __restrict__ k,
                                                                          const InT* __restrict__ v, const unsigned char* __restrict__ kv_mask,
-                                                                         OutT* __restrict__ out, int B, int T, int RPV) {
+                                                                         OutT* __restrict__ out, int B, int T, int RPV, int ATB_ROWS) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   constexpr int ROWB = kC * (int)sizeof(InT);                  // bytes per K or V row
-  constexpr int NROW = ATB_ROWS + 2 * HALF, W = 2 * HALF + 1;
+  constexpr int W = 2 * HALF + 1;
+  const int NROW = ATB_ROWS + 2 * HALF;
   InT* ks = reinterpret_cast<InT*>(att_smem);
   InT* vs = reinterpret_cast<InT*>(att_smem + (size_t)NROW * ROWB);
-  __shared__ unsigned char s_mask[NROW];
+  __shared__ unsigned char s_mask[ATB_MAX_ROWS + 2 * HALF];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tiles_per_video = (T + ATB_ROWS - 1) / ATB_ROWS;
   const int b = blockIdx.x / tiles_per_video;
@@ -848,16 +849,21 @@ extern "C" int avdf_attention(const void* q, const void* k, const void* v, const
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (window == 7) {                            // the window every shipped config uses: smem-tiled specialisation
     constexpr int HALF = 3;
-    const int grid = batch * ((t + ATB_ROWS - 1) / ATB_ROWS);
+    // query rows per CTA: 24 divides every level of the 768-row pyramid, and at 30 KB of K/V per CTA (16-bit) the
+    // 32 x 32 tiles of a batch-32 level-0 launch are resident in ONE wave (7 CTAs per SM)
+    static const int rows_env = getenv("AVDF_ATB_ROWS") ? atoi(getenv("AVDF_ATB_ROWS")) : 0;
+    const int rows = rows_env > 0 && rows_env <= ATB_MAX_ROWS ? rows_env : 24;
+    const int grid = batch * ((t + rows - 1) / rows);
     AVDF_DISPATCH_DTYPE(in_dtype, InT, AVDF_DISPATCH_DTYPE(out_dtype, OutT, {
-      const size_t smem = 2 * (size_t)(ATB_ROWS + 2 * HALF) * kC * sizeof(InT);
+      const size_t smem = 2 * (size_t)(rows + 2 * HALF) * kC * sizeof(InT);
       static bool attr_done = false;
       if (!attr_done) {
-        AVDF_CUDA(cudaFuncSetAttribute(attention_banded_kernel<InT, OutT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AVDF_CUDA(cudaFuncSetAttribute(attention_banded_kernel<InT, OutT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(2 * (size_t)(ATB_MAX_ROWS + 2 * HALF) * kC * sizeof(InT))));
         attr_done = true;
       }
       attention_banded_kernel<InT, OutT, HALF><<<grid, ATB_WARPS * 32, smem, st>>>((const InT*)q, (const InT*)k, (const InT*)v, kv_mask,
-                                                                                  (OutT*)out, batch, t, rpv);
+                                                                                  (OutT*)out, batch, t, rpv, rows);
     }));
     return check_launch("attention_banded_kernel");
   }

@@ -176,29 +176,27 @@ __device__ __forceinline__ float gelu_fast(float x) {
   // 0.5 x (1 + erf(x/sqrt2)) = x - 0.5 x erfc(z) for x >= 0, 0.5 x erfc(z) for x < 0
   return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
 }
-// the same on a packed pair: 11 packed FP ops + 4 MUFU + selects per TWO elements
+// the same on a packed pair, arranged for the fewest issue slots (the GELU MLP epilogue is bound by them):
+//   gelu(x) = relu(x) - |x| w,  w = 0.5 erfc(|x|/sqrt2) = e^{-x^2/2} t P(t) / 2,  relu(x) = x/2 + |x|/2
+//           = x/2 + |x| (1/2 - w)
+// i.e. no select on the sign of x; the 1/2 and the minus sign live in the polynomial coefficients, sqrt(1/2) and
+// log2(e)/2 in the two argument scalings: 11 packed FP ops + 4 MUFU + 2 LOP3 per TWO elements.
 __device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
   const f32x2 ax = x & 0x7fffffff7fffffffull;
-  const f32x2 z = mul2(ax, pk2(0.70710678118654752440f));
   float d0, d1, t0, t1, e0, e1;
-  upk2(fma2(pk2(0.3275911f), z, pk2(1.f)), d0, d1);
+  upk2(fma2(ax, pk2(0.3275911f * 0.70710678118654752440f), pk2(1.f)), d0, d1);
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
-  upk2(mul2(mul2(z, z), pk2(-1.4426950408889634f)), d0, d1);
+  upk2(mul2(mul2(x, pk2(-0.5f * 1.4426950408889634f)), x), d0, d1);       // -x^2/2 * log2(e)
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(d0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(d1));
   const f32x2 t = pk2(t0, t1);
-  f32x2 poly = fma2(pk2(1.061405429f), t, pk2(-1.453152027f));
-  poly = fma2(poly, t, pk2(1.421413741f));
-  poly = fma2(poly, t, pk2(-0.284496736f));
-  poly = fma2(poly, t, pk2(0.254829592f));
-  const f32x2 erfc_z = mul2(mul2(poly, t), pk2(e0, e1));
-  const f32x2 hx = mul2(x, pk2(0.5f));
-  const f32x2 neg = mul2(hx, erfc_z);                   // x < 0:  0.5 x erfc(z)
-  const f32x2 pos = add2(x, neg ^ 0x8000000080000000ull);   // x >= 0: x - 0.5 x erfc(z)
-  float x0, x1, p0, p1, n0, n1;
-  upk2(x, x0, x1); upk2(pos, p0, p1); upk2(neg, n0, n1);
-  return pk2(x0 >= 0.f ? p0 : n0, x1 >= 0.f ? p1 : n1);
+  f32x2 poly = fma2(pk2(-0.5f * 1.061405429f), t, pk2(0.5f * 1.453152027f));   // -P(t)/2
+  poly = fma2(poly, t, pk2(-0.5f * 1.421413741f));
+  poly = fma2(poly, t, pk2(0.5f * 0.284496736f));
+  poly = fma2(poly, t, pk2(-0.5f * 0.254829592f));
+  const f32x2 u = fma2(mul2(poly, t), pk2(e0, e1), pk2(0.5f));           // 1/2 - w
+  return fma2(ax, u, mul2(x, pk2(0.5f)));
 }
 __device__ __forceinline__ f32x2 act_tc2(f32x2 v, int act) {
   if (act == AVDF_ACT_RELU) { float a, b; upk2(v, a, b); return pk2(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
@@ -346,6 +344,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
     unsigned char* t32 = stage_smem + q * 8192;          // result tile (fp32: swizzle 128B)
     unsigned char* trs = stage_smem + q * 8192 + 4096;   // residual tile / second result tile
     const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 5 + q);
+    const uint32_t res_bar1 = bar_base + 8u * (2 * MAX_STAGES + 9 + q);   // second residual tile (in-place fp32 path)
     const int chunks = p.bn >> 5;
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
     const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
@@ -358,10 +357,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
     unsigned char* t16 = has32 ? trs : t32;
     const int sw7 = lane & 7;                    // 128B swizzle: 16-byte chunk j of row `lane` lives in slot j ^ (lane & 7)
     const int sw3 = (lane >> 1) & 3;             // 64B swizzle: chunk j of row `lane` lives in slot j ^ ((lane >> 1) & 3)
-    if (lane == 0) mbar_init(res_bar, 1);
+    if (lane == 0) { mbar_init(res_bar, 1); mbar_init(res_bar1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    uint32_t res_phase = 0, store_seq = 0;
+    uint32_t res_phase = 0, res_phase1 = 0, store_seq = 0;
     int it = 0, loaded_n0 = -1;
     // row mask of a tile's row owned by this thread (a global load: fetched one tile ahead so that its latency is
     // off the critical path of the tile's epilogue)
@@ -404,7 +403,25 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
           tma_load_3d(smem_u32(trs), &p.res_map[tc_.seg], res_bar, tc_.n0 + ch * 32, wt, wb);
         }
       };
-      if (has_res) fetch_residual(0);
+      // ---- residual + fp32 output only (attention projection, MLP down-projection): the residual block arrives by TMA in
+      //      the very tile the result leaves from (updated in place by the thread that owns the row), so the two 4 KB
+      //      tiles of this warp double-buffer the chunks: the residual of chunk c + 1 is in flight while chunk c is computed
+      //      (with one residual tile its ~1 us load latency was exposed on every 32-column chunk: the top stall in ncu)
+      constexpr bool RES32_OK = MODE >= 0 && OUTK == 1 && (MODE & 8) != 0 && (MODE & 16) == 0;
+      auto fetch_residual_into = [&](int ch) {    // chunk ch -> tile ch & 1 (lane 0; the tile's previous store has been read)
+        const uint32_t bar = (ch & 1) ? res_bar1 : res_bar;
+        mbar_arrive_expect_tx(bar, 4096);
+        tma_load_3d(smem_u32(t32 + ((ch & 1) << 12)), &p.res_map[tc_.seg], bar, tc_.n0 + ch * 32, wt, wb);
+      };
+      if (RES32_OK) {
+        if (lane == 0) {
+          tma_store_wait_read();                  // the previous tile's stores have read both tiles
+          fetch_residual_into(0);
+          if (chunks > 1) fetch_residual_into(1);
+        }
+      } else if (has_res) {
+        fetch_residual(0);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
@@ -530,6 +547,31 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
             x[4 * j + 2] = fmaf(pv.z, mk, x[4 * j + 2]); x[4 * j + 3] = fmaf(pv.w, mk, x[4 * j + 3]);
           }
         }
+        if (RES32_OK) {
+          unsigned char* tb = t32 + ((ch & 1) << 12);
+          if (ch >= 1 && ch + 1 < chunks && lane == 0) {   // tile (ch + 1) & 1 held chunk ch - 1: its store was committed one
+            tma_store_wait_read();                         // iteration ago; refill it with the residual of chunk ch + 1
+            fetch_residual_into(ch + 1);
+          }
+          if (ch & 1) { mbar_wait(res_bar1, res_phase1); res_phase1 ^= 1; }
+          else { mbar_wait(res_bar, res_phase); res_phase ^= 1; }
+          const float4* g4 = reinterpret_cast<const float4*>(s_gam + cl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* slot = reinterpret_cast<float4*>(tb + lane * 128 + ((j ^ sw7) << 4));
+            const float4 rv = *slot;
+            const float4 gg = g4[j];
+            *slot = make_float4(fmaf(gg.x, x[4 * j], rv.x * mk), fmaf(gg.y, x[4 * j + 1], rv.y * mk),
+                                fmaf(gg.z, x[4 * j + 2], rv.z * mk), fmaf(gg.w, x[4 * j + 3], rv.w * mk));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&p.o32_map[tc_.seg], smem_u32(tb), tc_.n0 + cl, wt, wb);
+            tma_store_commit();
+          }
+          continue;                                 // next chunk
+        }
         if (has_res) {                            // residual * mask + gamma * x
           mbar_wait(res_bar, res_phase);
           res_phase ^= 1;
@@ -629,7 +671,10 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   // N tile: 256 only where LayerNorm needs the whole row in one CTA; everything else uses the narrow configuration
   // (BN <= 128, two CTAs per SM)
   // (BN <= 128, two CTAs per SM). (A 256-wide tile for the K = 1024 MLP-down GEMM was measured: 31.4 vs 29.9 us, no gain.)
-  const int bn = a->ln_w ? (a->n_out >= MAX_BN ? MAX_BN : a->n_out) : (a->n_out % 128 == 0 ? 128 : (a->n_out > MAX_BN ? MAX_BN : a->n_out));
+  int bn = a->ln_w ? (a->n_out >= MAX_BN ? MAX_BN : a->n_out) : (a->n_out % 128 == 0 ? 128 : (a->n_out > MAX_BN ? MAX_BN : a->n_out));
+  // long-K launches (the MLP down-projection, K = 1024) are bound by the L2 -> SM operand traffic ((BM + bn) K bytes per
+  // tile): one 256-wide tile per row block reads the activations once instead of twice (measured 29.2 -> 26.7 us)
+  if (!a->ln_w && a->taps * a->c_in >= 1024 && a->n_out % 256 == 0) bn = 256;
   AVDF_CHECK_ARG(a->n_out % bn == 0, "bf16 path: n_out must be <= 256 or a multiple of 256");
   AVDF_CHECK_ARG(bn % 16 == 0 && bn >= 32, "bf16 path: unsupported n_out");
   AVDF_CHECK_ARG(!a->ln_w || a->n_out == bn, "bf16 path: fused LayerNorm needs n_out <= 256");

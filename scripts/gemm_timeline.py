@@ -42,3 +42,4 @@ run(32, 768, 256, 1024, False, act=0, half_out=True)
 run(32, 768, 256, 1024, False, act=0, half_out=False)
 run(32, 2304, 256, 256, False, act=0, half_out=True)
 run(32, 768, 1024, 256, True)
+run(32, 768, 256, 256, True)
