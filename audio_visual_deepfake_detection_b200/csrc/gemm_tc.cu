@@ -23,6 +23,7 @@
 #include <string.h>
 #include <type_traits>
 #include "gemm_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace avdf {
 namespace tc {
@@ -54,160 +55,13 @@ struct Params {
   unsigned long long* dbg;                   // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
 };
 
-// ---------------------------------------------------------------- PTX wrappers
+// ---------------------------------------------------------------- debug timeline
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #ifdef AVDF_GEMM_TIMELINE
 #define AVDF_TS(slot) do { if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 #else
 #define AVDF_TS(slot) do { } while (0)
 #endif
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (surfaced as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("avdf gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// asynchronous variant: the registers may be read only after tmem_ld_wait()
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
-// start address >> 4, LBO unused (0), SBO = 1024 B >> 4, descriptor version 1 (sm_100), layout SWIZZLE_128B (2).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-// exact-erf GELU (blocks.py:1239) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the 16-bit
-// output rounding of this path; rcp/ex2 are the 2-ulp MUFU approximations): 2 MUFU + 9 FMA-class ops instead of
-// erff's ~35 instructions -
-// the 256->1024 MLP GEMM epilogue is ALU-bound on this function.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t, e2;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(-1.4426950408889634f * z * z));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfc_z = poly * t * e2;                                      // 1 - erf(z), z >= 0
-  const float half_x = 0.5f * x;
-  // 0.5 x (1 + erf(x/sqrt2)) = x - 0.5 x erfc(z) for x >= 0, 0.5 x erfc(z) for x < 0
-  return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
-}
-// the same on a packed pair, arranged for the fewest issue slots (the GELU MLP epilogue is bound by them):
-//   gelu(x) = relu(x) - |x| w,  w = 0.5 erfc(|x|/sqrt2) = e^{-x^2/2} t P(t) / 2,  relu(x) = x/2 + |x|/2
-//           = x/2 + |x| (1/2 - w)
-// i.e. no select on the sign of x; the 1/2 and the minus sign live in the polynomial coefficients, sqrt(1/2) and
-// log2(e)/2 in the two argument scalings: 11 packed FP ops + 4 MUFU + 2 LOP3 per TWO elements.
-__device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
-  const f32x2 ax = x & 0x7fffffff7fffffffull;
-  float d0, d1, t0, t1, e0, e1;
-  upk2(fma2(ax, pk2(0.3275911f * 0.70710678118654752440f), pk2(1.f)), d0, d1);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
-  upk2(mul2(mul2(x, pk2(-0.5f * 1.4426950408889634f)), x), d0, d1);       // -x^2/2 * log2(e)
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(d0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(d1));
-  const f32x2 t = pk2(t0, t1);
-  f32x2 poly = fma2(pk2(-0.5f * 1.061405429f), t, pk2(0.5f * 1.453152027f));   // -P(t)/2
-  poly = fma2(poly, t, pk2(-0.5f * 1.421413741f));
-  poly = fma2(poly, t, pk2(0.5f * 0.284496736f));
-  poly = fma2(poly, t, pk2(-0.5f * 0.254829592f));
-  const f32x2 u = fma2(mul2(poly, t), pk2(e0, e1), pk2(0.5f));           // 1/2 - w
-  return fma2(ax, u, mul2(x, pk2(0.5f)));
-}
-__device__ __forceinline__ f32x2 act_tc2(f32x2 v, int act) {
-  if (act == AVDF_ACT_RELU) { float a, b; upk2(v, a, b); return pk2(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
-  if (act == AVDF_ACT_GELU) return gelu_fast2(v);
-  return v;
-}
-__device__ __forceinline__ float act_tc(float v, int act) {
-  if (act == AVDF_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == AVDF_ACT_GELU) return gelu_fast(v);
-  return v;
-}
 
 struct TileCoord { int seg, b0, t0, tt, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
@@ -643,23 +497,6 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
   }
 }
 
-// ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeFn get_encode() {
-  static EncodeFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeFn>(p);
-  }
-  return fn;
-}
-
 }  // namespace tc
 
 static unsigned long long* g_dbg = nullptr;
@@ -670,7 +507,6 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   AVDF_CHECK_ARG(a->n_out % 32 == 0, "bf16 path: n_out must be a multiple of 32");
   // N tile: 256 only where LayerNorm needs the whole row in one CTA; everything else uses the narrow configuration
   // (BN <= 128, two CTAs per SM)
-  // (BN <= 128, two CTAs per SM). (A 256-wide tile for the K = 1024 MLP-down GEMM was measured: 31.4 vs 29.9 us, no gain.)
   int bn = a->ln_w ? (a->n_out >= MAX_BN ? MAX_BN : a->n_out) : (a->n_out % 128 == 0 ? 128 : (a->n_out > MAX_BN ? MAX_BN : a->n_out));
   // long-K launches (the MLP down-projection, K = 1024) are bound by the L2 -> SM operand traffic ((BM + bn) K bytes per
   // tile): one 256-wide tile per row block reads the activations once instead of twice (measured 29.2 -> 26.7 us)

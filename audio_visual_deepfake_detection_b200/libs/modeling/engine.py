@@ -22,6 +22,7 @@ Kernel sequence per batch (reference lines each step replaces):
   postprocess         av_fd_no_recon.py:760-876 + libs/utils/nms.py = avdf_postprocess (one CTA per video)
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -134,6 +135,10 @@ class LocalizationEngine:
         self.in_dt, self.adt = {"fp32": (torch.float32, torch.float32), "bf16": (torch.bfloat16, torch.bfloat16),
                                 "mixed": (torch.bfloat16, torch.float16)}[precision]
         self.max_batch = int(max_batch)
+        # fused MLP kernel (one launch per block instead of two GEMMs); env AVDF_FUSED_MLP=0 switches it off,
+        # AVDF_FUSED_MLP_MIN_ROWS sets the smallest level (rows = batch * t) that uses it
+        self.fused_mlp = os.environ.get("AVDF_FUSED_MLP", "1") != "0"
+        self.fused_mlp_min_rows = int(os.environ.get("AVDF_FUSED_MLP_MIN_ROWS", "0"))
         self.C = c["embd_dim"]
         self.n_head = c["n_head"]
         self.c_in = c["video_input_dim"] + c["audio_input_dim"]
@@ -283,13 +288,19 @@ class LocalizationEngine:
                    row_mask=mask, residual=skip, gamma=ga, out_f32=y)
         l2 = self.buf("ln2", (B, T, C), self.adt)
         ops.ln_rows(y, *w.ln(pre + ".ln2"), l2, B * T)
-        h = self.buf("mlp_h", (B, T, 4 * C), self.adt)
-        self._gemm(l2, f"{pre}.mlp.0.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.mlp.0.bias"),
-                   act=ops.ACT_GELU, out_act=h)
         out = self.buf(out_name, (B, T, C), torch.float32)
         out_act = None
         if want_act_copy and self.adt != torch.float32:
             out_act = self.buf(out_name + "_act", (B, T, C), self.adt)
+        if self.fused_mlp and self.adt != torch.float32 and out_act is None and C == 256 and B * T >= self.fused_mlp_min_rows:
+            # one launch: the [B*T, 4C] activations stay in shared memory / TMEM (csrc/mlp_fused.cu)
+            ops.mlp_fused(l2, w.dense(f"{pre}.mlp.0.weight", l2.dtype), w.vec(f"{pre}.mlp.0.bias"),
+                          w.dense(f"{pre}.mlp.3.weight", l2.dtype), w.vec(f"{pre}.mlp.3.bias"),
+                          row_mask=mask, residual=y, gamma=gm, out=out)
+            return out, None
+        h = self.buf("mlp_h", (B, T, 4 * C), self.adt)
+        self._gemm(l2, f"{pre}.mlp.0.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.mlp.0.bias"),
+                   act=ops.ACT_GELU, out_act=h)
         # the residual y is already zero on masked rows (blocks.py:1311-1313)
         w2 = self.w.dense(f"{pre}.mlp.3.weight", h.dtype)
         ws = self.workspace(B * T * C * 4) if self.adt == torch.float32 else None

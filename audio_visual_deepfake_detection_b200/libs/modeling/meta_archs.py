@@ -262,7 +262,9 @@ class _LocalizationBase(nn.Module):
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         n0 = native.LAUNCHES["n"]
-        with torch.cuda.graph(graph):
+        # thread_local: other host threads (the streaming runner's packer allocating pinned staging, a data loader)
+        # may call the CUDA allocator while this thread records; in the default global mode that invalidates the capture
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             res = self.run_staged(staged, lane)
         return GraphedPass(graph, res, native.LAUNCHES["n"] - n0, staged)
 

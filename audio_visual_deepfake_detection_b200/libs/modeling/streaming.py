@@ -75,6 +75,7 @@ class StreamRunner:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.use_graph = True
+        self.cuda_lock = threading.Lock()    # staging (pinned / device) allocation vs. graph capture on the launching thread
         self.n_packers = 1           # more packers contend for the GIL and the copy pool (measured: 2 -> 0.56x)
 
     # ---------------------------------------------------------------- stages
@@ -89,7 +90,8 @@ class StreamRunner:
         if sum(chans) != eng.c_in:
             raise ValueError("streams carry %d channels, the model expects %d" % (sum(chans), eng.c_in))
         K = int(eng.test_cfg["max_seg_num"])
-        slot.ensure(rows, chans, eng.max_batch, K, eng.device, sum(float(c["duration"]) for c in chunk))
+        with self.cuda_lock:
+            slot.ensure(rows, chans, eng.max_batch, K, eng.device, sum(float(c["duration"]) for c in chunk))
         off = slot.h_off.numpy()
         jobs = []
         for s in range(3):
@@ -139,7 +141,8 @@ class StreamRunner:
         if self.use_graph and B == eng.max_batch:
             g = slot.graphs.get(B)
             if g is None:
-                g = self.model.capture(staged, lane=slot.index)
+                with self.cuda_lock:
+                    g = self.model.capture(staged, lane=slot.index)
                 slot.graphs[B] = g
             res = g.replay()
         else:

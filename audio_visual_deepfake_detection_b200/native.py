@@ -23,7 +23,7 @@ EXPORTS = [
     "avdf_abi_version", "avdf_last_error", "avdf_device_info", "avdf_interp_concat", "avdf_pack_feats",
     "avdf_nms_workspace_bytes", "avdf_nms_hard", "avdf_nms_soft",
     "avdf_postprocess_workspace_bytes", "avdf_postprocess",
-    "avdf_conv_gemm_workspace_bytes", "avdf_conv_gemm", "avdf_ln_dwconv_ln", "avdf_attention",
+    "avdf_conv_gemm_workspace_bytes", "avdf_conv_gemm", "avdf_mlp_fused", "avdf_ln_dwconv_ln", "avdf_attention",
     "avdf_ln_rows", "avdf_instnorm_lrelu", "avdf_fpn_fuse", "avdf_head_final",
     "avdf_vcls_exp12", "avdf_vcls_exp13",
 ]
@@ -75,6 +75,14 @@ class LnDwconvLnArgs(Structure):
     ]
 
 
+class MlpFusedArgs(Structure):
+    _fields_ = [
+        ("rows", c_int32), ("channels", c_int32), ("hidden", c_int32), ("dtype", c_int32),
+        ("x", c_void_p), ("w1", c_void_p), ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p),
+        ("row_mask", c_void_p), ("residual", c_void_p), ("gamma", c_void_p), ("out", c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -104,6 +112,7 @@ def lib():
     L.avdf_conv_gemm_workspace_bytes.restype = c_size_t
     L.avdf_conv_gemm_workspace_bytes.argtypes = [POINTER(ConvGemmArgs)]
     L.avdf_conv_gemm.argtypes = [POINTER(ConvGemmArgs), c_void_p]
+    L.avdf_mlp_fused.argtypes = [POINTER(MlpFusedArgs), c_void_p]
     L.avdf_ln_dwconv_ln.argtypes = [POINTER(LnDwconvLnArgs), c_void_p]
     L.avdf_attention.argtypes = [c_void_p] * 5 + [c_int32] * 8 + [c_void_p]
     L.avdf_ln_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p]

@@ -206,6 +206,29 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
 
 
 # ---------------------------------------------------------------------------- block kernels
+def mlp_fused(x, w1, b1, w2, b2, *, row_mask, residual, gamma, out):
+    """out = residual*mask + gamma * ((GELU(x w1^T + b1) w2^T + b2) * mask); x [..., 256] fp16|bf16, w1 [1024, 256],
+    w2 [256, 1024] of the same dtype, residual / out fp32 [..., 256]. One launch; the hidden activations stay on chip."""
+    L = nv.lib()
+    _chk(x, None, "x"); _chk(w1, x.dtype, "w1"); _chk(w2, x.dtype, "w2")
+    _chk(b1, torch.float32, "b1"); _chk(b2, torch.float32, "b2"); _chk(gamma, torch.float32, "gamma")
+    _chk(row_mask, torch.uint8, "row_mask"); _chk(residual, torch.float32, "residual"); _chk(out, torch.float32, "out")
+    C, H = x.shape[-1], w1.shape[0]
+    rows = x.numel() // C
+    assert w1.shape == (H, C) and w2.shape == (C, H) and out.numel() == rows * C and residual.numel() == rows * C
+    a = nv.MlpFusedArgs()
+    a.rows, a.channels, a.hidden, a.dtype = rows, C, H, _dt(x)
+    a.x, a.w1, a.w2 = x.data_ptr(), w1.data_ptr(), w2.data_ptr()
+    a.b1 = b1.data_ptr() if b1 is not None else None
+    a.b2 = b2.data_ptr() if b2 is not None else None
+    a.row_mask = row_mask.data_ptr() if row_mask is not None else None
+    a.gamma = gamma.data_ptr() if gamma is not None else None
+    a.residual, a.out = residual.data_ptr(), out.data_ptr()
+    _call("avdf_mlp_fused", L.avdf_mlp_fused, (ctypes.byref(a), nv.stream_ptr(),), launches=1,
+          work={"flops": 4.0 * rows * C * H, "bytes": rows * C * (x.element_size() + 8) + 2 * C * H * x.element_size(), "m": rows, "n": C, "k": H})
+    return out
+
+
 def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, dw, ln_out, outs, skip_out=None, out_rows=0,
                  out_row_offsets=None, tile_rows=0):
     """ln_in / ln_out: lists of (w, b); dw: list of [C,3]; outs: list of output tensors. Dense: each

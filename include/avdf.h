@@ -175,6 +175,22 @@ typedef struct avdf_ln_dwconv_ln_args {
 } avdf_ln_dwconv_ln_args;
 AVDF_API int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* args, void* stream);
 
+/* ---- fused transformer MLP (blocks.py:1236-1243 `self.mlp`, applied at blocks.py:1315-1316) ----
+ * out = residual * mask + gamma * ((GELU(x W1^T + b1) W2^T + b2) * mask), exact-erf GELU, fp32 accumulate; the
+ * [rows, hidden] activations stay on chip (16-bit, like the unfused path's intermediate tensor). channels = 256,
+ * hidden = 1024, dtype = AVDF_DTYPE_F16 | AVDF_DTYPE_BF16 (x, w1, w2). Equivalent to two avdf_conv_gemm calls. */
+typedef struct avdf_mlp_fused_args {
+  int32_t rows, channels, hidden, dtype;
+  const void* x;                 /* [rows, channels] */
+  const void* w1; const float* b1;   /* [hidden, channels], [hidden] */
+  const void* w2; const float* b2;   /* [channels, hidden], [channels] */
+  const uint8_t* row_mask;       /* [rows] or NULL */
+  const float* residual;         /* [rows, channels] fp32 */
+  const float* gamma;            /* [channels] or NULL (AffineDropPath scale, blocks.py:1316) */
+  float* out;                    /* [rows, channels] fp32 */
+} avdf_mlp_fused_args;
+AVDF_API int avdf_mlp_fused(const avdf_mlp_fused_args* args, void* stream);
+
 /* ---- multi-head attention over q,k,v [batch, t, C]; window > 1: band |i-j| <= window/2 with additive
  * -1e4 on masked keys and zeroed masked query rows (blocks.py:1152-1224); window <= 1: global with
  * -inf on masked keys (blocks.py:274-313). Row i of video b of q/k/v is at (b * qkv_rows_per_video + i) * C from the

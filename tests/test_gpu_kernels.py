@@ -521,3 +521,36 @@ def test_attention_stacked_qkv_and_interleaved_dwconv():
     ops.ln_dwconv_ln(dev(x), outs=[inter] * 3, out_rows=3 * T, out_row_offsets=[0, T, 2 * T], **kw)
     for i in range(3):
         assert torch.equal(inter[:, i * T:(i + 1) * T], dense[i])
+
+
+# --------------------------------------------------------------------------------------------- fused MLP
+@pytest.mark.parametrize("rows", [128, 100, 1000, 32 * 768])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_mlp_fused(rows, dt):
+    """avdf_mlp_fused == Linear(256,1024) -> exact GELU -> Linear(1024,256) -> mask, gamma, residual (blocks.py:1236-1243,
+    1315-1316) computed in fp32 by torch from the same 16-bit operands; the hidden activations are rounded to the
+    16-bit type once, like the kernel's on-chip tile (and the unfused path's intermediate tensor)."""
+    rng = np.random.RandomState(rows + (1 if dt == torch.float16 else 2))
+    C, H = 256, 1024
+    x = torch.from_numpy(rng.standard_normal((rows, C)).astype(np.float32)).to(dt)
+    w1 = torch.from_numpy((rng.standard_normal((H, C)) / 16).astype(np.float32)).to(dt)
+    w2 = torch.from_numpy((rng.standard_normal((C, H)) / 32).astype(np.float32)).to(dt)
+    b1 = torch.from_numpy(rng.normal(0, 0.3, H).astype(np.float32))
+    b2 = torch.from_numpy(rng.normal(0, 0.3, C).astype(np.float32))
+    gamma = torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32))
+    res = torch.from_numpy(rng.standard_normal((rows, C)).astype(np.float32))
+    mask = torch.from_numpy((rng.rand(rows) > 0.15).astype(np.uint8))
+    out = torch.full((rows, C), float("nan"), device=DEV)
+    ops.mlp_fused(dev(x), dev(w1), dev(b1), dev(w2), dev(b2), row_mask=dev(mask), residual=dev(res), gamma=dev(gamma), out=out)
+    h = F.gelu(x.float() @ w1.float().t() + b1).to(dt).float()
+    m = mask.float()[:, None]
+    want = res * m + gamma * ((h @ w2.float().t() + b2) * m)
+    assert rel_err(out.cpu(), want) < (2e-4 if dt == torch.float16 else 1e-3)   # bf16: hidden activations at rounding ties
+    # the same through the two-launch path
+    hid = torch.empty((1, rows, H), device=DEV, dtype=dt)
+    ops.conv_gemm(dev(x).view(1, rows, C), dev(w1), taps=1, batch=1, c_in=C, n_out=H, segs=[(rows, 0, 0)], a_rows=rows, o_rows=rows,
+                  bias=dev(b1), act=ops.ACT_GELU, out_h=hid)
+    out2 = torch.empty((1, rows, C), device=DEV)
+    ops.conv_gemm(hid, dev(w2), taps=1, batch=1, c_in=H, n_out=C, segs=[(rows, 0, 0)], a_rows=rows, o_rows=rows, bias=dev(b2),
+                  row_mask=dev(mask).view(1, rows), residual=dev(res).view(1, rows, C), gamma=dev(gamma), out_f32=out2)
+    assert rel_err(out.cpu(), out2.view(rows, C).cpu()) < 2e-4
