@@ -1,0 +1,91 @@
+// Debug hook (not in include/avdf.h): pacing of tcgen05.mma from shared-memory operands. One CTA per SM issues `iters`
+// groups of 4 K=16 instructions (one 64-wide K slice) of shape 128 x N x 16 on resident (uninitialised) operand tiles
+// and reports the globaltimer span per CTA - the per-instruction cost that bounds every GEMM of this library.
+#include <cuda.h>
+#include "tc_ptx.cuh"
+
+namespace avdf {
+namespace dbg {
+using namespace tc;
+
+__global__ void __launch_bounds__(128, 1) umma_pace_kernel(int n_cols, int iters, unsigned idesc, int two_acc, unsigned long long* out) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_;
+  __shared__ uint64_t ring_bar[8];
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar_), 1); for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&ring_bar[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = tmem_ptr;
+  if (warp == 1 && (two_acc & 8)) {
+    // warp-uniform issue: all 32 lanes run the loop, one elected lane (elect.sync) issues - the compiler keeps the
+    // operands in uniform registers and emits UTCHMMA without a per-thread election loop
+    const uint64_t da = make_sw128_desc(smem_u32(smem));
+    const uint64_t db = make_sw128_desc(smem_u32(smem + 16384));
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    const bool leader = elect_one();
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t d = tm + (((two_acc & 1) && (i & 1)) ? 256u : 0u);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+        if (two_acc & 2) umma_commit(smem_u32(&ring_bar[i & 7]));
+      }
+      __syncwarp();
+      if ((two_acc & 4) && i >= 4) mbar_wait(smem_u32(&ring_bar[(i - 4) & 7]), (uint32_t)(((i - 4) >> 3) & 1));
+    }
+    if (leader) umma_commit(smem_u32(&bar_));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar_), 0);
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
+  } else if (warp == 1 && lane == 0) {
+    const uint64_t da = make_sw128_desc(smem_u32(smem));
+    const uint64_t db = make_sw128_desc(smem_u32(smem + 16384));
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t d = tm + (((two_acc & 1) && (i & 1)) ? 256u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+      if (two_acc & 2) umma_commit(smem_u32(&ring_bar[i & 7]));      // a commit per K slice, like a smem ring
+      if ((two_acc & 4) && i >= 4) mbar_wait(smem_u32(&ring_bar[(i - 4) & 7]), (uint32_t)(((i - 4) >> 3) & 1));   // and a wait 4 slices back
+    }
+    umma_commit(smem_u32(&bar_));
+    mbar_wait(smem_u32(&bar_), 0);
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    out[blockIdx.x] = t1 - t0;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+  }
+  (void)n_cols;
+}
+
+}  // namespace dbg
+}  // namespace avdf
+
+extern "C" __attribute__((visibility("default"))) int avdf_debug_umma_pace(int n_cols, int iters, int two_acc, int ctas,
+                                                                           unsigned long long* out_ns, void* stream) {
+  using namespace avdf;
+  const unsigned idesc = (1u << 4) | ((unsigned)(n_cols >> 3) << 17) | ((unsigned)(128 >> 4) << 24);   // fp16 x fp16 -> fp32
+  const int smem = 16384 + 32768 + 1024;
+  AVDF_CUDA(cudaFuncSetAttribute(dbg::umma_pace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dbg::umma_pace_kernel<<<ctas, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(n_cols, iters, idesc, two_acc, out_ns);
+  return check_launch("umma_pace_kernel");
+}

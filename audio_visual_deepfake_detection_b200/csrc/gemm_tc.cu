@@ -141,37 +141,44 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc_ = decode_tile(p, tile);
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int d = tap - (p.taps >> 1);
-          int par = 0, dt = d;
-          if (p.stride == 2) { par = d & 1; dt = (d - par) / 2; }
-          for (int kb = 0; kb < kb_per_tap; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
+    // (the whole warp runs the loop and one elected lane issues: see elect_one() in tc_ptx.cuh)
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc_ = decode_tile(p, tile);
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int d = tap - (p.taps >> 1);
+        int par = 0, dt = d;
+        if (p.stride == 2) { par = d & 1; dt = (d - par) / 2; }
+        for (int kb = 0; kb < kb_per_tap; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (leader) {
             mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
             tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), kb * BK, par, tc_.t0 + dt, tc_.b0);
             tma_load_2d(smem_u32(smem_b + stage * b_stage), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
-            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+    // All 32 lanes run the loop (and wait on the barriers); ONE elected lane issues tcgen05.mma / commit from
+    // warp-uniform code. Issued under `if (lane == 0)` every instruction was wrapped in a per-thread election loop
+    // (~53 ns per issue measured, scripts/umma_pace.py) - longer than the 35 ns a 128x128x16 instruction takes.
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+      for (int ki = 0; ki < k_iters; ++ki) {
+        mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
-        for (int ki = 0; ki < k_iters; ++ki) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
+        if (leader) {
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * A_STAGE));
           const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * b_stage));
 #pragma unroll
@@ -179,8 +186,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
           if (ki == k_iters - 1) umma_commit(tfull_bar(acc));
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -191,6 +199,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
     // this warp's 32 rows x 32 or 64 columns; rows beyond the batch are clipped by the tensor map); the residual
     // block of the next chunk is prefetched by TMA into a swizzled tile (mbarrier).
     const EpiParams& e = p.epi;
+    const bool ep_leader = elect_one();        // the lane that issues this warp's TMA loads / stores, commits and waits
     const int q = warp - 4;
     const int N = p.n_out;
     const int et = threadIdx.x - 128;            // 0..127 among the epilogue threads
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
     unsigned char* t16 = has32 ? trs : t32;
     const int sw7 = lane & 7;                    // 128B swizzle: 16-byte chunk j of row `lane` lives in slot j ^ (lane & 7)
     const int sw3 = (lane >> 1) & 3;             // 64B swizzle: chunk j of row `lane` lives in slot j ^ ((lane >> 1) & 3)
-    if (lane == 0) { mbar_init(res_bar, 1); mbar_init(res_bar1, 1); }
+    if (ep_leader) { mbar_init(res_bar, 1); mbar_init(res_bar1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t res_phase = 0, res_phase1 = 0, store_seq = 0;
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
       const float mk = mk_next;
       mk_next = row_mask_of(tile + gridDim.x);    // in flight during this tile's epilogue
       auto fetch_residual = [&](int ch) {         // 32 rows x 128 B of the residual -> trs (TMA, swizzle 128B)
-        if (lane == 0) {
+        if (ep_leader) {
           mbar_arrive_expect_tx(res_bar, 4096);
           tma_load_3d(smem_u32(trs), &p.res_map[tc_.seg], res_bar, tc_.n0 + ch * 32, wt, wb);
         }
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
         tma_load_3d(smem_u32(t32 + ((ch & 1) << 12)), &p.res_map[tc_.seg], bar, tc_.n0 + ch * 32, wt, wb);
       };
       if (RES32_OK) {
-        if (lane == 0) {
+        if (ep_leader) {
           tma_store_wait_read();                  // the previous tile's stores have read both tiles
           fetch_residual_into(0);
           if (chunks > 1) fetch_residual_into(1);
@@ -310,11 +319,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
           if (ch + 2 >= chunks) {                  // all TMEM reads of this warp done: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (ep_leader) mbar_arrive(tempty_bar(acc));
           }
           unsigned char* tw = (store_seq++ & 1) ? trs : t32;
           const f32x2 mk2 = pk2(mk), nmean2 = pk2(-mean), rstd2 = pk2(rstd);
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (ep_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (ep_leader) {
             tma_store_3d(&p.o16w_map[tc_.seg], smem_u32(tw), tc_.n0 + ch * 32, wt, wb);
             tma_store_commit();
           }
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
         } else {                                  // all TMEM reads of this warp are issued: once they complete the
           tcgen05_fence_before();                 // MMA warp may overwrite the accumulator
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (ep_leader) mbar_arrive(tempty_bar(acc));
         }
         const int cl = ch * 32;
         {                                         // (acc + bias) * mask -> LayerNorm -> activation
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
         }
         if (RES32_OK) {
           unsigned char* tb = t32 + ((ch & 1) << 12);
-          if (ch >= 1 && ch + 1 < chunks && lane == 0) {   // tile (ch + 1) & 1 held chunk ch - 1: its store was committed one
+          if (ch >= 1 && ch + 1 < chunks && ep_leader) {   // tile (ch + 1) & 1 held chunk ch - 1: its store was committed one
             tma_store_wait_read();                         // iteration ago; refill it with the residual of chunk ch + 1
             fetch_residual_into(ch + 1);
           }
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (ep_leader) {
             tma_store_3d(&p.o32_map[tc_.seg], smem_u32(tb), tc_.n0 + cl, wt, wb);
             tma_store_commit();
           }
@@ -443,9 +452,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
         unsigned char* t16c = t16;
         if (!has32) {                               // 16-bit only: alternate halves of the 4 KB tile, one store may stay in flight
           t16c = t32 + ((store_seq++ & 1) << 11);
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (ep_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         } else {
-          if (lane == 0) tma_store_wait_read();
+          if (ep_leader) tma_store_wait_read();
         }
         __syncwarp();
         if (has32) {
@@ -469,25 +478,25 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
         }
         fence_async_smem();                       // generic-proxy smem writes -> visible to the async proxy (TMA)
         __syncwarp();
-        if (lane == 0) {
+        if (ep_leader) {
           if (has32) tma_store_3d(&p.o32_map[tc_.seg], smem_u32(t32), tc_.n0 + cl, wt, wb);
           if (has16) tma_store_3d(&p.o16_map[tc_.seg], smem_u32(t16c), tc_.n0 + cl, wt, wb);
           tma_store_commit();
         }
         if (has_res && ch + 1 < chunks) {         // next chunk's residual; if the 16-bit tile aliases the residual
           if (has16 && has32) {                   // tile, its store must have read it first
-            if (lane == 0) tma_store_wait_read();
+            if (ep_leader) tma_store_wait_read();
             __syncwarp();
           }
           fetch_residual(ch + 1);
         }
       }
       if (has_res && has16 && has32) {            // before the next tile's first residual prefetch
-        if (lane == 0) tma_store_wait_read();
+        if (ep_leader) tma_store_wait_read();
         __syncwarp();
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+    if (ep_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -42,7 +42,7 @@ struct Params {
   unsigned long long* dbg;      // optional (debug hook): globaltimer stamps of CTA 0's first tile, 3 x 96 slots
 };
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define MLPF_TS(role, slot) do { if (p.dbg && blockIdx.x == 0 && it == 0 && (slot) < 96) p.dbg[(role) * 96 + (slot)] = gtime_ns(); } while (0)
+#define MLPF_TS(role, slot) do { if (p.dbg && blockIdx.x == 0 && it == 0 && (slot) < 96 && (threadIdx.x & 31) == 0) p.dbg[(role) * 96 + (slot)] = gtime_ns(); } while (0)
 
 // barrier slots
 enum { B_XFULL = 0, B_XEMPTY, B_RFULL, B_REMPTY = B_RFULL + RING, B_A1FULL = B_REMPTY + RING, B_A1EMPTY = B_A1FULL + 2,
@@ -100,22 +100,30 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // (whole warp in the loop, one elected lane issues from warp-uniform code: elect_one() in tc_ptx.cuh)
+    const bool leader = elect_one();
+    {
       int stage = 0; uint32_t phase = 0; int it = 0;
       int nu = 0;
       auto load_unit = [&](const CUtensorMap* map, int c0, int c1) {
         mbar_wait(bar(B_REMPTY + stage), phase ^ 1);
         MLPF_TS(0, 1 + nu); ++nu;
-        mbar_arrive_expect_tx(bar(B_RFULL + stage), UNIT);
-        tma_load_2d(smem_u32(sring + stage * UNIT), map, bar(B_RFULL + stage), c0, c1);
+        if (leader) {
+          mbar_arrive_expect_tx(bar(B_RFULL + stage), UNIT);
+          tma_load_2d(smem_u32(sring + stage * UNIT), map, bar(B_RFULL + stage), c0, c1);
+        }
+        __syncwarp();
         if (++stage == RING) { stage = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
         mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);
         nu = 0;
         MLPF_TS(0, 0);
-        mbar_arrive_expect_tx(bar(B_XFULL), 4 * UNIT);
-        for (int s = 0; s < 4; ++s) tma_load_2d(smem_u32(sx + s * UNIT), &p.x_map, bar(B_XFULL), s * 64, tile * BM);
+        if (leader) {
+          mbar_arrive_expect_tx(bar(B_XFULL), 4 * UNIT);
+          for (int s = 0; s < 4; ++s) tma_load_2d(smem_u32(sx + s * UNIT), &p.x_map, bar(B_XFULL), s * 64, tile * BM);
+        }
+        __syncwarp();
         for (int s = 0; s < 4; ++s) load_unit(&p.w1_map, s * 64, chunk_of(0) * HC);
         for (int j = 0; j < NCHUNK; ++j) {
           if (j + 1 < NCHUNK)
@@ -127,7 +135,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       int stage = 0; uint32_t phase = 0; int it = 0;
       uint32_t n_a1[2] = {0, 0}, n_h = 0;
       auto g1 = [&](int j) {
@@ -137,15 +146,18 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         for (int s = 0; s < 4; ++s) {
           mbar_wait(bar(B_RFULL + stage), phase);
           tcgen05_fence_after();
-          const uint64_t da = make_sw128_desc(smem_u32(sx + s * UNIT));
-          const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
+          if (leader) {
+            const uint64_t da = make_sw128_desc(smem_u32(sx + s * UNIT));
+            const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + (uint32_t)(b * HC), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (s > 0 || k > 0) ? 1u : 0u);
-          umma_commit(bar(B_REMPTY + stage));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + (uint32_t)(b * HC), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (s > 0 || k > 0) ? 1u : 0u);
+            umma_commit(bar(B_REMPTY + stage));
+            if (s == 3) umma_commit(bar(B_A1FULL + b));
+          }
+          __syncwarp();
           if (++stage == RING) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar(B_A1FULL + b));
         ++n_a1[b];
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         for (int j = 0; j < NCHUNK; ++j) {
           if (j + 1 < NCHUNK) g1(j + 1);
           MLPF_TS(1, 2 + 4 * j);                  // G1(j+1) issued
-          if (j == NCHUNK - 2) umma_commit(bar(B_XEMPTY));         // every G1 of this tile is issued: x may be replaced
+          if (j == NCHUNK - 2 && leader) umma_commit(bar(B_XEMPTY));   // every G1 of this tile is issued: x may be replaced
           if (j == 0) { mbar_wait(bar(B_A2EMPTY), (uint32_t)(it & 1) ^ 1); tcgen05_fence_after(); }
           mbar_wait(bar(B_HFULL), n_h & 1);
           tcgen05_fence_after();
@@ -166,19 +178,25 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
             for (int s = 0; s < 2; ++s) {
               mbar_wait(bar(B_RFULL + stage), phase);
               tcgen05_fence_after();
-              const uint64_t da = make_sw128_desc(smem_u32(sh + s * UNIT));
-              const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
+              if (leader) {
+                const uint64_t da = make_sw128_desc(smem_u32(sh + s * UNIT));
+                const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tm_acc2 + (uint32_t)(h * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (j > 0 || s > 0 || k > 0) ? 1u : 0u);
-              umma_commit(bar(B_REMPTY + stage));
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tm_acc2 + (uint32_t)(h * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (j > 0 || s > 0 || k > 0) ? 1u : 0u);
+                umma_commit(bar(B_REMPTY + stage));
+              }
+              __syncwarp();
               if (++stage == RING) { stage = 0; phase ^= 1; }
             }
           }
-          umma_commit(bar(B_HEMPTY));
+          if (leader) {
+            umma_commit(bar(B_HEMPTY));
+            if (j == NCHUNK - 1) umma_commit(bar(B_A2FULL));
+          }
+          __syncwarp();
           ++n_h;
           MLPF_TS(1, 4 + 4 * j);                  // G2(j) issued
-          if (j == NCHUNK - 1) umma_commit(bar(B_A2FULL));
         }
       }
     }

@@ -12,6 +12,15 @@ namespace tc {
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (elect.sync): code under `if (elect_one())` is warp-uniform for the compiler, so
+// tcgen05.mma / commit / TMA issue compile to single uniform-datapath instructions. Under `if (lane == 0)` the compiler
+// cannot prove uniformity and wraps every such instruction in a per-thread election loop (R2UR x4, ELECT, BRA.U.ANY:
+// ~50 ns per tcgen05.mma, more than a 128x128x16 instruction takes on the tensor pipe).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

@@ -112,6 +112,31 @@ def test_batch_invariance_and_streams():
         assert a["video_id"] == c["video_id"]
 
 
+def test_fused_mlp_path_matches_two_launch_path():
+    """engine.fused_mlp routes every block's MLP through avdf_mlp_fused (one launch, hidden activations on chip). Per call
+    it agrees with the two-GEMM path to ~1e-6 (tests/test_gpu_kernels.py::test_mlp_fused); over the whole network
+    those last-bit differences pass through the 16-bit rounding points of later layers, so the dense outputs are
+    compared at the mixed-precision bar. The fused path itself stays batch invariant (bit-exact)."""
+    model, _ = build("exp12", "mixed")
+    durs = [4.03, 9.04, 26.37]
+    import interp_ref
+    items = [interp_ref.dataset_item(syn.synthetic_streams(d, 300 + i), d, f"v{i}") for i, d in enumerate(durs)]
+    base = model.dense_outputs(items)
+    eng = model.engine()
+    eng.fused_mlp, eng.fused_mlp_min_rows = True, 0
+    try:
+        fused = model.dense_outputs(items)
+        fused_out = model(items)
+        single = [model([it])[0] for it in items]
+    finally:
+        eng.fused_mlp = False
+    for a, b in zip(base[:2], fused[:2]):
+        for x, y in zip(a, b):
+            assert max_rel(y.cpu().numpy(), x.cpu().numpy()) < 5e-3
+    for b, c in zip(fused_out, single):
+        assert torch.equal(b["scores"], c["scores"]) and torch.equal(b["segments"], c["segments"])
+
+
 def test_reference_style_driver(tmp_path):
     """inference_one_epoch over a list-of-lists loader writes the reference's JSON records."""
     import json
