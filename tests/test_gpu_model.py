@@ -121,15 +121,17 @@ def test_fused_mlp_path_matches_two_launch_path():
     durs = [4.03, 9.04, 26.37]
     import interp_ref
     items = [interp_ref.dataset_item(syn.synthetic_streams(d, 300 + i), d, f"v{i}") for i, d in enumerate(durs)]
-    base = model.dense_outputs(items)
     eng = model.engine()
-    eng.fused_mlp, eng.fused_mlp_min_rows = True, 0
+    was = eng.fused_mlp
     try:
+        eng.fused_mlp = False
+        base = model.dense_outputs(items)
+        eng.fused_mlp, eng.fused_mlp_min_rows = True, 0
         fused = model.dense_outputs(items)
         fused_out = model(items)
         single = [model([it])[0] for it in items]
     finally:
-        eng.fused_mlp = False
+        eng.fused_mlp = was
     for a, b in zip(base[:2], fused[:2]):
         for x, y in zip(a, b):
             assert max_rel(y.cpu().numpy(), x.cpu().numpy()) < 5e-3
