@@ -288,16 +288,19 @@ class LocalizationEngine:
         gm = w.vec(pre + ".drop_path_mlp.scale") if w.has(pre + ".drop_path_mlp.scale") else None
         self._gemm(att, f"{pre}.attn.proj.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.attn.proj.bias"),
                    row_mask=mask, residual=skip, gamma=ga, out_f32=y)
-        l2 = self.buf("ln2", (B, T, C), self.adt)
-        ops.ln_rows(y, *w.ln(pre + ".ln2"), l2, B * T)
         out = self.buf(out_name, (B, T, C), torch.float32)
         out_act = None
         if want_act_copy and self.adt != torch.float32:
             out_act = self.buf(out_name + "_act", (B, T, C), self.adt)
+        l2 = self.buf("ln2", (B, T, C), self.adt)
+        ops.ln_rows(y, *w.ln(pre + ".ln2"), l2, B * T)
         if self.fused_mlp and self.adt != torch.float32 and out_act is None and C == 256 and B * T >= self.fused_mlp_min_rows:
-            # one launch: the [B*T, 4C] activations stay in shared memory / TMEM (csrc/mlp_fused.cu)
-            ops.mlp_fused(l2, w.dense(f"{pre}.mlp.0.weight", l2.dtype), w.vec(f"{pre}.mlp.0.bias"),
-                          w.dense(f"{pre}.mlp.3.weight", l2.dtype), w.vec(f"{pre}.mlp.3.bias"),
+            # one launch: the [B*T, 4C] activations stay in shared memory / TMEM (csrc/mlp_fused.cu). (Folding LN2 into
+            # the kernel was tried - two spare warps normalising the next 128-row tile straight into the operand
+            # layout - and measured slower, 14.7k vs 15.9k videos/s: ~10 us per tile that cannot be hidden because the
+            # x tile cannot be double-buffered in 227 KB. LN2 stays a separate 9 us launch.)
+            ops.mlp_fused(l2, w.dense(f"{pre}.mlp.0.weight", self.adt), w.vec(f"{pre}.mlp.0.bias"),
+                          w.dense(f"{pre}.mlp.3.weight", self.adt), w.vec(f"{pre}.mlp.3.bias"),
                           row_mask=mask, residual=y, gamma=gm, out=out)
             return out, None
         h = self.buf("mlp_h", (B, T, 4 * C), self.adt)
