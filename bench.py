@@ -100,9 +100,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_ready(self, timeout=3.0):
+        """Block until nvidia-smi has printed its first sample (it needs ~0.1-0.3 s to start)."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        self.first = len(self.rows)
+
+    def count(self):
+        return len(self.rows) - getattr(self, "first", 0)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.rows = self.rows[getattr(self, "first", 0):]
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -252,9 +265,13 @@ def run_ours(args):
             main.wait_stream(s_)
         return out
 
-    gather(run_steps(max(args.warmup, N_POOL), 0))
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    gather(run_steps(max(args.warmup, N_POOL), 0))
+    if sampler:
+        sampler.wait_ready()
+    barrier()
+    if sampler:
+        sampler.mark()                  # clocks are sampled (20 ms period) from here on, i.e. under the timed load
     native.LAUNCHES["n"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -267,6 +284,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    if sampler and sampler.count() < 3:
+        # a timed region shorter than a few sampling periods: keep the same load running (untimed) until nvidia-smi has
+        # reported at least 3 samples under it
+        t_more = time.time()
+        while sampler.count() < 3 and time.time() - t_more < 2.0:
+            run_steps(N_POOL, 0)
+            torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     value = world * args.steps * BATCH / (ms / 1000.0)
     assert allrec.shape[0] == world * args.steps * BATCH
