@@ -497,52 +497,74 @@ struct FpnParams {
   int lvl_off[AVDF_MAX_LEVELS], lvl_len[AVDF_MAX_LEVELS];
 };
 
+// Latency-bound as first written (18 dependent 1 KB row loads per output row behind run-time loop bounds: 125 us for
+// 74 MB): the level loop is unrolled over AVDF_MAX_LEVELS with predicates so that the loads of a tap (one row per
+// pyramid level above the output row) are in flight together, and a warp keeps the depthwise / LayerNorm weights of
+// its current level in registers (rows of a video are sorted by level).
 template <typename OutT>
-__global__ void __launch_bounds__(256) fpn_fuse_kernel(const FpnParams p) {
+__global__ void __launch_bounds__(256, 2) fpn_fuse_kernel(const FpnParams p) {
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 8;
   const long long rows = (long long)p.B * p.P;
+  int cur_l = -1;
+  float dwr[3][8], lw[8], lb[8];
   for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
     const int b = (int)(r / p.P);
     const int pr = (int)(r - (long long)b * p.P);
     int l = 0;
     while (l + 1 < p.n_levels && pr >= p.lvl_off[l + 1]) ++l;
     const int t = pr - p.lvl_off[l], T = p.lvl_len[l];
+    if (l != cur_l) {
+      const float* dw = p.dw_w + (size_t)l * kC * 3;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        dwr[0][k] = __ldg(dw + (c0 + k) * 3); dwr[1][k] = __ldg(dw + (c0 + k) * 3 + 1); dwr[2][k] = __ldg(dw + (c0 + k) * 3 + 2);
+      }
+      if (p.ln_w) {
+        Row8<float>::load(p.ln_w + (size_t)l * kC + c0, lw);
+        Row8<float>::load(p.ln_b + (size_t)l * kC + c0, lb);
+      }
+      cur_l = l;
+    }
     const float* lat_b = p.lat + (size_t)b * p.P * kC;
+    const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int tt = t + j - 1;
-      if (tt < 0 || tt >= T) continue;
+      const bool tin = tt >= 0 && tt < T;
       // L_l[tt] = lat_l[tt] + (lat_{l+1}[tt>>1] + (... )) summed from the top level down (necks.py:76-80)
+      float a[AVDF_MAX_LEVELS][8];
+#pragma unroll
+      for (int jl = 0; jl < AVDF_MAX_LEVELS; ++jl) {
+        const int dl = jl - l;
+        const int ts = tt >> (dl > 0 ? dl : 0);
+        const bool ok = tin && jl < p.n_levels && dl >= 0 && ts < p.lvl_len[jl];
+        if (ok) Row8<float>::load(lat_b + (size_t)(p.lvl_off[jl] + ts) * kC + c0, a[jl]);
+        else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a[jl][k] = 0.f;
+        }
+      }
       float sum[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) sum[k] = 0.f;
-      for (int jl = p.n_levels - 1; jl >= l; --jl) {
-        const int ts = tt >> (jl - l);
-        if (ts >= p.lvl_len[jl]) continue;
-        float a[8];
-        Row8<float>::load(lat_b + (size_t)(p.lvl_off[jl] + ts) * kC + c0, a);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum[k] += a[k];
-      }
-      const float* dw = p.dw_w + (size_t)l * kC * 3;
+      for (int jl = AVDF_MAX_LEVELS - 1; jl >= 0; --jl)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(__ldg(dw + (c0 + k) * 3 + j), sum[k], acc[k]);
+        for (int k = 0; k < 8; ++k) sum[k] += a[jl][k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(dwr[j][k], sum[k], acc[k]);
     }
-    const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] *= mk;
     if (p.ln_w) {
       float m, rs;
       row_stats(acc, m, rs);
-      float w[8], bb[8];
-      Row8<float>::load(p.ln_w + (size_t)l * kC + c0, w);
-      Row8<float>::load(p.ln_b + (size_t)l * kC + c0, bb);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m) * rs, w[k], bb[k]);
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m) * rs, lw[k], lb[k]);
     }
     Row8<OutT>::store(reinterpret_cast<OutT*>(p.out) + (size_t)r * kC + c0, acc);
   }
@@ -558,6 +580,95 @@ struct HeadParams {
   int lvl_off[AVDF_MAX_LEVELS], lvl_len[AVDF_MAX_LEVELS]; float lvl_scale[AVDF_MAX_LEVELS];
 };
 
+// Column-blocked variant: the kernel above re-reads every lateral row up to 18 times through L2 (~600 MB for a 50 MB
+// tensor: L2-bandwidth bound, ~100 us). Here a CTA owns FPB level-0 positions of one video and the rows of all coarser
+// levels above them (FPB >> l rows at level l, plus one halo row on each side for the k3 taps): phase 1 builds the
+// top-down sums L_l[t] = L_{l+1}[t >> 1] + lat_l[t] once per row in shared memory (coarsest level first, same
+// summation order as necks.py:76-80), phase 2 runs the depthwise conv + mask + LayerNorm from shared memory.
+// Every lateral row is read once per CTA (plus halos).
+constexpr int FPB = 32;                       // level-0 positions per CTA
+template <typename OutT>
+__global__ void __launch_bounds__(256) fpn_fuse_cols_kernel(const FpnParams p) {
+  extern __shared__ __align__(16) float fpn_smem[];          // [sum_l (FPB >> l) + 2][256]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * 8;
+  const int blocks_per_video = p.lvl_len[0] / FPB;
+  const int b = blockIdx.x / blocks_per_video;
+  const int blk = blockIdx.x - b * blocks_per_video;
+  const float* lat_b = p.lat + (size_t)b * p.P * kC;
+  int row0[AVDF_MAX_LEVELS];                                 // first smem row of level l (its row i holds position s_l - 1 + i)
+  {
+    int acc_rows = 0;
+#pragma unroll
+    for (int l = 0; l < AVDF_MAX_LEVELS; ++l) { row0[l] = acc_rows; acc_rows += (FPB >> l) + 2; }
+  }
+  // phase 1: coarsest level first
+  for (int l = p.n_levels - 1; l >= 0; --l) {
+    const int n = (FPB >> l) + 2, s = ((blk * FPB) >> l) - 1, T = p.lvl_len[l];
+    for (int i = warp; i < n; i += 8) {
+      const int pos = s + i;
+      float v[8];
+      if (pos >= 0 && pos < T) {
+        Row8<float>::load(lat_b + (size_t)(p.lvl_off[l] + pos) * kC + c0, v);
+        if (l + 1 < p.n_levels && (pos >> 1) < p.lvl_len[l + 1]) {
+          const int pi = (pos >> 1) - (((blk * FPB) >> (l + 1)) - 1);
+          float u[8];
+          lds8(fpn_smem + (size_t)(row0[l + 1] + pi) * kC + c0, u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = u[k] + v[k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;                // outside the level: the conv's zero padding
+      }
+      float* d = fpn_smem + (size_t)(row0[l] + i) * kC + c0;
+      *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+  }
+  // phase 2: depthwise k3 + mask + LayerNorm, warp per output row, levels in order (weights cached per level)
+  for (int l = 0; l < p.n_levels; ++l) {
+    const int n = FPB >> l, s = (blk * FPB) >> l;
+    if (warp >= n && n < 8) continue;                          // fewer rows than warps at the top levels
+    float dwr[3][8], lw[8], lb[8];
+    const float* dw = p.dw_w + (size_t)l * kC * 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dwr[0][k] = __ldg(dw + (c0 + k) * 3); dwr[1][k] = __ldg(dw + (c0 + k) * 3 + 1); dwr[2][k] = __ldg(dw + (c0 + k) * 3 + 2);
+    }
+    if (p.ln_w) {
+      Row8<float>::load(p.ln_w + (size_t)l * kC + c0, lw);
+      Row8<float>::load(p.ln_b + (size_t)l * kC + c0, lb);
+    }
+    for (int i = warp; i < n; i += 8) {
+      const size_t r = (size_t)b * p.P + p.lvl_off[l] + s + i;
+      const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float u[8];
+        lds8(fpn_smem + (size_t)(row0[l] + i + j) * kC + c0, u);   // smem row i + j holds position s + i + j - 1
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(dwr[j][k], u[k], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] *= mk;
+      if (p.ln_w) {
+        float m, rs;
+        row_stats(acc, m, rs);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m) * rs, lw[k], lb[k]);
+      }
+      Row8<OutT>::store(reinterpret_cast<OutT*>(p.out) + r * kC + c0, acc);
+    }
+  }
+}
+
+// The 3 x 3 x 256 weights live in registers (72 per lane, loaded once per warp) and the six activation rows of an
+// output row are loaded together: as first written every row re-read 9 KB of weights through L1 (58 us for 50 MB).
 template <typename InT>
 __global__ void __launch_bounds__(256) head_final_kernel(const HeadParams p) {
   const int lane = threadIdx.x & 31;
@@ -565,38 +676,50 @@ __global__ void __launch_bounds__(256) head_final_kernel(const HeadParams p) {
   const long long rows = (long long)p.B * p.P;
   const InT* cf = reinterpret_cast<const InT*>(p.cls_feat);
   const InT* rf = reinterpret_cast<const InT*>(p.reg_feat);
+  float wc[3][8], wr0[3][8], wr1[3][8];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    Row8<float>::load(p.cls_w + j * kC + c0, wc[j]);
+    Row8<float>::load(p.reg_w + j * kC + c0, wr0[j]);
+    Row8<float>::load(p.reg_w + 3 * kC + j * kC + c0, wr1[j]);
+  }
+  const float cb = p.cls_b[0], rb0 = p.reg_b[0], rb1 = p.reg_b[1];
   for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
     const int b = (int)(r / p.P);
     const int pr = (int)(r - (long long)b * p.P);
     int l = 0;
     while (l + 1 < p.n_levels && pr >= p.lvl_off[l + 1]) ++l;
     const int t = pr - p.lvl_off[l], T = p.lvl_len[l];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float xc[3][8], xr[3][8];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int tt = t + j - 1;
-      if (tt < 0 || tt >= T) continue;
-      const size_t row = (size_t)r + (j - 1);
-      float x[8], w[8];
-      Row8<InT>::load(cf + row * kC + c0, x);
-      Row8<float>::load(p.cls_w + j * kC + c0, w);
+      if (tt >= 0 && tt < T) {
+        const size_t row = (size_t)(r + (j - 1));
+        Row8<InT>::load(cf + row * kC + c0, xc[j]);
+        Row8<InT>::load(rf + row * kC + c0, xr[j]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a0 = fmaf(w[k], x[k], a0);
-      Row8<InT>::load(rf + row * kC + c0, x);
-      Row8<float>::load(p.reg_w + j * kC + c0, w);
+        for (int k = 0; k < 8; ++k) { xc[j][k] = 0.f; xr[j][k] = 0.f; }
+      }
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a1 = fmaf(w[k], x[k], a1);
-      Row8<float>::load(p.reg_w + 3 * kC + j * kC + c0, w);
+    for (int j = 0; j < 3; ++j) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a2 = fmaf(w[k], x[k], a2);
+      for (int k = 0; k < 8; ++k) a0 = fmaf(wc[j][k], xc[j][k], a0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a1 = fmaf(wr0[j][k], xr[j][k], a1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a2 = fmaf(wr1[j][k], xr[j][k], a2);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) {
       const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
-      p.logits[r] = (a0 + p.cls_b[0]) * mk;
+      p.logits[r] = (a0 + cb) * mk;
       const float sc = p.lvl_scale[l];
-      p.offsets[2 * r] = fmaxf(((a1 + p.reg_b[0]) * mk) * sc, 0.f);
-      p.offsets[2 * r + 1] = fmaxf(((a2 + p.reg_b[1]) * mk) * sc, 0.f);
+      p.offsets[2 * r] = fmaxf(((a1 + rb0) * mk) * sc, 0.f);
+      p.offsets[2 * r + 1] = fmaxf(((a2 + rb1) * mk) * sc, 0.f);
     }
   }
 }
@@ -921,8 +1044,23 @@ extern "C" int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float*
   p.lat = lat; p.mask = mask; p.dw_w = dw_w; p.ln_w = ln_w; p.ln_b = ln_b; p.out = out; p.B = batch; p.n_levels = n_levels;
   p.P = fill_levels(n_levels, level_len, p.lvl_off, p.lvl_len);
   if (batch == 0) return AVDF_OK;
-  const int grid = grid_for((long long)batch * p.P, 8, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (level_len[0] % FPB == 0 && (FPB >> (n_levels - 1)) >= 1) {    // column-blocked kernel (every shipped config)
+    int smem_rows = 0;
+    for (int l = 0; l < AVDF_MAX_LEVELS; ++l) smem_rows += (FPB >> l) + 2;
+    const size_t smem = (size_t)smem_rows * kC * sizeof(float);
+    const int grid = batch * (level_len[0] / FPB);
+    AVDF_DISPATCH_DTYPE(out_dtype, OutT, {
+      static bool attr_done = false;
+      if (!attr_done) {
+        AVDF_CUDA(cudaFuncSetAttribute(fpn_fuse_cols_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+      }
+      fpn_fuse_cols_kernel<OutT><<<grid, 256, smem, st>>>(p);
+    });
+    return check_launch("fpn_fuse_cols_kernel");
+  }
+  const int grid = grid_for((long long)batch * p.P, 8, sm_count());
   AVDF_DISPATCH_DTYPE(out_dtype, OutT, (fpn_fuse_kernel<OutT><<<grid, 256, 0, st>>>(p)));
   return check_launch("fpn_fuse_kernel");
 }

@@ -413,9 +413,11 @@ def test_instnorm_lrelu():
         assert rel_err(out.cpu(), want) < 5e-6
 
 
-def test_fpn_fuse_and_head_final():
+@pytest.mark.parametrize("lens", [[96, 48, 24, 12, 6, 3], [768, 384, 192, 96, 48, 24], [40, 20, 10, 5]])
+def test_fpn_fuse_and_head_final(lens):
+    """[96..3] / [768..24]: the column-blocked fpn kernel (level 0 divisible by 32); [40..5]: the row-per-warp kernel."""
     rng = np.random.RandomState(4)
-    B, C, lens = 2, 256, [96, 48, 24, 12, 6, 3]
+    B, C = 2, 256
     P, L = sum(lens), len(lens)
     offs = np.cumsum([0] + lens)
     lat = torch.from_numpy(rng.standard_normal((B, P, C)).astype(np.float32))
@@ -436,7 +438,7 @@ def test_fpn_fuse_and_head_final():
     # head_final on top
     cw = torch.from_numpy((rng.standard_normal((1, C, 3)) / 10).astype(np.float32)); cb = torch.tensor([-1.0])
     rw = torch.from_numpy((rng.standard_normal((2, C, 3)) / 10).astype(np.float32)); rb = torch.tensor([0.3, -0.2])
-    scales = [0.8, 0.9, 1.0, 1.1, 1.2, 1.3]
+    scales = [0.8, 0.9, 1.0, 1.1, 1.2, 1.3][:L]
     cf = torch.from_numpy(rng.standard_normal((B, P, C)).astype(np.float32)); rf = torch.from_numpy(rng.standard_normal((B, P, C)).astype(np.float32))
     logits = torch.zeros((B, P), device=DEV); offsets = torch.zeros((B, P, 2), device=DEV)
     ops.head_final(dev(cf), dev(rf), dev(mask.astype(np.uint8)), dev(cw.permute(0, 2, 1).reshape(1, -1)), dev(cb),
