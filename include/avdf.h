@@ -20,6 +20,9 @@
  *                                   postprocessing) + libs/utils/nms.py:8-190 (NMSop, SoftNMSop,
  *                                   seg_voting, batched_nms)
  *   avdf_interp_concat              libs/datasets/deepfake_video_audio.py:513-547 (F.interpolate x3 + cat)
+ *   avdf_host_pack                  HOST: DataLoader collate + pin of the raw stream arrays,
+ *                                   libs/datasets/deepfake_video_audio.py:547-558 (dataset item) and the
+ *                                   per-video `.to(device)` of libs/modeling/av_fd_no_recon.py:476-477
  *   avdf_pack_feats                 preprocessing, libs/modeling/av_fd_no_recon.py:431-479 (pad + batch layout)
  *   avdf_conv_gemm                  MaskedConv1D (libs/modeling/blocks.py:13-63) as used by the
  *                                   embedding (backbones.py:437-445), the 1x1 projections and MLP of the
@@ -232,6 +235,11 @@ AVDF_API int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_wt
 AVDF_API int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* seg_w /* [C] */,
                     const float* seg_b, const float* cls_w /* [2] */, const float* cls_b, float* out,
                     int32_t batch, int32_t t, int32_t channels, void* stream);
+
+/* ---- HOST: gather n byte spans (src[i] -> dst[i], nbytes[i] bytes; all HOST pointers, any alignment; dst is normally
+ * a slice of a pinned staging buffer) with up to n_threads threads of a pool that lives inside the library
+ * (non-temporal stores). Synchronous; concurrent calls are serialised. No CUDA call is made. */
+AVDF_API int avdf_host_pack(const void* const* src, void* const* dst, const size_t* nbytes, int32_t n, int32_t n_threads);
 
 #ifdef __cplusplus
 }

@@ -12,9 +12,8 @@ raw = bench.make_raw_batches(4, use_video, 11)
 r = model.runner()
 for _ in model.stream(raw): pass
 slot = r.slots[0]
-for nthreads in (4, 8, 16, 32):
-    from concurrent.futures import ThreadPoolExecutor
-    r.pool = ThreadPoolExecutor(max_workers=nthreads)
+for nthreads in (1, 2, 4, 8, 16, 32):
+    r.n_threads = nthreads
     ts = []
     for i in range(12):
         t0 = time.perf_counter(); r._pack(slot, raw[i % 4]); ts.append(time.perf_counter() - t0)
