@@ -419,35 +419,57 @@ __global__ void __launch_bounds__(ATB_WARPS * 32) attention_banded_kernel(const 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over channels of fp32 rows (C = 256 * NCH)
 // ------------------------------------------------------------------------------------------------
+// A warp normalises LNR_ROWS rows per iteration (their loads are in flight together: one 1 KB row per warp left the
+// kernel latency-bound at ~3 TB/s) and the host sizes the grid so that every CTA runs the same number of iterations.
+constexpr int LNR_ROWS = 2;
 template <typename OutT, int NCH>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bvec, OutT* __restrict__ out, long long rows) {
   const int lane = threadIdx.x & 31;
   const int C = kC * NCH;
-  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
-    float v[NCH][8];
-    float s = 0.f;
+  for (long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * LNR_ROWS; r0 < rows; r0 += (long long)gridDim.x * 8 * LNR_ROWS) {
+    float v[LNR_ROWS][NCH][8];
+    float s[LNR_ROWS];
 #pragma unroll
-    for (int h = 0; h < NCH; ++h) {
-      Row8<float>::load(x + (size_t)r * C + h * kC + lane * 8, v[h]);
+    for (int i = 0; i < LNR_ROWS; ++i) {
+      const long long r = r0 + i < rows ? r0 + i : rows - 1;      // a tail warp re-reads the last row and skips the store
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += v[h][k];
+      for (int h = 0; h < NCH; ++h) Row8<float>::load(x + (size_t)r * C + h * kC + lane * 8, v[i][h]);
     }
-    const float mean = warp_sum(s) / (float)C;
-    float qq = 0.f;
 #pragma unroll
-    for (int h = 0; h < NCH; ++h)
+    for (int i = 0; i < LNR_ROWS; ++i) {
+      s[i] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { const float d = v[h][k] - mean; qq = fmaf(d, d, qq); }
-    const float rstd = 1.f / sqrtf(warp_sum(qq) / (float)C + kLnEps);
+      for (int h = 0; h < NCH; ++h)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[i] += v[i][h][k];
+    }
+    float mean[LNR_ROWS], qq[LNR_ROWS];
+#pragma unroll
+    for (int i = 0; i < LNR_ROWS; ++i) mean[i] = warp_sum(s[i]) / (float)C;
+#pragma unroll
+    for (int i = 0; i < LNR_ROWS; ++i) {
+      qq[i] = 0.f;
+#pragma unroll
+      for (int h = 0; h < NCH; ++h)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = v[i][h][k] - mean[i]; qq[i] = fmaf(d, d, qq[i]); }
+    }
+    float rstd[LNR_ROWS];
+#pragma unroll
+    for (int i = 0; i < LNR_ROWS; ++i) rstd[i] = 1.f / sqrtf(warp_sum(qq[i]) / (float)C + kLnEps);
 #pragma unroll
     for (int h = 0; h < NCH; ++h) {
       float ww[8], bb[8];
       Row8<float>::load(w + h * kC + lane * 8, ww);
       Row8<float>::load(bvec + h * kC + lane * 8, bb);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[h][k] = fmaf((v[h][k] - mean) * rstd, ww[k], bb[k]);
-      Row8<OutT>::store(out + (size_t)r * C + h * kC + lane * 8, v[h]);
+      for (int i = 0; i < LNR_ROWS; ++i) {
+        if (r0 + i >= rows) break;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][h][k] = fmaf((v[i][h][k] - mean[i]) * rstd[i], ww[k], bb[k]);
+        Row8<OutT>::store(out + (size_t)(r0 + i) * C + h * kC + lane * 8, v[i][h]);
+      }
     }
   }
 }
@@ -485,6 +507,53 @@ __global__ void __launch_bounds__(32 * IN_TY) instnorm_lrelu_kernel(const float*
     float v = (xb[(size_t)t * C] - mean) * rstd;
     v = v >= 0.f ? v : v * slope;
     store1(ob + (size_t)t * C, v);
+  }
+}
+
+// Same, with the thread's T / IN_TY values held in registers: x is read once instead of three times (the launches of
+// this path have T <= 768). Same summation order as the kernel above.
+template <typename OutT, int NR>
+__global__ void __launch_bounds__(32 * IN_TY) instnorm_lrelu_reg_kernel(const float* __restrict__ x, OutT* __restrict__ out,
+                                                                       int T, int C, float slope) {
+  __shared__ float red[IN_TY][33];
+  const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  const float* xb = x + (size_t)b * T * C + c;
+  OutT* ob = out + (size_t)b * T * C + c;
+  float v[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int t = threadIdx.y + i * IN_TY;
+    v[i] = t < T ? xb[(size_t)t * C] : 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) s += v[i];            // rows beyond T hold 0
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < IN_TY; ++i) tot += red[i][threadIdx.x];
+  const float mean = tot / (float)T;
+  __syncthreads();
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (threadIdx.y + i * IN_TY < T) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  }
+  red[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < IN_TY; ++i) tot += red[i][threadIdx.x];
+  const float rstd = 1.f / sqrtf(tot / (float)T + kLnEps);
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int t = threadIdx.y + i * IN_TY;
+    if (t < T) {
+      float y = (v[i] - mean) * rstd;
+      y = y >= 0.f ? y : y * slope;
+      store1(ob + (size_t)t * C, y);
+    }
   }
 }
 
@@ -891,7 +960,10 @@ __global__ void __launch_bounds__(256) vcls_exp13_kernel(const InT* __restrict__
 static int grid_for(long long work_items, int per_cta, int sms) {
   long long want = (work_items + per_cta - 1) / per_cta;
   long long cap = (long long)sms * 8;
-  if (want > cap) want = cap;
+  if (want > cap) {                      // grid-stride: the same number of iterations for every CTA (no ragged last wave)
+    const long long iters = (want + cap - 1) / cap;
+    want = (want + iters - 1) / iters;
+  }
   return (int)(want < 1 ? 1 : want);
 }
 static int sm_count() {
@@ -1004,7 +1076,7 @@ extern "C" int avdf_ln_rows(const float* x, const float* w, const float* b, void
   AVDF_CHECK_ARG(rows >= 0, "rows < 0");
   AVDF_CHECK_DTYPE(out_dtype, "out_dtype");
   if (rows == 0) return AVDF_OK;
-  const int grid = grid_for(rows, 8, sm_count());
+  const int grid = grid_for(rows, 8 * LNR_ROWS, sm_count());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (channels == 256) AVDF_DISPATCH_DTYPE(out_dtype, OutT, (ln_rows_kernel<OutT, 1><<<grid, 256, 0, st>>>(x, w, b, (OutT*)out, rows)));
   else if (channels == 512) AVDF_DISPATCH_DTYPE(out_dtype, OutT, (ln_rows_kernel<OutT, 2><<<grid, 256, 0, st>>>(x, w, b, (OutT*)out, rows)));
@@ -1021,7 +1093,15 @@ extern "C" int avdf_instnorm_lrelu(const float* x, void* out, int32_t out_dtype,
   if (batch == 0) return AVDF_OK;
   dim3 grid(channels / 32, batch), block(32, IN_TY);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  AVDF_DISPATCH_DTYPE(out_dtype, OutT, (instnorm_lrelu_kernel<OutT><<<grid, block, 0, st>>>(x, (OutT*)out, t, channels, slope)));
+  const int nr = (t + IN_TY - 1) / IN_TY;
+#define AVDF_IN_REG(NR) AVDF_DISPATCH_DTYPE(out_dtype, OutT, (instnorm_lrelu_reg_kernel<OutT, NR><<<grid, block, 0, st>>>(x, (OutT*)out, t, channels, slope)))
+  if (nr <= 3) AVDF_IN_REG(3);
+  else if (nr <= 6) AVDF_IN_REG(6);
+  else if (nr <= 12) AVDF_IN_REG(12);
+  else if (nr <= 24) AVDF_IN_REG(24);
+  else if (nr <= 48) AVDF_IN_REG(48);
+  else AVDF_DISPATCH_DTYPE(out_dtype, OutT, (instnorm_lrelu_kernel<OutT><<<grid, block, 0, st>>>(x, (OutT*)out, t, channels, slope)));
+#undef AVDF_IN_REG
   return check_launch("instnorm_lrelu_kernel");
 }
 
