@@ -18,6 +18,11 @@
 //                       pipelines per SM overlap those chains.
 //   wide   (BN = 256):  3 stages x (16 KB A + 32 KB W), 2 x 256 TMEM columns, one CTA per SM (LayerNorm over the row
 //                       needs all 256 channels in one CTA; the big-K embedding GEMMs are MMA-bound).
+//   weight-stationary (BN = 256, 1x1, K <= 256): the CTA's 256 x K weight block (128 KB) is loaded ONCE and stays in
+//                       shared memory; a CTA is pinned to one (segment, n-tile) group and walks its 128-row tiles, so
+//                       only A (16 KB per K block, 3 stages) streams. The narrow configuration re-reads a 64 KB weight
+//                       tile for every 128 x 128 output tile: 128 KB of L2 -> SM traffic per tile at ~80 GB/s per SM is
+//                       1.6 us, the bound of the K = 256 launches (q/k/v, attention projection, FPN laterals).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -38,6 +43,8 @@ __host__ __device__ constexpr int b_stage_of(int bn) { return (bn <= 128 ? 128 :
 __host__ __device__ constexpr int smem_bytes_of(int bn) {
   return n_stages_of(bn) * (A_STAGE + b_stage_of(bn)) + 1024 /*barriers*/ + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024 /*align slack*/;
 }
+constexpr int WS_A_STAGES = 3, WS_W_BLOCKS = 4;      // weight-stationary: 3 x 16 KB of A in flight, 4 x 32 KB of resident W
+constexpr int WS_SMEM_BYTES = WS_A_STAGES * A_STAGE + WS_W_BLOCKS * MAX_BN * BK * 2 + 1024 + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024;
 
 struct Params {
   CUtensorMap a_map[AVDF_MAX_LEVELS];
@@ -50,6 +57,7 @@ struct Params {
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
   int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
   int n_out, c_in, taps, stride, bn, n_tiles_n, n_tiles_m, total_tiles;
+  int ws, ws_groups, ws_per;                 // weight-stationary: (segment, n-tile) groups, CTAs per group
   unsigned idesc;
   EpiParams epi;
   unsigned long long* dbg;                   // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
@@ -88,17 +96,19 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
 constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (pe ? 16 : 0); }
 
 // OUTK >= 0 fixes which outputs exist: bit 0 fp32, bit 1 16-bit copy, bit 2 the 16-bit copy is fp16 (else bf16).
-template <int MODE, int OUTK>
-__global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
+// WS: the weight-stationary configuration (compile-time, so that the streaming variants carry none of its state).
+template <int MODE, int OUTK, bool WS = false>
+__global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024 B alignment for the 128B swizzle atoms (an offset into the array keeps the shared address space visible
   // to the compiler: LDS/STS instead of generic loads)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  const int n_stages = n_stages_of(p.bn);
+  constexpr bool ws = WS;
+  const int n_stages = ws ? WS_A_STAGES : n_stages_of(p.bn);
   const int b_stage = b_stage_of(p.bn);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + n_stages * A_STAGE;
-  unsigned char* after = smem + n_stages * (A_STAGE + b_stage);
+  unsigned char* smem_b = smem + n_stages * A_STAGE;       // ws: WS_W_BLOCKS resident K blocks of the weights
+  unsigned char* after = smem_b + (ws ? WS_W_BLOCKS : n_stages) * b_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
   // bars: full[3], empty[3], tmem_full[2], tmem_empty[2], tmem ptr, residual[4]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
@@ -109,6 +119,15 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * MAX_STAGES + 13);       // ws: the resident weight block has landed
+  // i-th tile of this CTA (-1: none). Persistent launches stride the m-fastest tile list by the grid; weight-stationary
+  // launches pin a CTA to one (segment, n-tile) group - one weight block - and stride that group's m-tiles.
+  auto tile_at = [&](int i) -> int {
+    if (!ws) { const int t_ = blockIdx.x + i * gridDim.x; return t_ < p.total_tiles ? t_ : -1; }
+    const int g = blockIdx.x % p.ws_groups, j = blockIdx.x / p.ws_groups + i * p.ws_per;
+    const int sg = g % p.seg.n_seg, nt = g / p.seg.n_seg;
+    return j < p.seg_tile_start[sg + 1] - p.seg_tile_start[sg] ? nt * p.n_tiles_m + p.seg_tile_start[sg] + j : -1;
+  };
   const int acc_cols = p.bn <= 128 ? 128 : 256;      // two accumulators: 256 or 512 TMEM columns per CTA
   const uint32_t tmem_cols = 2u * acc_cols;
 
@@ -123,6 +142,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -144,8 +164,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
     // (the whole warp runs the loop and one elected lane issues: see elect_one() in tc_ptx.cuh)
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       const TileCoord tc_ = decode_tile(p, tile);
+      if (ws && it == 0 && leader) {             // the group's weight block: k_iters boxes of (64, bn), once
+        mbar_arrive_expect_tx(wfull_bar, (uint32_t)(k_iters * p.bn * BK * 2));
+        for (int kb = 0; kb < k_iters; ++kb)
+          tma_load_2d(smem_u32(smem_b + kb * b_stage), &p.w_map, wfull_bar, kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
+      }
       for (int tap = 0; tap < p.taps; ++tap) {
         const int d = tap - (p.taps >> 1);
         int par = 0, dt = d;
@@ -153,9 +178,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
         for (int kb = 0; kb < kb_per_tap; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (leader) {
-            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+            mbar_arrive_expect_tx(full_bar(stage), ws ? (uint32_t)A_STAGE : stage_bytes);
             tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), kb * BK, par, tc_.t0 + dt, tc_.b0);
-            tma_load_2d(smem_u32(smem_b + stage * b_stage), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
+            if (!ws) tma_load_2d(smem_u32(smem_b + stage * b_stage), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
           }
           __syncwarp();
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -168,10 +193,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
     // warp-uniform code. Issued under `if (lane == 0)` every instruction was wrapped in a per-thread election loop
     // (~53 ns per issue measured, scripts/umma_pace.py) - longer than the 35 ns a 128x128x16 instruction takes.
     const bool leader = elect_one();
-    int stage = 0; uint32_t phase = 0; int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; tile_at(it) >= 0; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if (ws && it == 0) mbar_wait(wfull_bar, 0);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
@@ -180,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
         tcgen05_fence_after();
         if (leader) {
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * A_STAGE));
-          const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * b_stage));
+          const uint64_t db = make_sw128_desc(smem_u32(smem_b + (ws ? ki : stage) * b_stage));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)          // +32 B per K=16 step inside the swizzle atom
             umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
@@ -224,19 +250,19 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t res_phase = 0, res_phase1 = 0, store_seq = 0;
-    int it = 0, loaded_n0 = -1;
+    int loaded_n0 = -1;
     // row mask of a tile's row owned by this thread (a global load: fetched one tile ahead so that its latency is
     // off the critical path of the tile's epilogue)
     auto row_mask_of = [&](int tile_) -> float {
-      if (tile_ >= p.total_tiles || !e.row_mask) return 1.f;
+      if (tile_ < 0 || !e.row_mask) return 1.f;
       const TileCoord c = decode_tile(p, tile_);
       const int r_ = q * 32 + lane;
       const int b_ = c.b0 + r_ / c.tt, t_ = c.t0 + (r_ & (c.tt - 1));
       if (b_ >= p.seg.batch) return 1.f;
       return e.row_mask[(size_t)b_ * p.seg.o_rows + p.seg.o_row[c.seg] + t_] ? 1.f : 0.f;
     };
-    float mk_next = row_mask_of(blockIdx.x);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    float mk_next = row_mask_of(tile_at(0));
+    for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       const TileCoord tc_ = decode_tile(p, tile);
       const int vec0 = tc_.n0 + p.seg.w_row[tc_.seg];   // first entry of this tile's per-channel vectors
       if (vec0 != loaded_n0) {                   // per-channel epilogue vectors of this n-tile -> smem
@@ -259,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
       const bool valid = b < p.seg.batch;
       const int wb = tc_.b0 + (q * 32) / tc_.tt, wt = tc_.t0 + ((q * 32) & (tc_.tt - 1));   // box origin (video, time)
       const float mk = mk_next;
-      mk_next = row_mask_of(tile + gridDim.x);    // in flight during this tile's epilogue
+      mk_next = row_mask_of(tile_at(it + 1));     // in flight during this tile's epilogue
       auto fetch_residual = [&](int ch) {         // 32 rows x 128 B of the residual -> trs (TMA, swizzle 128B)
         if (ep_leader) {
           mbar_arrive_expect_tx(res_bar, 4096);
@@ -509,6 +535,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_gemm_tc_kernel(const __grid_c
 }  // namespace tc
 
 static unsigned long long* g_dbg = nullptr;
+static int g_ws_mode = 0;                     // weight-stationary configuration: -1 auto, 0 never (default: see scripts/gemm_ws_bench.py), 1 wherever it is legal
 
 int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   using namespace tc;
@@ -520,6 +547,32 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   // long-K launches (the MLP down-projection, K = 1024) are bound by the L2 -> SM operand traffic ((BM + bn) K bytes per
   // tile): one 256-wide tile per row block reads the activations once instead of twice (measured 29.2 -> 26.7 us)
   if (!a->ln_w && a->taps * a->c_in >= 1024 && a->n_out % 256 == 0) bn = 256;
+  // weight-stationary: 1x1, K <= 256, 256-wide n-tiles, every segment with the same number of m-tiles (a CTA is
+  // pinned to one (segment, n-tile) group). Worth it when a CTA gets to reuse its weight block over several tiles.
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    AVDF_CUDA(cudaGetDevice(&dev));
+    AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  bool ws = g_ws_mode != 0 && a->taps == 1 && a->stride == 1 && a->c_in <= WS_W_BLOCKS * BK && a->n_out % MAX_BN == 0 && a->n_seg >= 1;
+  int ws_groups = 0, ws_per = 0;
+  if (ws) {
+    int per_seg = -1;
+    for (int s = 0; s < a->n_seg; ++s) {
+      const int T = a->seg_t_out[s];
+      int tt = T & (-T);
+      if (tt > BM) tt = BM;
+      const int n = T > 0 ? (T / tt) * ceil_div(a->batch, BM / tt) : 0;
+      if (per_seg < 0) per_seg = n; else if (n != per_seg) ws = false;
+    }
+    ws_groups = a->n_seg * (a->n_out / MAX_BN);
+    ws_per = sms / ws_groups < per_seg ? sms / ws_groups : per_seg;
+    // auto: at least ~2.5 tiles per CTA, else the two co-resident CTAs of the narrow configuration hide the per-tile
+    // latency chain better than one weight-stationary CTA
+    if (ws_per < 1 || (g_ws_mode < 0 && per_seg * 2 < ws_per * 5)) ws = false;
+  }
+  if (ws) bn = MAX_BN;
   AVDF_CHECK_ARG(a->n_out % bn == 0, "bf16 path: n_out must be <= 256 or a multiple of 256");
   AVDF_CHECK_ARG(bn % 16 == 0 && bn >= 32, "bf16 path: unsupported n_out");
   AVDF_CHECK_ARG(!a->ln_w || a->n_out == bn, "bf16 path: fused LayerNorm needs n_out <= 256");
@@ -593,6 +646,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   p.seg_tile_start[a->n_seg] = tiles;
   p.n_tiles_m = tiles;
   p.total_tiles = tiles * p.n_tiles_n;
+  if (ws) { p.ws = 1; p.ws_groups = ws_groups; p.ws_per = ws_per; }
   {
     cuuint64_t dims[2] = {(cuuint64_t)a->taps * a->c_in, (cuuint64_t)(a->n_w_rows > 0 ? a->n_w_rows : a->n_out)};
     cuuint64_t strides[1] = {(cuuint64_t)a->taps * a->c_in * 2};
@@ -609,11 +663,9 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   if (p.total_tiles == 0) return AVDF_OK;
 
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    AVDF_CUDA(cudaGetDevice(&dev));
-    AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static bool attrs_done = false;
+  if (!attrs_done) {
+    attrs_done = true;
     // (mode, output kind) pairs the inference path uses get their own instantiation; anything else runs the generic one
 #define AVDF_TC_VARIANTS(X)                                                                                   \
     X(mode_of(false, AVDF_ACT_NONE, false, false), 1) X(mode_of(false, AVDF_ACT_NONE, false, false), 6)           \
@@ -622,22 +674,36 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     X(mode_of(false, AVDF_ACT_GELU, false, false), 6) X(mode_of(false, AVDF_ACT_GELU, false, false), 2)           \
     X(mode_of(true, AVDF_ACT_RELU, false, false), 6) X(mode_of(true, AVDF_ACT_RELU, false, false), 2)             \
     X(mode_of(true, AVDF_ACT_RELU, false, false), 1) X(mode_of(true, AVDF_ACT_RELU, false, true), 1)
+    // weight-stationary instantiations: q/k/v (16-bit out), attention projection (residual, fp32 out), FPN laterals (fp32 out)
+#define AVDF_TC_WS_VARIANTS(X)                                                                                \
+    X(mode_of(false, AVDF_ACT_NONE, false, false), 6) X(mode_of(false, AVDF_ACT_NONE, true, false), 1)            \
+    X(mode_of(false, AVDF_ACT_NONE, false, false), 1)
 #define AVDF_SET_SMEM(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(MAX_BN)));
+#define AVDF_SET_SMEM_WS(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
     AVDF_SET_SMEM(-1, -1)
     AVDF_TC_VARIANTS(AVDF_SET_SMEM)
+    AVDF_SET_SMEM_WS(-1, -1)
+    AVDF_TC_WS_VARIANTS(AVDF_SET_SMEM_WS)
 #undef AVDF_SET_SMEM
+#undef AVDF_SET_SMEM_WS
   }
   AVDF_CHECK_ARG((long long)a->batch * a->o_rows_per_video * a->n_out < (1ll << 31), "output larger than 2^31 elements");
   const int ctas_per_sm = bn <= 128 ? 2 : 1;      // narrow tiles: two co-resident CTAs per SM
-  const int grid = p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm;
-  const int smem_bytes = smem_bytes_of(bn);
+  const int grid = ws ? ws_groups * ws_per : (p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm);
+  const int smem_bytes = ws ? WS_SMEM_BYTES : smem_bytes_of(bn);
   const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr);
   const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
   bool launched = false;
-#define AVDF_LAUNCH(M, O) if (!launched && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
+#define AVDF_LAUNCH(M, O) if (!launched && !ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
+#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, true><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
   AVDF_TC_VARIANTS(AVDF_LAUNCH)
+  AVDF_TC_WS_VARIANTS(AVDF_LAUNCH_WS)
 #undef AVDF_LAUNCH
-  if (!launched) conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, smem_bytes, st>>>(p);
+#undef AVDF_LAUNCH_WS
+  if (!launched) {
+    if (ws) conv_gemm_tc_kernel<-1, -1, true><<<grid, THREADS, smem_bytes, st>>>(p);
+    else conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, smem_bytes, st>>>(p);
+  }
   return check_launch("conv_gemm_tc_kernel");
 }
 
@@ -648,4 +714,11 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
 extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_timeline(unsigned long long* dev_buf) {
   avdf::g_dbg = dev_buf;
   return 0;
+}
+// Debug / test hook: weight-stationary configuration -1 auto, 0 never (default), 1 wherever it is legal. Returns the
+// previous setting.
+extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_ws(int mode) {
+  const int prev = avdf::g_ws_mode;
+  avdf::g_ws_mode = mode;
+  return prev;
 }

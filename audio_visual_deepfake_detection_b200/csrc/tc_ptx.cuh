@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("avdf gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (clock64() - t0 > 4000000000LL) { printf("avdf tcgen05 kernel: mbarrier timeout (block %d thread %d, barrier at smem 0x%x, parity %u)\n", blockIdx.x, threadIdx.x, bar, parity); __trap(); }
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {

@@ -18,6 +18,7 @@ import interp_ref
 import model_ref
 import nms_ref
 from make_golden import sweep_inputs
+from audio_visual_deepfake_detection_b200 import native as nv
 from audio_visual_deepfake_detection_b200 import ops
 from audio_visual_deepfake_detection_b200.libs.utils import synthetic as syn
 
@@ -499,6 +500,63 @@ def test_conv_gemm_stacked_weight_blocks(mode):
         assert rel_err(out[:, i * T:(i + 1) * T].cpu(), want) < (2e-5 if mode == "fp32" else 2e-4), i
         if out_h is not None:
             assert rel_err(out_h[:, i * T:(i + 1) * T].float().cpu(), want) < 2e-3
+
+
+WS_CASES = [
+    # name, B, T, c_in, n_out, n_seg, bias, act, residual, out16_only
+    ("qkv_stacked_16bit", 37, 96, 256, 256, 3, True, ops.ACT_NONE, False, True),       # <0,6,WS>: 3 groups, ragged last batch tile
+    ("proj_res_fp32", 150, 128, 256, 256, 1, True, ops.ACT_NONE, True, False),         # <8,1,WS>: 150 tiles on <= 148 CTAs (2 tiles on some)
+    ("lateral_fp32_small_t", 33, 24, 256, 256, 1, False, ops.ACT_NONE, False, False),  # <0,1,WS>: several videos per tile
+    ("gelu_n1024_k128", 9, 64, 128, 1024, 1, True, ops.ACT_GELU, False, True),         # generic WS variant, 4 n-tile groups, 2 K blocks
+]
+
+
+@pytest.mark.parametrize("case", WS_CASES, ids=[c[0] for c in WS_CASES])
+@pytest.mark.parametrize("adt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_conv_gemm_weight_stationary(case, adt):
+    """The weight-stationary configuration (W resident in shared memory, CTA pinned to a (segment, n-tile) group) forced
+    on through the debug hook; the same launches in the streaming configuration must agree with it bit for bit."""
+    name, B, T, cin, nout, n_seg, has_bias, act, has_res, out16_only = case
+    rng = np.random.RandomState(zlib.crc32(name.encode()) % 1000)
+    a = torch.from_numpy(rng.standard_normal((B, n_seg * T, cin)).astype(np.float32))
+    ws = [torch.from_numpy((rng.standard_normal((nout, cin)) / math.sqrt(cin)).astype(np.float32)) for _ in range(n_seg)]
+    bias = torch.from_numpy(rng.normal(0, 0.3, n_seg * nout).astype(np.float32)) if has_bias else None
+    res = torch.from_numpy(rng.standard_normal((B, n_seg * T, nout)).astype(np.float32)) if has_res else None
+    gamma = torch.from_numpy(rng.uniform(0.5, 1.5, nout).astype(np.float32)) if has_res else None
+    valid = rng.randint(T // 2, T + 1, B); valid[0] = T
+    mask = np.tile(np.arange(T)[None] < valid[:, None], (1, n_seg)).astype(np.uint8)
+    L = nv.lib()
+    outs = {}
+    default_mode = L.avdf_debug_gemm_ws(0)
+    try:
+        for ws_mode in (1, 0):
+            L.avdf_debug_gemm_ws(ws_mode)
+            o32 = None if out16_only else torch.zeros((B, n_seg * T, nout), device=DEV)
+            o16 = torch.zeros((B, n_seg * T, nout), dtype=adt, device=DEV) if out16_only else None
+            ops.conv_gemm(dev(a, adt), dev(torch.cat(ws), adt), taps=1, batch=B, c_in=cin, n_out=nout,
+                          segs=[(T, i * T, i * T, i * nout) for i in range(n_seg)], a_rows=n_seg * T, o_rows=n_seg * T,
+                          bias=None if bias is None else dev(bias), row_mask=dev(mask) if not out16_only else None, act=act,
+                          residual=None if res is None else dev(res), gamma=None if gamma is None else dev(gamma),
+                          out_f32=o32, out_h=o16)
+            torch.cuda.synchronize()
+            outs[ws_mode] = (o16 if out16_only else o32).float().cpu()
+    finally:
+        L.avdf_debug_gemm_ws(default_mode)
+    aq = a.to(adt).float()
+    m = torch.from_numpy(mask).float()[..., None] if not out16_only else 1.0
+    for i in range(n_seg):
+        sl = slice(i * T, (i + 1) * T)
+        y = aq[:, sl] @ ws[i].to(adt).float().t()
+        if bias is not None:
+            y = y + bias[i * nout:(i + 1) * nout]
+        y = y * (m[:, sl] if not out16_only else 1.0)
+        if act == ops.ACT_GELU:
+            y = model_ref.gelu_erf(y)
+        if res is not None:
+            y = res[:, sl] * m[:, sl] + gamma * y
+        assert rel_err(outs[1][:, sl], y) < (1e-2 if out16_only else 2e-4), (name, i)
+    if act == ops.ACT_NONE:                 # (the GELU case runs the scalar formula in one configuration, the packed one in the other)
+        assert torch.equal(outs[1], outs[0])
 
 
 def test_attention_stacked_qkv_and_interleaved_dwconv():
