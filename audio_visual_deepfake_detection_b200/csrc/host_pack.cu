@@ -147,3 +147,35 @@ extern "C" int avdf_host_pack(const void* const* src, void* const* dst, const si
   pool().run(pieces, n_threads);
   return AVDF_OK;
 }
+
+// 1 when every span lies in page-locked (pinned / registered) host memory, else 0 (also without a usable driver):
+// such a batch needs no staging copy at all.
+extern "C" int avdf_host_all_pinned(const void* const* src, const size_t* nbytes, int32_t n) {
+  if (n <= 0 || !src || !nbytes) return 0;
+  for (int i = 0; i < n; ++i) {
+    if (nbytes[i] == 0) continue;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src[i]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (at.type != cudaMemoryTypeHost) return 0;
+    // the last byte too: a span must not run past its registration
+    if (cudaPointerGetAttributes(&at, static_cast<const unsigned char*>(src[i]) + nbytes[i] - 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (at.type != cudaMemoryTypeHost) return 0;
+  }
+  return 1;
+}
+
+// n asynchronous host -> device copies on `stream` (src: pinned host memory, dst: device): the zero-staging path of the
+// feature ingestion - the copy engine reads the caller's arrays directly. The caller keeps the sources alive and
+// unchanged until the stream has passed the copies.
+extern "C" int avdf_h2d_gather(const void* const* src, void* const* dst, const size_t* nbytes, int32_t n, void* stream) {
+  using namespace avdf;
+  AVDF_CHECK_ARG(n >= 0, "n >= 0");
+  AVDF_CHECK_ARG(n == 0 || (src && dst && nbytes), "null span arrays");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n; ++i) {
+    if (nbytes[i] == 0) continue;
+    AVDF_CHECK_ARG(src[i] && dst[i], "null span pointer");
+    AVDF_CUDA(cudaMemcpyAsync(dst[i], src[i], nbytes[i], cudaMemcpyHostToDevice, st));
+  }
+  return AVDF_OK;
+}

@@ -1,7 +1,8 @@
 """Host <-> device pipeline of the raw-stream entry point (`model.forward_streams`, `model.stream`).
 
 Per batch of <= max_batch videos:
-  pack   (host threads)  every video's [T_s, C_s] fp32 arrays are gathered into ONE pinned buffer per stream by
+  pack   (host threads)  (skipped when the caller's arrays are page-locked: `avdf_h2d_gather` then copies them to the
+                         device where they are) every video's [T_s, C_s] fp32 arrays are gathered into ONE pinned buffer per stream by
                          `avdf_host_pack` (the library's own thread pool; row offsets + per-video metadata alongside)
   H2D    (copy engine)   pinned -> static device staging buffers, asynchronous on the compute stream
   GPU                    the whole pass (interp/concat -> model -> decode -> NMS) replayed as ONE CUDA graph
@@ -34,6 +35,7 @@ class _Slot:
         self.done = torch.cuda.Event()
         self.stream = torch.cuda.Stream()     # slots run on their own streams: copies and kernels of consecutive batches overlap
         self.ids, self.B, self.busy = None, 0, False
+        self.direct = None                    # (src, device dst, nbytes, n, keep-alive) of a batch whose arrays are pinned
 
     def ensure(self, rows, chans, max_batch, K, device, seconds):
         """Staging capacity. The captured graph holds the device staging pointers, so growing them forces a
@@ -76,8 +78,10 @@ class StreamRunner:
         self.n_threads = n_threads or int(os.environ.get("AVDF_PACK_THREADS", "0")) or max(2, min(16, (os.cpu_count() or 4) // local_world))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.n_direct = 0            # batches whose (pinned) arrays went to the device without a staging copy
         self.use_graph = True
         self.cuda_lock = threading.Lock()    # staging (pinned / device) allocation vs. graph capture on the launching thread
+        self.zero_copy = os.environ.get("AVDF_ZERO_COPY", "1") != "0"    # pinned source arrays go to the copy engine directly
         self.n_packers = int(os.environ.get("AVDF_PACKERS", "1"))   # packer threads (measured 1 / 2 / 3: 15.56k / 15.45k / 15.39k videos/s: the gather itself is already parallel)
 
     # ---------------------------------------------------------------- stages
@@ -108,11 +112,25 @@ class StreamRunner:
                 if a.shape[1] != chans[s]:
                     raise ValueError("stream %s: video %d has %d channels, the batch has %d" % (STREAMS[s], b, a.shape[1], chans[s]))
                 src.append(a.ctypes.data); dst.append(base + int(off[s, b]) * row_bytes); nbytes.append(a.nbytes)
-        # the gather runs on the library's own thread pool (csrc/host_pack.cu: 256 KB pieces, non-temporal stores); ctypes
-        # releases the GIL for the call
         n = len(src)
-        native.check(native.lib().avdf_host_pack((ctypes.c_void_p * n)(*src), (ctypes.c_void_p * n)(*dst), (ctypes.c_size_t * n)(*nbytes),
-                                                 n, self.n_threads), "avdf_host_pack")
+        lib_ = native.lib()
+        c_src, c_n = (ctypes.c_void_p * n)(*src), (ctypes.c_size_t * n)(*nbytes)
+        slot.direct = None
+        if self.zero_copy and lib_.avdf_host_all_pinned(c_src, c_n, n) == 1:
+            # the caller's arrays are page-locked (e.g. a loader that reads .npy files into a pinned pool): the copy engine
+            # reads them where they are - no staging copy, no host core touches the features
+            dev_dst, k = [], 0
+            for s in range(3):
+                if arrs[s] is None:
+                    continue
+                dbase, row_bytes = slot.dev[s].data_ptr(), chans[s] * 4
+                dev_dst += [dbase + int(off[s, b]) * row_bytes for b in range(B)]
+            slot.direct = (c_src, (ctypes.c_void_p * n)(*dev_dst), c_n, n, arrs)      # arrs: keeps the sources alive
+            self.n_direct += 1
+        else:
+            # the gather runs on the library's own thread pool (csrc/host_pack.cu: 256 KB pieces, non-temporal stores);
+            # ctypes releases the GIL for the call
+            native.check(lib_.avdf_host_pack(c_src, (ctypes.c_void_p * n)(*dst), c_n, n, self.n_threads), "avdf_host_pack")
         meta = slot.h_meta.numpy()
         for b, c in enumerate(chunk):
             first = c["streams"]["video"] if present[0] else c["streams"]["byola"]
@@ -130,9 +148,13 @@ class StreamRunner:
     def _launch_on_stream(self, slot):
         eng, B = self.eng, slot.B
         nbytes = 0
+        if slot.direct is not None:
+            c_src, c_dst, c_n, n, _ = slot.direct
+            native.check(native.lib().avdf_h2d_gather(c_src, c_dst, c_n, n, native.stream_ptr()), "avdf_h2d_gather")
         for s in range(3):
             if slot.chans[s]:
-                slot.dev[s][:slot.rows[s]].copy_(slot.host[s][:slot.rows[s]], non_blocking=True)
+                if slot.direct is None:
+                    slot.dev[s][:slot.rows[s]].copy_(slot.host[s][:slot.rows[s]], non_blocking=True)
                 nbytes += slot.rows[s] * slot.chans[s] * 4
         slot.d_off.copy_(slot.h_off, non_blocking=True)
         slot.d_meta.copy_(slot.h_meta, non_blocking=True)
@@ -160,6 +182,7 @@ class StreamRunner:
     def _collect(self, slot):
         slot.done.synchronize()
         slot.busy = False
+        slot.direct = None                # the copy engine is done with the caller's arrays
         B = slot.B
         # one clone per result array (the pinned buffers are reused by the next batch), then cheap per-video views
         segs, scores, vcls = slot.h_segs[:B].clone(), slot.h_scores[:B].clone(), slot.h_vcls[:B].clone()

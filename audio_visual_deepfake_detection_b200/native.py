@@ -25,7 +25,7 @@ EXPORTS = [
     "avdf_postprocess_workspace_bytes", "avdf_postprocess",
     "avdf_conv_gemm_workspace_bytes", "avdf_conv_gemm", "avdf_mlp_fused", "avdf_ln_dwconv_ln", "avdf_attention",
     "avdf_ln_rows", "avdf_instnorm_lrelu", "avdf_fpn_fuse", "avdf_head_final",
-    "avdf_vcls_exp12", "avdf_vcls_exp13", "avdf_host_pack",
+    "avdf_vcls_exp12", "avdf_vcls_exp13", "avdf_host_pack", "avdf_host_all_pinned", "avdf_h2d_gather",
 ]
 
 
@@ -123,6 +123,8 @@ def lib():
     L.avdf_vcls_exp12.argtypes = [c_void_p, c_int32] + [c_void_p] * 7 + [c_int32] * 3 + [c_void_p]
     L.avdf_vcls_exp13.argtypes = [c_void_p, c_int32] + [c_void_p] * 6 + [c_int32] * 3 + [c_void_p]
     L.avdf_host_pack.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t), c_int32, c_int32]
+    L.avdf_host_all_pinned.argtypes = [POINTER(c_void_p), POINTER(c_size_t), c_int32]
+    L.avdf_h2d_gather.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t), c_int32, c_void_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("avdf_last_error", "avdf_nms_workspace_bytes", "avdf_postprocess_workspace_bytes",

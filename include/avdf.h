@@ -241,6 +241,12 @@ AVDF_API int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_w 
  * (non-temporal stores). Synchronous; concurrent calls are serialised. No CUDA call is made. */
 AVDF_API int avdf_host_pack(const void* const* src, void* const* dst, const size_t* nbytes, int32_t n, int32_t n_threads);
 
+/* HOST: 1 when every span [src[i], src[i] + nbytes[i]) is page-locked host memory (cudaHostAlloc / cudaHostRegister), else 0. */
+AVDF_API int avdf_host_all_pinned(const void* const* src, const size_t* nbytes, int32_t n);
+/* n asynchronous copies src[i] (pinned HOST) -> dst[i] (DEVICE) on `stream`: ingestion without a staging copy. The sources
+ * must stay alive and unchanged until the stream has passed the copies. */
+AVDF_API int avdf_h2d_gather(const void* const* src, void* const* dst, const size_t* nbytes, int32_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

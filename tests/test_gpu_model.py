@@ -112,6 +112,38 @@ def test_batch_invariance_and_streams():
         assert a["video_id"] == c["video_id"]
 
 
+def test_stream_from_pinned_arrays_skips_the_staging_copy():
+    """model.stream on page-locked source arrays (avdf_host_all_pinned -> avdf_h2d_gather: the copy engine reads the caller's
+    memory) returns exactly what the staging path (avdf_host_pack into pinned slots) returns, batch after batch."""
+    model, use_video = build("exp12", "mixed")
+    rng = np.random.RandomState(5)
+    batches = []
+    for bi in range(5):                                             # ragged batch sizes, more batches than would fit one slot
+        durs = rng.uniform(4.1, 14.0, size=[3, 1, 4, 2, 3][bi])
+        batches.append([{"video_id": f"b{bi}v{i}", "duration": float(d), "streams": syn.synthetic_streams(float(d), 1000 + 10 * bi + i)}
+                        for i, d in enumerate(durs)])
+    pinned = []
+    for chunk in batches:
+        new_chunk = []
+        for c in chunk:
+            st = {}
+            for k, a in c["streams"].items():
+                t = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+                t.numpy()[...] = a
+                st[k] = t.numpy() if k != "emo" else t              # numpy views and torch tensors both
+            new_chunk.append({**c, "streams": st})
+        pinned.append(new_chunk)
+    runner = model.runner()
+    n0 = runner.n_direct
+    want = [r for out in model.stream(iter(batches)) for r in out]
+    assert runner.n_direct == n0                                    # pageable arrays: staged
+    got = [r for out in model.stream(iter(pinned)) for r in out]
+    assert runner.n_direct == n0 + len(batches)                     # pinned arrays: direct
+    assert [r["video_id"] for r in got] == [r["video_id"] for r in want]
+    for a, b in zip(want, got):
+        assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["segments"], b["segments"]) and torch.equal(a["video_cls"], b["video_cls"])
+
+
 def test_fused_mlp_path_matches_two_launch_path():
     """engine.fused_mlp routes every block's MLP through avdf_mlp_fused (one launch, hidden activations on chip). Per call
     it agrees with the two-GEMM path to ~1e-6 (tests/test_gpu_kernels.py::test_mlp_fused); over the whole network

@@ -80,3 +80,13 @@ def test_concurrent_callers_do_not_mix_jobs():
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert not errs, errs
+
+
+def test_pageable_arrays_are_not_reported_pinned():
+    """Ordinary numpy memory is never 'pinned' (also on a box without a GPU driver: the query fails -> 0 -> staging path)."""
+    a = np.zeros(1 << 16, dtype=np.float32)
+    S = (ctypes.c_void_p * 1)(a.ctypes.data)
+    N = (ctypes.c_size_t * 1)(a.nbytes)
+    L = native.lib()
+    assert L.avdf_host_all_pinned(S, N, 1) == 0
+    assert L.avdf_host_all_pinned(None, None, 0) == 0
