@@ -22,6 +22,25 @@ BYOLA_FPS = 12.497      # deepfake_video_audio.py:415
 EMOTION_FPS = 50        # deepfake_video_audio.py:416
 
 
+def _load_npy_pinned(path):
+    """A C-ordered fp32 `.npy` file read directly into a page-locked buffer (file -> pinned memory is the only host copy);
+    None for any other layout (the caller falls back to np.load)."""
+    with open(path, "rb") as f:
+        try:
+            major, _ = np.lib.format.read_magic(f)
+            shape, fortran, dtype = (np.lib.format.read_array_header_1_0 if major == 1 else np.lib.format.read_array_header_2_0)(f)
+        except Exception:
+            return None
+        if fortran or dtype != np.dtype("<f4") or len(shape) != 2:
+            return None
+        buf = torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
+        want = buf.nbytes
+        got = f.readinto(memoryview(buf).cast("B")) if want else 0
+        if got != want:
+            raise IOError("%s: truncated .npy payload (%d of %d bytes)" % (path, got, want))
+        return buf
+
+
 class _InferenceBase(Dataset):
     USE_VIDEO = True
 
@@ -29,12 +48,16 @@ class _InferenceBase(Dataset):
                  video_feat_folder=None, audio_feat_folder=None, audio_byola_feat_folder=None, audio_emo_feat_folder=None,
                  audio_file_ext=None, num_classes=1, input_dim=None, video_input_dim=None, audio_input_dim=None,
                  feat_stride=1, num_frames=1, test_folder=None, trunc_thresh=0.5, max_seq_len=768, force_upsampling=True,
-                 **unused):
+                 pin_memory=False, **unused):
         assert not is_training, "training datasets are outside the accelerated inference path"
         assert num_classes == 1
         if not force_upsampling or feat_stride <= 0:
             raise RuntimeError("not implemented")       # same as the reference's case 3 (:502-503)
         self.sub_index = sub_index
+        # new: read the .npy payloads straight into page-locked memory, so that model.stream() hands them to the copy engine
+        # without a staging copy (libs/modeling/streaming.py). In-process loading only: pinned pages do not survive the
+        # pickling of DataLoader worker processes.
+        self.pin_memory = bool(pin_memory)
         self.video_feat_folder = video_feat_folder if self.USE_VIDEO else None
         self.audio_byola_feat_folder = audio_byola_feat_folder
         self.audio_emo_feat_folder = audio_emo_feat_folder
@@ -66,7 +89,12 @@ class _InferenceBase(Dataset):
         return len(self.data_list)
 
     def _load(self, folder, vid):
-        return np.load(os.path.join(folder, vid.replace(".mp4", ".npy"))).astype(np.float32, copy=False)
+        path = os.path.join(folder, vid.replace(".mp4", ".npy"))
+        if self.pin_memory:
+            arr = _load_npy_pinned(path)
+            if arr is not None:
+                return arr
+        return np.load(path).astype(np.float32, copy=False)
 
     def __getitem__(self, idx):
         v = self.data_list[idx]

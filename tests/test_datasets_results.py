@@ -104,6 +104,33 @@ def test_dataset_to_model_matches_reference_items(tmp_path):
 
 
 @pytest.mark.gpu
+def test_pinned_dataset_items_stream_without_staging(tmp_path):
+    """pin_memory=True: the .npy payloads are read straight into page-locked buffers (byte-identical to np.load), and
+    model.stream() sends them to the device without the host gather."""
+    from audio_visual_deepfake_detection_b200.libs.core import load_config_for
+    from audio_visual_deepfake_detection_b200.libs.modeling import make_meta_arch, EXP12
+    durs = [4.03, 9.04, 6.2, 12.5]
+    folders = write_corpus(str(tmp_path), durs, long_audio=True)
+    plain = make_inference_dataset("deepfake_video_audioEmoBYOLA_inference", False, ["test"], 3, **dataset_kwargs(folders))
+    pinned = make_inference_dataset("deepfake_video_audioEmoBYOLA_inference", False, ["test"], 3, pin_memory=True, **dataset_kwargs(folders))
+    a, b = [plain[i] for i in range(4)], [pinned[i] for i in range(4)]
+    for x, y in zip(a, b):
+        for k in x["streams"]:
+            assert np.array_equal(x["streams"][k], y["streams"][k]) and y["streams"][k].dtype == np.float32
+    cfg = load_config_for(EXP12)
+    model = make_meta_arch(cfg["model_name"], **cfg["model"], max_batch=4)
+    model.load_state_dict(syn.synthetic_state_dict(cfg["model"], EXP12, seed=0))
+    model.to("cuda").eval()
+    runner = model.runner()
+    want = [r for out in model.stream(iter([a])) for r in out]
+    n0 = runner.n_direct
+    got = [r for out in model.stream(iter([b])) for r in out]
+    assert runner.n_direct == n0 + 1
+    for u, v in zip(want, got):
+        assert torch.equal(u["scores"], v["scores"]) and torch.equal(u["segments"], v["segments"])
+
+
+@pytest.mark.gpu
 def test_inference_cli_end_to_end(tmp_path):
     """`python inference.py cfg sub_index ckpt --merge` on a synthetic corpus: the reference's CLI contract."""
     import subprocess
