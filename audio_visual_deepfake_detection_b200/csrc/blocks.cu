@@ -957,6 +957,9 @@ __global__ void __launch_bounds__(256) vcls_exp13_kernel(const InT* __restrict__
   }
 }
 
+int attention_banded_mma(const void* q, const void* k, const void* v, const unsigned char* kv_mask, void* out, int in_dtype,
+                         int out_dtype, int batch, int t, int rpv, cudaStream_t st);       // attention_mma.cu
+
 static int grid_for(long long work_items, int per_cta, int sms) {
   long long want = (work_items + per_cta - 1) / per_cta;
   long long cap = (long long)sms * 8;
@@ -1042,6 +1045,10 @@ extern "C" int avdf_attention(const void* q, const void* k, const void* v, const
   AVDF_CHECK_ARG(rpv >= t, "qkv_rows_per_video smaller than t");
   if (batch == 0) return AVDF_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (window == 7 && in_dtype != AVDF_DTYPE_F32) {   // 16-bit operands: tensor-core kernel (attention_mma.cu)
+    static const bool use_mma = !(getenv("AVDF_ATT_MMA") && atoi(getenv("AVDF_ATT_MMA")) == 0);
+    if (use_mma) return attention_banded_mma(q, k, v, kv_mask, out, in_dtype, out_dtype, batch, t, rpv, st);
+  }
   if (window == 7) {                            // the window every shipped config uses: smem-tiled specialisation
     constexpr int HALF = 3;
     // query rows per CTA: 24 divides every level of the 768-row pyramid, and at 30 KB of K/V per CTA (16-bit) the
