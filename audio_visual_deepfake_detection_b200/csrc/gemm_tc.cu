@@ -43,8 +43,14 @@ __host__ __device__ constexpr int b_stage_of(int bn) { return (bn <= 128 ? 128 :
 __host__ __device__ constexpr int smem_bytes_of(int bn) {
   return n_stages_of(bn) * (A_STAGE + b_stage_of(bn)) + 1024 /*barriers*/ + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024 /*align slack*/;
 }
-constexpr int WS_A_STAGES = 3, WS_W_BLOCKS = 4;      // weight-stationary: 3 x 16 KB of A in flight, 4 x 32 KB of resident W
-constexpr int WS_SMEM_BYTES = WS_A_STAGES * A_STAGE + WS_W_BLOCKS * MAX_BN * BK * 2 + 1024 + EPI_VEC_BYTES + STAGE_TILE_BYTES + 1024;
+// weight-stationary: 2 x 16 KB of A in flight, 4 x 32 KB of resident W, EIGHT epilogue warps (a weight-stationary CTA is alone
+// on its SM; with four, the epilogue - ~4.2 us per 128 x 256 tile - was the limit, scripts/gemm_ws_bench.py), each with its
+// two 4 KB staging tiles; bias + gamma only (no fused LayerNorm). 231,936 of the 232,448 bytes a CTA can have: the
+// dynamic shared-memory window must start 1024-aligned (it does: the first KB of an SM's shared memory is reserved).
+constexpr int WS_A_STAGES = 2, WS_W_BLOCKS = 4, WS_EPI_WARPS = 8;
+constexpr int WS_BAR_BYTES = 512, WS_VEC_BYTES = 2 * MAX_BN * 4;
+constexpr int WS_SMEM_BYTES = WS_A_STAGES * A_STAGE + WS_W_BLOCKS * MAX_BN * BK * 2 + WS_BAR_BYTES + WS_VEC_BYTES + WS_EPI_WARPS * 8192;
+constexpr int WS_THREADS = 128 + WS_EPI_WARPS * 32;
 
 struct Params {
   CUtensorMap a_map[AVDF_MAX_LEVELS];
@@ -98,7 +104,7 @@ constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0)
 // OUTK >= 0 fixes which outputs exist: bit 0 fp32, bit 1 16-bit copy, bit 2 the 16-bit copy is fp16 (else bf16).
 // WS: the weight-stationary configuration (compile-time, so that the streaming variants carry none of its state).
 template <int MODE, int OUTK, bool WS = false>
-__global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024 B alignment for the 128B swizzle atoms (an offset into the array keeps the shared address space visible
   // to the compiler: LDS/STS instead of generic loads)
@@ -109,17 +115,23 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + n_stages * A_STAGE;       // ws: WS_W_BLOCKS resident K blocks of the weights
   unsigned char* after = smem_b + (ws ? WS_W_BLOCKS : n_stages) * b_stage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(after);
+  // ws: the staging tiles come first (they need the 1024-byte alignment `after` has), then barriers and vectors
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ws ? after + WS_EPI_WARPS * 8192 : after);
   // bars: full[3], empty[3], tmem_full[2], tmem_empty[2], tmem ptr, residual[4]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
-  float* epi_smem = reinterpret_cast<float*>(after + 1024);
-  unsigned char* stage_smem = after + 1024 + EPI_VEC_BYTES;
+  float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + (ws ? WS_BAR_BYTES : 1024));
+  unsigned char* stage_smem = ws ? after : after + 1024 + EPI_VEC_BYTES;
+  constexpr int EPI_WARPS = ws ? WS_EPI_WARPS : 4;
+  if (ws && (smem_u32(smem_dyn) & 1023u) != 0) {          // no slack for re-alignment in this configuration
+    if (threadIdx.x == 0) printf("avdf gemm_tc: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
-  const uint32_t wfull_bar = bar_base + 8u * (2 * MAX_STAGES + 13);       // ws: the resident weight block has landed
+  const uint32_t wfull_bar = bar_base + 8u * (2 * MAX_STAGES + 21);       // ws: the resident weight block has landed
   // i-th tile of this CTA (-1: none). Persistent launches stride the m-fastest tile list by the grid; weight-stationary
   // launches pin a CTA to one (segment, n-tile) group - one weight block - and stride that group's m-tiles.
   auto tile_at = [&](int i) -> int {
@@ -141,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,15 +238,19 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
     // block of the next chunk is prefetched by TMA into a swizzled tile (mbarrier).
     const EpiParams& e = p.epi;
     const bool ep_leader = elect_one();        // the lane that issues this warp's TMA loads / stores, commits and waits
-    const int q = warp - 4;
+    const int wi = warp - 4;                     // epilogue warp 0 .. EPI_WARPS - 1
+    const int q = wi & 3;                        // TMEM lane quarter (= warp % 4) / 32-row block of the tile
+    const int team = wi >> 2;                    // ws: two warps share a row block and split its columns
     const int N = p.n_out;
     const int et = threadIdx.x - 128;            // 0..127 among the epilogue threads
-    float* s_bias = epi_smem; float* s_lnw = epi_smem + MAX_BN; float* s_lnb = epi_smem + 2 * MAX_BN; float* s_gam = epi_smem + 3 * MAX_BN;
-    unsigned char* t32 = stage_smem + q * 8192;          // result tile (fp32: swizzle 128B)
-    unsigned char* trs = stage_smem + q * 8192 + 4096;   // residual tile / second result tile
-    const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 5 + q);
-    const uint32_t res_bar1 = bar_base + 8u * (2 * MAX_STAGES + 9 + q);   // second residual tile (in-place fp32 path)
-    const int chunks = p.bn >> 5;
+    float* s_bias = epi_smem; float* s_lnw = epi_smem + MAX_BN; float* s_lnb = epi_smem + 2 * MAX_BN; float* s_gam = epi_smem + (ws ? 1 : 3) * MAX_BN;
+    if (ws) { s_lnw = s_bias; s_lnb = s_bias; }   // (never read: the weight-stationary configuration has no fused LayerNorm)
+    unsigned char* t32 = stage_smem + wi * 8192;          // result tile (fp32: swizzle 128B)
+    unsigned char* trs = stage_smem + wi * 8192 + 4096;   // residual tile / second result tile
+    const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 5 + wi);
+    const uint32_t res_bar1 = bar_base + 8u * (2 * MAX_STAGES + 13 + wi);   // second residual tile (in-place fp32 path)
+    const int chunks = (p.bn >> 5) / (EPI_WARPS / 4);     // 32-column chunks this warp handles: [ch0, ch1)
+    const int ch0 = team * chunks, ch1 = ch0 + chunks;
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
     const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
     const bool has_pe = MODE < 0 ? (e.pe != nullptr) : ((MODE & 16) != 0);
@@ -266,14 +282,16 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
       const TileCoord tc_ = decode_tile(p, tile);
       const int vec0 = tc_.n0 + p.seg.w_row[tc_.seg];   // first entry of this tile's per-channel vectors
       if (vec0 != loaded_n0) {                   // per-channel epilogue vectors of this n-tile -> smem
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < p.bn; i += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        for (int i = et; i < p.bn; i += EPI_WARPS * 32) {
           s_bias[i] = e.bias ? __ldg(e.bias + vec0 + i) : 0.f;
-          s_lnw[i] = e.ln_w ? __ldg(e.ln_w + vec0 + i) : 1.f;
-          s_lnb[i] = e.ln_b ? __ldg(e.ln_b + vec0 + i) : 0.f;
+          if (!ws) {
+            s_lnw[i] = e.ln_w ? __ldg(e.ln_w + vec0 + i) : 1.f;
+            s_lnb[i] = e.ln_b ? __ldg(e.ln_b + vec0 + i) : 0.f;
+          }
           s_gam[i] = e.gamma ? __ldg(e.gamma + vec0 + i) : 1.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         loaded_n0 = vec0;
       }
       const int acc = it & 1;
@@ -305,11 +323,11 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
       if (RES32_OK) {
         if (ep_leader) {
           tma_store_wait_read();                  // the previous tile's stores have read both tiles
-          fetch_residual_into(0);
-          if (chunks > 1) fetch_residual_into(1);
+          fetch_residual_into(ch0);
+          if (chunks > 1) fetch_residual_into(ch0 + 1);
         }
       } else if (has_res) {
-        fetch_residual(0);
+        fetch_residual(ch0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -337,12 +355,12 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
       //      (TMEM wait, proxy fence, warp sync, TMA issue, store-read wait); the two 4 KB tiles alternate
       constexpr bool WIDE_OK = MODE >= 0 && OUTK >= 0 && (OUTK & 3) == 2 && (MODE & 24) == 0;
       if (WIDE_OK && (chunks & 1) == 0) {
-        for (int ch = 0; ch < chunks; ch += 2) {
+        for (int ch = ch0; ch < ch1; ch += 2) {
           uint32_t va[32], vb[32];
           tmem_ld32_issue(taddr + ch * 32, va);
           tmem_ld32_issue(taddr + (ch + 1) * 32, vb);
           tmem_ld_wait();
-          if (ch + 2 >= chunks) {                  // all TMEM reads of this warp done: release the accumulator
+          if (ch + 2 >= ch1) {                     // all TMEM reads of this warp done: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
             if (ep_leader) mbar_arrive(tempty_bar(acc));
@@ -395,13 +413,13 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
         continue;                                   // next tile
       }
       uint32_t vr[32];                            // accumulator block of the current chunk (raw bits)
-      tmem_ld32_issue(taddr, vr);
-      for (int ch = 0; ch < chunks; ++ch) {
+      tmem_ld32_issue(taddr + ch0 * 32, vr);
+      for (int ch = ch0; ch < ch1; ++ch) {
         tmem_ld_wait();
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vr[i]);
-        if (ch + 1 < chunks) {
+        if (ch + 1 < ch1) {
           tmem_ld32_issue(taddr + (ch + 1) * 32, vr);   // next block's TMEM read overlaps this block's math
         } else {                                  // all TMEM reads of this warp are issued: once they complete the
           tcgen05_fence_before();                 // MMA warp may overwrite the accumulator
@@ -438,7 +456,7 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
         }
         if (RES32_OK) {
           unsigned char* tb = t32 + ((ch & 1) << 12);
-          if (ch >= 1 && ch + 1 < chunks && ep_leader) {   // tile (ch + 1) & 1 held chunk ch - 1: its store was committed one
+          if (ch > ch0 && ch + 1 < ch1 && ep_leader) {   // tile (ch + 1) & 1 held chunk ch - 1: its store was committed one
             tma_store_wait_read();                         // iteration ago; refill it with the residual of chunk ch + 1
             fetch_residual_into(ch + 1);
           }
@@ -509,7 +527,7 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
           if (has16) tma_store_3d(&p.o16_map[tc_.seg], smem_u32(t16c), tc_.n0 + cl, wt, wb);
           tma_store_commit();
         }
-        if (has_res && ch + 1 < chunks) {         // next chunk's residual; if the 16-bit tile aliases the residual
+        if (has_res && ch + 1 < ch1) {         // next chunk's residual; if the 16-bit tile aliases the residual
           if (has16 && has32) {                   // tile, its store must have read it first
             if (ep_leader) tma_store_wait_read();
             __syncwarp();
@@ -535,7 +553,7 @@ __global__ void __launch_bounds__(THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const
 }  // namespace tc
 
 static unsigned long long* g_dbg = nullptr;
-static int g_ws_mode = 0;                     // weight-stationary configuration: -1 auto, 0 never (default: see scripts/gemm_ws_bench.py), 1 wherever it is legal
+static int g_ws_mode = -1;                    // weight-stationary configuration: -1 auto (default), 0 never, 1 wherever it is legal
 
 int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   using namespace tc;
@@ -555,7 +573,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     AVDF_CUDA(cudaGetDevice(&dev));
     AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  bool ws = g_ws_mode != 0 && a->taps == 1 && a->stride == 1 && a->c_in <= WS_W_BLOCKS * BK && a->n_out % MAX_BN == 0 && a->n_seg >= 1;
+  bool ws = g_ws_mode != 0 && a->taps == 1 && a->stride == 1 && a->c_in <= WS_W_BLOCKS * BK && a->n_out % MAX_BN == 0 && a->n_seg >= 1 && !a->ln_w;
   int ws_groups = 0, ws_per = 0;
   if (ws) {
     int per_seg = -1;
@@ -568,9 +586,11 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     }
     ws_groups = a->n_seg * (a->n_out / MAX_BN);
     ws_per = sms / ws_groups < per_seg ? sms / ws_groups : per_seg;
-    // auto: at least ~2.5 tiles per CTA, else the two co-resident CTAs of the narrow configuration hide the per-tile
-    // latency chain better than one weight-stationary CTA
-    if (ws_per < 1 || (g_ws_mode < 0 && per_seg * 2 < ws_per * 5)) ws = false;
+    // auto: only where it was measured to win (scripts/gemm_ws_bench.py: the stacked q/k/v projection at level 0, 14.8 vs
+    // 16.7 us) - 16-bit output without activation / residual (the instantiated fast variant), three or more weight groups
+    // and >= 3.5 tiles per CTA; everywhere else the two co-resident CTAs of the narrow configuration are as fast or faster
+    const bool qkv_like = a->out_h && !a->out_f32 && a->out_h_dtype == AVDF_DTYPE_F16 && a->act == AVDF_ACT_NONE && !a->residual && !a->pe;
+    if (ws_per < 1 || (g_ws_mode < 0 && !(qkv_like && ws_groups >= 3 && per_seg * 2 >= ws_per * 7))) ws = false;
   }
   if (ws) bn = MAX_BN;
   AVDF_CHECK_ARG(a->n_out % bn == 0, "bf16 path: n_out must be <= 256 or a multiple of 256");
@@ -695,13 +715,13 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
   bool launched = false;
 #define AVDF_LAUNCH(M, O) if (!launched && !ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
-#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, true><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
+#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, true><<<grid, WS_THREADS, smem_bytes, st>>>(p); launched = true; }
   AVDF_TC_VARIANTS(AVDF_LAUNCH)
   AVDF_TC_WS_VARIANTS(AVDF_LAUNCH_WS)
 #undef AVDF_LAUNCH
 #undef AVDF_LAUNCH_WS
   if (!launched) {
-    if (ws) conv_gemm_tc_kernel<-1, -1, true><<<grid, THREADS, smem_bytes, st>>>(p);
+    if (ws) conv_gemm_tc_kernel<-1, -1, true><<<grid, WS_THREADS, smem_bytes, st>>>(p);
     else conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, smem_bytes, st>>>(p);
   }
   return check_launch("conv_gemm_tc_kernel");
@@ -715,7 +735,7 @@ extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_timeline(u
   avdf::g_dbg = dev_buf;
   return 0;
 }
-// Debug / test hook: weight-stationary configuration -1 auto, 0 never (default), 1 wherever it is legal. Returns the
+// Debug / test hook: weight-stationary configuration -1 auto (default), 0 never, 1 wherever it is legal. Returns the
 // previous setting.
 extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_ws(int mode) {
   const int prev = avdf::g_ws_mode;
