@@ -33,7 +33,7 @@
 namespace avdf {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, MAX_BN = 256, MAX_STAGES = 3;
+constexpr int BM = 128, BK = 64, MAX_BN = 256, MAX_STAGES = 4;
 constexpr int A_STAGE = BM * BK * 2;          // 16384
 constexpr int EPI_VEC_BYTES = 4 * MAX_BN * 4; // bias / ln_w / ln_b / gamma of the current n-tile
 constexpr int STAGE_TILE_BYTES = 4 * 2 * 4096;   // per epilogue warp: a 4 KB result tile + a 4 KB residual / second result tile
@@ -47,9 +47,15 @@ __host__ __device__ constexpr int smem_bytes_of(int bn) {
 // on its SM; with four, the epilogue - ~4.2 us per 128 x 256 tile - was the limit, scripts/gemm_ws_bench.py), each with its
 // two 4 KB staging tiles; bias + gamma only (no fused LayerNorm). 231,936 of the 232,448 bytes a CTA can have: the
 // dynamic shared-memory window must start 1024-aligned (it does: the first KB of an SM's shared memory is reserved).
-constexpr int WS_A_STAGES = 2, WS_W_BLOCKS = 4, WS_EPI_WARPS = 8;
+// The 16-bit-output variants (the q/k/v projection) need only ONE 4 KB staging tile per warp, which pays for FOUR A stages:
+// with two, the globaltimer stamps (scripts/gemm_epilogue_timeline.py) showed the epilogue idle 2.5 of every 4.0 us - the
+// TMA -> MMA -> commit -> refill chain of a stage is ~1.2 us and a tile needs four of them.
+constexpr int WS_W_BLOCKS = 4, WS_EPI_WARPS = 8;
+__host__ __device__ constexpr int ws_a_stages(bool out16_only) { return out16_only ? 4 : 2; }
+__host__ __device__ constexpr int ws_stage_bytes(bool out16_only) { return out16_only ? 4096 : 8192; }   // per epilogue warp
 constexpr int WS_BAR_BYTES = 512, WS_VEC_BYTES = 2 * MAX_BN * 4;
-constexpr int WS_SMEM_BYTES = WS_A_STAGES * A_STAGE + WS_W_BLOCKS * MAX_BN * BK * 2 + WS_BAR_BYTES + WS_VEC_BYTES + WS_EPI_WARPS * 8192;
+constexpr int WS_SMEM_BYTES = ws_a_stages(false) * A_STAGE + WS_W_BLOCKS * MAX_BN * BK * 2 + WS_BAR_BYTES + WS_VEC_BYTES + WS_EPI_WARPS * ws_stage_bytes(false);
+static_assert(WS_SMEM_BYTES == ws_a_stages(true) * A_STAGE + WS_W_BLOCKS * MAX_BN * BK * 2 + WS_BAR_BYTES + WS_VEC_BYTES + WS_EPI_WARPS * ws_stage_bytes(true), "both layouts use the same total");
 constexpr int WS_THREADS = 128 + WS_EPI_WARPS * 32;
 
 struct Params {
@@ -110,13 +116,14 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
   // to the compiler: LDS/STS instead of generic loads)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr bool ws = WS;
-  const int n_stages = ws ? WS_A_STAGES : n_stages_of(p.bn);
+  constexpr bool OUT16_ONLY = MODE >= 0 && OUTK >= 0 && (OUTK & 3) == 2 && (MODE & 24) == 0;   // the "wide" epilogue pass
+  const int n_stages = ws ? ws_a_stages(OUT16_ONLY) : n_stages_of(p.bn);
   const int b_stage = b_stage_of(p.bn);
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + n_stages * A_STAGE;       // ws: WS_W_BLOCKS resident K blocks of the weights
   unsigned char* after = smem_b + (ws ? WS_W_BLOCKS : n_stages) * b_stage;
   // ws: the staging tiles come first (they need the 1024-byte alignment `after` has), then barriers and vectors
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ws ? after + WS_EPI_WARPS * 8192 : after);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ws ? after + WS_EPI_WARPS * ws_stage_bytes(OUT16_ONLY) : after);
   // bars: full[3], empty[3], tmem_full[2], tmem_empty[2], tmem ptr, residual[4]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + (ws ? WS_BAR_BYTES : 1024));
@@ -245,8 +252,10 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
     const int et = threadIdx.x - 128;            // 0..127 among the epilogue threads
     float* s_bias = epi_smem; float* s_lnw = epi_smem + MAX_BN; float* s_lnb = epi_smem + 2 * MAX_BN; float* s_gam = epi_smem + (ws ? 1 : 3) * MAX_BN;
     if (ws) { s_lnw = s_bias; s_lnb = s_bias; }   // (never read: the weight-stationary configuration has no fused LayerNorm)
-    unsigned char* t32 = stage_smem + wi * 8192;          // result tile (fp32: swizzle 128B)
-    unsigned char* trs = stage_smem + wi * 8192 + 4096;   // residual tile / second result tile
+    constexpr int STG = ws ? ws_stage_bytes(OUT16_ONLY) : 8192;
+    constexpr bool ONE_TILE = STG == 4096;                  // ws, 16-bit output: a single staging tile per warp
+    unsigned char* t32 = stage_smem + wi * STG;             // result tile (fp32: swizzle 128B)
+    unsigned char* trs = ONE_TILE ? t32 : t32 + 4096;       // residual tile / second result tile
     const uint32_t res_bar = bar_base + 8u * (2 * MAX_STAGES + 5 + wi);
     const uint32_t res_bar1 = bar_base + 8u * (2 * MAX_STAGES + 13 + wi);   // second residual tile (in-place fp32 path)
     const int chunks = (p.bn >> 5) / (EPI_WARPS / 4);     // 32-column chunks this warp handles: [ch0, ch1)
@@ -357,9 +366,11 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
       if (WIDE_OK && (chunks & 1) == 0) {
         for (int ch = ch0; ch < ch1; ch += 2) {
           uint32_t va[32], vb[32];
+          if (wi == 0 && it == 0) AVDF_TS(2 + 6 * ((ch - ch0) >> 1 & 1));       // accumulator ready, step starts
           tmem_ld32_issue(taddr + ch * 32, va);
           tmem_ld32_issue(taddr + (ch + 1) * 32, vb);
           tmem_ld_wait();
+          if (wi == 0 && it == 0) AVDF_TS(3 + 6 * ((ch - ch0) >> 1 & 1));       // TMEM read done
           if (ch + 2 >= ch1) {                     // all TMEM reads of this warp done: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
@@ -367,8 +378,12 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
           }
           unsigned char* tw = (store_seq++ & 1) ? trs : t32;
           const f32x2 mk2 = pk2(mk), nmean2 = pk2(-mean), rstd2 = pk2(rstd);
-          if (ep_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (ep_leader) {
+            if (ONE_TILE) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
           __syncwarp();
+          if (wi == 0 && it == 0) AVDF_TS(4 + 6 * ((ch - ch0) >> 1 & 1));       // staging tile free
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int cl = (ch + half) * 32;
@@ -403,13 +418,17 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
               *reinterpret_cast<uint4*>(tw + lane * 128 + (((half * 4 + j) ^ sw7) << 4)) = uo;
             }
           }
+          if (wi == 0 && it == 0) AVDF_TS(5 + 6 * ((ch - ch0) >> 1 & 1));       // math + STS issued
           fence_async_smem();
           __syncwarp();
+          if (wi == 0 && it == 0) AVDF_TS(6 + 6 * ((ch - ch0) >> 1 & 1));       // proxy fence done
           if (ep_leader) {
             tma_store_3d(&p.o16w_map[tc_.seg], smem_u32(tw), tc_.n0 + ch * 32, wt, wb);
             tma_store_commit();
           }
+          if (wi == 0 && it == 0) AVDF_TS(7 + 6 * ((ch - ch0) >> 1 & 1));       // TMA store issued
         }
+        if (wi == 0 && it == 1) AVDF_TS(14);        // second tile's epilogue starts
         continue;                                   // next tile
       }
       uint32_t vr[32];                            // accumulator block of the current chunk (raw bits)
