@@ -108,14 +108,20 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
 constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (pe ? 16 : 0); }
 
 // OUTK >= 0 fixes which outputs exist: bit 0 fp32, bit 1 16-bit copy, bit 2 the 16-bit copy is fp16 (else bf16).
-// WS: the weight-stationary configuration (compile-time, so that the streaming variants carry none of its state).
-template <int MODE, int OUTK, bool WS = false>
-__global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
+// CFG (compile-time, so that the streaming variants carry none of the other configurations' state):
+//   0  streaming, four epilogue warps (narrow tiles: two CTAs per SM)
+//   1  weight-stationary, eight epilogue warps
+//   2  wide (BN = 256: fused LayerNorm, K >= 1024) with EIGHT epilogue warps: the two warps of a TMEM lane quarter split the
+//      columns; LayerNorm statistics are exchanged through shared memory (one named barrier per row block). With four
+//      warps the LayerNorm epilogue (two TMEM passes over 256 columns) took longer than the K = 768 main loop.
+constexpr int W8_SMEM_BYTES = smem_bytes_of(MAX_BN) + 4 * 8192 /* four more staging pairs */ + 4096 /* LayerNorm partial sums */;
+template <int MODE, int OUTK, int CFG = 0>
+__global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024 B alignment for the 128B swizzle atoms (an offset into the array keeps the shared address space visible
   // to the compiler: LDS/STS instead of generic loads)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  constexpr bool ws = WS;
+  constexpr bool ws = CFG == 1, w8 = CFG == 2;
   constexpr bool OUT16_ONLY = MODE >= 0 && OUTK >= 0 && (OUTK & 3) == 2 && (MODE & 24) == 0;   // the "wide" epilogue pass
   const int n_stages = ws ? ws_a_stages(OUT16_ONLY) : n_stages_of(p.bn);
   const int b_stage = b_stage_of(p.bn);
@@ -128,7 +134,8 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   float* epi_smem = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + (ws ? WS_BAR_BYTES : 1024));
   unsigned char* stage_smem = ws ? after : after + 1024 + EPI_VEC_BYTES;
-  constexpr int EPI_WARPS = ws ? WS_EPI_WARPS : 4;
+  constexpr int EPI_WARPS = CFG ? WS_EPI_WARPS : 4;
+  unsigned char* part_smem = stage_smem + EPI_WARPS * 8192;       // w8: LayerNorm partial sums [tile parity][team][row] (float2)
   if (ws && (smem_u32(smem_dyn) & 1023u) != 0) {          // no slack for re-alignment in this configuration
     if (threadIdx.x == 0) printf("avdf gemm_tc: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
       float mean = 0.f, rstd = 1.f;
       if (has_ln) {                               // row statistics over all bn columns (this thread owns the whole row)
         float s = 0.f, ss = 0.f;
-        for (int ch = 0; ch < chunks; ++ch) {
+        for (int ch = ch0; ch < ch1; ++ch) {
           float v[32];
           tmem_ld32(taddr + ch * 32, v);
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + ch * 32);
@@ -355,6 +362,13 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
             s += (x0 + x1) + (x2 + x3);
             ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
           }
+        }
+        if (w8) {                                 // the other half of the row's columns belongs to the partner warp
+          float2* part = reinterpret_cast<float2*>(part_smem) + (it & 1) * 256;
+          part[team * 128 + q * 32 + lane] = make_float2(s, ss);
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          const float2 pa = part[q * 32 + lane], pb = part[128 + q * 32 + lane];
+          s = pa.x + pb.x; ss = pa.y + pb.y;
         }
         mean = s / (float)p.bn;
         const float var = fmaxf(ss / (float)p.bn - mean * mean, 0.f);
@@ -572,6 +586,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : THREADS, WS ? 1 : 2) conv_ge
 }  // namespace tc
 
 static unsigned long long* g_dbg = nullptr;
+static bool g_w8 = !(getenv("AVDF_GEMM_W8") && atoi(getenv("AVDF_GEMM_W8")) == 0);   // wide tiles: eight epilogue warps (0: four)
 static int g_ws_mode = -1;                    // weight-stationary configuration: -1 auto (default), 0 never, 1 wherever it is legal
 
 int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
@@ -718,29 +733,44 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     X(mode_of(false, AVDF_ACT_NONE, false, false), 6) X(mode_of(false, AVDF_ACT_NONE, true, false), 1)            \
     X(mode_of(false, AVDF_ACT_NONE, false, false), 1)
 #define AVDF_SET_SMEM(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_of(MAX_BN)));
-#define AVDF_SET_SMEM_WS(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+    // wide tiles with eight epilogue warps: LayerNorm + ReLU (embedding, head towers), K >= 1024 (DownBlock convs, MLP down-projection)
+#define AVDF_TC_W8_VARIANTS(X)                                                                                \
+    X(mode_of(true, AVDF_ACT_RELU, false, false), 6) X(mode_of(true, AVDF_ACT_RELU, false, false), 2)             \
+    X(mode_of(true, AVDF_ACT_RELU, false, false), 1) X(mode_of(true, AVDF_ACT_RELU, false, true), 1)              \
+    X(mode_of(false, AVDF_ACT_NONE, false, false), 1) X(mode_of(false, AVDF_ACT_NONE, true, false), 1)            \
+    X(mode_of(false, AVDF_ACT_NONE, true, false), 7) X(mode_of(false, AVDF_ACT_NONE, true, false), 3)
+#define AVDF_SET_SMEM_WS(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+#define AVDF_SET_SMEM_W8(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, W8_SMEM_BYTES));
     AVDF_SET_SMEM(-1, -1)
     AVDF_TC_VARIANTS(AVDF_SET_SMEM)
     AVDF_SET_SMEM_WS(-1, -1)
     AVDF_TC_WS_VARIANTS(AVDF_SET_SMEM_WS)
+    AVDF_SET_SMEM_W8(-1, -1)
+    AVDF_TC_W8_VARIANTS(AVDF_SET_SMEM_W8)
 #undef AVDF_SET_SMEM
 #undef AVDF_SET_SMEM_WS
+#undef AVDF_SET_SMEM_W8
   }
   AVDF_CHECK_ARG((long long)a->batch * a->o_rows_per_video * a->n_out < (1ll << 31), "output larger than 2^31 elements");
   const int ctas_per_sm = bn <= 128 ? 2 : 1;      // narrow tiles: two co-resident CTAs per SM
   const int grid = ws ? ws_groups * ws_per : (p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm);
-  const int smem_bytes = ws ? WS_SMEM_BYTES : smem_bytes_of(bn);
+  const bool w8 = !ws && bn == MAX_BN && g_w8;
+  const int smem_bytes = ws ? WS_SMEM_BYTES : (w8 ? W8_SMEM_BYTES : smem_bytes_of(bn));
   const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr);
   const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
   bool launched = false;
-#define AVDF_LAUNCH(M, O) if (!launched && !ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
-#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, true><<<grid, WS_THREADS, smem_bytes, st>>>(p); launched = true; }
+#define AVDF_LAUNCH(M, O) if (!launched && !ws && !w8 && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
+#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, 1><<<grid, WS_THREADS, smem_bytes, st>>>(p); launched = true; }
+#define AVDF_LAUNCH_W8(M, O) if (!launched && w8 && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, 2><<<grid, WS_THREADS, smem_bytes, st>>>(p); launched = true; }
   AVDF_TC_VARIANTS(AVDF_LAUNCH)
   AVDF_TC_WS_VARIANTS(AVDF_LAUNCH_WS)
+  AVDF_TC_W8_VARIANTS(AVDF_LAUNCH_W8)
 #undef AVDF_LAUNCH
 #undef AVDF_LAUNCH_WS
+#undef AVDF_LAUNCH_W8
   if (!launched) {
-    if (ws) conv_gemm_tc_kernel<-1, -1, true><<<grid, WS_THREADS, smem_bytes, st>>>(p);
+    if (ws) conv_gemm_tc_kernel<-1, -1, 1><<<grid, WS_THREADS, smem_bytes, st>>>(p);
+    else if (w8) conv_gemm_tc_kernel<-1, -1, 2><<<grid, WS_THREADS, smem_bytes, st>>>(p);
     else conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, smem_bytes, st>>>(p);
   }
   return check_launch("conv_gemm_tc_kernel");
@@ -753,6 +783,12 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
 extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_timeline(unsigned long long* dev_buf) {
   avdf::g_dbg = dev_buf;
   return 0;
+}
+// Debug / test hook: wide tiles with eight (1, default) or four (0) epilogue warps. Returns the previous setting.
+extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_w8(int on) {
+  const int prev = avdf::g_w8 ? 1 : 0;
+  avdf::g_w8 = on != 0;
+  return prev;
 }
 // Debug / test hook: weight-stationary configuration -1 auto (default), 0 never, 1 wherever it is legal. Returns the
 // previous setting.

@@ -559,6 +559,52 @@ def test_conv_gemm_weight_stationary(case, adt):
         assert torch.equal(outs[1], outs[0])
 
 
+@pytest.mark.parametrize("case", ["ln_relu_16bit", "ln_relu_pe_fp32", "k1024_res_both"])
+def test_conv_gemm_wide_tiles_eight_epilogue_warps(case):
+    """256-wide tiles run with eight epilogue warps (two per row block, splitting the columns; LayerNorm statistics exchanged
+    through shared memory). More tiles than SMs, ragged masks; checked against torch and against the four-warp configuration."""
+    rng = np.random.RandomState({"ln_relu_16bit": 1, "ln_relu_pe_fp32": 2, "k1024_res_both": 3}[case])
+    adt = torch.float16
+    if case == "k1024_res_both":
+        B, T, cin, nout, taps, has_ln, act, has_pe, has_res = 160, 128, 1024, 256, 1, False, ops.ACT_NONE, False, True
+    else:
+        B, T, cin, nout, taps, has_ln, act, has_pe, has_res = 170, 128, 256, 256, 3, True, ops.ACT_RELU, case == "ln_relu_pe_fp32", False
+    x = torch.from_numpy(rng.standard_normal((B, T, cin)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((nout, cin, taps)) / math.sqrt(cin * taps)).astype(np.float32))
+    bias = torch.from_numpy(rng.normal(0, 0.3, nout).astype(np.float32)) if not has_ln else None
+    ln = _ln_params(rng, nout) if has_ln else None
+    pe = torch.from_numpy(rng.normal(0, 0.1, (T, nout)).astype(np.float32)) if has_pe else None
+    res = torch.from_numpy(rng.standard_normal((B, T, nout)).astype(np.float32)) if has_res else None
+    gamma = torch.from_numpy(rng.uniform(0.5, 1.5, nout).astype(np.float32)) if has_res else None
+    valid = rng.randint(T // 2, T + 1, B); valid[0] = T
+    mask = (np.arange(T)[None] < valid[:, None])
+    want = _conv_ref(x.to(adt).float(), w.to(adt).float(), bias, taps, 1, torch.from_numpy(mask), ln, act, pe, res, gamma)
+    wp = w.permute(0, 2, 1).reshape(nout, taps * cin).contiguous()
+    L = nv.lib()
+    outs = {}
+    prev = L.avdf_debug_gemm_w8(1)
+    try:
+        for on in (1, 0):
+            L.avdf_debug_gemm_w8(on)
+            o32 = torch.zeros((B, T, nout), device=DEV) if case != "ln_relu_16bit" else None
+            o16 = torch.zeros((B, T, nout), dtype=adt, device=DEV) if case != "ln_relu_pe_fp32" else None
+            ops.conv_gemm(dev(x, adt), dev(wp, adt), taps=taps, stride=1, batch=B, c_in=cin, n_out=nout, segs=[(T, 0, 0)], a_rows=T, o_rows=T,
+                          bias=None if bias is None else dev(bias), row_mask=dev(mask.astype(np.uint8)),
+                          ln=None if ln is None else (dev(ln[0]), dev(ln[1])), act=act, pe=None if pe is None else dev(pe),
+                          residual=None if res is None else dev(res), gamma=None if gamma is None else dev(gamma), out_f32=o32, out_h=o16)
+            torch.cuda.synchronize()
+            outs[on] = (None if o32 is None else o32.cpu(), None if o16 is None else o16.float().cpu())
+    finally:
+        L.avdf_debug_gemm_w8(prev)
+    for on in (1, 0):
+        if outs[on][0] is not None:
+            assert rel_err(outs[on][0], want) < 2e-4, (case, on)
+        if outs[on][1] is not None:
+            assert rel_err(outs[on][1], want) < 1e-2, (case, on)
+    if outs[1][0] is not None:                  # the two configurations differ only in the summation order of the LayerNorm statistics
+        assert rel_err(outs[1][0], outs[0][0]) < 2e-6
+
+
 def test_attention_stacked_qkv_and_interleaved_dwconv():
     rng = np.random.RandomState(10)
     B, T, C = 3, 80, 256
