@@ -671,67 +671,92 @@ __global__ void __launch_bounds__(256) fpn_fuse_cols_kernel(const FpnParams p) {
 #pragma unroll
     for (int l = 0; l < AVDF_MAX_LEVELS; ++l) { row0[l] = acc_rows; acc_rows += (FPB >> l) + 2; }
   }
-  // phase 1: coarsest level first
-  for (int l = p.n_levels - 1; l >= 0; --l) {
+  // phase 0: every lateral row this CTA needs, all levels at once (cp.async, one wait): fetched level by level behind
+  // the top-down dependency the six global-load round trips were serialised (~80 us for 75 MB)
+  for (int l = 0; l < p.n_levels; ++l) {
     const int n = (FPB >> l) + 2, s = ((blk * FPB) >> l) - 1, T = p.lvl_len[l];
     for (int i = warp; i < n; i += 8) {
       const int pos = s + i;
-      float v[8];
-      if (pos >= 0 && pos < T) {
-        Row8<float>::load(lat_b + (size_t)(p.lvl_off[l] + pos) * kC + c0, v);
-        if (l + 1 < p.n_levels && (pos >> 1) < p.lvl_len[l + 1]) {
-          const int pi = (pos >> 1) - (((blk * FPB) >> (l + 1)) - 1);
-          float u[8];
-          lds8(fpn_smem + (size_t)(row0[l + 1] + pi) * kC + c0, u);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = u[k] + v[k];
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = 0.f;                // outside the level: the conv's zero padding
-      }
       float* d = fpn_smem + (size_t)(row0[l] + i) * kC + c0;
-      *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      if (pos >= 0 && pos < T) {
+        const float* g = lat_b + (size_t)(p.lvl_off[l] + pos) * kC + c0;
+        const unsigned sd = (unsigned)__cvta_generic_to_shared(d);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sd), "l"(g) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sd + 16), "l"(g + 4) : "memory");
+      } else {                                                 // outside the level: the conv's zero padding
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // phase 1: top-down sums in shared memory, coarsest level first (L_l[t] = L_{l+1}[t >> 1] + lat_l[t])
+  for (int l = p.n_levels - 2; l >= 0; --l) {
+    const int n = (FPB >> l) + 2, s = ((blk * FPB) >> l) - 1, T = p.lvl_len[l];
+    for (int i = warp; i < n; i += 8) {
+      const int pos = s + i;
+      if (pos >= 0 && pos < T && (pos >> 1) < p.lvl_len[l + 1]) {
+        const int pi = (pos >> 1) - (((blk * FPB) >> (l + 1)) - 1);
+        float* d = fpn_smem + (size_t)(row0[l] + i) * kC + c0;
+        float v[8], u[8];
+        lds8(d, v);
+        lds8(fpn_smem + (size_t)(row0[l + 1] + pi) * kC + c0, u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = u[k] + v[k];
+        *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
     __syncthreads();
   }
-  // phase 2: depthwise k3 + mask + LayerNorm, warp per output row, levels in order (weights cached per level)
+  // phase 2: depthwise k3 + mask + LayerNorm. The output rows are cut into items of <= 8 rows of ONE level and an item
+  // belongs to one warp, which loads that level's weights once, as six 16-byte loads of its 24 contiguous floats (every
+  // warp walking every level re-loaded them six times with 24 scalar loads 96 bytes apart: ~4600 L1 sector requests per
+  // warp, what bounded the kernel at ~80 us).
+  int item = 0;
   for (int l = 0; l < p.n_levels; ++l) {
     const int n = FPB >> l, s = (blk * FPB) >> l;
-    if (warp >= n && n < 8) continue;                          // fewer rows than warps at the top levels
-    float dwr[3][8], lw[8], lb[8];
-    const float* dw = p.dw_w + (size_t)l * kC * 3;
+    for (int first = 0; first < n; first += 8, ++item) {
+      if ((item & 7) != warp) continue;
+      const int cnt = min(8, n - first);
+      float dwr[3][8], lw[8], lb[8];
+      {
+        const float4* dw4 = reinterpret_cast<const float4*>(p.dw_w + (size_t)l * kC * 3 + (size_t)c0 * 3);   // [8 channels][3 taps]
+        float wv[24];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      dwr[0][k] = __ldg(dw + (c0 + k) * 3); dwr[1][k] = __ldg(dw + (c0 + k) * 3 + 1); dwr[2][k] = __ldg(dw + (c0 + k) * 3 + 2);
-    }
-    if (p.ln_w) {
-      Row8<float>::load(p.ln_w + (size_t)l * kC + c0, lw);
-      Row8<float>::load(p.ln_b + (size_t)l * kC + c0, lb);
-    }
-    for (int i = warp; i < n; i += 8) {
-      const size_t r = (size_t)b * p.P + p.lvl_off[l] + s + i;
-      const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
-      float acc[8];
+        for (int q = 0; q < 6; ++q) { const float4 t4 = __ldg(dw4 + q); wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w; }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float u[8];
-        lds8(fpn_smem + (size_t)(row0[l] + i + j) * kC + c0, u);   // smem row i + j holds position s + i + j - 1
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(dwr[j][k], u[k], acc[k]);
+        for (int k = 0; k < 8; ++k) { dwr[0][k] = wv[3 * k]; dwr[1][k] = wv[3 * k + 1]; dwr[2][k] = wv[3 * k + 2]; }
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] *= mk;
       if (p.ln_w) {
-        float m, rs;
-        row_stats(acc, m, rs);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m) * rs, lw[k], lb[k]);
+        Row8<float>::load(p.ln_w + (size_t)l * kC + c0, lw);
+        Row8<float>::load(p.ln_b + (size_t)l * kC + c0, lb);
       }
-      Row8<OutT>::store(reinterpret_cast<OutT*>(p.out) + r * kC + c0, acc);
+      for (int i = first; i < first + cnt; ++i) {
+        const size_t r = (size_t)b * p.P + p.lvl_off[l] + s + i;
+        const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float u[8];
+          lds8(fpn_smem + (size_t)(row0[l] + i + j) * kC + c0, u);   // smem row i + j holds position s + i + j - 1
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(dwr[j][k], u[k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= mk;
+        if (p.ln_w) {
+          float m, rs;
+          row_stats(acc, m, rs);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf((acc[k] - m) * rs, lw[k], lb[k]);
+        }
+        Row8<OutT>::store(reinterpret_cast<OutT*>(p.out) + r * kC + c0, acc);
+      }
     }
   }
 }
