@@ -474,7 +474,7 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "bf16", "fp32"])
     ap.add_argument("--ref-videos", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=4, help="batches in flight at once (each on its own stream and buffer set)")
+    ap.add_argument("--lanes", type=int, default=8, help="batches in flight at once (each on its own stream and buffer set)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event timings of one step to this json")
     args = ap.parse_args()
