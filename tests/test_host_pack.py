@@ -90,3 +90,13 @@ def test_pageable_arrays_are_not_reported_pinned():
     L = native.lib()
     assert L.avdf_host_all_pinned(S, N, 1) == 0
     assert L.avdf_host_all_pinned(None, None, 0) == 0
+
+
+def test_h2d_gather_rejects_bad_arguments_without_touching_cuda():
+    L = native.lib()
+    assert L.avdf_h2d_gather(None, None, None, 0, None) == 0                 # nothing to copy
+    assert L.avdf_h2d_gather(None, None, None, 2, None) == -1 and b"invalid argument" in L.avdf_last_error()
+    assert L.avdf_h2d_gather(None, None, None, -1, None) == -1
+    one = (ctypes.c_void_p * 1)(None)
+    assert L.avdf_h2d_gather(one, one, (ctypes.c_size_t * 1)(64), 1, None) == -1   # null span with a non-zero size
+    assert L.avdf_h2d_gather(one, one, (ctypes.c_size_t * 1)(0), 1, None) == 0     # empty spans are skipped
