@@ -18,6 +18,11 @@ _DUR_Q = [(0.0, 4.03), (0.05, 5.18), (0.25, 6.02), (0.5, 7.42), (0.75, 10.37), (
 BYOLA_FPS = 12.497   # deepfake_video_audio.py:415
 EMO_FPS = 50         # deepfake_video_audio.py:416
 VIDEO_FPS = 25
+# (video_frames, audio_frames @ 16 kHz) of the 12 clips of the reference's tinydataset (tinydataset/metadata/**/*.json:
+# BASELINE.json configs[0]); the features themselves are not shipped (.MISSING_LARGE_BLOBS), so the streams of these
+# shapes are synthetic too
+TINYDATASET_SHAPES = [(240, 154496), (237, 152576), (237, 152576), (240, 154496), (176, 113216), (181, 116736),
+                      (181, 116736), (176, 113216), (139, 89216), (134, 86016), (134, 86016), (139, 89216)]
 
 
 def synthetic_state_dict(model_cfg: dict, model_name: str, seed: int = 0) -> dict:
@@ -80,3 +85,20 @@ def synthetic_streams(duration: float, seed: int, video_dim=256, byola_dim=2048,
     out["byola"] = np.abs(rng.standard_normal((t_b, byola_dim))).astype(np.float32)
     out["emo"] = rng.standard_normal((t_e, emo_dim)).astype(np.float32)
     return out
+
+
+def tinydataset_streams(index: int, seed: int, video_dim=256, byola_dim=2048, emo_dim=768):
+    """(duration, streams) shaped like clip `index` of the reference's tinydataset: the visual stream has one row per
+    video frame, the audio streams the extractors' frame rates over audio_frames / 16 kHz (truncated like
+    deepfake_video_audio.py:482-483)."""
+    vf, af = TINYDATASET_SHAPES[index]
+    duration = af / 16000.0
+    rng = np.random.RandomState(seed)
+    t_b = max(2, int(BYOLA_FPS * duration - 0.3657))
+    t_e = max(2, int(EMO_FPS * duration - 0.817))
+    out = {}
+    if video_dim:
+        out["video"] = rng.standard_normal((vf, video_dim)).astype(np.float32)
+    out["byola"] = np.abs(rng.standard_normal((t_b, byola_dim))).astype(np.float32)
+    out["emo"] = rng.standard_normal((t_e, emo_dim)).astype(np.float32)
+    return duration, out

@@ -1,0 +1,35 @@
+"""North-star parity bar in the precision and at the batch size bench.py runs: >= 256 synthetic videos per config (the 12
+tinydataset-shaped clips of BASELINE.json configs[0] first, then AV-Deepfake1M-length clips), batch 32,
+precision "mixed", hard AND soft NMS, through the raw-stream entry point (interp/concat on the GPU + CUDA graph), against
+the oracle run one video at a time like the reference (av_fd_no_recon.py:456, 760-876; libs/utils/nms.py:103-190).
+
+Asserted for every video:
+  (i)   dense logits / offsets within 1e-2 of the oracle's (max |diff| / max |ref|), video_cls within 2e-2;
+  (ii)  the CUDA post-processing is EXACT at this batch size: the oracle's decode + NMS + voting + seconds applied to the
+        CUDA path's own dense outputs returns the very sets the CUDA path returned (scores bit-equal, boundaries 1e-4 s);
+  (iii) final sets after the 0.2 score filter vs the reference: same membership and start/end within 1e-3 s, except
+        where the reference itself sits within the measured tolerance of a threshold (oracle/parity.py: score vs
+        min_score incl. every decayed score, ordering ties, IoU vs iou_threshold / voting_thresh) or a boundary moved by
+        no more than the video's own dense boundary tolerance. Those are counted and printed; anything else fails.
+AVDF_PARITY_VIDEOS overrides the number of videos per config (default 256)."""
+import json
+import os
+
+import pytest
+
+import parity_common
+
+pytestmark = pytest.mark.gpu
+N_VIDEOS = int(os.environ.get("AVDF_PARITY_VIDEOS", "256"))
+
+
+@pytest.mark.parametrize("case", ["audio_only", "exp12", "exp13"])
+def test_final_sets_batch32_mixed(case):
+    res = parity_common.run_parity(case, N_VIDEOS, precision="mixed", batch=32)
+    print("\nPARITY " + json.dumps(res))
+    de = res["dense_err"]
+    assert de["logits"] < 1e-2 and de["offsets"] < 1e-2 and de["vcls"] < 2e-2, de
+    for method, st in res["sets"].items():
+        assert not st["post_exact_fail"], (method, st["post_exact_fail"][:5])
+        assert not st["unexplained"], (method, st["unexplained"][:3])
+        assert st["identical"] + st["explained"] == st["videos"]
