@@ -217,8 +217,7 @@ int attention_banded_mma(const void* q, const void* k, const void* v, const unsi
   static const int warps_env = getenv("AVDF_ATT_WARPS") ? atoi(getenv("AVDF_ATT_WARPS")) : 0;
   // 64 query rows per CTA while that still gives every SM two CTAs, else 32 (measured, batch 32: T = 768 14.9 vs 15.4 us,
   // T = 192 6.6 vs 5.9 us)
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int sms = device_sm_count();
   const int warps = warps_env == 4 || warps_env == 2 || warps_env == 1 ? warps_env
                                                                          : (batch * ((t + 63) / 64) * (4 / AM_HEADS) >= 2 * sms ? 4 : 2);
   const int rows = 16 * warps;
@@ -227,11 +226,7 @@ int attention_banded_mma(const void* q, const void* k, const void* v, const unsi
 #define AVDF_AM(InT) do { if (warps == 4) AVDF_AM_W(InT, 4); else if (warps == 1) AVDF_AM_W(InT, 1); else AVDF_AM_W(InT, 2); } while (0)
 #define AVDF_AM_W(InT, W)                                                                                                  \
   AVDF_DISPATCH_DTYPE(out_dtype, OutT, {                                                                                   \
-    static bool attr_done = false;                                                                                         \
-    if (!attr_done) {                                                                                                      \
-      AVDF_CUDA(cudaFuncSetAttribute(attention_banded_mma_kernel<InT, OutT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      attr_done = true;                                                                                                    \
-    }                                                                                                                      \
+    AVDF_SMEM_ATTR_ONCE((attention_banded_mma_kernel<InT, OutT, W>), 2 * (64 + 16) * AM_PITCH);                            \
     attention_banded_mma_kernel<InT, OutT, W><<<grid, W * 32, smem, st>>>((const InT*)q, (const InT*)k, (const InT*)v, kv_mask, \
                                                                              (OutT*)out, batch, t, rpv);                  \
   })

@@ -994,11 +994,7 @@ static int grid_for(long long work_items, int per_cta, int sms) {
   }
   return (int)(want < 1 ? 1 : want);
 }
-static int sm_count() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  return sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 }  // namespace avdf
 
@@ -1044,11 +1040,7 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
 #define AVDF_LDL(S, NS)                                                                                              \
   AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, {                                                                          \
     const size_t smem = (size_t)(NS * 9 + LDL_WARPS * LDL_DEPTH) * kC * sizeof(float);                               \
-    static bool attr_done = false;                                                                                   \
-    if (!attr_done) {                                                                                                \
-      AVDF_CUDA(cudaFuncSetAttribute(ln_dwconv_ln_kernel<OutT, S, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_done = true;                                                                                              \
-    }                                                                                                                \
+    AVDF_SMEM_ATTR_ONCE((ln_dwconv_ln_kernel<OutT, S, NS>), smem);                                                   \
     ln_dwconv_ln_kernel<OutT, S, NS><<<grid, LDL_WARPS * 32, smem, st>>>(p);                                         \
   })
   if (a->stride == 1) { if (a->n_streams == 1) AVDF_LDL(1, 1); else if (a->n_streams == 2) AVDF_LDL(1, 2); else AVDF_LDL(1, 3); }
@@ -1083,12 +1075,7 @@ extern "C" int avdf_attention(const void* q, const void* k, const void* v, const
     const int grid = batch * ((t + rows - 1) / rows);
     AVDF_DISPATCH_DTYPE(in_dtype, InT, AVDF_DISPATCH_DTYPE(out_dtype, OutT, {
       const size_t smem = 2 * (size_t)(rows + 2 * HALF) * kC * sizeof(InT);
-      static bool attr_done = false;
-      if (!attr_done) {
-        AVDF_CUDA(cudaFuncSetAttribute(attention_banded_kernel<InT, OutT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(2 * (size_t)(ATB_MAX_ROWS + 2 * HALF) * kC * sizeof(InT))));
-        attr_done = true;
-      }
+      AVDF_SMEM_ATTR_ONCE((attention_banded_kernel<InT, OutT, HALF>), 2 * (size_t)(ATB_MAX_ROWS + 2 * HALF) * kC * sizeof(InT));
       attention_banded_kernel<InT, OutT, HALF><<<grid, ATB_WARPS * 32, smem, st>>>((const InT*)q, (const InT*)k, (const InT*)v, kv_mask,
                                                                                   (OutT*)out, batch, t, rpv, rows);
     }));
@@ -1163,11 +1150,7 @@ extern "C" int avdf_fpn_fuse(const float* lat, const uint8_t* mask, const float*
     const size_t smem = (size_t)smem_rows * kC * sizeof(float);
     const int grid = batch * (level_len[0] / FPB);
     AVDF_DISPATCH_DTYPE(out_dtype, OutT, {
-      static bool attr_done = false;
-      if (!attr_done) {
-        AVDF_CUDA(cudaFuncSetAttribute(fpn_fuse_cols_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-      }
+      AVDF_SMEM_ATTR_ONCE(fpn_fuse_cols_kernel<OutT>, smem);
       fpn_fuse_cols_kernel<OutT><<<grid, 256, smem, st>>>(p);
     });
     return check_launch("fpn_fuse_cols_kernel");

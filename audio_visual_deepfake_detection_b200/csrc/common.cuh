@@ -134,4 +134,26 @@ __device__ __forceinline__ float load1(const __half* p) { return __half2float(*p
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- per-device host state (runtime.cu). A process may drive several GPUs (the reference yaml ships devices:
+// ['cuda:3']): the SM count and the "opt-in shared-memory attribute already set" flags are properties of the CURRENT
+// device, not of the process.
+int current_device();          // cudaGetDevice, -1 on error
+int device_sm_count();         // SM count of the current device (cached per device)
+struct DeviceOnce {            // one bit per device ordinal; marked only AFTER the guarded setup succeeded
+  unsigned long long bits[4] = {0, 0, 0, 0};
+  bool done(int dev) const { return dev >= 0 && dev < 256 && ((__atomic_load_n(&bits[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull); }
+  void mark(int dev) { if (dev >= 0 && dev < 256) __atomic_fetch_or(&bits[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device); idempotent, so a race between two host
+// threads is harmless; a failure returns the error and leaves the flag clear.
+#define AVDF_SMEM_ATTR_ONCE(kernel, bytes)                                                                   \
+  do {                                                                                                       \
+    static avdf::DeviceOnce once_;                                                                           \
+    const int dev_ = avdf::current_device();                                                                 \
+    if (!once_.done(dev_)) {                                                                                 \
+      AVDF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));    \
+      once_.mark(dev_);                                                                                      \
+    }                                                                                                        \
+  } while (0)
+
 }  // namespace avdf

@@ -601,12 +601,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   if (!a->ln_w && a->taps * a->c_in >= 1024 && a->n_out % 256 == 0) bn = 256;
   // weight-stationary: 1x1, K <= 256, 256-wide n-tiles, every segment with the same number of m-tiles (a CTA is
   // pinned to one (segment, n-tile) group). Worth it when a CTA gets to reuse its weight block over several tiles.
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    AVDF_CUDA(cudaGetDevice(&dev));
-    AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sms = device_sm_count();
   bool ws = g_ws_mode != 0 && a->taps == 1 && a->stride == 1 && a->c_in <= WS_W_BLOCKS * BK && a->n_out % MAX_BN == 0 && a->n_seg >= 1 && !a->ln_w;
   int ws_groups = 0, ws_per = 0;
   if (ws) {
@@ -717,9 +712,9 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
   if (p.total_tiles == 0) return AVDF_OK;
 
-  static bool attrs_done = false;
-  if (!attrs_done) {
-    attrs_done = true;
+  static DeviceOnce attrs_once;          // per device; marked only after every attribute call succeeded
+  const int cur_dev = current_device();
+  if (!attrs_once.done(cur_dev)) {
     // (mode, output kind) pairs the inference path uses get their own instantiation; anything else runs the generic one
 #define AVDF_TC_VARIANTS(X)                                                                                   \
     X(mode_of(false, AVDF_ACT_NONE, false, false), 1) X(mode_of(false, AVDF_ACT_NONE, false, false), 6)           \
@@ -750,6 +745,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
 #undef AVDF_SET_SMEM
 #undef AVDF_SET_SMEM_WS
 #undef AVDF_SET_SMEM_W8
+    attrs_once.mark(cur_dev);
   }
   AVDF_CHECK_ARG((long long)a->batch * a->o_rows_per_video * a->n_out < (1ll << 31), "output larger than 2^31 elements");
   const int ctas_per_sm = bn <= 128 ? 2 : 1;      // narrow tiles: two co-resident CTAs per SM

@@ -384,14 +384,9 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   p.dbg = g_mlpf_dbg;
   const unsigned fmt = f16 ? 0u : 1u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(128 >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    AVDF_CUDA(cudaGetDevice(&dev));
-    AVDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    AVDF_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    AVDF_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  }
+  const int sms = device_sm_count();
+  AVDF_SMEM_ATTR_ONCE(mlp_fused_kernel<true>, SMEM_BYTES);
+  AVDF_SMEM_ATTR_ONCE(mlp_fused_kernel<false>, SMEM_BYTES);
   const int grid = p.tiles < sms ? p.tiles : sms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (f16) mlp_fused_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p);

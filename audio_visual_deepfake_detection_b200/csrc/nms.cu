@@ -391,6 +391,7 @@ struct PostParams {
   const float* vid_stride; const float* vid_half_nframes; const float* vid_fps; const float* vid_duration;  // [B] or null
   float* out_segs; float* out_scores; int* out_count;   // [B,max_num,2], [B,max_num], [B]
   void* gws; size_t gws_per_video;                       // used when candidates exceed NMS_SMEM_CAP
+  float* rec_ring; unsigned* rec_counter; int rec_cap; const int* vid_index; const float* vid_cls;   // optional result records
 };
 
 __global__ void __launch_bounds__(NMS_THREADS, 1) postprocess_kernel(const PostParams prm) {
@@ -420,6 +421,27 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) postprocess_kernel(const PostP
   const bool big = n > NMS_SMEM_CAP;
   Cand c = big ? carve(reinterpret_cast<unsigned char*>(prm.gws) + (size_t)b * prm.gws_per_video, n)
                : carve(smem_raw, NMS_SMEM_CAP);
+  if (prm.soft < 0) {
+    // nms_method 'none' (av_fd_no_recon.py:847-858): every decoded candidate, in decode order, to seconds
+    float st = 1.f, hn = 0.f, fps = 1.f, dur = 0.f;
+    const bool to_sec = prm.vid_fps != nullptr;
+    if (to_sec) { st = prm.vid_stride[b]; hn = prm.vid_half_nframes[b]; fps = prm.vid_fps[b]; dur = prm.vid_duration[b]; }
+    for (int q = threadIdx.x; q < n; q += NMS_THREADS) {
+      float v0 = all_segs[2 * q], v1 = all_segs[2 * q + 1];
+      if (to_sec) {
+        v0 = __fdiv_rn(__fadd_rn(__fmul_rn(v0, st), hn), fps);
+        v1 = __fdiv_rn(__fadd_rn(__fmul_rn(v1, st), hn), fps);
+        if (v0 <= 0.f) v0 = __fmul_rn(v0, 0.f);
+        if (v1 <= 0.f) v1 = __fmul_rn(v1, 0.f);
+        if (v0 >= dur) v0 = __fadd_rn(__fmul_rn(v0, 0.f), dur);
+        if (v1 >= dur) v1 = __fadd_rn(__fmul_rn(v1, 0.f), dur);
+      }
+      prm.out_segs[((size_t)b * cap + q) * 2] = v0; prm.out_segs[((size_t)b * cap + q) * 2 + 1] = v1;
+      prm.out_scores[(size_t)b * cap + q] = all_scores[q];
+    }
+    if (threadIdx.x == 0) prm.out_count[b] = n;
+    return;
+  }
   const int K = prm.max_num;
   // pick buffers live after the candidate arrays' hole[] region is no longer needed -> use out_* directly
   float* o_segs = prm.out_segs + (size_t)b * K * 2;
@@ -510,6 +532,25 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) postprocess_kernel(const PostP
     o_segs[2 * rank] = v0; o_segs[2 * rank + 1] = v1; o_scores[rank] = s;
   }
   if (threadIdx.x == 0) prm.out_count[b] = k;
+  if (prm.rec_ring != nullptr) {
+    // one fixed-size record per video into the ring: [index, count, video_cls, scores[K], segs[K][2]]
+    __shared__ unsigned s_row;
+    __syncthreads();                                   // this CTA's o_segs / o_scores writes are visible to the block
+    if (threadIdx.x == 0) s_row = atomicAdd(prm.rec_counter, 1u) % (unsigned)prm.rec_cap;
+    __syncthreads();
+    float* rec = prm.rec_ring + (size_t)s_row * (3 + 3 * K);
+    if (threadIdx.x == 0) {
+      rec[0] = prm.vid_index ? (float)prm.vid_index[b] : (float)b;
+      rec[1] = (float)k;
+      rec[2] = prm.vid_cls ? prm.vid_cls[b] : 0.f;
+    }
+    for (int q = threadIdx.x; q < K; q += NMS_THREADS) {
+      const bool live = q < k;
+      rec[3 + q] = live ? o_scores[q] : 0.f;
+      rec[3 + K + 2 * q] = live ? o_segs[2 * q] : 0.f;
+      rec[3 + K + 2 * q + 1] = live ? o_segs[2 * q + 1] : 0.f;
+    }
+  }
 }
 
 static size_t nms_smem_bytes() { return (size_t)NMS_SMEM_CAP * 6 * sizeof(float); }
@@ -532,11 +573,7 @@ static int launch_standalone(const float* segs, const float* scores, int32_t n, 
   AVDF_CHECK_ARG(segs && scores && out_idx, "null pointer");
   const int use_gws = n > NMS_SMEM_CAP;
   if (use_gws) AVDF_CHECK_ARG(ws != nullptr && ws_bytes >= avdf_nms_workspace_bytes(n), "workspace too small");
-  static bool attr_set = false;
-  if (!attr_set) {
-    AVDF_CUDA(cudaFuncSetAttribute(nms_standalone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes()));
-    attr_set = true;
-  }
+  AVDF_SMEM_ATTR_ONCE(nms_standalone_kernel, nms_smem_bytes());
   nms_standalone_kernel<<<1, NMS_THREADS, use_gws ? 0 : nms_smem_bytes(), st>>>(
       segs, scores, n, thr, sigma, min_score, method, max_num, dets, reinterpret_cast<long long*>(out_idx),
       out_count, ws, use_gws);
@@ -593,6 +630,12 @@ extern "C" int avdf_postprocess(const avdf_postprocess_args* a, void* stream) {
   }
   p.iou_thr = a->iou_threshold; p.min_score = a->min_score; p.sigma = a->sigma; p.voting_thresh = a->voting_thresh;
   p.max_num = a->max_seg_num; p.soft = a->use_soft_nms; p.method = a->soft_method;
+  AVDF_CHECK_ARG(a->use_soft_nms >= -1 && a->use_soft_nms <= 1, "use_soft_nms must be 0 (hard), 1 (soft) or -1 (no NMS)");
+  if (a->rec_ring) {
+    AVDF_CHECK_ARG(a->rec_counter && a->rec_cap > 0, "record ring needs a counter and a capacity");
+    AVDF_CHECK_ARG(a->use_soft_nms >= 0, "records are written after NMS only");
+    p.rec_ring = a->rec_ring; p.rec_counter = a->rec_counter; p.rec_cap = a->rec_cap; p.vid_index = a->vid_index; p.vid_cls = a->vid_cls;
+  }
   p.vid_stride = a->vid_feat_stride; p.vid_half_nframes = a->vid_half_nframes; p.vid_fps = a->vid_fps;
   p.vid_duration = a->vid_duration;
   if (p.vid_fps) AVDF_CHECK_ARG(p.vid_stride && p.vid_half_nframes && p.vid_duration, "incomplete video meta arrays");
@@ -601,11 +644,7 @@ extern "C" int avdf_postprocess(const avdf_postprocess_args* a, void* stream) {
   p.gws_per_video = (size_t)a->cand_cap * 6 * sizeof(float);
   if (a->cand_cap > NMS_SMEM_CAP)
     AVDF_CHECK_ARG(a->workspace && a->workspace_bytes >= avdf_postprocess_workspace_bytes(a->batch, a->cand_cap), "workspace too small");
-  static bool attr_set = false;
-  if (!attr_set) {
-    AVDF_CUDA(cudaFuncSetAttribute(postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes()));
-    attr_set = true;
-  }
+  AVDF_SMEM_ATTR_ONCE(postprocess_kernel, nms_smem_bytes());
   postprocess_kernel<<<a->batch, NMS_THREADS, nms_smem_bytes(), reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("postprocess_kernel");
 }

@@ -21,6 +21,23 @@ int check_launch(const char* what) {
   }
   return AVDF_OK;
 }
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
+int device_sm_count() {
+  static int sms[256];
+  const int dev = current_device();
+  if (dev < 0 || dev >= 256) return 148;
+  int v = __atomic_load_n(&sms[dev], __ATOMIC_RELAXED);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    __atomic_store_n(&sms[dev], v, __ATOMIC_RELAXED);
+  }
+  return v;
+}
 }  // namespace avdf
 
 extern "C" int avdf_abi_version(void) { return AVDF_ABI_VERSION; }

@@ -180,6 +180,10 @@ class LocalizationEngine:
         self._mask_cache = {}
         self._pe_cache = {}
         self._ws = None
+        # while a CUDA graph is being captured: every cached tensor the launches point at (mask tables, workspaces) is
+        # appended here and kept alive by the GraphedPass - evicting the cache or growing a workspace must not free
+        # memory a captured graph still reads
+        self._capture_refs = None
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name, shape, dtype):
@@ -199,6 +203,8 @@ class LocalizationEngine:
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             self._ws[self.lane] = ws
+        if self._capture_refs is not None:
+            self._capture_refs.append(ws)
         return ws
 
     def padded_len(self, t):
@@ -233,6 +239,8 @@ class LocalizationEngine:
                 self._mask_cache.clear()
             self._mask_cache[key] = out
             m = out
+        if self._capture_refs is not None:
+            self._capture_refs.append(m)
         return m
 
     def pe(self, L):
@@ -474,29 +482,35 @@ class LocalizationEngine:
                        w.vec("reg_head.offset_head.conv.bias"), self._scales, logits, offsets, batch=B, level_len=lens)
         return logits, offsets, vcls, masks, lens
 
-    def postprocess(self, logits, offsets, masks, lens, meta, nms_method=None):
-        """meta: device fp32 [4, B] rows = feat_stride, 0.5*feat_num_frames, fps, duration (or None)."""
+    def postprocess(self, logits, offsets, masks, lens, meta, nms_method=None, records=None, vcls=None):
+        """meta: device fp32 [4, B] rows = feat_stride, 0.5*feat_num_frames, fps, duration (or None).
+        records: optional (ring [cap, 3 + 3K] f32, counter [1] i32, vid_index [B] i32 | None): every video appends its
+        fixed-size result record to the ring (the unit the multi-GPU gather moves)."""
         tc = self.test_cfg
         B, P = logits.shape
         K = int(tc["max_seg_num"])
         method = nms_method or tc["nms_method"]
-        if method not in ("hard", "soft"):
-            raise AvdfError("nms_method %r is not on the accelerated path" % (method,))
+        if method not in ("hard", "soft", "none"):
+            raise AvdfError("nms_method %r is not one of 'hard', 'soft', 'none'" % (method,))
         if tc["multiclass_nms"] and self.num_classes > 1:
             raise AvdfError("multiclass NMS with more than one class is not on the accelerated path")
         cs = self.buf("cand_segs", (B, P, 2), torch.float32)
         cc = self.buf("cand_scores", (B, P), torch.float32)
         cn = self.buf("cand_count", (B,), torch.int32)
-        osg = self.buf("out_segs", (B, K, 2), torch.float32)
-        osc = self.buf("out_scores", (B, K), torch.float32)
+        n_out = P if method == "none" else K        # 'none': every decoded candidate is returned (av_fd_no_recon.py:847)
+        osg = self.buf("out_segs", (B, n_out, 2), torch.float32)
+        osc = self.buf("out_scores", (B, n_out), torch.float32)
         ocn = self.buf("out_count", (B,), torch.int32)
         # multiclass with a single class == class-agnostic without voting (nms.py:123-156)
         voting = 0.0 if tc["multiclass_nms"] else tc["voting_thresh"]
+        rec = None
+        if records is not None and method != "none":
+            rec = (records[0], records[1], records[2], vcls)
         ops.postprocess(B, logits=logits, offsets=offsets, mask=masks["pyr"], level_len=lens,
                         level_stride=[float(s) for s in self.strides], pre_nms_thresh=tc["pre_nms_thresh"],
                         pre_nms_topk=tc["pre_nms_topk"], duration_thresh=tc["duration_thresh"], cand_segs=cs, cand_scores=cc,
                         cand_count=cn, iou_threshold=tc["iou_threshold"], min_score=tc["min_score"], sigma=tc["nms_sigma"],
-                        voting_thresh=voting, max_seg_num=K, use_soft_nms=(method == "soft"),
+                        voting_thresh=voting, max_seg_num=K, use_soft_nms=(None if method == "none" else method == "soft"),
                         vid_meta=None if meta is None else [meta[0], meta[1], meta[2], meta[3]],
-                        out_segs=osg, out_scores=osc, out_count=ocn)
+                        out_segs=osg, out_scores=osc, out_count=ocn, records=rec)
         return osg, osc, ocn

@@ -30,6 +30,22 @@ from .models import register_backbone, register_generator, register_meta_arch, r
 from .spec import EXP12, EXP13, state_dict_spec
 
 
+def _on_model_device(fn):
+    """Run a method with the model's device current: the library launches on the current device and graph capture
+    records on it, whatever device the caller's thread happens to have selected (the reference yaml ships
+    devices: ['cuda:3'] and inference.py only calls model.to(device))."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        dev = self.engine().device
+        if dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return fn(self, *args, **kwargs)
+        return fn(self, *args, **kwargs)
+    return wrapped
+
+
 class _LocalizationBase(nn.Module):
     MODEL_NAME = None
 
@@ -106,6 +122,18 @@ class _LocalizationBase(nn.Module):
     def device(self):
         return self._device
 
+    _TEST_ATTRS = ("pre_nms_thresh", "pre_nms_topk", "iou_threshold", "min_score", "max_seg_num", "duration_thresh",
+                   "multiclass_nms", "nms_sigma", "voting_thresh", "nms_method")
+
+    def test_key(self):
+        """The test-time configuration as the reference reads it: from the `test_*` attributes at CALL time
+        (av_fd_no_recon.py:229-241, 760-876). Captured CUDA graphs are keyed by it."""
+        return tuple(getattr(self, "test_" + k) for k in self._TEST_ATTRS)
+
+    def _sync_test_cfg(self, eng):
+        for k in self._TEST_ATTRS:
+            eng.test_cfg[k] = getattr(self, "test_" + k)
+
     def engine(self):
         if self._engine is None:
             if self._sd is None:
@@ -138,6 +166,7 @@ class _LocalizationBase(nn.Module):
         return out
 
     @torch.no_grad()
+    @_on_model_device
     def _forward_items(self, items):
         eng = self.engine()
         B = len(items)
@@ -153,6 +182,7 @@ class _LocalizationBase(nn.Module):
         return self._run(eng, x, lens, items)
 
     @torch.no_grad()
+    @_on_model_device
     def dense_outputs(self, items):
         """Diagnostics / parity tests: the dense head outputs of `items` (<= max_batch videos) as CPU tensors:
         logits [B, P], offsets [B, P, 2], video_cls [B] (levels concatenated in pyramid order)."""
@@ -196,6 +226,7 @@ class _LocalizationBase(nn.Module):
     #   run_staged    GPU:   interp_concat -> forward -> decode/NMS; returns DEVICE tensors, no host sync
     #   fetch         D2H:   results -> the reference's list of dicts
     def pack_streams(self, chunk, feat_stride=1, num_frames=1):
+        from .streaming import video_meta
         L = self.max_seq_len
         B = len(chunk)
         packed = {"ids": [c["video_id"] for c in chunk], "streams": [], "offs": [], "B": B}
@@ -214,13 +245,11 @@ class _LocalizationBase(nn.Module):
         meta = np.empty((4, B), np.float32)
         for b, c in enumerate(chunk):
             first = c["streams"]["video"] if "video" in c["streams"] else c["streams"]["byola"]
-            t_first = first.shape[0]
-            fs = float((t_first - 1) * feat_stride + num_frames) / L      # deepfake_video_audio.py:495-497
-            # av_fd_no_recon.py:860-865: python-float scalars enter the fp32 tensor expression
-            meta[:, b] = (np.float32(fs), np.float32(0.5 * fs), np.float32(t_first / c["duration"]), np.float32(c["duration"]))
+            meta[:, b] = video_meta(c, first.shape[0], L, feat_stride, num_frames)
         packed["meta"] = torch.from_numpy(meta)
         return packed
 
+    @_on_model_device
     def stage(self, packed):
         dev = self.engine().device
         staged = dict(packed)
@@ -238,19 +267,26 @@ class _LocalizationBase(nn.Module):
         return n
 
     @torch.no_grad()
+    @_on_model_device
     def run_staged(self, staged, lane=0):
         """lane selects the engine's buffer set: batches that are in flight at the same time (different CUDA
         streams) must use different lanes."""
         eng = self.engine()
+        self._sync_test_cfg(eng)
         eng.lane = lane
         B, L = staged["B"], eng.max_seq_len
         x = eng.buf("x_in_%d" % L, (B, L, eng.c_in), eng.in_dt)
         ops.interp_concat(staged["streams"], staged["offs"], L, x)
         logits, offsets, vcls, masks, lens = eng.forward_dense(x, [L] * B)
-        osg, osc, ocn = eng.postprocess(logits, offsets, masks, lens, staged["meta"], nms_method=self.test_nms_method)
+        rec = staged.get("records")      # (ring, counter): result records for the multi-GPU gather, written by the kernel
+        if rec is not None:
+            rec = (rec[0], rec[1], staged.get("vidx"))
+        osg, osc, ocn = eng.postprocess(logits, offsets, masks, lens, staged["meta"], nms_method=self.test_nms_method,
+                                        records=rec, vcls=vcls)
         eng.lane = 0
         return {"ids": staged["ids"], "segs": osg, "scores": osc, "counts": ocn, "vcls": vcls}
 
+    @_on_model_device
     def capture(self, staged, lane=0):
         """Record the whole pass over a staged (device-resident) batch into a CUDA graph: ~190 kernel launches
         become one cudaGraphLaunch, which removes the host launch cost that otherwise bounds the step
@@ -264,9 +300,15 @@ class _LocalizationBase(nn.Module):
         n0 = native.LAUNCHES["n"]
         # thread_local: other host threads (the streaming runner's packer allocating pinned staging, a data loader)
         # may call the CUDA allocator while this thread records; in the default global mode that invalidates the capture
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            res = self.run_staged(staged, lane)
-        return GraphedPass(graph, res, native.LAUNCHES["n"] - n0, staged)
+        eng = self.engine()
+        eng._capture_refs = []
+        try:
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                res = self.run_staged(staged, lane)
+            keep = eng._capture_refs
+        finally:
+            eng._capture_refs = None
+        return GraphedPass(graph, res, native.LAUNCHES["n"] - n0, staged, keep)
 
     @staticmethod
     def fetch(res):
@@ -284,6 +326,7 @@ class _LocalizationBase(nn.Module):
 
     def _run(self, eng, x, valid, items):
         B = x.shape[0]
+        self._sync_test_cfg(eng)
         logits, offsets, vcls, masks, lens = eng.forward_dense(x, valid)
         meta = np.empty((4, B), np.float32)
         for b, it in enumerate(items):                        # av_fd_no_recon.py:860-865 (python-float scalars -> fp32)
@@ -297,8 +340,9 @@ class _LocalizationBase(nn.Module):
 class GraphedPass:
     """A captured pass (see _LocalizationBase.capture)."""
 
-    def __init__(self, graph, result, n_launches, staged):
+    def __init__(self, graph, result, n_launches, staged, keep=None):
         self.graph, self.result, self.n_launches, self.staged = graph, result, n_launches, staged
+        self.keep = keep          # mask tables / workspaces the captured launches point at (see engine._capture_refs)
 
     def replay(self):
         from ... import native

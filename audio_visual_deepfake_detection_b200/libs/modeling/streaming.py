@@ -25,15 +25,31 @@ from ... import native
 STREAMS = ("video", "byola", "emo")
 
 
+def video_meta(c, t_first, L, feat_stride=1, num_frames=1):
+    """(feat_stride, 0.5 * feat_num_frames, fps, duration) of one raw-stream item as fp32, i.e. the scalars
+    av_fd_no_recon.py:860-865 feeds into its fp32 tensor expression. An item that carries the dataset's own
+    'feat_stride' / 'feat_num_frames' / 'fps' (libs/datasets/deepfake_video_audio.py:461, 495-500) is taken at its word;
+    otherwise they are derived the way the dataset derives them under force_upsampling from the length of the first
+    stream and the dataset-level feat_stride / num_frames."""
+    fs = c.get("feat_stride")
+    if fs is None:
+        fs = float((t_first - 1) * feat_stride + num_frames) / L        # deepfake_video_audio.py:495-497
+    nf = c.get("feat_num_frames", fs)
+    fps = c.get("fps")
+    if fps is None:
+        fps = t_first / c["duration"]
+    return (np.float32(fs), np.float32(0.5 * nf), np.float32(fps), np.float32(c["duration"]))
+
+
 class _Slot:
     def __init__(self, runner, index):
         self.runner, self.index = runner, index
         self.cap = [0, 0, 0]              # rows
         self.host = [None, None, None]
         self.dev = [None, None, None]
-        self.graphs = {}                  # batch size -> GraphedPass
+        self.graphs = {}                  # (batch size, test-time config) -> GraphedPass
         self.done = torch.cuda.Event()
-        self.stream = torch.cuda.Stream()     # slots run on their own streams: copies and kernels of consecutive batches overlap
+        self.stream = torch.cuda.Stream(device=runner.eng.device)     # slots run on their own streams: copies and kernels of consecutive batches overlap
         self.ids, self.B, self.busy = None, 0, False
         self.direct = None                    # (src, device dst, nbytes, n, keep-alive) of a batch whose arrays are pinned
 
@@ -71,7 +87,8 @@ class StreamRunner:
         n_slots = n_slots or int(os.environ.get("AVDF_STREAM_SLOTS", "10"))
         self.model = model
         self.eng = model.engine()
-        self.slots = [_Slot(self, i) for i in range(n_slots)]
+        with torch.cuda.device(self.eng.device):
+            self.slots = [_Slot(self, i) for i in range(n_slots)]
         self.next = 0
         # copy workers: the host cores are shared by the ranks of a node (torchrun exports LOCAL_WORLD_SIZE)
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
@@ -134,16 +151,14 @@ class StreamRunner:
         meta = slot.h_meta.numpy()
         for b, c in enumerate(chunk):
             first = c["streams"]["video"] if present[0] else c["streams"]["byola"]
-            t_first = first.shape[0]
-            fs = float((t_first - 1) * feat_stride + num_frames) / L        # deepfake_video_audio.py:495-497
-            # av_fd_no_recon.py:860-865: python-float scalars enter an fp32 tensor expression
-            meta[:, b] = (np.float32(fs), np.float32(0.5 * fs), np.float32(t_first / c["duration"]), np.float32(c["duration"]))
+            meta[:, b] = video_meta(c, first.shape[0], L, feat_stride, num_frames)
         slot.rows, slot.chans, slot.B, slot.ids = rows, chans, B, [c["video_id"] for c in chunk]
 
     def _launch(self, slot):
-        slot.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(slot.stream):
-            self._launch_on_stream(slot)
+        with torch.cuda.device(self.eng.device):      # the caller's thread may have another device selected
+            slot.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(slot.stream):
+                self._launch_on_stream(slot)
 
     def _launch_on_stream(self, slot):
         eng, B = self.eng, slot.B
@@ -163,14 +178,19 @@ class StreamRunner:
                   "streams": [slot.dev[s] if slot.chans[s] else None for s in range(3)],
                   "offs": [slot.d_off[s, :B + 1] if slot.chans[s] else None for s in range(3)]}
         if self.use_graph and B == eng.max_batch:
-            g = slot.graphs.get(B)
+            key = (B, self.model.test_key())      # the test-time config is baked into the captured launches
+            g = slot.graphs.get(key)
             if g is None:
                 with self.cuda_lock:
                     g = self.model.capture(staged, lane=slot.index)
-                slot.graphs[B] = g
+                slot.graphs[key] = g
             res = g.replay()
         else:
             res = self.model.run_staged(staged, lane=slot.index)
+        if res["segs"].shape[1] != slot.h_segs.shape[1]:      # nms_method 'none': every decoded candidate comes back
+            n_out = res["segs"].shape[1]
+            slot.h_segs = torch.zeros((eng.max_batch, n_out, 2), dtype=torch.float32, pin_memory=True)
+            slot.h_scores = torch.zeros((eng.max_batch, n_out), dtype=torch.float32, pin_memory=True)
         slot.h_segs[:B].copy_(res["segs"], non_blocking=True)
         slot.h_scores[:B].copy_(res["scores"], non_blocking=True)
         slot.h_counts[:B].copy_(res["counts"], non_blocking=True)
@@ -195,11 +215,12 @@ class StreamRunner:
     def run(self, chunk):
         """One batch, synchronously."""
         slot = self.slots[0]
-        if slot.busy:
-            self._collect(slot)
-        self._pack(slot, chunk)
-        self._launch(slot)
-        return self._collect(slot)
+        with torch.cuda.device(self.eng.device):
+            if slot.busy:
+                self._collect(slot)
+            self._pack(slot, chunk)
+            self._launch(slot)
+            return self._collect(slot)
 
     def stream(self, batches):
         """Generator over an iterable of batches (each <= max_batch videos): yields every batch's results in order.
@@ -219,6 +240,9 @@ class StreamRunner:
 
         def packer():
             try:
+                # a fresh thread starts on device 0: pinned allocations and cudaPointerGetAttributes would create a context
+                # there for every rank of a torchrun job
+                torch.cuda.set_device(self.eng.device)
                 while True:
                     slot = free.get()
                     if slot is None:

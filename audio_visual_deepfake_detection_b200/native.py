@@ -46,6 +46,7 @@ class PostprocessArgs(Structure):
         ("vid_feat_stride", c_void_p), ("vid_half_nframes", c_void_p), ("vid_fps", c_void_p), ("vid_duration", c_void_p),
         ("out_segs", c_void_p), ("out_scores", c_void_p), ("out_count", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("rec_ring", c_void_p), ("rec_counter", c_void_p), ("rec_cap", c_int32), ("vid_index", c_void_p), ("vid_cls", c_void_p),
     ]
 
 

@@ -25,11 +25,22 @@ def _dt(t):
     raise TypeError("unsupported dtype %s" % t.dtype)
 
 
+# Device of the tensors of the call being marshalled. The library launches on the CURRENT device and takes the stream it is
+# given, so every entry point runs with the tensors' device current and on that device's current stream - a model on
+# 'cuda:3' (what the reference yaml ships) must not launch on GPU 0.
+_dev = [None]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream(_dev[0]).cuda_stream)
+
+
 def _chk(t, dtype=None, name="tensor"):
     if t is None:
         return
     if not t.is_cuda:
         raise nv.AvdfError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    _dev[0] = t.device
     if not t.is_contiguous():
         raise nv.AvdfError("%s must be contiguous" % name)
     if dtype is not None and t.dtype != dtype:
@@ -43,6 +54,14 @@ class Profile:
 
 
 def _call(name, fn, args, launches=1, work=None):
+    dev = _dev[0]
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call_on_current(name, fn, args, launches, work)
+    return _call_on_current(name, fn, args, launches, work)
+
+
+def _call_on_current(name, fn, args, launches, work):
     if Profile.on:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -81,7 +100,7 @@ def interp_concat(streams, offsets, t_out, out):
     _chk(out, None, "out")
     assert out.shape == (batch, t_out, sum(cs)), (out.shape, batch, t_out, cs)
     _call("avdf_interp_concat", L.avdf_interp_concat, (ptrs[0], ptrs[1], ptrs[2], offs[0], offs[1], offs[2], batch, cs[0], cs[1], cs[2],
-                                  t_out, nv.ptr(out), _dt(out), nv.stream_ptr(),), launches=1, work={"bytes": _nbytes(*[t for t in streams if t is not None]) + _nbytes(out)})
+                                  t_out, nv.ptr(out), _dt(out), _stream(),), launches=1, work={"bytes": _nbytes(*[t for t in streams if t is not None]) + _nbytes(out)})
     return out
 
 
@@ -91,7 +110,7 @@ def pack_feats(feats_ct, out):
     _chk(feats_ct, torch.float32, "feats"); _chk(out, None, "out")
     C, T = feats_ct.shape
     assert out.shape[1] == C and out.shape[0] >= T
-    _call("avdf_pack_feats", L.avdf_pack_feats, (nv.ptr(feats_ct), C, T, out.shape[0], nv.ptr(out), _dt(out), nv.stream_ptr(),), launches=1, work=None)
+    _call("avdf_pack_feats", L.avdf_pack_feats, (nv.ptr(feats_ct), C, T, out.shape[0], nv.ptr(out), _dt(out), _stream(),), launches=1, work=None)
 
 
 # ---------------------------------------------------------------------------- NMS
@@ -105,7 +124,7 @@ def nms_hard(segs, scores, iou_threshold, max_num=0):
     wsb = L.avdf_nms_workspace_bytes(n)
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=scores.device)
     _call("avdf_nms_hard", L.avdf_nms_hard, (nv.ptr(segs), nv.ptr(scores), n, float(iou_threshold), int(max_num), nv.ptr(out_idx),
-                             nv.ptr(out_count), nv.ptr(ws), wsb, nv.stream_ptr(),), launches=1, work=None)
+                             nv.ptr(out_count), nv.ptr(ws), wsb, _stream(),), launches=1, work=None)
     return out_idx[: int(out_count.item())]
 
 
@@ -120,15 +139,17 @@ def nms_soft(segs, scores, dets, iou_threshold, sigma, min_score, method, max_nu
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=scores.device)
     _call("avdf_nms_soft", L.avdf_nms_soft, (nv.ptr(segs), nv.ptr(scores), n, nv.ptr(dets), float(iou_threshold), float(sigma),
                              float(min_score), int(method), int(max_num), nv.ptr(out_idx), nv.ptr(out_count),
-                             nv.ptr(ws), wsb, nv.stream_ptr(),), launches=1, work=None)
+                             nv.ptr(ws), wsb, _stream(),), launches=1, work=None)
     return out_idx[: int(out_count.item())]
 
 
 def postprocess(batch, *, logits=None, offsets=None, mask=None, level_len=(), level_stride=(), pre_nms_thresh=0.001,
                 pre_nms_topk=2000, duration_thresh=0.001, cand_segs, cand_scores, cand_count, iou_threshold, min_score,
                 sigma, voting_thresh, max_seg_num, use_soft_nms, soft_method=2, vid_meta=None, out_segs, out_scores,
-                out_count, workspace=None):
-    """Fused decode + batched_nms (class-agnostic) + seconds conversion; one CTA per video."""
+                out_count, workspace=None, records=None):
+    """Fused decode + batched_nms (class-agnostic) + seconds conversion; one CTA per video. use_soft_nms: True / False,
+    or None for nms_method 'none' (the decoded candidates, out_* sized cand_cap). records: optional
+    (ring [cap, 3 + 3K] f32, counter [1] i32, vid_index [B] i32 | None, vid_cls [B] f32 | None)."""
     L = nv.lib()
     a = nv.PostprocessArgs()
     a.batch = batch
@@ -143,7 +164,15 @@ def postprocess(batch, *, logits=None, offsets=None, mask=None, level_len=(), le
     a.cand_segs, a.cand_scores, a.cand_count = cand_segs.data_ptr(), cand_scores.data_ptr(), cand_count.data_ptr()
     a.cand_cap = cand_scores.shape[1]
     a.iou_threshold, a.min_score, a.sigma, a.voting_thresh = float(iou_threshold), float(min_score), float(sigma), float(voting_thresh)
-    a.max_seg_num, a.use_soft_nms, a.soft_method = int(max_seg_num), int(bool(use_soft_nms)), int(soft_method)
+    a.max_seg_num, a.use_soft_nms, a.soft_method = int(max_seg_num), (-1 if use_soft_nms is None else int(bool(use_soft_nms))), int(soft_method)
+    if records is not None:
+        ring, counter, vidx, vcls = records
+        _chk(ring, torch.float32, "rec_ring"); _chk(counter, torch.int32, "rec_counter"); _chk(vidx, torch.int32, "vid_index"); _chk(vcls, torch.float32, "vid_cls")
+        if ring.shape[1] != 3 + 3 * int(max_seg_num):
+            raise ValueError("record rows must hold 3 + 3 * max_seg_num floats")
+        a.rec_ring, a.rec_counter, a.rec_cap = ring.data_ptr(), counter.data_ptr(), ring.shape[0]
+        a.vid_index = vidx.data_ptr() if vidx is not None else None
+        a.vid_cls = vcls.data_ptr() if vcls is not None else None
     if vid_meta is not None:
         for t in vid_meta:
             _chk(t, torch.float32, "vid_meta")
@@ -155,7 +184,7 @@ def postprocess(batch, *, logits=None, offsets=None, mask=None, level_len=(), le
         if workspace is None or workspace.numel() * workspace.element_size() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=out_segs.device)
         a.workspace, a.workspace_bytes = workspace.data_ptr(), need
-    _call("avdf_postprocess", L.avdf_postprocess, (ctypes.byref(a), nv.stream_ptr(),), launches=1, work=None)
+    _call("avdf_postprocess", L.avdf_postprocess, (ctypes.byref(a), _stream(),), launches=1, work=None)
 
 
 def postprocess_workspace_bytes(batch, cand_cap):
@@ -201,7 +230,7 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
         if workspace is None or workspace.numel() * workspace.element_size() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=a.device)
         g.workspace, g.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
-    _call("avdf_conv_gemm", L.avdf_conv_gemm, (ctypes.byref(g), nv.stream_ptr(),), launches=2 if g.dtype == DTYPE_F32 else 1, work={"flops": 2.0 * batch * sum(sg[0] for sg in segs) * n_out * taps * c_in, "m": batch * sum(sg[0] for sg in segs), "n": n_out, "k": taps * c_in,
+    _call("avdf_conv_gemm", L.avdf_conv_gemm, (ctypes.byref(g), _stream(),), launches=2 if g.dtype == DTYPE_F32 else 1, work={"flops": 2.0 * batch * sum(sg[0] for sg in segs) * n_out * taps * c_in, "m": batch * sum(sg[0] for sg in segs), "n": n_out, "k": taps * c_in,
                 "bytes": _nbytes(a, w, out_f32, out_h, residual)})
 
 
@@ -224,7 +253,7 @@ def mlp_fused(x, w1, b1, w2, b2, *, row_mask, residual, gamma, out):
     a.row_mask = row_mask.data_ptr() if row_mask is not None else None
     a.gamma = gamma.data_ptr() if gamma is not None else None
     a.residual, a.out = residual.data_ptr(), out.data_ptr()
-    _call("avdf_mlp_fused", L.avdf_mlp_fused, (ctypes.byref(a), nv.stream_ptr(),), launches=1,
+    _call("avdf_mlp_fused", L.avdf_mlp_fused, (ctypes.byref(a), _stream(),), launches=1,
           work={"flops": 4.0 * rows * C * H, "bytes": rows * C * (x.element_size() + 8) + 2 * C * H * x.element_size(), "m": rows, "n": C, "k": H})
     return out
 
@@ -255,7 +284,7 @@ def ln_dwconv_ln(src, *, batch, t_src, t_virt, shift, stride, mask_out, ln_in, d
     a.tile_rows = int(tile_rows)
     C, t_out = src.shape[-1], t_virt // stride
     nbytes = batch * min(t_src, t_virt) * C * 4 + n * batch * t_out * C * outs[0].element_size() + (batch * t_out * C * 4 if skip_out is not None else 0)
-    _call("avdf_ln_dwconv_ln", L.avdf_ln_dwconv_ln, (ctypes.byref(a), nv.stream_ptr(),), launches=1, work={"bytes": nbytes})
+    _call("avdf_ln_dwconv_ln", L.avdf_ln_dwconv_ln, (ctypes.byref(a), _stream(),), launches=1, work={"bytes": nbytes})
 
 
 def attention(q, k, v, kv_mask, out, *, batch, t, n_head, window, qkv=None):
@@ -273,26 +302,26 @@ def attention(q, k, v, kv_mask, out, *, batch, t, n_head, window, qkv=None):
         qp, kp, vp = nv.ptr(q), nv.ptr(k), nv.ptr(v)
     _chk(out, None, "out"); _chk(kv_mask, torch.uint8, "kv_mask")
     _call("avdf_attention", L.avdf_attention, (qp, kp, vp, nv.ptr(kv_mask), nv.ptr(out), _dt(q), _dt(out), batch, t, rpv,
-                              q.shape[-1], n_head, window, nv.stream_ptr(),), launches=1, work={"bytes": (_nbytes(qkv) if qkv is not None else _nbytes(q, k, v)) + _nbytes(out)})
+                              q.shape[-1], n_head, window, _stream(),), launches=1, work={"bytes": (_nbytes(qkv) if qkv is not None else _nbytes(q, k, v)) + _nbytes(out)})
 
 
 def ln_rows(x, w, b, out, rows):
     L = nv.lib()
     _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b"); _chk(out, None, "out")
-    _call("avdf_ln_rows", L.avdf_ln_rows, (nv.ptr(x), nv.ptr(w), nv.ptr(b), nv.ptr(out), _dt(out), rows, x.shape[-1], nv.stream_ptr(),), launches=1, work={"bytes": rows * x.shape[-1] * (4 + out.element_size())})
+    _call("avdf_ln_rows", L.avdf_ln_rows, (nv.ptr(x), nv.ptr(w), nv.ptr(b), nv.ptr(out), _dt(out), rows, x.shape[-1], _stream(),), launches=1, work={"bytes": rows * x.shape[-1] * (4 + out.element_size())})
 
 
 def instnorm_lrelu(x, out, *, batch, t, channels, slope=0.2):
     L = nv.lib()
     _chk(x, torch.float32, "x"); _chk(out, None, "out")
-    _call("avdf_instnorm_lrelu", L.avdf_instnorm_lrelu, (nv.ptr(x), nv.ptr(out), _dt(out), batch, t, channels, float(slope), nv.stream_ptr(),), launches=1, work={"bytes": batch * t * channels * (4 + out.element_size())})
+    _call("avdf_instnorm_lrelu", L.avdf_instnorm_lrelu, (nv.ptr(x), nv.ptr(out), _dt(out), batch, t, channels, float(slope), _stream(),), launches=1, work={"bytes": batch * t * channels * (4 + out.element_size())})
 
 
 def fpn_fuse(lat, mask, dw_w, ln_w, ln_b, out, *, batch, level_len):
     L = nv.lib()
     _chk(lat, torch.float32, "lat"); _chk(mask, torch.uint8, "mask"); _chk(dw_w, torch.float32, "dw_w"); _chk(out, None, "out")
     _call("avdf_fpn_fuse", L.avdf_fpn_fuse, (nv.ptr(lat), nv.ptr(mask), nv.ptr(dw_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(out), _dt(out), batch,
-                             lat.shape[-1], len(level_len), _levels(level_len), nv.stream_ptr(),), launches=1, work={"bytes": _nbytes(lat, out)})
+                             lat.shape[-1], len(level_len), _levels(level_len), _stream(),), launches=1, work={"bytes": _nbytes(lat, out)})
 
 
 def head_final(cls_feat, reg_feat, mask, cls_w, cls_b, reg_w, reg_b, level_scale, logits, offsets, *, batch, level_len):
@@ -303,7 +332,7 @@ def head_final(cls_feat, reg_feat, mask, cls_w, cls_b, reg_w, reg_b, level_scale
     sc = (c_float * len(level_scale))(*[float(s) for s in level_scale])
     _call("avdf_head_final", L.avdf_head_final, (nv.ptr(cls_feat), nv.ptr(reg_feat), _dt(cls_feat), nv.ptr(mask), nv.ptr(cls_w), nv.ptr(cls_b),
                                nv.ptr(reg_w), nv.ptr(reg_b), sc, nv.ptr(logits), nv.ptr(offsets), batch, cls_feat.shape[-1],
-                               len(level_len), _levels(level_len), nv.stream_ptr(),), launches=1, work=None)
+                               len(level_len), _levels(level_len), _stream(),), launches=1, work=None)
 
 
 def vcls_exp12(z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, *, batch, t):
@@ -312,7 +341,7 @@ def vcls_exp12(z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, *, batch, t)
     for x in (conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out):
         _chk(x, torch.float32, "vcls tensor")
     _call("avdf_vcls_exp12", L.avdf_vcls_exp12, (nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(lin1_w), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(lin2_w),
-                               nv.ptr(lin2_b), nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr(),), launches=1, work=None)
+                               nv.ptr(lin2_b), nv.ptr(out), batch, t, z.shape[-1], _stream(),), launches=1, work=None)
 
 
 def vcls_exp13(z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, *, batch, t):
@@ -321,4 +350,4 @@ def vcls_exp13(z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, *, batch, t):
     for x in (conv0_w, seg_w, seg_b, cls_w, cls_b, out):
         _chk(x, torch.float32, "vcls tensor")
     _call("avdf_vcls_exp13", L.avdf_vcls_exp13, (nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(seg_w), nv.ptr(seg_b), nv.ptr(cls_w), nv.ptr(cls_b),
-                               nv.ptr(out), batch, t, z.shape[-1], nv.stream_ptr(),), launches=1, work=None)
+                               nv.ptr(out), batch, t, z.shape[-1], _stream(),), launches=1, work=None)

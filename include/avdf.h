@@ -113,7 +113,9 @@ typedef struct avdf_postprocess_args {
   int32_t cand_cap;
   /* batched_nms (class-agnostic path, nms.py:160-190) */
   float iou_threshold, min_score, sigma, voting_thresh;
-  int32_t max_seg_num, use_soft_nms, soft_method;
+  int32_t max_seg_num, use_soft_nms, soft_method;   /* use_soft_nms: 0 hard, 1 soft, -1 no NMS (test_cfg nms_method
+                                                     * 'none', av_fd_no_recon.py:847: the decoded candidates go straight
+                                                     * to the seconds conversion; out_* then hold cand_cap entries per video) */
   /* seconds conversion (all NULL: stay on the feature grid) */
   const float* vid_feat_stride;  /* [batch] */
   const float* vid_half_nframes; /* [batch] 0.5 * feat_num_frames */
@@ -124,6 +126,15 @@ typedef struct avdf_postprocess_args {
   float* out_scores;             /* [batch, max_seg_num]    */
   int32_t* out_count;            /* [batch]                 */
   void* workspace; size_t workspace_bytes;
+  /* optional result records for the multi-GPU gather (the reference's per-video JSON record,
+   * libs/utils/train_utils.py:577-595): every video appends ONE fixed-size fp32 row
+   *   [video index, count, video_cls, scores[max_seg_num], segs[max_seg_num][2]]
+   * to rec_ring at row atomicAdd(rec_counter, 1) % rec_cap. All NULL / 0: no records. */
+  float* rec_ring;               /* [rec_cap, 3 + 3 * max_seg_num] */
+  uint32_t* rec_counter;         /* [1] device counter, owned by the caller */
+  int32_t rec_cap;
+  const int32_t* vid_index;      /* [batch] global video index of every row of the batch */
+  const float* vid_cls;          /* [batch] video-level logit */
 } avdf_postprocess_args;          /* host struct */
 AVDF_API size_t avdf_postprocess_workspace_bytes(int32_t batch, int32_t cand_cap);
 AVDF_API int avdf_postprocess(const avdf_postprocess_args* args, void* stream);

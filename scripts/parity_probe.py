@@ -11,5 +11,6 @@ import parity_common  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 for case in (sys.argv[2:] or ["audio_only", "exp12", "exp13"]):
-    print(json.dumps(parity_common.run_parity(case, n)))
-    sys.stdout.flush()
+    for weights in ("dense", "sparse"):
+        print(json.dumps(parity_common.run_parity(case, n, weights=weights)))
+        sys.stdout.flush()

@@ -49,11 +49,14 @@ def oracle_from_dense(om, logits, offsets, lens, item, method):
     return segs.numpy().reshape(-1, 2), scores.numpy()
 
 
+WEIGHTS = {"dense": -3.0, "sparse": -7.0}      # cls prior bias of the synthetic weights (see synthetic_state_dict)
+
+
 def run_parity(case, n_videos, precision="mixed", batch=32, methods=("hard", "soft"), seed0=5000, via_streams=True,
-               log=print):
+               weights="dense"):
     model_name, overrides, use_video, wseed = MODEL_CASES[case]
     cfg = load_config_for(model_name, dict(overrides))
-    sd = syn.synthetic_state_dict(cfg["model"], model_name, seed=wseed)
+    sd = syn.synthetic_state_dict(cfg["model"], model_name, seed=wseed, cls_bias=WEIGHTS[weights])
     model = make_meta_arch(cfg["model_name"], **cfg["model"], precision=precision, max_batch=batch)
     model.load_state_dict(sd)
     model.to("cuda").eval()
@@ -78,7 +81,7 @@ def run_parity(case, n_videos, precision="mixed", batch=32, methods=("hard", "so
             got[m] = model(items)
     # ---- oracle, one video per call like the reference
     stats = {m: {"videos": n_videos, "identical": 0, "membership_diff": 0, "boundary_only": 0, "explained": 0, "unexplained": [],
-                 "post_exact_fail": [], "max_dt_matched": 0.0, "n_members_ref": 0, "n_dt_over": 0, "max_dt_over_tol_ratio": 0.0}
+                 "post_exact_fail": [], "post_max_dscore": 0.0, "post_max_dt": 0.0, "max_dt_matched": 0.0, "n_members_ref": 0, "n_dt_over": 0, "max_dt_over_tol_ratio": 0.0}
              for m in methods}
     dense_err = {"logits": 0.0, "offsets": 0.0, "vcls": 0.0, "score_abs": 0.0}
     for vi, item in enumerate(items):
@@ -103,8 +106,14 @@ def run_parity(case, n_videos, precision="mixed", batch=32, methods=("hard", "so
             chk_s, chk_p = oracle_from_dense(om, gl[vi], go[vi], lens, item, m)
             g_s, g_p = got[m][vi]["segments"].numpy().reshape(-1, 2), got[m][vi]["scores"].numpy()
             # (ii) the CUDA post-processing is exact on its own dense outputs
-            if not (len(g_p) == len(chk_p) and np.array_equal(g_p, chk_p) and np.allclose(g_s, chk_s, atol=1e-4, rtol=0)):
-                st["post_exact_fail"].append(item["video_id"])
+            # (scores to 2e-6: the kernel's sigmoid is 1 / (1 + expf(-x)) with CUDA's expf, torch.sigmoid differs by an ulp)
+            if len(g_p) != len(chk_p):
+                st["post_exact_fail"].append({"video": item["video_id"], "n": [len(g_p), len(chk_p)]})
+            elif len(g_p):
+                ds, dt = float(np.abs(g_p - chk_p).max()), float(np.abs(g_s - chk_s).max())
+                st["post_max_dscore"] = max(st["post_max_dscore"], ds); st["post_max_dt"] = max(st["post_max_dt"], dt)
+                if ds > 2e-6 or dt > 1e-4:
+                    st["post_exact_fail"].append({"video": item["video_id"], "dscore": ds, "dt": dt})
             # (iii) final sets vs the reference
             c = parity.compare_sets(g_s, g_p, ref_s, ref_p)
             st["n_members_ref"] += c["n_ref"]
@@ -129,4 +138,4 @@ def run_parity(case, n_videos, precision="mixed", batch=32, methods=("hard", "so
             else:
                 st["unexplained"].append({"video": item["video_id"], "cmp": c, "margins": {k: float(v) for k, v in mg.items()},
                                           "tol_s": tol_s, "tol_x": tol_x})
-    return {"case": case, "precision": precision, "batch": batch, "dense_err": dense_err, "sets": stats}
+    return {"case": case, "weights": weights, "precision": precision, "batch": batch, "dense_err": dense_err, "sets": stats}

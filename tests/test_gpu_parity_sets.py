@@ -23,9 +23,13 @@ pytestmark = pytest.mark.gpu
 N_VIDEOS = int(os.environ.get("AVDF_PARITY_VIDEOS", "256"))
 
 
+@pytest.mark.parametrize("weights", ["dense", "sparse"])
 @pytest.mark.parametrize("case", ["audio_only", "exp12", "exp13"])
-def test_final_sets_batch32_mixed(case):
-    res = parity_common.run_parity(case, N_VIDEOS, precision="mixed", batch=32)
+def test_final_sets_batch32_mixed(case, weights):
+    """weights: "dense" = the golden fixtures' synthetic weights (~1000 of 1512 points above 0.2: a stress case in which
+    the reference itself sits within 1e-5..1e-3 of a threshold in every video); "sparse" = cls prior -7: a handful of
+    segments per video, like a trained detector."""
+    res = parity_common.run_parity(case, N_VIDEOS, precision="mixed", batch=32, weights=weights)
     print("\nPARITY " + json.dumps(res))
     de = res["dense_err"]
     assert de["logits"] < 1e-2 and de["offsets"] < 1e-2 and de["vcls"] < 2e-2, de
