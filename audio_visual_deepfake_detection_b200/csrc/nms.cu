@@ -392,6 +392,7 @@ struct PostParams {
   float* out_segs; float* out_scores; int* out_count;   // [B,max_num,2], [B,max_num], [B]
   void* gws; size_t gws_per_video;                       // used when candidates exceed NMS_SMEM_CAP
   float* rec_ring; unsigned* rec_counter; int rec_cap; const int* vid_index; const float* vid_cls;   // optional result records
+  int* out_index;                                        // optional [B, max_num]: candidate index of every output
 };
 
 __global__ void __launch_bounds__(NMS_THREADS, 1) postprocess_kernel(const PostParams prm) {
@@ -530,6 +531,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) postprocess_kernel(const PostP
       if (v1 >= dur) v1 = __fadd_rn(__fmul_rn(v1, 0.f), dur);
     }
     o_segs[2 * rank] = v0; o_segs[2 * rank + 1] = v1; o_scores[rank] = s;
+    if (prm.out_index) prm.out_index[(size_t)b * K + rank] = idx_sh[q];
   }
   if (threadIdx.x == 0) prm.out_count[b] = k;
   if (prm.rec_ring != nullptr) {
@@ -640,6 +642,7 @@ extern "C" int avdf_postprocess(const avdf_postprocess_args* a, void* stream) {
   p.vid_duration = a->vid_duration;
   if (p.vid_fps) AVDF_CHECK_ARG(p.vid_stride && p.vid_half_nframes && p.vid_duration, "incomplete video meta arrays");
   p.out_segs = a->out_segs; p.out_scores = a->out_scores; p.out_count = a->out_count;
+  p.out_index = a->out_index;
   p.gws = a->workspace;
   p.gws_per_video = (size_t)a->cand_cap * 6 * sizeof(float);
   if (a->cand_cap > NMS_SMEM_CAP)

@@ -110,16 +110,17 @@ class PackedWeights:
 
 # Operand formats of the tensor-core GEMMs (accumulation is always fp32 in TMEM, the residual stream,
 # LayerNorm statistics, softmax and the last head convolutions are always fp32):
-#   "mixed" (default)  bf16 for GEMMs whose A operand is the raw feature tensor, fp16 for all others. Measured
-#                      logit error 4e-3 relative (bar: 1e-2); same tensor-core rate and bytes as pure bf16.
-#   "bf16"             bf16 operands everywhere: 1.2e-2 on the synthetic worst-case weights - the same error the
-#                      reference itself shows under torch.autocast(bfloat16).
+#   "mixed" (default)  bf16 for GEMMs whose A operand is the raw feature tensor (unbounded range), fp16 for all others
+#                      (normalised activations). Measured logit error <= 5.6e-3, offsets <= 1.2e-3 relative over 3 x 256
+#                      videos at batch 32 (bar: 1e-2); same tensor-core rate and bytes as pure bf16.
 #   "fp32"             CUDA-core fp32 parity mode (bar: 1e-4).
-PRECISIONS = ("mixed", "bf16", "fp32")
+# Pure bf16 operands were measured at 1.2e-2 on the synthetic worst-case weights - over BASELINE.json's 1e-2 bar (the
+# reference itself under torch.autocast(bfloat16) shows the same) - so that format is not offered.
+PRECISIONS = ("mixed", "fp32")
 
 
 class LocalizationEngine:
-    def __init__(self, model_cfg, model_name, state_dict, device, precision="bf16", max_batch=32):
+    def __init__(self, model_cfg, model_name, state_dict, device, precision="mixed", max_batch=32):
         if not torch.cuda.is_available():
             raise AvdfError("LocalizationEngine needs a CUDA device: the path has no CPU fallback")
         if precision not in PRECISIONS:
@@ -132,8 +133,7 @@ class LocalizationEngine:
         self.precision = precision
         # in_dt: format of the raw feature tensor (unbounded values -> bf16 range); adt: format of every
         # other GEMM operand (LayerNorm / InstanceNorm / softmax / GELU outputs: bounded -> fp16 mantissa)
-        self.in_dt, self.adt = {"fp32": (torch.float32, torch.float32), "bf16": (torch.bfloat16, torch.bfloat16),
-                                "mixed": (torch.bfloat16, torch.float16)}[precision]
+        self.in_dt, self.adt = {"fp32": (torch.float32, torch.float32), "mixed": (torch.bfloat16, torch.float16)}[precision]
         self.max_batch = int(max_batch)
         # fused MLP kernel (csrc/mlp_fused.cu: one launch per block, the [rows, 1024] activations never leave the SM):
         # 51 vs 59 us per level-0 block next to the two GEMM launches, +4 % videos/s with 4 batches in flight, same

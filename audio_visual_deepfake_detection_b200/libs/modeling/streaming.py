@@ -78,6 +78,8 @@ class _Slot:
             self.h_scores = torch.zeros((max_batch, K), dtype=torch.float32, pin_memory=True)
             self.h_counts = torch.zeros((max_batch,), dtype=torch.int32, pin_memory=True)
             self.h_vcls = torch.zeros((max_batch,), dtype=torch.float32, pin_memory=True)
+            self.h_vidx = torch.zeros((max_batch,), dtype=torch.int32, pin_memory=True)
+            self.d_vidx = torch.zeros((max_batch,), dtype=torch.int32, device=device)
         if grown:
             self.graphs.clear()           # captured kernels hold the old staging pointers
 
@@ -99,7 +101,23 @@ class StreamRunner:
         self.use_graph = True
         self.cuda_lock = threading.Lock()    # staging (pinned / device) allocation vs. graph capture on the launching thread
         self.zero_copy = os.environ.get("AVDF_ZERO_COPY", "1") != "0"    # pinned source arrays go to the copy engine directly
-        self.n_packers = int(os.environ.get("AVDF_PACKERS", "1"))   # packer threads (measured 1 / 2 / 3: 15.56k / 15.45k / 15.39k videos/s: the gather itself is already parallel)
+        self.n_packers = int(os.environ.get("AVDF_PACKERS", "1"))
+        self.records = None          # (ring, counter): device-side result records (see enable_records)   # packer threads (measured 1 / 2 / 3: 15.56k / 15.45k / 15.39k videos/s: the gather itself is already parallel)
+
+    def enable_records(self, capacity):
+        """Every video of the following batches appends one fixed-size fp32 record ([item['index'], count, video_cls,
+        scores[K], segs[K][2]]) to a device ring of `capacity` rows, written by the postprocess kernel: the unit the
+        multi-GPU gather moves (libs/utils/sharding.py). Returns (ring, counter); None switches records off."""
+        if capacity is None:
+            self.records = None
+            return None
+        K = int(self.model.test_max_seg_num)
+        with torch.cuda.device(self.eng.device):
+            ring = torch.zeros((max(1, int(capacity)), 3 + 3 * K), dtype=torch.float32, device=self.eng.device)
+            ring[:, 0] = -1.0
+            counter = torch.zeros(1, dtype=torch.int32, device=self.eng.device)
+        self.records = (ring, counter)
+        return self.records
 
     # ---------------------------------------------------------------- stages
     def _pack(self, slot, chunk, feat_stride=1, num_frames=1):
@@ -152,6 +170,9 @@ class StreamRunner:
         for b, c in enumerate(chunk):
             first = c["streams"]["video"] if present[0] else c["streams"]["byola"]
             meta[:, b] = video_meta(c, first.shape[0], L, feat_stride, num_frames)
+        vidx = slot.h_vidx.numpy()
+        for b, c in enumerate(chunk):
+            vidx[b] = int(c.get("index", b))
         slot.rows, slot.chans, slot.B, slot.ids = rows, chans, B, [c["video_id"] for c in chunk]
 
     def _launch(self, slot):
@@ -173,12 +194,17 @@ class StreamRunner:
                 nbytes += slot.rows[s] * slot.chans[s] * 4
         slot.d_off.copy_(slot.h_off, non_blocking=True)
         slot.d_meta.copy_(slot.h_meta, non_blocking=True)
+        if self.records is not None:
+            slot.d_vidx.copy_(slot.h_vidx, non_blocking=True)
         self.h2d_bytes += nbytes + slot.h_off.numel() * 4 + slot.h_meta.numel() * 4
         staged = {"ids": slot.ids, "B": B, "meta": slot.d_meta[:, :B] if B == eng.max_batch else slot.d_meta[:, :B].contiguous(),
                   "streams": [slot.dev[s] if slot.chans[s] else None for s in range(3)],
                   "offs": [slot.d_off[s, :B + 1] if slot.chans[s] else None for s in range(3)]}
+        if self.records is not None:
+            staged["records"], staged["vidx"] = self.records, slot.d_vidx[:B]
         if self.use_graph and B == eng.max_batch:
-            key = (B, self.model.test_key())      # the test-time config is baked into the captured launches
+            # the test-time config and the record ring are baked into the captured launches
+            key = (B, self.model.test_key(), None if self.records is None else self.records[0].data_ptr())
             g = slot.graphs.get(key)
             if g is None:
                 with self.cuda_lock:

@@ -62,3 +62,50 @@ def inference_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, eval
         with open(f"{output_folder}/data_left.json", "w", encoding="utf-8") as f:
             json.dump(batch_results, f, ensure_ascii=False, indent=4)
     return batch_results
+
+
+def inference_sharded(dataset, model, output_folder, batch_size=32, rank=0, world=1, print_freq=0):
+    """Multi-GPU form of inference_one_epoch: one process per GPU (torchrun), rank r takes videos r, r + world, ... of the
+    dataset (the reference splits its list into 7 files run as 7 processes, libs/datasets/deepfake_video_audio.py:420-431,
+    inference.py:116-124); each rank streams its shard through `model.stream` (pinned staging, H2D, CUDA graph), the
+    postprocess kernel appends one fixed-size record per video to a device ring, and ONE all-gather of those records
+    (NCCL) is the path's only exchange. Rank 0 writes `data_left.json` in dataset order, exactly the records
+    inference_one_epoch writes for the same list. Returns the records on rank 0, None elsewhere."""
+    from .sharding import gather_records, shard_indices, unpack_records
+    model.eval()
+    n = len(dataset)
+    mine = shard_indices(n, rank, world)
+    K = int(model.test_max_seg_num)
+    if model.test_nms_method == "none":
+        raise NotImplementedError("nms_method 'none' returns a variable number of segments: use inference_one_epoch per shard")
+    runner = model.runner()
+    ring, counter = runner.enable_records(max(1, len(mine)))
+
+    def batches():
+        for i in range(0, len(mine), batch_size):
+            chunk = []
+            for j in mine[i:i + batch_size]:
+                item = dict(dataset[j])
+                item["index"] = j
+                chunk.append(item)
+            yield chunk
+    done = 0
+    try:
+        for out in model.stream(batches()):
+            done += len(out)
+            if print_freq and rank == 0 and (done // batch_size) % print_freq == 0:
+                print("Test: [{0:05d}/{1:05d}]".format(done, len(mine)))
+        torch.cuda.synchronize(ring.device)
+        assert int(counter.item()) == len(mine), (int(counter.item()), len(mine))
+        rec = gather_records(ring[:len(mine)], n, world)
+    finally:
+        runner.enable_records(None)
+    if rank != 0:
+        return None
+    by_index = unpack_records(rec, K)
+    assert len(by_index) == n, (len(by_index), n)
+    results = [result_item(dataset.data_list[j]["id"], by_index[j]) for j in range(n)]
+    os.makedirs(output_folder, exist_ok=True)
+    with open(f"{output_folder}/data_left.json", "w", encoding="utf-8") as f:
+        json.dump(results, f, ensure_ascii=False, indent=4)
+    return results

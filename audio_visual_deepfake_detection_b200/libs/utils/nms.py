@@ -58,11 +58,13 @@ def _single_class(segs_d, scores_d, iou_threshold, min_score, max_seg_num, use_s
     out_segs = torch.empty((1, K, 2), dtype=torch.float32, device=dev)
     out_scores = torch.empty((1, K), dtype=torch.float32, device=dev)
     out_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    out_index = torch.zeros((1, K), dtype=torch.int32, device=dev)
     ops.postprocess(1, cand_segs=segs_d.view(1, n, 2), cand_scores=scores_d.view(1, n), cand_count=cand_count,
                     iou_threshold=iou_threshold, min_score=min_score, sigma=sigma, voting_thresh=voting_thresh,
-                    max_seg_num=K, use_soft_nms=use_soft_nms, out_segs=out_segs, out_scores=out_scores, out_count=out_count)
+                    max_seg_num=K, use_soft_nms=use_soft_nms, out_segs=out_segs, out_scores=out_scores, out_count=out_count,
+                    out_index=out_index)
     k = int(out_count.item())
-    return out_segs[0, :k], out_scores[0, :k]
+    return out_segs[0, :k], out_scores[0, :k], out_index[0, :k]
 
 
 def batched_nms(segs, scores, cls_idxs, iou_threshold, min_score, max_seg_num, use_soft_nms=True, multiclass=True,
@@ -79,18 +81,14 @@ def batched_nms(segs, scores, cls_idxs, iou_threshold, min_score, max_seg_num, u
         new_segs, new_scores, new_cls = [], [], []
         for class_id in torch.unique(cls_cpu):
             cur = torch.where(cls_cpu == class_id)[0].to(dev)
-            s, p = _single_class(segs_d[cur].contiguous(), scores_d[cur].contiguous(), iou_threshold, min_score,
-                                 max_seg_num, use_soft_nms, sigma, 0.0)
+            s, p, _ = _single_class(segs_d[cur].contiguous(), scores_d[cur].contiguous(), iou_threshold, min_score,
+                                    max_seg_num, use_soft_nms, sigma, 0.0)
             new_segs.append(s); new_scores.append(p)
             new_cls.append(torch.full((p.numel(),), int(class_id), dtype=cls_idxs.dtype))
         new_segs, new_scores, new_cls = torch.cat(new_segs).cpu(), torch.cat(new_scores).cpu(), torch.cat(new_cls)
         _, idxs = new_scores.sort(descending=True, stable=True)
         k = min(max_seg_num, new_segs.shape[0])
         return new_segs[idxs[:k]], new_scores[idxs[:k]], new_cls[idxs[:k]]
-    s, p = _single_class(segs_d, scores_d, iou_threshold, min_score, max_seg_num, use_soft_nms, sigma, voting_thresh)
-    # class-agnostic: every candidate carries its own label; with one class they are all equal (nms.py:159-180)
-    labels = cls_idxs.cpu()
-    lab = labels[:1].expand(p.numel()).clone() if labels.numel() and bool((labels == labels[0]).all()) else None
-    if lab is None:
-        raise AvdfError("class-agnostic NMS over several classes is not on the accelerated path")
-    return s.cpu(), p.cpu(), lab
+    s, p, idx = _single_class(segs_d, scores_d, iou_threshold, min_score, max_seg_num, use_soft_nms, sigma, voting_thresh)
+    # class-agnostic (nms.py:159-180): one NMS over all candidates; every pick keeps the label of its candidate
+    return s.cpu(), p.cpu(), cls_idxs.cpu()[idx.cpu().long()]

@@ -47,6 +47,7 @@ class PostprocessArgs(Structure):
         ("out_segs", c_void_p), ("out_scores", c_void_p), ("out_count", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("rec_ring", c_void_p), ("rec_counter", c_void_p), ("rec_cap", c_int32), ("vid_index", c_void_p), ("vid_cls", c_void_p),
+        ("out_index", c_void_p),
     ]
 
 

@@ -146,7 +146,7 @@ def nms_soft(segs, scores, dets, iou_threshold, sigma, min_score, method, max_nu
 def postprocess(batch, *, logits=None, offsets=None, mask=None, level_len=(), level_stride=(), pre_nms_thresh=0.001,
                 pre_nms_topk=2000, duration_thresh=0.001, cand_segs, cand_scores, cand_count, iou_threshold, min_score,
                 sigma, voting_thresh, max_seg_num, use_soft_nms, soft_method=2, vid_meta=None, out_segs, out_scores,
-                out_count, workspace=None, records=None):
+                out_count, workspace=None, records=None, out_index=None):
     """Fused decode + batched_nms (class-agnostic) + seconds conversion; one CTA per video. use_soft_nms: True / False,
     or None for nms_method 'none' (the decoded candidates, out_* sized cand_cap). records: optional
     (ring [cap, 3 + 3K] f32, counter [1] i32, vid_index [B] i32 | None, vid_cls [B] f32 | None)."""
@@ -179,6 +179,8 @@ def postprocess(batch, *, logits=None, offsets=None, mask=None, level_len=(), le
         a.vid_feat_stride, a.vid_half_nframes, a.vid_fps, a.vid_duration = [t.data_ptr() for t in vid_meta]
     _chk(out_segs, torch.float32, "out_segs"); _chk(out_scores, torch.float32, "out_scores"); _chk(out_count, torch.int32, "out_count")
     a.out_segs, a.out_scores, a.out_count = out_segs.data_ptr(), out_scores.data_ptr(), out_count.data_ptr()
+    _chk(out_index, torch.int32, "out_index")
+    a.out_index = out_index.data_ptr() if out_index is not None else None
     need = L.avdf_postprocess_workspace_bytes(batch, a.cand_cap)
     if need:
         if workspace is None or workspace.numel() * workspace.element_size() < need:

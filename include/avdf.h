@@ -135,6 +135,9 @@ typedef struct avdf_postprocess_args {
   int32_t rec_cap;
   const int32_t* vid_index;      /* [batch] global video index of every row of the batch */
   const float* vid_cls;          /* [batch] video-level logit */
+  /* optional: index (into the video's candidate list) of every returned segment, in output order - the label of a
+   * pick in class-agnostic NMS over several classes is cls_idxs[index] (libs/utils/nms.py:159-180) */
+  int32_t* out_index;            /* [batch, max_seg_num] */
 } avdf_postprocess_args;          /* host struct */
 AVDF_API size_t avdf_postprocess_workspace_bytes(int32_t batch, int32_t cand_cap);
 AVDF_API int avdf_postprocess(const avdf_postprocess_args* args, void* stream);

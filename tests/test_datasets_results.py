@@ -164,3 +164,62 @@ def test_inference_cli_end_to_end(tmp_path):
         kept = [[s, seg[0], seg[1]] for s, seg in zip(x["scores"], x["segments"]) if s > 0.2] or [[0, 0, 0]]
         assert pred[x["video_id"]] == kept
     assert len(open(out_dir / "prediction.txt").read().splitlines()) == 5
+
+
+def _cli_setup(tmp_path, durs):
+    import yaml
+    from audio_visual_deepfake_detection_b200.libs.core import load_config_for
+    from audio_visual_deepfake_detection_b200.libs.modeling import EXP12
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    folders = write_corpus(str(tmp_path / "data"), durs)
+    cfg = yaml.load(open(os.path.join(root, "configs", "deepfake_exp12_test.yaml")), Loader=yaml.FullLoader)
+    cfg["dataset"].update(video_feat_folder=folders["video"], audio_byola_feat_folder=folders["byola"],
+                          audio_emo_feat_folder=folders["emo"], test_folder=folders["lists"])
+    cfg["loader"] = {"batch_size": 1, "num_workers": 0}
+    cfg_path = str(tmp_path / "cfg.yaml")
+    yaml.dump(cfg, open(cfg_path, "w"))
+    full = load_config_for(EXP12)
+    sd = syn.synthetic_state_dict(full["model"], EXP12, seed=0)
+    return root, folders, cfg_path, full, sd
+
+
+@pytest.mark.gpu
+def test_inference_sharded_single_rank_equals_inference_one_epoch(tmp_path):
+    """inference_sharded (records written by the postprocess kernel, gathered, unpacked) == inference_one_epoch, record
+    for record, on one rank; partial last batch included."""
+    from audio_visual_deepfake_detection_b200.libs.modeling import make_meta_arch
+    from audio_visual_deepfake_detection_b200.libs.utils import inference_one_epoch, inference_sharded
+    durs = [4.03, 5.5, 7.42, 9.04, 6.2, 11.0, 4.7]
+    root, folders, cfg_path, full, sd = _cli_setup(tmp_path, durs)
+    ds = make_inference_dataset("deepfake_video_audioEmoBYOLA_inference", False, ["test"], 3, **dataset_kwargs(folders))
+    model = make_meta_arch(full["model_name"], **full["model"], max_batch=4)
+    model.load_state_dict(sd)
+    model.to("cuda").eval()
+    a = inference_one_epoch(make_data_loader(ds, False, None, 4, 0), model, -1, output_folder=str(tmp_path / "a"))
+    b = inference_sharded(ds, model, str(tmp_path / "b"), batch_size=4)
+    assert json.load(open(tmp_path / "a" / "data_left.json")) == json.load(open(tmp_path / "b" / "data_left.json"))
+    assert [r["video_id"] for r in b] == [r["video_id"] for r in a] and len(b) == len(durs)
+
+
+@pytest.mark.gpu
+def test_two_rank_inference_equals_one_rank(tmp_path):
+    """`torchrun --nproc-per-node 2 inference.py cfg sub ckpt` writes the same records as one process
+    (rank-strided shards, one NCCL all-gather of the kernel-written records). Needs two GPUs."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    durs = [4.03, 5.5, 7.42, 9.04, 6.2, 11.0, 4.7, 8.8, 5.1]
+    root, folders, cfg_path, full, sd = _cli_setup(tmp_path, durs)
+    outs = []
+    for tag, launcher in (("one", [sys.executable]),
+                          ("two", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29611"])):
+        ckpt = str(tmp_path / tag / "epoch_010.pth.tar")
+        os.makedirs(os.path.dirname(ckpt))
+        torch.save({"epoch": 10, "state_dict_ema": {"module." + k: v for k, v in sd.items()}}, ckpt)
+        r = subprocess.run(launcher + [os.path.join(root, "inference.py"), cfg_path, "3", ckpt, "-b", "4", "--merge"],
+                           capture_output=True, text=True, cwd=root, timeout=900)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs.append(json.load(open(tmp_path / tag / "3" / "data_left.json")))
+    assert outs[0] == outs[1]

@@ -64,10 +64,9 @@ def test_fp32_mode_vs_reference(case):
             assert r["labels"].dtype == torch.long and r["video_cls"].shape == (1,)
 
 
-# bar per operand format: "mixed" (the default: bf16 raw features, fp16 bounded activations) must meet the
-# north-star 1e-2; pure "bf16" operands sit at 1.2e-2 on these worst-case synthetic weights (AffineDropPath
-# scales ~1 instead of the trained ~1e-2), which is also what the reference shows under autocast(bf16).
-@pytest.mark.parametrize("precision,bar", [("mixed", 1e-2), ("bf16", 3e-2)])
+# "mixed" (the default: bf16 raw features, fp16 bounded activations) must meet the north-star 1e-2. (Pure bf16 operands
+# sit at 1.2e-2 on these worst-case synthetic weights - as the reference does under autocast(bf16) - and are not offered.)
+@pytest.mark.parametrize("precision,bar", [("mixed", 1e-2)])
 @pytest.mark.parametrize("case", list(MODEL_CASES))
 def test_bf16_mode_vs_reference(case, precision, bar):
     model, use_video = build(case, precision)
@@ -81,19 +80,29 @@ def test_bf16_mode_vs_reference(case, precision, bar):
         assert e1 < bar and e2 < bar, (vi, e1, e2)
         np.testing.assert_allclose(vcls[vi].numpy(), g[f"v{vi}_video_cls"][0], atol=2e-2, rtol=2e-2)
     print("worst max-rel error", precision, case, worst)
-    # final sets: identical membership after the 0.2 score filter, start/end within 1e-3 s, is the north-star
-    # bar; with bf16 operands a candidate whose score sits within the logit tolerance of a threshold may flip,
-    # so count mismatching videos and require the sets to agree wherever the reference has a clear margin.
+    # the final-set bar (identical membership after the 0.2 filter, start/end within 1e-3 s) is asserted at the benchmarked
+    # batch size over hundreds of videos in tests/test_gpu_parity_sets.py; here: the post-processing of these four videos
+    # is exact on the path's own dense outputs, hard and soft
+    import model_ref
+    import parity_common
+    model_name, overrides, _, wseed = MODEL_CASES[case]
+    cfg = load_config_for(model_name, dict(overrides))
+    om = model_ref.OracleModel(cfg["model"], syn.synthetic_state_dict(cfg["model"], model_name, seed=wseed), model_name)
     for method in ("hard", "soft"):
         model.test_nms_method = method
         out = model(items)
         for vi, r in enumerate(out):
-            gp, gs = g[f"v{vi}_{method}_scores"], g[f"v{vi}_{method}_segments"].reshape(-1, 2)
-            keep_ref = gp > 0.2
-            keep_got = r["scores"].numpy() > 0.2
-            margin = np.abs(gp - 0.2).min() if len(gp) else 1.0
-            if margin > 0.02 and method == "hard" and precision == "mixed":
-                assert abs(int(keep_got.sum()) - int(keep_ref.sum())) <= 1, (case, vi, method, keep_got.sum(), keep_ref.sum())
+            L = model.engine().padded_len(int(items[vi]["feats"].shape[-1]))
+            want_s, want_p = parity_common.oracle_from_dense(om, logits[vi].numpy(), offsets[vi].numpy(), model.engine().level_lens(L),
+                                                             items[vi], method)
+            assert len(want_p) == r["scores"].numel(), (case, vi, method)
+            np.testing.assert_allclose(r["scores"].numpy(), want_p, atol=2e-6)
+            np.testing.assert_allclose(r["segments"].numpy().reshape(-1, 2), want_s, atol=1e-4)
+
+
+def test_bf16_operand_format_is_not_offered():
+    with pytest.raises(ValueError):
+        build("exp12", "bf16")[0].engine()
 
 
 def test_batch_invariance_and_streams():
@@ -212,6 +221,11 @@ def test_api_edge_cases():
         assert torch.equal(got[1], want[1])
         np.testing.assert_allclose(got[0].numpy(), want[0].numpy().reshape(-1, 2), atol=1e-4)
     labels = torch.from_numpy((np.arange(1512) % 3).astype(np.int64))
+    for soft in (False, True):          # class-agnostic NMS over several classes: labels follow the picks (nms.py:159-180)
+        got = batched_nms(s, p, labels, 0.1, 0.2, 100, use_soft_nms=soft, multiclass=False, sigma=0.75, voting_thresh=0.9)
+        want = nms_ref.batched_nms(s, p, labels, 0.1, 0.2, 100, use_soft_nms=soft, multiclass=False, sigma=0.75, voting_thresh=0.9)
+        assert torch.equal(got[1], want[1]) and torch.equal(got[2], want[2]) and len(set(got[2].tolist())) > 1
+        np.testing.assert_allclose(got[0].numpy(), want[0].numpy().reshape(-1, 2), atol=1e-4)
     got = batched_nms(s, p, labels, 0.1, 0.2, 100, use_soft_nms=False, multiclass=True, sigma=0.75, voting_thresh=0.9)
     want = nms_ref.batched_nms(s, p, labels, 0.1, 0.2, 100, use_soft_nms=False, multiclass=True, sigma=0.75, voting_thresh=0.9)
     assert torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
