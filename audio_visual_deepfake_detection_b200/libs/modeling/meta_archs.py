@@ -294,7 +294,9 @@ class _LocalizationBase(nn.Module):
         the staged tensors and writes the engine's static buffers, so `staged` must stay alive and unchanged in
         place; replay() returns the same device-side result dict as run_staged()."""
         from ... import native
-        self.run_staged(staged, lane)               # allocates every static buffer / cache outside the capture
+        warm = dict(staged)
+        warm.pop("records", None)                   # the warm-up pass must not append result records
+        self.run_staged(warm, lane)                 # allocates every static buffer / cache outside the capture
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         n0 = native.LAUNCHES["n"]
