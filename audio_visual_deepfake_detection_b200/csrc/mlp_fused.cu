@@ -35,9 +35,10 @@ constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;    // + alignment slack
 
 struct Params {
   CUtensorMap x_map, w1_map, w2_map;
-  const float* residual; float* out;
+  const float* residual; float* out; void* out_h;
   const float* b1; const float* b2; const float* gamma; const unsigned char* row_mask;
   int rows, tiles;
+  int oh_t, oh_pitch, oh_row0;  // 16-bit copy: row r = b * oh_t + t lands at row b * oh_pitch + oh_row0 + t (oh_t = 0: dense)
   unsigned idesc;
   unsigned long long* dbg;      // optional (debug hook): globaltimer stamps of CTA 0's first tile, 3 x 96 slots
 };
@@ -275,6 +276,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
       //      residual of the next chunk being in flight (registers) while this one is computed
       const float* res_base = p.residual + (size_t)wrow * C + g * 128 + lane;
       float* out_base = p.out + (size_t)wrow * C + g * 128 + lane;
+      // optional 16-bit copy of the result (the operand of the FPN lateral conv / the next level's block): same dtype as x
+      unsigned short* outh_base = p.out_h ? reinterpret_cast<unsigned short*>(p.out_h) + g * 128 + lane : nullptr;
       const int nrow = min(32, p.rows - wrow);    // rows of this warp's block inside the tensor (<= 0: none)
       float rres[32];
 #pragma unroll
@@ -313,7 +316,18 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         for (int rr = 0; rr < 32; ++rr) {         // row rr of the block: 32 lanes = 32 consecutive columns
           const float v = *reinterpret_cast<const float*>(t0 + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
           const float mrow = __shfl_sync(0xffffffffu, mk, rr);
-          if (rr < nrow) out_base[(size_t)rr * C + ch * 32] = fmaf(rres[rr], mrow, v);
+          if (rr < nrow) {
+            const float o = fmaf(rres[rr], mrow, v);
+            out_base[(size_t)rr * C + ch * 32] = o;
+            if (outh_base) {
+              unsigned short hb;
+              if (F16) { const __half hh = __float2half_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
+              else { const __nv_bfloat16 hh = __float2bfloat16_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
+              const int r_ = wrow + rr;
+              const size_t dr = p.oh_t ? (size_t)(r_ / p.oh_t) * p.oh_pitch + p.oh_row0 + (r_ % p.oh_t) : (size_t)r_;
+              outh_base[dr * C + ch * 32] = hb;
+            }
+          }
         }
         if (ch + 1 < 4) {
 #pragma unroll
@@ -378,7 +392,11 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   if ((rc = enc2(&p.x_map, dt, 2, a->x, C, a->rows, 64, 128, "x"))) return rc;
   if ((rc = enc2(&p.w1_map, dt, 2, a->w1, C, HID, 64, 128, "w1"))) return rc;
   if ((rc = enc2(&p.w2_map, dt, 2, a->w2, HID, C, 64, 128, "w2"))) return rc;
-  p.residual = a->residual; p.out = a->out;
+  p.residual = a->residual; p.out = a->out; p.out_h = a->out_h;
+  p.oh_t = a->out_h_t; p.oh_pitch = a->out_h_pitch; p.oh_row0 = a->out_h_row0;
+  AVDF_CHECK_ARG(a->out_h_t >= 0 && (a->out_h_t == 0 || (a->rows % a->out_h_t == 0 && a->out_h_pitch >= a->out_h_t + a->out_h_row0)),
+                 "out_h_t must divide rows and fit the destination pitch");
+  AVDF_CHECK_ARG(!a->out_h || (reinterpret_cast<uintptr_t>(a->out_h) & 15) == 0, "out_h must be 16-byte aligned");
   p.b1 = a->b1; p.b2 = a->b2; p.gamma = a->gamma; p.row_mask = a->row_mask;
   p.rows = a->rows; p.tiles = (a->rows + BM - 1) / BM;
   p.dbg = g_mlpf_dbg;

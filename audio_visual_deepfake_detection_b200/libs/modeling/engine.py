@@ -277,7 +277,7 @@ class LocalizationEngine:
                       o_rows=o_rows, bias=bias, row_mask=row_mask, ln=ln, act=act, pe=pe, residual=residual, gamma=gamma,
                       out_f32=out_f32, out_h=out_h, workspace=ws)
 
-    def _attn_and_mlp(self, pre, B, T, mask, skip, window, out_name, want_act_copy):
+    def _attn_and_mlp(self, pre, B, T, mask, skip, window, out_name, want_act_copy, pyr=None):
         """Shared tail of TransformerBlock / MutilModelTransformerBlock after the dwconv+LN stage:
         q,k,v 1x1 -> attention -> proj(+skip) -> LN2 -> MLP(+residual). Returns (out_f32, out_act|None)."""
         C, w = self.C, self.w
@@ -298,19 +298,23 @@ class LocalizationEngine:
                    row_mask=mask, residual=skip, gamma=ga, out_f32=y)
         out = self.buf(out_name, (B, T, C), torch.float32)
         out_act = None
+        fused = self.fused_mlp and self.adt != torch.float32 and C == 256 and B * T >= self.fused_mlp_min_rows
         if want_act_copy and self.adt != torch.float32:
-            out_act = self.buf(out_name + "_act", (B, T, C), self.adt)
+            # pyr = (pyramid buffer [B, P, C], first row of this level): the 16-bit copy goes straight into the operand of
+            # the single FPN lateral launch (fused-MLP path only)
+            out_act = pyr[0] if (pyr is not None and fused) else self.buf(out_name + "_act", (B, T, C), self.adt)
         l2 = self.buf("ln2", (B, T, C), self.adt)
         ops.ln_rows(y, *w.ln(pre + ".ln2"), l2, B * T)
-        if self.fused_mlp and self.adt != torch.float32 and out_act is None and C == 256 and B * T >= self.fused_mlp_min_rows:
+        if fused:
             # one launch: the [B*T, 4C] activations stay in shared memory / TMEM (csrc/mlp_fused.cu). (Folding LN2 into
             # the kernel was tried - two spare warps normalising the next 128-row tile straight into the operand
             # layout - and measured slower, 14.7k vs 15.9k videos/s: ~10 us per tile that cannot be hidden because the
             # x tile cannot be double-buffered in 227 KB. LN2 stays a separate 9 us launch.)
             ops.mlp_fused(l2, w.dense(f"{pre}.mlp.0.weight", self.adt), w.vec(f"{pre}.mlp.0.bias"),
                           w.dense(f"{pre}.mlp.3.weight", self.adt), w.vec(f"{pre}.mlp.3.bias"),
-                          row_mask=mask, residual=y, gamma=gm, out=out)
-            return out, None
+                          row_mask=mask, residual=y, gamma=gm, out=out, out_h=out_act,
+                          out_h_level=(T, pyr[0].shape[1], pyr[1]) if (pyr is not None and out_act is not None) else None)
+            return out, out_act
         h = self.buf("mlp_h", (B, T, 4 * C), self.adt)
         self._gemm(l2, f"{pre}.mlp.0.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.mlp.0.bias"),
                    act=ops.ACT_GELU, out_act=h)
@@ -322,7 +326,7 @@ class LocalizationEngine:
                       workspace=ws)
         return out, (out if self.adt == torch.float32 else out_act)
 
-    def transformer_block(self, pre, x, B, T, masks, level, stride, window, out_name, want_act_copy=False):
+    def transformer_block(self, pre, x, B, T, masks, level, stride, window, out_name, want_act_copy=False, pyr=None):
         """TransformerBlock.forward (blocks.py:1307-1317); x fp32 [B, T, C] at pyramid level `level`."""
         C, w = self.C, self.w
         To = T // stride
@@ -335,9 +339,9 @@ class LocalizationEngine:
                          dw=[w.dw(f"{pre}.attn.{n}_conv.conv.weight") for n in ("query", "key", "value")],
                          ln_out=[w.ln(f"{pre}.attn.{n}_norm") for n in ("query", "key", "value")], outs=[qkvn] * 3,
                          out_rows=3 * To, out_row_offsets=[0, To, 2 * To], skip_out=skip if stride == 2 else None)
-        return self._attn_and_mlp(pre, B, To, mask, skip, window, out_name, want_act_copy)
+        return self._attn_and_mlp(pre, B, To, mask, skip, window, out_name, want_act_copy, pyr)
 
-    def mm_block(self, pre, xq, kv, B, Tq, Tkv, masks, level, window, out_name, want_act_copy=False):
+    def mm_block(self, pre, xq, kv, B, Tq, Tkv, masks, level, window, out_name, want_act_copy=False, pyr=None):
         """MutilModelTransformerBlock.forward (blocks.py:866-876): q from xq [B,Tq,C]; k,v from kv [B,Tkv,C]
         nearest-resampled to Tq (backbones.py:487,490)."""
         C, w = self.C, self.w
@@ -359,7 +363,7 @@ class LocalizationEngine:
                 shift = -int(round(math.log2(Tkv // Tq)))
             ops.ln_dwconv_ln(kv, batch=B, t_src=Tkv, t_virt=Tq, shift=shift, stride=1, mask_out=mask, ln_in=lni[1:],
                              dw=dws[1:], ln_out=lno[1:], outs=[qkvn] * 2, out_rows=3 * Tq, out_row_offsets=[Tq, 2 * Tq])
-        return self._attn_and_mlp(pre, B, Tq, mask, xq, window, out_name, want_act_copy)
+        return self._attn_and_mlp(pre, B, Tq, mask, xq, window, out_name, want_act_copy, pyr)
 
     # ------------------------------------------------------------------ the pass
     def video_cls(self, x_act, B, L, masks):
@@ -429,22 +433,34 @@ class LocalizationEngine:
         feats_act = [None] * self.n_levels
         T = L
         nb = self.arch[2]
+        # fused-MLP path: every level's 16-bit feature copy lands in ONE pyramid buffer, the FPN lateral convs become one
+        # launch with six weight blocks (necks.py:62-75)
+        one_lateral = self.fused_mlp and adt != torch.float32 and self.fused_mlp_min_rows == 0
+        pyr_act = self.buf("pyr_act", (B, P, C), adt) if one_lateral else None
         for i in range(nb):
             x, x_act_copy = self.transformer_block(f"backbone.branch.{i}", x, B, T, masks, i, 2, self.win[1 + i],
-                                                   "feat%d" % (i + 1), want_act_copy=True)
+                                                   "feat%d" % (i + 1), want_act_copy=True,
+                                                   pyr=(pyr_act, offs[i + 1]) if one_lateral else None)
             T //= 2
             feats_act[i + 1] = x_act_copy
             lh, lh_act = self.mm_block(f"backbone.lh_branch.{i}", lh, x, B, L, T, masks, 0, w0, "lh%d" % (i & 1),
-                                       want_act_copy=(i == nb - 1))
+                                       want_act_copy=(i == nb - 1), pyr=(pyr_act, offs[0]) if one_lateral else None)
             if i + 1 < nb:            # hh_branch[last] is never consumed (backbones.py:485-495)
                 x, _ = self.mm_block(f"backbone.hh_branch.{i}", x, lh, B, T, L, masks, i + 1, w0, "hh%d" % i)
         feats_act[0] = lh_act
         # ---- neck (necks.py:62-93)
         lat = self.buf("lat", (B, P, C), torch.float32)
-        for l in range(self.n_levels):
-            bias = w.vec(f"neck.lateral_convs.{l}.conv.bias") if w.has(f"neck.lateral_convs.{l}.conv.bias") else None
-            self._gemm(feats_act[l], f"neck.lateral_convs.{l}.conv.weight", B=B, segs=[(lens[l], 0, offs[l])], a_rows=lens[l],
+        has_lat_bias = w.has("neck.lateral_convs.0.conv.bias")
+        if one_lateral:
+            keys = [f"neck.lateral_convs.{l}.conv.weight" for l in range(self.n_levels)]
+            bias = w.stack_vec([f"neck.lateral_convs.{l}.conv.bias" for l in range(self.n_levels)]) if has_lat_bias else None
+            self._gemm(pyr_act, keys, B=B, segs=[(lens[l], offs[l], offs[l], l * C) for l in range(self.n_levels)], a_rows=P,
                        o_rows=P, bias=bias, row_mask=masks["pyr"], out_f32=lat)
+        else:
+            for l in range(self.n_levels):
+                bias = w.vec(f"neck.lateral_convs.{l}.conv.bias") if has_lat_bias else None
+                self._gemm(feats_act[l], f"neck.lateral_convs.{l}.conv.weight", B=B, segs=[(lens[l], 0, offs[l])], a_rows=lens[l],
+                           o_rows=P, bias=bias, row_mask=masks["pyr"], out_f32=lat)
         fpn = self.buf("fpn", (B, P, C), adt)
         if not hasattr(self, "_fpn_params"):
             dw = torch.stack([w.dw(f"neck.fpn_convs.{l}.conv.weight") for l in range(self.n_levels)]).contiguous()

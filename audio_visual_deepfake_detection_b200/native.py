@@ -81,7 +81,8 @@ class MlpFusedArgs(Structure):
     _fields_ = [
         ("rows", c_int32), ("channels", c_int32), ("hidden", c_int32), ("dtype", c_int32),
         ("x", c_void_p), ("w1", c_void_p), ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p),
-        ("row_mask", c_void_p), ("residual", c_void_p), ("gamma", c_void_p), ("out", c_void_p),
+        ("row_mask", c_void_p), ("residual", c_void_p), ("gamma", c_void_p), ("out", c_void_p), ("out_h", c_void_p),
+        ("out_h_t", c_int32), ("out_h_pitch", c_int32), ("out_h_row0", c_int32),
     ]
 
 

@@ -237,7 +237,7 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
 
 
 # ---------------------------------------------------------------------------- block kernels
-def mlp_fused(x, w1, b1, w2, b2, *, row_mask, residual, gamma, out):
+def mlp_fused(x, w1, b1, w2, b2, *, row_mask, residual, gamma, out, out_h=None, out_h_level=None):
     """out = residual*mask + gamma * ((GELU(x w1^T + b1) w2^T + b2) * mask); x [..., 256] fp16|bf16, w1 [1024, 256],
     w2 [256, 1024] of the same dtype, residual / out fp32 [..., 256]. One launch; the hidden activations stay on chip."""
     L = nv.lib()
@@ -255,6 +255,10 @@ def mlp_fused(x, w1, b1, w2, b2, *, row_mask, residual, gamma, out):
     a.row_mask = row_mask.data_ptr() if row_mask is not None else None
     a.gamma = gamma.data_ptr() if gamma is not None else None
     a.residual, a.out = residual.data_ptr(), out.data_ptr()
+    _chk(out_h, x.dtype, "out_h")
+    a.out_h = out_h.data_ptr() if out_h is not None else None
+    if out_h_level is not None:          # (t, pitch, row0): out_h is a [batch, pitch, C] pyramid buffer, this level at row0
+        a.out_h_t, a.out_h_pitch, a.out_h_row0 = [int(v) for v in out_h_level]
     _call("avdf_mlp_fused", L.avdf_mlp_fused, (ctypes.byref(a), _stream(),), launches=1,
           work={"flops": 4.0 * rows * C * H, "bytes": rows * C * (x.element_size() + 8) + 2 * C * H * x.element_size(), "m": rows, "n": C, "k": H})
     return out

@@ -205,6 +205,10 @@ typedef struct avdf_mlp_fused_args {
   const float* residual;         /* [rows, channels] fp32 */
   const float* gamma;            /* [channels] or NULL (AffineDropPath scale, blocks.py:1316) */
   float* out;                    /* [rows, channels] fp32 */
+  void* out_h;                   /* optional 16-bit copy of out (same dtype as x) or NULL */
+  int32_t out_h_t, out_h_pitch, out_h_row0;   /* 0: the copy is dense [rows, channels]; else rows = batch * out_h_t and row
+                                               * b * out_h_t + t goes to row b * out_h_pitch + out_h_row0 + t (one level of
+                                               * a [batch, P, channels] pyramid buffer, necks.py:62-93's input) */
 } avdf_mlp_fused_args;
 AVDF_API int avdf_mlp_fused(const avdf_mlp_fused_args* args, void* stream);
 

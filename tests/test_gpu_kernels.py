@@ -660,3 +660,28 @@ def test_mlp_fused(rows, dt):
     ops.conv_gemm(hid, dev(w2), taps=1, batch=1, c_in=H, n_out=C, segs=[(rows, 0, 0)], a_rows=rows, o_rows=rows, bias=dev(b2),
                   row_mask=dev(mask).view(1, rows), residual=dev(res).view(1, rows, C), gamma=dev(gamma), out_f32=out2)
     assert rel_err(out.cpu(), out2.view(rows, C).cpu()) < 2e-4
+
+
+def test_mlp_fused_16bit_copy_into_pyramid_level():
+    """out_h: the 16-bit copy of the fused MLP's result, dense or scattered into one level of a [batch, P, C] pyramid
+    buffer (the operand of the single FPN lateral launch)."""
+    rng = np.random.RandomState(77)
+    C, H, B, T, P, row0 = 256, 1024, 3, 96, 200, 40
+    rows = B * T
+    dt = torch.float16
+    x = torch.from_numpy(rng.standard_normal((rows, C)).astype(np.float32)).to(dt)
+    w1 = torch.from_numpy((rng.standard_normal((H, C)) / 16).astype(np.float32)).to(dt)
+    w2 = torch.from_numpy((rng.standard_normal((C, H)) / 32).astype(np.float32)).to(dt)
+    b1 = torch.from_numpy(rng.normal(0, 0.3, H).astype(np.float32)); b2 = torch.from_numpy(rng.normal(0, 0.3, C).astype(np.float32))
+    res = torch.from_numpy(rng.standard_normal((rows, C)).astype(np.float32))
+    out = torch.empty((rows, C), device=DEV)
+    dense = torch.zeros((rows, C), device=DEV, dtype=dt)
+    ops.mlp_fused(dev(x), dev(w1), dev(b1), dev(w2), dev(b2), row_mask=None, residual=dev(res), gamma=None, out=out, out_h=dense)
+    assert torch.equal(dense, out.to(dt))
+    pyr = torch.full((B, P, C), 7.0, device=DEV, dtype=dt)
+    out2 = torch.empty((rows, C), device=DEV)
+    ops.mlp_fused(dev(x), dev(w1), dev(b1), dev(w2), dev(b2), row_mask=None, residual=dev(res), gamma=None, out=out2, out_h=pyr,
+                  out_h_level=(T, P, row0))
+    assert torch.equal(out2, out)
+    assert torch.equal(pyr[:, row0:row0 + T].reshape(rows, C), dense)
+    assert bool((pyr[:, :row0] == 7.0).all()) and bool((pyr[:, row0 + T:] == 7.0).all())
