@@ -262,6 +262,234 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same operator, second layout (default). The kernel above runs one warp per output row with all three streams'
+// folded constants in shared memory: 36 constant LDS.128 per row put it on the LSU data pipe (ncu: 61 % of peak, twice
+// the issue-slot utilisation), and the input LayerNorm of a row is the head of every row's dependency chain. Here a CTA
+// owns LDL2_ROWS consecutive output rows of one video and works in two phases:
+//   A  all warps: input LayerNorm statistics of the tile's source rows (+ halo), ONCE per row; the normalised rows go to
+//      shared memory (pre-affine: the per-stream affine is folded into the conv constants as before)
+//   B  warp = (stream, slice of the tile's rows): the stream's folded constants live in REGISTERS for the whole slice
+//      (A0, A1, A2, Bsum, ln_out w / b for the lane's 8 channels: 48 registers), so a row costs 2 LDS.128 (the new
+//      window row) + 12 FMA2 + the LayerNorm reduction + 4 FMA2 + the 16-byte stores. Edge rows (a tap outside the
+//      sequence) fetch the per-tap bias terms from a small shared table.
+// Same arithmetic and operation order per element as the first layout (1 / sqrt is the bare MUFU here: last-ulp differences).
+// ------------------------------------------------------------------------------------------------
+constexpr int LDL2_ROWS = 32;          // output rows per CTA
+constexpr int LDL2_WARPS = 6;          // 1, 2 or 3 streams -> 6, 3 or 2 warps per stream
+template <int STRIDE> __host__ __device__ constexpr int ldl2_src_rows() { return STRIDE * (LDL2_ROWS - 1) + 3; }
+
+__device__ __forceinline__ float rsqrt_fast(float x) {      // MUFU.RSQ, 2 ulp; the argument is >= 1e-5 (no denormal path)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Both phases are chains of dependent instructions per row (load -> sums -> 5 butterfly steps -> rsqrt -> scale), ~16
+// cycles from issue to issue (ncu: 0.28 warp instructions per cycle and scheduler with 4.5 resident warps): every warp
+// therefore works on LDL2_PA source rows (phase A) and LDL2_RPI<STRIDE> output rows (phase B) at once, their chains
+// interleaved by the unrolled loops.
+constexpr int LDL2_PA = 3;
+template <int STRIDE> __host__ __device__ constexpr int ldl2_rpi() { return STRIDE == 1 ? 4 : 2; }
+
+template <typename OutT, int STRIDE, int NS, bool SKIP>
+__global__ void __launch_bounds__(LDL2_WARPS * 32, 2) ln_dwconv_ln2_kernel(const LdlParams p) {
+  constexpr int SRC = ldl2_src_rows<STRIDE>();
+  constexpr int RPI = ldl2_rpi<STRIDE>();
+  constexpr int WIN = STRIDE * (RPI - 1) + 3;         // window rows of one iteration
+  extern __shared__ __align__(16) float ldl2_smem[];
+  float (*xh)[kC] = reinterpret_cast<float (*)[kC]>(ldl2_smem);                         // [SRC][256] normalised source rows
+  float (*eb)[3][kC] = reinterpret_cast<float (*)[3][kC]>(ldl2_smem + SRC * kC);        // [NS][tap][256] dw_j * b_in
+  float (*raw)[kC] = reinterpret_cast<float (*)[kC]>(ldl2_smem + (SRC + NS * 3) * kC);  // [SRC][256] raw rows (SKIP only)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_per_video = (p.t_out + LDL2_ROWS - 1) / LDL2_ROWS;
+  const int b = blockIdx.x / tiles_per_video;
+  const int t0 = (blockIdx.x - b * tiles_per_video) * LDL2_ROWS;
+  const int t1 = min(t0 + LDL2_ROWS, p.t_out);
+  const float* src_b = p.src + (size_t)b * p.t_src * kC;
+  const int pos_first = STRIDE * t0 - 1, pos_last = STRIDE * (t1 - 1) + 1;
+  const f32x2 zero2 = pk2(0.f);
+  for (int i = threadIdx.x; i < NS * kC; i += LDL2_WARPS * 32) {
+    const int s = i / kC, c = i - s * kC;
+    const float bb = p.ln_in_b[s][c];
+    eb[s][0][c] = p.dw_w[s][3 * c] * bb; eb[s][1][c] = p.dw_w[s][3 * c + 1] * bb; eb[s][2][c] = p.dw_w[s][3 * c + 2] * bb;
+  }
+  // ---- phase A: normalise every source position of the tile once
+  for (int base = pos_first + warp; base <= pos_last; base += LDL2_WARPS * LDL2_PA) {
+    f32x2 nxt[LDL2_PA][4];
+    bool ok[LDL2_PA];
+#pragma unroll
+    for (int j = 0; j < LDL2_PA; ++j) {
+      const int pos = base + j * LDL2_WARPS;
+      ok[j] = pos <= pos_last && pos >= 0 && pos < p.t_virt;
+      const int r = ok[j] ? (p.shift >= 0 ? (pos >> p.shift) : (pos << (-p.shift))) : 0;
+      const float* g = src_b + (size_t)r * kC;
+      const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(g + 4 * lane));
+      const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(g + 128 + 4 * lane));
+      nxt[j][0] = a.x; nxt[j][1] = a.y; nxt[j][2] = c.x; nxt[j][3] = c.y;
+    }
+    float pivot[LDL2_PA];
+    f32x2 st[LDL2_PA];
+#pragma unroll
+    for (int j = 0; j < LDL2_PA; ++j) {
+      float n0, n1;
+      upk2(nxt[j][0], n0, n1);
+      pivot[j] = __shfl_sync(0xffffffffu, n0, 0);
+      const f32x2 npiv = pk2(-pivot[j]);
+      f32x2 s2 = zero2, q2 = zero2;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const f32x2 d = add2(nxt[j][k], npiv); s2 = add2(s2, d); q2 = fma2(d, d, q2); }
+      st[j] = pk2(hsum2(s2), hsum2(q2));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < LDL2_PA; ++j) st[j] = add2(st[j], __shfl_xor_sync(0xffffffffu, st[j], o));
+    }
+#pragma unroll
+    for (int j = 0; j < LDL2_PA; ++j) {
+      if (!ok[j]) continue;
+      const int pos = base + j * LDL2_WARPS;
+      float su, sq;
+      upk2(st[j], su, sq);
+      const float dm = su * (1.f / kC);
+      const float rstd = rsqrt_fast(fmaxf(sq * (1.f / kC) - dm * dm, 0.f) + kLnEps);
+      const f32x2 nmean = pk2(-(pivot[j] + dm)), rs2 = pk2(rstd);
+      f32x2 o4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o4[k] = mul2(add2(nxt[j][k], nmean), rs2);
+      float* d = xh[pos - pos_first];
+      *reinterpret_cast<ulonglong2*>(d + 4 * lane) = make_ulonglong2(o4[0], o4[1]);
+      *reinterpret_cast<ulonglong2*>(d + 128 + 4 * lane) = make_ulonglong2(o4[2], o4[3]);
+      if (SKIP) {
+        float* rr = raw[pos - pos_first];
+        *reinterpret_cast<ulonglong2*>(rr + 4 * lane) = make_ulonglong2(nxt[j][0], nxt[j][1]);
+        *reinterpret_cast<ulonglong2*>(rr + 128 + 4 * lane) = make_ulonglong2(nxt[j][2], nxt[j][3]);
+      }
+    }
+  }
+  // the tile's mask bytes, one per lane
+  unsigned tile_mask = 0xffffffffu;
+  if (p.mask_out) {
+    const bool mbit = (t0 + lane < t1) ? (p.mask_out[(size_t)b * p.t_out + t0 + lane] != 0) : true;
+    tile_mask = __ballot_sync(0xffffffffu, mbit);
+  }
+  // ---- phase B: this warp's stream and row slice; the stream's constants in registers
+  constexpr int WPS = LDL2_WARPS / NS;          // warps per stream
+  const int s = warp / WPS, part = warp - s * WPS;
+  f32x2 A0[4], A1[4], A2[4], Bs[4], Wo[4], Bo[4];
+  {
+    const float* wi = p.ln_in_w[s]; const float* bi = p.ln_in_b[s]; const float* dw = p.dw_w[s];
+    const float* wo = p.ln_out_w[s]; const float* bo = p.ln_out_b[s];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = (k < 2 ? 0 : 128) + 4 * lane + 2 * (k & 1);
+      float a0[2], a1[2], a2[2], bs[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float w = __ldg(wi + c + e), bb = __ldg(bi + c + e);
+        const float d0 = __ldg(dw + 3 * (c + e)), d1 = __ldg(dw + 3 * (c + e) + 1), d2 = __ldg(dw + 3 * (c + e) + 2);
+        a0[e] = d0 * w; a1[e] = d1 * w; a2[e] = d2 * w; bs[e] = d0 * bb + d1 * bb + d2 * bb;
+      }
+      A0[k] = pk2(a0[0], a0[1]); A1[k] = pk2(a1[0], a1[1]); A2[k] = pk2(a2[0], a2[1]); Bs[k] = pk2(bs[0], bs[1]);
+      Wo[k] = pk2(__ldg(wo + c), __ldg(wo + c + 1)); Bo[k] = pk2(__ldg(bo + c), __ldg(bo + c + 1));
+    }
+  }
+  __syncthreads();
+  const int n_rows = t1 - t0;
+  const int per = ((n_rows + WPS - 1) / WPS + RPI - 1) / RPI * RPI;      // rows per warp, a multiple of RPI
+  const int ra = t0 + part * per, rb = min(ra + per, t1);
+  OutT* out_s = reinterpret_cast<OutT*>(p.out[s]);
+  for (int tb = ra; tb < rb; tb += RPI) {
+    const int w0 = STRIDE * (tb - t0);           // window row j of this iteration = xh[w0 + j] = position STRIDE tb - 1 + j
+    const int pos0 = STRIDE * tb - 1;
+    f32x2 xw[WIN][4];
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) {
+      const int pos = pos0 + j;
+      if (pos >= 0 && pos < p.t_virt && pos <= pos_last) lds8p(xh[w0 + j], lane, xw[j]);
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xw[j][k] = zero2;
+      }
+    }
+    f32x2 acc[RPI][4], st[RPI];
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      const int t = tb + r;
+      const int j0 = STRIDE * r;                 // taps: window rows j0, j0 + 1, j0 + 2
+      const bool ok0 = pos0 + j0 >= 0, ok2 = pos0 + j0 + 2 < p.t_virt;       // the centre tap is always inside
+      const bool keep = t < rb && ((tile_mask >> (t - t0)) & 1u);
+      if (!keep) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[r][k] = zero2;
+      } else if (ok0 && ok2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[r][k] = fma2(A2[k], xw[j0 + 2][k], fma2(A1[k], xw[j0 + 1][k], fma2(A0[k], xw[j0][k], Bs[k])));
+      } else {                                   // edge row: per-tap bias terms, in the first layout's order
+        f32x2 b0[4], b1[4], b2[4];
+        lds8p(eb[s][0], lane, b0); lds8p(eb[s][1], lane, b1); lds8p(eb[s][2], lane, b2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          f32x2 a = zero2;
+          if (ok0) a = add2(a, fma2(A0[k], xw[j0][k], b0[k]));
+          a = add2(a, fma2(A1[k], xw[j0 + 1][k], b1[k]));
+          if (ok2) a = add2(a, fma2(A2[k], xw[j0 + 2][k], b2[k]));
+          acc[r][k] = a;
+        }
+      }
+      const f32x2 s2 = add2(add2(acc[r][0], acc[r][1]), add2(acc[r][2], acc[r][3]));
+      f32x2 q2 = mul2(acc[r][0], acc[r][0]);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) q2 = fma2(acc[r][k], acc[r][k], q2);
+      st[r] = pk2(hsum2(s2), hsum2(q2));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < RPI; ++r) st[r] = add2(st[r], __shfl_xor_sync(0xffffffffu, st[r], o));
+    }
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      const int t = tb + r;
+      if (t >= rb) continue;
+      float su, sq;
+      upk2(st[r], su, sq);
+      const float m2 = su * (1.f / kC);
+      const float r2 = rsqrt_fast(fmaxf(sq * (1.f / kC) - m2 * m2, 0.f) + kLnEps);
+      const f32x2 rr = pk2(r2), mm = pk2(-m2 * r2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[r][k] = fma2(fma2(acc[r][k], rr, mm), Wo[k], Bo[k]);
+      store8p(out_s + ((size_t)b * p.out_rows + t) * kC, lane, acc[r]);
+    }
+    if (SKIP && s == 0) {                        // MaxPool1d(3, 2, 1) of the raw rows, -inf padding (STRIDE == 2)
+#pragma unroll
+      for (int r = 0; r < RPI; ++r) {
+        const int t = tb + r;
+        if (t >= rb) continue;
+        const int j0 = STRIDE * r;
+        const bool ok0 = pos0 + j0 >= 0, ok2 = pos0 + j0 + 2 < p.t_virt;
+        f32x2 r0[4], r1[4], r2v[4];
+        lds8p(raw[w0 + j0 + 1], lane, r1);
+        if (ok0) lds8p(raw[w0 + j0], lane, r0);
+        if (ok2) lds8p(raw[w0 + j0 + 2], lane, r2v);
+        float mx[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float m0, m1, l0, l1, h0, h1;
+          upk2(r1[k], m0, m1);
+          if (ok0) { upk2(r0[k], l0, l1); m0 = fmaxf(m0, l0); m1 = fmaxf(m1, l1); }
+          if (ok2) { upk2(r2v[k], h0, h1); m0 = fmaxf(m0, h0); m1 = fmaxf(m1, h1); }
+          mx[2 * k] = m0; mx[2 * k + 1] = m1;
+        }
+        float* so = p.skip_out + ((size_t)b * p.t_out + t) * kC;
+        store4(so + 4 * lane, mx[0], mx[1], mx[2], mx[3]);
+        store4(so + 128 + 4 * lane, mx[4], mx[5], mx[6], mx[7]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention: warp per query row, 8 lanes per head (head dim 64), online softmax in fp32
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_ROWS = 4, ATT_WARPS = 8;
@@ -1025,6 +1253,26 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   p.n_streams = a->n_streams;
   if (a->batch == 0) return AVDF_OK;
   AVDF_CHECK_ARG(a->tile_rows == 0 || a->tile_rows == 2 || a->tile_rows == 4 || a->tile_rows == 8, "tile_rows must be 0 (auto), 2, 4 or 8");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const int ldl_v1 = getenv("AVDF_LDL_V1") ? atoi(getenv("AVDF_LDL_V1")) : 0;
+  if (a->tile_rows == 0 && !ldl_v1 && a->n_streams >= 2) {
+    // second layout (see ln_dwconv_ln2_kernel): one CTA per 32 output rows of a video. Measured (batch 32, T = 768, us):
+    // three streams 30.9 -> 27.7, stride 2 39.1 -> 33.2, ONE stream 16.5 -> 18.6 (nothing to share between streams: the
+    // first layout's per-warp cp.async pipeline wins), so single-stream launches, an explicit tile_rows (tests, scripts)
+    // and AVDF_LDL_V1=1 keep the first layout
+    const int grid2 = a->batch * ((p.t_out + LDL2_ROWS - 1) / LDL2_ROWS);
+#define AVDF_LDL2(S, NS, SK)                                                                                         \
+  AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, {                                                                          \
+    const size_t smem = (size_t)(ldl2_src_rows<S>() * (SK ? 2 : 1) + NS * 3) * kC * sizeof(float);                   \
+    AVDF_SMEM_ATTR_ONCE((ln_dwconv_ln2_kernel<OutT, S, NS, SK>), smem);                                              \
+    ln_dwconv_ln2_kernel<OutT, S, NS, SK><<<grid2, LDL2_WARPS * 32, smem, st>>>(p);                                  \
+  })
+    if (a->stride == 1) { if (a->n_streams == 1) AVDF_LDL2(1, 1, false); else if (a->n_streams == 2) AVDF_LDL2(1, 2, false); else AVDF_LDL2(1, 3, false); }
+    else if (a->skip_out) { if (a->n_streams == 1) AVDF_LDL2(2, 1, true); else if (a->n_streams == 2) AVDF_LDL2(2, 2, true); else AVDF_LDL2(2, 3, true); }
+    else { if (a->n_streams == 1) AVDF_LDL2(2, 1, false); else if (a->n_streams == 2) AVDF_LDL2(2, 2, false); else AVDF_LDL2(2, 3, false); }
+#undef AVDF_LDL2
+    return check_launch("ln_dwconv_ln2_kernel");
+  }
   // rows per warp tile: the largest of 8 / 4 / 2 that still gives (almost) every resident warp a tile - shorter tiles
   // re-normalise 2 halo rows per tile but shorten the serial per-warp chain of the small pyramid levels
   const long long warp_slots = (long long)sm_count() * 3 * LDL_WARPS;
@@ -1036,7 +1284,6 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   p.rows = rows;
   const long long tiles = (long long)a->batch * ((p.t_out + rows - 1) / rows);
   const int grid = grid_for(tiles, LDL_WARPS, sm_count());
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define AVDF_LDL(S, NS)                                                                                              \
   AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, {                                                                          \
     const size_t smem = (size_t)(NS * 9 + LDL_WARPS * LDL_DEPTH) * kC * sizeof(float);                               \

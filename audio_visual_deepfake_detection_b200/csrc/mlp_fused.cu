@@ -278,6 +278,9 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
       float* out_base = p.out + (size_t)wrow * C + g * 128 + lane;
       // optional 16-bit copy of the result (the operand of the FPN lateral conv / the next level's block): same dtype as x
       unsigned short* outh_base = p.out_h ? reinterpret_cast<unsigned short*>(p.out_h) + g * 128 + lane : nullptr;
+      // destination row of this lane's row of the block (lane = row here; fetched by shuffle in the store loop)
+      int my_dr = wrow + lane;
+      if (p.out_h && p.oh_t) my_dr = (my_dr / p.oh_t) * p.oh_pitch + p.oh_row0 + (my_dr % p.oh_t);
       const int nrow = min(32, p.rows - wrow);    // rows of this warp's block inside the tensor (<= 0: none)
       float rres[32];
 #pragma unroll
@@ -316,17 +319,14 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         for (int rr = 0; rr < 32; ++rr) {         // row rr of the block: 32 lanes = 32 consecutive columns
           const float v = *reinterpret_cast<const float*>(t0 + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
           const float mrow = __shfl_sync(0xffffffffu, mk, rr);
-          if (rr < nrow) {
-            const float o = fmaf(rres[rr], mrow, v);
-            out_base[(size_t)rr * C + ch * 32] = o;
-            if (outh_base) {
-              unsigned short hb;
-              if (F16) { const __half hh = __float2half_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
-              else { const __nv_bfloat16 hh = __float2bfloat16_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
-              const int r_ = wrow + rr;
-              const size_t dr = p.oh_t ? (size_t)(r_ / p.oh_t) * p.oh_pitch + p.oh_row0 + (r_ % p.oh_t) : (size_t)r_;
-              outh_base[dr * C + ch * 32] = hb;
-            }
+          const float o = fmaf(rres[rr], mrow, v);
+          if (rr < nrow) out_base[(size_t)rr * C + ch * 32] = o;
+          if (outh_base != nullptr) {              // (warp-uniform)
+            const int dr = __shfl_sync(0xffffffffu, my_dr, rr);
+            unsigned short hb;
+            if (F16) { const __half hh = __float2half_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
+            else { const __nv_bfloat16 hh = __float2bfloat16_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
+            if (rr < nrow) outh_base[(size_t)dr * C + ch * 32] = hb;
           }
         }
         if (ch + 1 < 4) {

@@ -138,31 +138,26 @@ __device__ __forceinline__ float gelu_fast(float x) {
   // 0.5 x (1 + erf(x/sqrt2)) = x - 0.5 x erfc(z) for x >= 0, 0.5 x erfc(z) for x < 0
   return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
 }
-// The same on a packed pair, arranged for the XU (MUFU) pipe: the A&S form above costs 2 MUFU per element (rcp + ex2) and
-// the GELU epilogues were bound by exactly that pipe (scripts/gelu_pace.cu: 4 MUFU per pair = 32 XU cycles per warp against
-// 17 issue slots). Here only the Gaussian factor uses the MUFU:
-//   gelu(x) = relu(x) - |x| w,   w = Phi(-|x|) = e^{-x^2/2} R(|x|),   R(a) = erfcx(a / sqrt 2) / 2
-// R is smooth and slowly varying: a degree-8 polynomial on [0, 4.5] (Chebyshev fit, |error of gelu| <= 9.4e-6 over the
-// whole line; beyond 4.5 the argument is clamped and the Gaussian factor takes w to 0: w(4.5) = 3.4e-6). With
-// relu(x) = x/2 + |x|/2 and the sign and the 1/2 folded into the coefficients:  gelu(x) = x/2 + |x| (1/2 - w):
-// 8 + 6 packed FP ops + 2 MUFU + 2 LOP3 + 2 FMNMX per TWO elements.
+// the same on a packed pair, arranged for the fewest issue slots (the GELU MLP epilogue is bound by them):
+//   gelu(x) = relu(x) - |x| w,  w = 0.5 erfc(|x|/sqrt2) = e^{-x^2/2} t P(t) / 2,  relu(x) = x/2 + |x|/2
+//           = x/2 + |x| (1/2 - w)
+// i.e. no select on the sign of x; the 1/2 and the minus sign live in the polynomial coefficients, sqrt(1/2) and
+// log2(e)/2 in the two argument scalings: 11 packed FP ops + 4 MUFU + 2 LOP3 per TWO elements.
 __device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
   const f32x2 ax = x & 0x7fffffff7fffffffull;
-  float a0, a1, d0, d1, e0, e1;
-  upk2(ax, a0, a1);
-  const f32x2 ac = pk2(fminf(a0, 4.5f), fminf(a1, 4.5f));
+  float d0, d1, t0, t1, e0, e1;
+  upk2(fma2(ax, pk2(0.3275911f * 0.70710678118654752440f), pk2(1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
   upk2(mul2(mul2(x, pk2(-0.5f * 1.4426950408889634f)), x), d0, d1);       // -x^2/2 * log2(e)
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(d0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(d1));
-  f32x2 r = fma2(pk2(-1.034432898e-05f), ac, pk2(2.295496379e-04f));          // -R(a), Horner
-  r = fma2(r, ac, pk2(-2.218732843e-03f));
-  r = fma2(r, ac, pk2(1.243336592e-02f));
-  r = fma2(r, ac, pk2(-4.580179602e-02f));
-  r = fma2(r, ac, pk2(1.208889112e-01f));
-  r = fma2(r, ac, pk2(-2.453661710e-01f));
-  r = fma2(r, ac, pk2(3.982341290e-01f));
-  r = fma2(r, ac, pk2(-4.999817610e-01f));
-  const f32x2 u = fma2(r, pk2(e0, e1), pk2(0.5f));                          // 1/2 - w
+  const f32x2 t = pk2(t0, t1);
+  f32x2 poly = fma2(pk2(-0.5f * 1.061405429f), t, pk2(0.5f * 1.453152027f));   // -P(t)/2
+  poly = fma2(poly, t, pk2(-0.5f * 1.421413741f));
+  poly = fma2(poly, t, pk2(0.5f * 0.284496736f));
+  poly = fma2(poly, t, pk2(-0.5f * 0.254829592f));
+  const f32x2 u = fma2(mul2(poly, t), pk2(e0, e1), pk2(0.5f));           // 1/2 - w
   return fma2(ax, u, mul2(x, pk2(0.5f)));
 }
 __device__ __forceinline__ f32x2 act_tc2(f32x2 v, int act) {
