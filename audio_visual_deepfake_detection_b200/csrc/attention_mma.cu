@@ -63,6 +63,7 @@ template <typename InT, typename OutT, int AM_WARPS>
 __global__ void __launch_bounds__(AM_WARPS * 32) attention_banded_mma_kernel(const InT* __restrict__ q, const InT* __restrict__ k,
                                                                             const InT* __restrict__ v, const unsigned char* __restrict__ kv_mask,
                                                                             OutT* __restrict__ out, int B, int T, int RPV) {
+  pdl_trigger();                 // the output-projection GEMM may start its prologue now (it waits for this grid)
   constexpr bool BF16 = std::is_same<InT, __nv_bfloat16>::value;
   constexpr int HALF = 3;
   constexpr int AM_ROWS = 16 * AM_WARPS, AM_KEYS = AM_ROWS + 16;

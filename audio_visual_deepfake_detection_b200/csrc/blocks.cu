@@ -93,6 +93,7 @@ template <typename OutT> __device__ __forceinline__ void store8p(OutT* row, int 
 template <typename OutT, int STRIDE, int NS>
 __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const LdlParams p) {
   // per stream: A0, A1, A2, Bsum, B0, B1, B2, ln_out_w, ln_out_b  (9 x 256 floats)
+  pdl_trigger();                 // the projection GEMM that follows may start its prologue now (it waits for this grid)
   extern __shared__ __align__(16) float ldl_smem[];
   float (*sp)[9][kC] = reinterpret_cast<float (*)[9][kC]>(ldl_smem);                                   // [NS][9][256]
   float (*ring)[LDL_DEPTH][kC] = reinterpret_cast<float (*)[LDL_DEPTH][kC]>(ldl_smem + NS * 9 * kC);   // [warps][depth][256]
@@ -293,6 +294,7 @@ template <int STRIDE> __host__ __device__ constexpr int ldl2_rpi() { return STRI
 
 template <typename OutT, int STRIDE, int NS, bool SKIP>
 __global__ void __launch_bounds__(LDL2_WARPS * 32, 2) ln_dwconv_ln2_kernel(const LdlParams p) {
+  pdl_trigger();                 // the projection GEMM that follows may start its prologue now (it waits for this grid)
   constexpr int SRC = ldl2_src_rows<STRIDE>();
   constexpr int RPI = ldl2_rpi<STRIDE>();
   constexpr int WIN = STRIDE * (RPI - 1) + 3;         // window rows of one iteration
@@ -653,6 +655,7 @@ constexpr int LNR_ROWS = 2;
 template <typename OutT, int NCH>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bvec, OutT* __restrict__ out, long long rows) {
+  pdl_trigger();                 // the fused MLP that follows may start its prologue now (it waits for this grid)
   const int lane = threadIdx.x & 31;
   const int C = kC * NCH;
   for (long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * LNR_ROWS; r0 < rows; r0 += (long long)gridDim.x * 8 * LNR_ROWS) {

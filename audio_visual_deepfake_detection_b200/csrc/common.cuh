@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 #include "../../include/avdf.h"
 
@@ -133,6 +134,26 @@ __device__ __forceinline__ float load1(const __half* p) { return __half2float(*p
   AVDF_CHECK_ARG((dt) == AVDF_DTYPE_F32 || (dt) == AVDF_DTYPE_BF16 || (dt) == AVDF_DTYPE_F16, what)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch (PDL). A kernel launched through launch_pdl() may start while the previous kernel of
+// the stream is still running - as soon as every CTA of that kernel has executed pdl_trigger() or exited - and must
+// execute pdl_wait() before it touches anything the previous kernel wrote (the wait returns when the previous grid has
+// completed and its memory is visible). What runs before pdl_wait() - barrier initialisation, TMEM allocation,
+// tensor-map prefetch, loads of weights - overlaps the previous kernel's tail. Kernels launched normally are unaffected
+// by pdl_trigger(). AVDF_PDL=0 switches the launch attribute off (plain stream order).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- per-device host state (runtime.cu). A process may drive several GPUs (the reference yaml ships devices:
 // ['cuda:3']): the SM count and the "opt-in shared-memory attribute already set" flags are properties of the CURRENT

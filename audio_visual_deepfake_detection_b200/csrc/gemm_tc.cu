@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (warp == 0) AVDF_TS(1);
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; its outputs (A, residual) are
+  // touched only from here on. Our own dependents may start their prologue right away.
+  pdl_trigger();
+  pdl_wait();
 
   const int kb_per_tap = p.c_in / BK;
   const int k_iters = p.taps * kb_per_tap;
@@ -755,9 +759,10 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr);
   const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
   bool launched = false;
-#define AVDF_LAUNCH(M, O) if (!launched && !ws && !w8 && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O><<<grid, THREADS, smem_bytes, st>>>(p); launched = true; }
-#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, 1><<<grid, WS_THREADS, smem_bytes, st>>>(p); launched = true; }
-#define AVDF_LAUNCH_W8(M, O) if (!launched && w8 && mode == (M) && outk == (O)) { conv_gemm_tc_kernel<M, O, 2><<<grid, WS_THREADS, smem_bytes, st>>>(p); launched = true; }
+  cudaError_t lerr = cudaSuccess;
+#define AVDF_LAUNCH(M, O) if (!launched && !ws && !w8 && mode == (M) && outk == (O)) { lerr = launch_pdl(conv_gemm_tc_kernel<M, O>, grid, THREADS, smem_bytes, st, p); launched = true; }
+#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { lerr = launch_pdl(conv_gemm_tc_kernel<M, O, 1>, grid, WS_THREADS, smem_bytes, st, p); launched = true; }
+#define AVDF_LAUNCH_W8(M, O) if (!launched && w8 && mode == (M) && outk == (O)) { lerr = launch_pdl(conv_gemm_tc_kernel<M, O, 2>, grid, WS_THREADS, smem_bytes, st, p); launched = true; }
   AVDF_TC_VARIANTS(AVDF_LAUNCH)
   AVDF_TC_WS_VARIANTS(AVDF_LAUNCH_WS)
   AVDF_TC_W8_VARIANTS(AVDF_LAUNCH_W8)
@@ -765,10 +770,11 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
 #undef AVDF_LAUNCH_WS
 #undef AVDF_LAUNCH_W8
   if (!launched) {
-    if (ws) conv_gemm_tc_kernel<-1, -1, 1><<<grid, WS_THREADS, smem_bytes, st>>>(p);
-    else if (w8) conv_gemm_tc_kernel<-1, -1, 2><<<grid, WS_THREADS, smem_bytes, st>>>(p);
-    else conv_gemm_tc_kernel<-1, -1><<<grid, THREADS, smem_bytes, st>>>(p);
+    if (ws) lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1, 1>, grid, WS_THREADS, smem_bytes, st, p);
+    else if (w8) lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1, 2>, grid, WS_THREADS, smem_bytes, st, p);
+    else lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1>, grid, THREADS, smem_bytes, st, p);
   }
+  if (lerr != cudaSuccess) { set_error("conv_gemm_tc_kernel: launch failed: %s", cudaGetErrorString(lerr)); return AVDF_ERR_CUDA; }
   return check_launch("conv_gemm_tc_kernel");
 }
 

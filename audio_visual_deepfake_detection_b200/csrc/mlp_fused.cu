@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tm_acc2 = tmem_base + 256u;
+  // programmatic dependent launch: the prologue above (barriers, TMEM, bias vectors) overlapped the previous kernel's tail
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -407,7 +410,8 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   AVDF_SMEM_ATTR_ONCE(mlp_fused_kernel<false>, SMEM_BYTES);
   const int grid = p.tiles < sms ? p.tiles : sms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (f16) mlp_fused_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p);
-  else mlp_fused_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  const cudaError_t lerr = f16 ? launch_pdl(mlp_fused_kernel<true>, grid, THREADS, SMEM_BYTES, st, p)
+                               : launch_pdl(mlp_fused_kernel<false>, grid, THREADS, SMEM_BYTES, st, p);
+  if (lerr != cudaSuccess) { set_error("mlp_fused_kernel: launch failed: %s", cudaGetErrorString(lerr)); return AVDF_ERR_CUDA; }
   return check_launch("mlp_fused_kernel");
 }

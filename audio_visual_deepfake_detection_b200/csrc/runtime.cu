@@ -1,6 +1,7 @@
 // Error plumbing and device queries of the C-ABI.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace avdf {
@@ -21,6 +22,11 @@ int check_launch(const char* what) {
   }
   return AVDF_OK;
 }
+bool pdl_enabled() {
+  static const int on = getenv("AVDF_PDL") ? atoi(getenv("AVDF_PDL")) : 1;
+  return on != 0;
+}
+
 int current_device() {
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
