@@ -3,14 +3,28 @@
 // The two GEMMs of the unfused path (256 -> 1024 with a GELU epilogue, 1024 -> 256 with the residual epilogue) move the
 // [rows, 1024] hidden activations through L2/HBM twice and re-read their operands per 128x128 tile; here a CTA owns
 // 128 rows, keeps x resident in shared memory and walks the hidden dimension in chunks of 128:
-//     G1(j): acc1[j & 1] (TMEM, 128 cols)  = x . W1[j]^T                        4 K-slices of 64
+//     G1(j): acc1[j & 1] (TMEM, 128 cols)  = x . W1[j]^T                        K = 256
 //     E1(j): TMEM -> +b1 -> GELU -> 16-bit -> shared memory, in the K-major 128B-swizzled layout tcgen05.mma reads
-//     G2(j): acc2 (TMEM, 256 cols)        += h_j . W2[:, j]^T                   2 output halves x 2 K-slices of 64
-// so the hidden activations never leave the SM. 384 threads: warp 0 TMA producer (x tile + a 5-slot ring of 16 KB weight
-// tiles), warp 1 MMA issuer (G1(j+1) is issued before G2(j): the tensor pipe works while the epilogue warps run GELU
-// on chunk j), warp 2 TMEM allocator, warps 4-11 epilogue (two warpgroups: TMEM lane quarter = warp % 4, column half
-// = warpgroup). Final epilogue: acc2 -> +b2, mask, gamma, residual (TMA-loaded into the tile the result leaves from,
-// double-buffered) -> TMA store. Per 128-row tile the SM reads 64 KB of x and 1 MB of weights (L2-resident).
+//     G2(j): acc2 (TMEM, 256 cols)        += h_j . W2[:, j]^T                   K = 128
+// so the hidden activations never leave the SM.
+//
+// The kernel runs as clusters of TWO CTAs on the two SMs of a TPC and issues cta_group::2 MMAs (M = 256: 128 rows per
+// CTA). Each CTA keeps its own x / hidden tiles and accumulators but loads only HALF of every weight tile (64 of the 128
+// W1 rows of a chunk, 128 of the 256 W2 rows): per 128 rows an SM ingests 0.5 MB of weights instead of 1 MB and the
+// tensor core reads 6-8 KB instead of 8 KB of shared memory per instruction. The single-CTA version of this kernel was
+// bound by exactly that: its globaltimer stamps showed the MMA warp issuing back to back at ~70 ns per 128x128x16
+// instruction (35 ns when nothing else uses shared memory) - operand reads (256 KB per chunk) + TMA writes (128 KB) + the
+// epilogue's stores were ~420 KB per chunk against 128 B/clk of shared-memory bandwidth (profiles/README.md, round 2).
+// Barriers the MMA warp WAITS on live in the leader CTA (cluster rank 0): both CTAs' TMA loads credit their bytes there
+// (cp.async.bulk.tensor .cta_group::2) and both CTAs' epilogue warps arrive there (mapa + mbarrier.arrive
+// .shared::cluster); barriers the MMA warp SIGNALS are reached in both CTAs by multicast commits.
+//
+// 384 threads per CTA: warp 0 TMA producer (x tile + a 5-slot ring of 16 KB weight half-tiles), warp 1 MMA issuer (leader
+// CTA only; G1(j+1) is issued before G2(j): the tensor pipe works while the epilogue warps run GELU on chunk j), warp 2
+// TMEM allocator, warps 4-11 epilogue (two warpgroups: TMEM lane quarter = warp % 4, column half = warpgroup). Final
+// epilogue: acc2 -> +b2, mask, gamma, + residual, thread = row in the TMEM-native layout: the residual block arrives by TMA
+// in the swizzled 4 KB tile the result leaves from (two tiles per warp, the first residual block is fetched while the
+// chunk loop still runs), global memory is touched by TMA only (rows beyond the tensor are clipped by the tensor map).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,23 +37,32 @@ using namespace tc;
 
 constexpr int C = 256, HID = 1024, BM = 128, HC = 128, NCHUNK = HID / HC;
 constexpr int UNIT = 128 * 64 * 2;            // one [128 rows x 64 K] 16-bit operand tile, 128B-swizzled
-constexpr int RING = 7;
-constexpr int THREADS = 384;
+constexpr int RING = 5;                       // a chunk needs 4 slots (2 of W1, 2 of W2)
+#ifndef AVDF_MLP_GELU_WARPS
+#define AVDF_MLP_GELU_WARPS 8
+#endif
+constexpr int EPI_WARPS = 8;                  // warps of the final epilogue (two per TMEM lane quarter: 128 columns each)
+constexpr int GELU_WARPS = AVDF_MLP_GELU_WARPS;   // warps of the per-chunk GELU epilogue: 8 (64 hidden columns each) or 16 (32 each)
+static_assert(GELU_WARPS == 8 || GELU_WARPS == 16, "GELU warps");
+constexpr int GCOLS = HC / (GELU_WARPS / 4);  // hidden columns of a chunk per GELU warp
+constexpr int THREADS = 128 + GELU_WARPS * 32;
 // shared memory (offsets from a 1024-aligned base)
 constexpr int OFF_X = 0;                      // 4 units
-constexpr int OFF_H = OFF_X + 4 * UNIT;       // 2 units (the hidden chunk); the final epilogue reuses them as 8 x 4 KB transposition tiles
-constexpr int OFF_RING = OFF_H + 2 * UNIT;    // RING units
-constexpr int OFF_VEC = OFF_RING + RING * UNIT;     // b1[1024], b2[256], gamma[256]
+constexpr int OFF_H = OFF_X + 4 * UNIT;       // 2 units (the hidden chunk); the final epilogue reuses them as 8 x 4 KB tiles
+constexpr int OFF_STG = OFF_H + 2 * UNIT;     // 8 x 4 KB: every epilogue warp's first residual / result tile
+constexpr int OFF_RING = OFF_STG + EPI_WARPS * 4096;   // RING units
+constexpr int OFF_VEC = OFF_RING + RING * UNIT;        // b1[1024], b2[256], gamma[256]
 constexpr int OFF_BAR = OFF_VEC + (HID + 2 * C) * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;    // + alignment slack
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;       // + alignment slack
 
 struct Params {
-  CUtensorMap x_map, w1_map, w2_map;
-  const float* residual; float* out; void* out_h;
+  CUtensorMap x_map, w1_map, w2_map;   // boxes: x (64, 128), W1 (64, 64 rows: this CTA's half of a chunk), W2 (64, 128 rows)
+  CUtensorMap res_map, out_map;        // fp32 [rows, 256], box (32 columns, 32 rows), swizzle 128B
+  void* out_h;
   const float* b1; const float* b2; const float* gamma; const unsigned char* row_mask;
   int rows, tiles;
   int oh_t, oh_pitch, oh_row0;  // 16-bit copy: row r = b * oh_t + t lands at row b * oh_pitch + oh_row0 + t (oh_t = 0: dense)
-  unsigned idesc;
+  unsigned idesc, idesc2;       // M 256 x N 128 (G1), M 256 x N 256 (G2)
   unsigned long long* dbg;      // optional (debug hook): globaltimer stamps of CTA 0's first tile, 3 x 96 slots
 };
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -47,7 +70,8 @@ __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t;
 
 // barrier slots
 enum { B_XFULL = 0, B_XEMPTY, B_RFULL, B_REMPTY = B_RFULL + RING, B_A1FULL = B_REMPTY + RING, B_A1EMPTY = B_A1FULL + 2,
-       B_HFULL = B_A1EMPTY + 2, B_HEMPTY, B_A2FULL, B_A2EMPTY, B_COUNT };
+       B_HFULL = B_A1EMPTY + 2, B_HEMPTY, B_A2FULL, B_A2EMPTY, B_RES, B_COUNT = B_RES + 2 * EPI_WARPS };
+static_assert(B_COUNT * 8 + 8 <= 512, "barrier block");
 
 template <bool F16>
 __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_constant__ Params p) {
@@ -55,6 +79,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* sx = smem + OFF_X;
   unsigned char* sh = smem + OFF_H;
+  unsigned char* sstg = smem + OFF_STG;
   unsigned char* sring = smem + OFF_RING;
   float* s_b1 = reinterpret_cast<float*>(smem + OFF_VEC);
   float* s_b2 = s_b1 + HID;
@@ -64,6 +89,11 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
   const uint32_t bar_base = smem_u32(bars);
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rank of this CTA in its pair; the unit of the tile loop is a PAIR of 128-row tiles (tile 2u + rank is this CTA's)
+  const uint32_t rank = cluster_ctarank();
+  const int unit0 = (int)(blockIdx.x >> 1), unit_step = (int)(gridDim.x >> 1), n_units = (p.tiles + 1) / 2;
+  // barrier `i` of the leader CTA as a shared::cluster address (the barriers the MMA warp waits on)
+  auto lbar = [&](int i) { return mapa_rank(bar(i), 0u); };
   // hidden chunk handled in step j: the same order in every CTA, so a row's fp32 accumulation order (and with it the
   // result bits) does not depend on which tile / CTA the row falls into (batch invariance). Rotating the order per CTA
   // to spread the weight reads over L2 slices was measured: no gain.
@@ -73,28 +103,31 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.x_map) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.w1_map) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.w2_map) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.res_map) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.out_map) : "memory");
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_XEMPTY), 1);
     for (int s = 0; s < RING; ++s) { mbar_init(bar(B_RFULL + s), 1); mbar_init(bar(B_REMPTY + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar(B_A1FULL + s), 1); mbar_init(bar(B_A1EMPTY + s), 8); }
-    mbar_init(bar(B_HFULL), 8); mbar_init(bar(B_HEMPTY), 1);
-    mbar_init(bar(B_A2FULL), 1); mbar_init(bar(B_A2EMPTY), 8);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(B_A1FULL + s), 1); mbar_init(bar(B_A1EMPTY + s), 2 * GELU_WARPS); }
+    mbar_init(bar(B_HFULL), 2 * GELU_WARPS); mbar_init(bar(B_HEMPTY), 1);
+    mbar_init(bar(B_A2FULL), 1); mbar_init(bar(B_A2EMPTY), 2 * EPI_WARPS);
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(bar(B_RES + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 2) {       // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   if (warp >= 4) {                               // per-channel vectors, once per CTA
-    for (int i = threadIdx.x - 128; i < HID; i += 256) s_b1[i] = p.b1 ? __ldg(p.b1 + i) : 0.f;
-    for (int i = threadIdx.x - 128; i < C; i += 256) {
+    for (int i = threadIdx.x - 128; i < HID; i += GELU_WARPS * 32) s_b1[i] = p.b1 ? __ldg(p.b1 + i) : 0.f;
+    for (int i = threadIdx.x - 128; i < C; i += GELU_WARPS * 32) {
       s_b2[i] = p.b2 ? __ldg(p.b2 + i) : 0.f;
       s_gam[i] = p.gamma ? __ldg(p.gamma + i) : 1.f;
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();                            // the peer's barriers are initialised before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tm_acc2 = tmem_base + 256u;
@@ -103,195 +136,218 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
   pdl_wait();
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
+    // ---------------------------------------------------------------- TMA producer (both CTAs)
     // (whole warp in the loop, one elected lane issues from warp-uniform code: elect_one() in tc_ptx.cuh)
+    // A ring slot (16 KB) holds this CTA's half of one MMA group's B operand: two K slices of 64 W1 rows (G1) or one K
+    // slice of 128 W2 rows (G2). The bytes of both CTAs are credited to the LEADER's full barrier (its producer posts the
+    // expected 32 KB); slots are released in both CTAs by multicast commits.
     const bool leader = elect_one();
-    {
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      int nu = 0;
-      auto load_unit = [&](const CUtensorMap* map, int c0, int c1) {
-        mbar_wait(bar(B_REMPTY + stage), phase ^ 1);
-        MLPF_TS(0, 1 + nu); ++nu;
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    int nu = 0;
+    auto begin_slot = [&]() -> uint32_t {
+      mbar_wait(bar(B_REMPTY + stage), phase ^ 1);
+      MLPF_TS(0, 1 + nu); ++nu;
+      if (leader && rank == 0) mbar_arrive_expect_tx(bar(B_RFULL + stage), 2 * UNIT);
+      return lbar(B_RFULL + stage);
+    };
+    auto end_slot = [&]() { __syncwarp(); if (++stage == RING) { stage = 0; phase ^= 1; } };
+    auto load_w1 = [&](int chunk, int u) {       // K slices 2u, 2u + 1 of this CTA's 64 rows of W1 chunk `chunk`
+      const uint32_t fb = begin_slot();
+      if (leader) {
+        tma_load_2d_pair(smem_u32(sring + stage * UNIT), &p.w1_map, fb, (2 * u) * 64, chunk * HC + (int)rank * 64);
+        tma_load_2d_pair(smem_u32(sring + stage * UNIT + UNIT / 2), &p.w1_map, fb, (2 * u + 1) * 64, chunk * HC + (int)rank * 64);
+      }
+      end_slot();
+    };
+    auto load_w2 = [&](int chunk, int sl) {      // K slice sl of this CTA's 128 rows of W2[:, chunk]
+      const uint32_t fb = begin_slot();
+      if (leader) tma_load_2d_pair(smem_u32(sring + stage * UNIT), &p.w2_map, fb, chunk * HC + sl * 64, (int)rank * 128);
+      end_slot();
+    };
+    for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      const int tile = 2 * unit + (int)rank;
+      mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);
+      nu = 0;
+      MLPF_TS(0, 0);
+      if (leader) {
+        if (rank == 0) mbar_arrive_expect_tx(bar(B_XFULL), 8 * UNIT);
+        const uint32_t xb = lbar(B_XFULL);
+        for (int s = 0; s < 4; ++s) tma_load_2d_pair(smem_u32(sx + s * UNIT), &p.x_map, xb, s * 64, tile * BM);
+      }
+      __syncwarp();
+      for (int u = 0; u < 2; ++u) load_w1(chunk_of(0), u);
+      for (int j = 0; j < NCHUNK; ++j) {
+        if (j + 1 < NCHUNK)
+          for (int u = 0; u < 2; ++u) load_w1(chunk_of(j + 1), u);
+        for (int sl = 0; sl < 2; ++sl) load_w2(chunk_of(j), sl);
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ---------------------------------------------------------------- MMA issuer (leader CTA, for both CTAs)
+    // G1(j): 2 ring slots x 2 K slices x 4 instructions of 256 x 128 x 16; G2(j): 2 ring slots x 4 instructions of
+    // 256 x 256 x 16 (each CTA holds half of the B rows at the same shared-memory offsets)
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    uint32_t n_a1[2] = {0, 0}, n_h = 0;
+    auto g1 = [&](int j) {
+      const int b = j & 1;
+      mbar_wait(bar(B_A1EMPTY + b), (n_a1[b] & 1) ^ 1);
+      tcgen05_fence_after();
+      for (int u = 0; u < 2; ++u) {
+        mbar_wait(bar(B_RFULL + stage), phase);
+        tcgen05_fence_after();
         if (leader) {
-          mbar_arrive_expect_tx(bar(B_RFULL + stage), UNIT);
-          tma_load_2d(smem_u32(sring + stage * UNIT), map, bar(B_RFULL + stage), c0, c1);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t da = make_sw128_desc(smem_u32(sx + (2 * u + ks) * UNIT));
+            const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT + ks * (UNIT / 2)));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_pair(tmem_base + (uint32_t)(b * HC), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (u > 0 || ks > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(bar(B_REMPTY + stage));
+          if (u == 1) umma_commit_pair(bar(B_A1FULL + b));
         }
         __syncwarp();
         if (++stage == RING) { stage = 0; phase ^= 1; }
-      };
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);
-        nu = 0;
-        MLPF_TS(0, 0);
-        if (leader) {
-          mbar_arrive_expect_tx(bar(B_XFULL), 4 * UNIT);
-          for (int s = 0; s < 4; ++s) tma_load_2d(smem_u32(sx + s * UNIT), &p.x_map, bar(B_XFULL), s * 64, tile * BM);
-        }
-        __syncwarp();
-        for (int s = 0; s < 4; ++s) load_unit(&p.w1_map, s * 64, chunk_of(0) * HC);
-        for (int j = 0; j < NCHUNK; ++j) {
-          if (j + 1 < NCHUNK)
-            for (int s = 0; s < 4; ++s) load_unit(&p.w1_map, s * 64, chunk_of(j + 1) * HC);
-          for (int h = 0; h < 2; ++h)
-            for (int s = 0; s < 2; ++s) load_unit(&p.w2_map, chunk_of(j) * HC + s * 64, h * 128);
-        }
       }
-    }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    const bool leader = elect_one();
-    {
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      uint32_t n_a1[2] = {0, 0}, n_h = 0;
-      auto g1 = [&](int j) {
-        const int b = j & 1;
-        mbar_wait(bar(B_A1EMPTY + b), (n_a1[b] & 1) ^ 1);
+      ++n_a1[b];
+    };
+    for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      mbar_wait(bar(B_XFULL), (uint32_t)(it & 1));
+      tcgen05_fence_after();
+      MLPF_TS(1, 0);
+      g1(0);
+      MLPF_TS(1, 1);
+      for (int j = 0; j < NCHUNK; ++j) {
+        if (j + 1 < NCHUNK) g1(j + 1);
+        MLPF_TS(1, 2 + 4 * j);                  // G1(j+1) issued
+        if (j == NCHUNK - 2 && leader) umma_commit_pair(bar(B_XEMPTY));   // every G1 of this tile is issued: x may be replaced
+        if (j == 0) { mbar_wait(bar(B_A2EMPTY), (uint32_t)(it & 1) ^ 1); tcgen05_fence_after(); }
+        mbar_wait(bar(B_HFULL), n_h & 1);
         tcgen05_fence_after();
-        for (int s = 0; s < 4; ++s) {
+        MLPF_TS(1, 3 + 4 * j);                  // hidden chunk j ready
+        for (int sl = 0; sl < 2; ++sl) {
           mbar_wait(bar(B_RFULL + stage), phase);
           tcgen05_fence_after();
           if (leader) {
-            const uint64_t da = make_sw128_desc(smem_u32(sx + s * UNIT));
+            const uint64_t da = make_sw128_desc(smem_u32(sh + sl * UNIT));
             const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + (uint32_t)(b * HC), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (s > 0 || k > 0) ? 1u : 0u);
-            umma_commit(bar(B_REMPTY + stage));
-            if (s == 3) umma_commit(bar(B_A1FULL + b));
+              umma_bf16_pair(tm_acc2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc2, (j > 0 || sl > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(bar(B_REMPTY + stage));
           }
           __syncwarp();
           if (++stage == RING) { stage = 0; phase ^= 1; }
         }
-        ++n_a1[b];
-      };
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        mbar_wait(bar(B_XFULL), (uint32_t)(it & 1));
-        tcgen05_fence_after();
-        MLPF_TS(1, 0);
-        g1(0);
-        MLPF_TS(1, 1);
-        for (int j = 0; j < NCHUNK; ++j) {
-          if (j + 1 < NCHUNK) g1(j + 1);
-          MLPF_TS(1, 2 + 4 * j);                  // G1(j+1) issued
-          if (j == NCHUNK - 2 && leader) umma_commit(bar(B_XEMPTY));   // every G1 of this tile is issued: x may be replaced
-          if (j == 0) { mbar_wait(bar(B_A2EMPTY), (uint32_t)(it & 1) ^ 1); tcgen05_fence_after(); }
-          mbar_wait(bar(B_HFULL), n_h & 1);
-          tcgen05_fence_after();
-          MLPF_TS(1, 3 + 4 * j);                  // hidden chunk j ready
-          for (int h = 0; h < 2; ++h) {
-            for (int s = 0; s < 2; ++s) {
-              mbar_wait(bar(B_RFULL + stage), phase);
-              tcgen05_fence_after();
-              if (leader) {
-                const uint64_t da = make_sw128_desc(smem_u32(sh + s * UNIT));
-                const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(tm_acc2 + (uint32_t)(h * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (j > 0 || s > 0 || k > 0) ? 1u : 0u);
-                umma_commit(bar(B_REMPTY + stage));
-              }
-              __syncwarp();
-              if (++stage == RING) { stage = 0; phase ^= 1; }
-            }
-          }
-          if (leader) {
-            umma_commit(bar(B_HEMPTY));
-            if (j == NCHUNK - 1) umma_commit(bar(B_A2FULL));
-          }
-          __syncwarp();
-          ++n_h;
-          MLPF_TS(1, 4 + 4 * j);                  // G2(j) issued
+        if (leader) {
+          umma_commit_pair(bar(B_HEMPTY));
+          if (j == NCHUNK - 1) umma_commit_pair(bar(B_A2FULL));
         }
+        __syncwarp();
+        ++n_h;
+        MLPF_TS(1, 4 + 4 * j);                  // G2(j) issued
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- epilogue warps
-    const int wi = warp - 4;                    // 0..7
+    // ---------------------------------------------------------------- epilogue warps (both CTAs)
+    const int wi = warp - 4;                    // 0..GELU_WARPS-1
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
-    const int g = wi >> 2;                      // column half (warpgroup)
+    const int cg = wi >> 2;                     // GELU: this warp's group of GCOLS hidden columns of a chunk
+    const int g = cg & 1;                       // final epilogue (warps 0..7): column half
+    const bool fin = wi < EPI_WARPS;            // takes part in the final epilogue
     const int r = q * 32 + lane;                // tile row owned by this thread
     const int sw7 = lane & 7;                   // (r & 7) == (lane & 7)
-    unsigned char* t0 = sh + wi * 4096;         // final epilogue: this warp's 32 x 32 fp32 transposition tile, a slice of the
-                                                // hidden tile (free once acc2 is complete)
+    // final epilogue: this warp's two 32 x 32 fp32 tiles (128B-swizzled rows). tA is the warp's own all the time; tB is a
+    // slice of the hidden tile, free from the moment acc2 is complete until the next tile's first hidden chunk
+    unsigned char* tA = sstg + (wi & 7) * 4096;
+    unsigned char* tB = sh + (wi & 7) * 4096;
+    const uint32_t res_bar[2] = {bar(B_RES + 2 * (wi & 7)), bar(B_RES + 2 * (wi & 7) + 1)};
+    uint32_t res_phase[2] = {0, 0};
+    const uint32_t a1empty_bar[2] = {lbar(B_A1EMPTY), lbar(B_A1EMPTY + 1)};
+    const uint32_t hfull_bar = lbar(B_HFULL), a2empty_bar = lbar(B_A2EMPTY);
     uint32_t n_a1[2] = {0, 0}, n_h = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      const int tile = 2 * unit + (int)rank;
       const int row = tile * BM + r;
       float mk = 1.f;
       if (p.row_mask) mk = (row < p.rows && __ldg(p.row_mask + row)) ? 1.f : 0.f;
       const int wrow = tile * BM + q * 32;      // first row of this warp's 32-row boxes
+      const int col0 = g * 128;                 // first of this warp's 128 output columns
+      auto fetch_residual = [&](int ch) {       // lane 0: residual block of chunk ch -> tile ch & 1
+        mbar_arrive_expect_tx(res_bar[ch & 1], 4096);
+        tma_load_2d(smem_u32((ch & 1) ? tB : tA), &p.res_map, res_bar[ch & 1], col0 + ch * 32, wrow);
+      };
+      if (fin && lane == 0) fetch_residual(0);  // tA was drained at the end of the previous tile
       for (int j = 0; j < NCHUNK; ++j) {
         const int b = j & 1;
         mbar_wait(bar(B_A1FULL + b), n_a1[b] & 1);
         ++n_a1[b];
         tcgen05_fence_after();
         if (wi == 0 && lane == 0) MLPF_TS(2, 4 * j);          // acc1 chunk j complete
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * HC + g * 64);
-        uint32_t va[32], vb[32];
-        tmem_ld32_issue(taddr, va);
-        tmem_ld32_issue(taddr + 32, vb);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * HC + cg * GCOLS);
+        uint32_t va[GCOLS];
+        tmem_ld32_issue(taddr, *reinterpret_cast<uint32_t(*)[32]>(va));
+        if (GCOLS == 64) tmem_ld32_issue(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(va + GCOLS - 32));
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_A1EMPTY + b));
-        unsigned char* hrow = sh + g * UNIT + r * 128;   // this warpgroup's 64 hidden columns = K-slice g of the chunk
-        const float* bias = s_b1 + chunk_of(j) * HC + g * 64;
-        uint4 hv[8];                              // the row's 64 activations, 16-bit: computed before the buffer is free
+        if (lane == 0) mbar_arrive_cluster(a1empty_bar[b]);
+        // this warp's GCOLS hidden columns inside the chunk's K-major tile: K slice (64 columns) and first 16-byte slot
+        unsigned char* hrow = sh + ((cg * GCOLS) >> 6) * UNIT + r * 128;
+        const int slot0 = ((cg * GCOLS) & 63) >> 3;
+        const float* bias = s_b1 + chunk_of(j) * HC + cg * GCOLS;
+        uint4 hv[GCOLS / 8];                      // the row's activations, 16-bit: computed before the buffer is free
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t* vv = half == 0 ? va : vb;
-          const float4* b4 = reinterpret_cast<const float4*>(bias + half * 32);
+        for (int jj = 0; jj < GCOLS / 8; ++jj) { // 8 columns -> one 16-byte chunk of the 128 B row
+          f32x2 y[4];
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {       // 8 columns -> one 16-byte chunk of the 128 B row
-            f32x2 y[4];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float4 bb = b4[2 * jj + u];
-              y[2 * u] = gelu_fast2(add2(pk2(__uint_as_float(vv[8 * jj + 4 * u]), __uint_as_float(vv[8 * jj + 4 * u + 1])), pk2(bb.x, bb.y)));
-              y[2 * u + 1] = gelu_fast2(add2(pk2(__uint_as_float(vv[8 * jj + 4 * u + 2]), __uint_as_float(vv[8 * jj + 4 * u + 3])), pk2(bb.z, bb.w)));
-            }
-            uint4 uo;
-            float f0, f1;
-            if (F16) {
-              upk2(y[0], f0, f1); uo.x = pack_f16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_f16x2(f0, f1);
-              upk2(y[2], f0, f1); uo.z = pack_f16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_f16x2(f0, f1);
-            } else {
-              upk2(y[0], f0, f1); uo.x = pack_bf16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_bf16x2(f0, f1);
-              upk2(y[2], f0, f1); uo.z = pack_bf16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_bf16x2(f0, f1);
-            }
-            hv[half * 4 + jj] = uo;
+          for (int u = 0; u < 2; ++u) {
+            const float4 bb = b4[2 * jj + u];
+            y[2 * u] = gelu_poly2(add2(pk2(__uint_as_float(va[8 * jj + 4 * u]), __uint_as_float(va[8 * jj + 4 * u + 1])), pk2(bb.x, bb.y)));
+            y[2 * u + 1] = gelu_poly2(add2(pk2(__uint_as_float(va[8 * jj + 4 * u + 2]), __uint_as_float(va[8 * jj + 4 * u + 3])), pk2(bb.z, bb.w)));
           }
+          uint4 uo;
+          float f0, f1;
+          if (F16) {
+            upk2(y[0], f0, f1); uo.x = pack_f16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_f16x2(f0, f1);
+            upk2(y[2], f0, f1); uo.z = pack_f16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_f16x2(f0, f1);
+          } else {
+            upk2(y[0], f0, f1); uo.x = pack_bf16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_bf16x2(f0, f1);
+            upk2(y[2], f0, f1); uo.z = pack_bf16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_bf16x2(f0, f1);
+          }
+          hv[jj] = uo;
         }
         if (wi == 0 && lane == 0) MLPF_TS(2, 4 * j + 1);      // GELU math done
         mbar_wait(bar(B_HEMPTY), (n_h & 1) ^ 1);           // G2 of the previous chunk has read the hidden tile
         ++n_h;
         if (wi == 0 && lane == 0) MLPF_TS(2, 4 * j + 2);      // hidden buffer free
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(hrow + ((c ^ sw7) << 4)) = hv[c];
+        for (int c = 0; c < GCOLS / 8; ++c) *reinterpret_cast<uint4*>(hrow + (((slot0 + c) ^ sw7) << 4)) = hv[c];
         fence_async_smem();                       // generic-proxy writes -> visible to tcgen05.mma (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_HFULL));
+        if (lane == 0) mbar_arrive_cluster(hfull_bar);
         if (wi == 0 && lane == 0) MLPF_TS(2, 4 * j + 3);      // hidden chunk published
       }
-      // ---- final epilogue: this warp's 32 rows x 128 columns of acc2 in 4 chunks of 32 columns.
-      //      thread = row for the TMEM read and the per-row mask; the chunk is transposed through a 4 KB swizzled tile so
-      //      that the residual loads and the output stores are plain coalesced 128-byte rows (lane = column), the
-      //      residual of the next chunk being in flight (registers) while this one is computed
-      const float* res_base = p.residual + (size_t)wrow * C + g * 128 + lane;
-      float* out_base = p.out + (size_t)wrow * C + g * 128 + lane;
-      // optional 16-bit copy of the result (the operand of the FPN lateral conv / the next level's block): same dtype as x
-      unsigned short* outh_base = p.out_h ? reinterpret_cast<unsigned short*>(p.out_h) + g * 128 + lane : nullptr;
-      // destination row of this lane's row of the block (lane = row here; fetched by shuffle in the store loop)
-      int my_dr = wrow + lane;
-      if (p.out_h && p.oh_t) my_dr = (my_dr / p.oh_t) * p.oh_pitch + p.oh_row0 + (my_dr % p.oh_t);
-      const int nrow = min(32, p.rows - wrow);    // rows of this warp's block inside the tensor (<= 0: none)
-      float rres[32];
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr) rres[rr] = rr < nrow ? __ldg(res_base + (size_t)rr * C) : 0.f;
+      // ---- final epilogue: this warp's 32 rows x 128 columns of acc2 in 4 chunks of 32 columns, thread = row.
+      //      chunk c lives in tile c & 1: residual in (TMA), updated in place, result out (TMA); the residual of chunk
+      //      c + 1 is in flight while chunk c is computed, the one of chunk c + 2 is fetched once chunk c's store has
+      //      read the tile
+      if (fin) {
       mbar_wait(bar(B_A2FULL), (uint32_t)(it & 1));
       tcgen05_fence_after();
       if (wi == 0 && lane == 0) MLPF_TS(2, 40);
-      const uint32_t taddr2 = tm_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 128);
+      if (lane == 0) fetch_residual(1);           // the hidden tile (tB) is free now
+      const uint32_t taddr2 = tm_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+      // optional 16-bit copy of the result (the operand of the FPN lateral conv / the next level's block): same dtype as x;
+      // rows leave transposed (lane = column) as 64-byte row pieces
+      unsigned short* outh_base = p.out_h ? reinterpret_cast<unsigned short*>(p.out_h) + col0 + lane : nullptr;
+      int my_dr = wrow + lane;                    // destination row of this lane's row of the block
+      if (p.out_h && p.oh_t) my_dr = (my_dr / p.oh_t) * p.oh_pitch + p.oh_row0 + (my_dr % p.oh_t);
+      const int nrow = min(32, p.rows - wrow);    // rows of this warp's block inside the tensor (<= 0: none)
       uint32_t vr[32];
       tmem_ld32_issue(taddr2, vr);
 #pragma unroll 1
@@ -305,49 +361,57 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         } else {
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_A2EMPTY));
+          if (lane == 0) mbar_arrive_cluster(a2empty_bar);
         }
-        const int cl = g * 128 + ch * 32;
-        const float4* b4 = reinterpret_cast<const float4*>(s_b2 + cl);
-        const float4* g4 = reinterpret_cast<const float4*>(s_gam + cl);
+        unsigned char* tb = (ch & 1) ? tB : tA;
+        mbar_wait(res_bar[ch & 1], res_phase[ch & 1]);
+        res_phase[ch & 1] ^= 1;
+        const float4* b4 = reinterpret_cast<const float4*>(s_b2 + col0 + ch * 32);
+        const float4* g4 = reinterpret_cast<const float4*>(s_gam + col0 + ch * 32);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {          // gamma * ((acc + b2) * mask), row-major into the tile
+        for (int jj = 0; jj < 8; ++jj) {          // residual * mask + gamma * ((acc + b2) * mask), in place
+          float4* slot = reinterpret_cast<float4*>(tb + lane * 128 + ((jj ^ sw7) << 4));
+          const float4 rv = *slot;
           const float4 bb = b4[jj], gg = g4[jj];
-          *reinterpret_cast<float4*>(t0 + lane * 128 + ((jj ^ sw7) << 4)) =
-              make_float4(gg.x * ((x[4 * jj] + bb.x) * mk), gg.y * ((x[4 * jj + 1] + bb.y) * mk),
-                          gg.z * ((x[4 * jj + 2] + bb.z) * mk), gg.w * ((x[4 * jj + 3] + bb.w) * mk));
+          *slot = make_float4(fmaf(rv.x, mk, gg.x * ((x[4 * jj] + bb.x) * mk)), fmaf(rv.y, mk, gg.y * ((x[4 * jj + 1] + bb.y) * mk)),
+                              fmaf(rv.z, mk, gg.z * ((x[4 * jj + 2] + bb.z) * mk)), fmaf(rv.w, mk, gg.w * ((x[4 * jj + 3] + bb.w) * mk)));
         }
+        fence_async_smem();
         __syncwarp();
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {         // row rr of the block: 32 lanes = 32 consecutive columns
-          const float v = *reinterpret_cast<const float*>(t0 + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
-          const float mrow = __shfl_sync(0xffffffffu, mk, rr);
-          const float o = fmaf(rres[rr], mrow, v);
-          if (rr < nrow) out_base[(size_t)rr * C + ch * 32] = o;
-          if (outh_base != nullptr) {              // (warp-uniform)
+        if (lane == 0) {
+          tma_store_2d(&p.out_map, smem_u32(tb), col0 + ch * 32, wrow);
+          tma_store_commit();
+        }
+        if (outh_base != nullptr) {               // (warp-uniform)
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {       // row rr of the block: 32 lanes = 32 consecutive columns
+            const float o = *reinterpret_cast<const float*>(tb + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
             const int dr = __shfl_sync(0xffffffffu, my_dr, rr);
             unsigned short hb;
             if (F16) { const __half hh = __float2half_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
             else { const __nv_bfloat16 hh = __float2bfloat16_rn(o); hb = *reinterpret_cast<const unsigned short*>(&hh); }
             if (rr < nrow) outh_base[(size_t)dr * C + ch * 32] = hb;
           }
+          __syncwarp();
         }
-        if (ch + 1 < 4) {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) rres[rr] = rr < nrow ? __ldg(res_base + (size_t)rr * C + (ch + 1) * 32) : 0.f;
+        if (ch + 2 < 4 && lane == 0) {            // refill this tile with the residual of chunk ch + 2
+          tma_store_wait_read();
+          fetch_residual(ch + 2);
         }
-        __syncwarp();                             // the tile is rewritten by the next chunk
       }
       if (wi == 0 && lane == 0) MLPF_TS(2, 41);
-      // every warp's tile lives in the hidden tile, which other warps overwrite in the next tile's first chunk
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (lane == 0) tma_store_wait_read();       // both tiles drained: tB returns to the hidden tile, tA takes the next residual
+      }
+      // every warp's tB lives in the hidden tile, which other warps overwrite in the next tile's first chunk
+      asm volatile("bar.sync 1, %0;" ::"n"(GELU_WARPS * 32) : "memory");
     }
+    if (fin && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();                             // the leader's MMAs read the peer's shared memory and write its TMEM
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -393,9 +457,11 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   };
   int rc;
   if ((rc = enc2(&p.x_map, dt, 2, a->x, C, a->rows, 64, 128, "x"))) return rc;
-  if ((rc = enc2(&p.w1_map, dt, 2, a->w1, C, HID, 64, 128, "w1"))) return rc;
+  if ((rc = enc2(&p.w1_map, dt, 2, a->w1, C, HID, 64, 64, "w1"))) return rc;
   if ((rc = enc2(&p.w2_map, dt, 2, a->w2, HID, C, 64, 128, "w2"))) return rc;
-  p.residual = a->residual; p.out = a->out; p.out_h = a->out_h;
+  if ((rc = enc2(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->residual, C, a->rows, 32, 32, "residual"))) return rc;
+  if ((rc = enc2(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, C, a->rows, 32, 32, "out"))) return rc;
+  p.out_h = a->out_h;
   p.oh_t = a->out_h_t; p.oh_pitch = a->out_h_pitch; p.oh_row0 = a->out_h_row0;
   AVDF_CHECK_ARG(a->out_h_t >= 0 && (a->out_h_t == 0 || (a->rows % a->out_h_t == 0 && a->out_h_pitch >= a->out_h_t + a->out_h_row0)),
                  "out_h_t must divide rows and fit the destination pitch");
@@ -404,14 +470,19 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   p.rows = a->rows; p.tiles = (a->rows + BM - 1) / BM;
   p.dbg = g_mlpf_dbg;
   const unsigned fmt = f16 ? 0u : 1u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(128 >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+  // instruction descriptors: D = f32, A/B format, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 over the two CTAs of a pair)
+  const unsigned m_field = (unsigned)((2 * BM) >> 4) << 24;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(128 >> 3) << 17) | m_field;
+  p.idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(256 >> 3) << 17) | m_field;
   const int sms = device_sm_count();
   AVDF_SMEM_ATTR_ONCE(mlp_fused_kernel<true>, SMEM_BYTES);
   AVDF_SMEM_ATTR_ONCE(mlp_fused_kernel<false>, SMEM_BYTES);
-  const int grid = p.tiles < sms ? p.tiles : sms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const cudaError_t lerr = f16 ? launch_pdl(mlp_fused_kernel<true>, grid, THREADS, SMEM_BYTES, st, p)
-                               : launch_pdl(mlp_fused_kernel<false>, grid, THREADS, SMEM_BYTES, st, p);
+  // clusters of two CTAs (one TPC); a pair walks pairs of 128-row tiles
+  const int units = (p.tiles + 1) / 2, max_pairs = sms / 2;
+  const int grid = 2 * (units < max_pairs ? units : max_pairs);
+  const cudaError_t lerr = f16 ? launch_pdl_cluster(mlp_fused_kernel<true>, grid, THREADS, SMEM_BYTES, st, 2, p)
+                               : launch_pdl_cluster(mlp_fused_kernel<false>, grid, THREADS, SMEM_BYTES, st, 2, p);
   if (lerr != cudaSuccess) { set_error("mlp_fused_kernel: launch failed: %s", cudaGetErrorString(lerr)); return AVDF_ERR_CUDA; }
   return check_launch("mlp_fused_kernel");
 }

@@ -114,6 +114,61 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2, clusters of two CTAs)
+// A pair of CTAs on the two SMs of a TPC issues ONE tcgen05.mma for a 256-row tile: each CTA supplies its own 128 rows
+// of A and HALF of the B operand (N/2 rows) from its own shared memory, at the same offsets in both CTAs, and receives its
+// 128 rows of D in its own TMEM. Only the leader (cluster rank 0) issues MMAs; barriers the MMA warp waits on live in the
+// leader (the peer's TMA loads and threads signal them remotely), barriers the MMA warp signals are reached in both CTAs
+// by a multicast commit.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  // default semantics (release at CTA scope), like CUTLASS' ClusterBarrier::arrive: what the arrivals publish here is
+  // either TMEM reads (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync) or shared-memory tiles already
+  // pushed to the async proxy (fence.proxy.async). `.release.cluster` was measured at ~0.5 us per arrive on the issuing lane.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("avdf tcgen05 kernel: cluster mbarrier timeout (block %d thread %d, barrier at smem 0x%x, parity %u)\n", blockIdx.x, threadIdx.x, bar, parity); __trap(); }
+  }
+}
+// TMA load into this CTA's shared memory whose completion bytes are credited to a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the pair's MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+
 // K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
 // start address >> 4, LBO unused (0), SBO = 1024 B >> 4, descriptor version 1 (sm_100), layout SWIZZLE_128B (2).
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
@@ -138,31 +193,33 @@ __device__ __forceinline__ float gelu_fast(float x) {
   // 0.5 x (1 + erf(x/sqrt2)) = x - 0.5 x erfc(z) for x >= 0, 0.5 x erfc(z) for x < 0
   return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
 }
-// the same on a packed pair, arranged for the fewest issue slots (the GELU MLP epilogue is bound by them):
-//   gelu(x) = relu(x) - |x| w,  w = 0.5 erfc(|x|/sqrt2) = e^{-x^2/2} t P(t) / 2,  relu(x) = x/2 + |x|/2
-//           = x/2 + |x| (1/2 - w)
-// i.e. no select on the sign of x; the 1/2 and the minus sign live in the polynomial coefficients, sqrt(1/2) and
-// log2(e)/2 in the two argument scalings: 11 packed FP ops + 4 MUFU + 2 LOP3 per TWO elements.
-__device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
+// The same on a packed pair with ONE MUFU per element (the A&S form above costs two, rcp + ex2, and the GELU epilogues were
+// bound by the XU pipe: scripts/gelu_pace.cu). Only the Gaussian factor uses the XU pipe,
+//   gelu(x) = x/2 + |x| (1/2 - w),   w = Phi(-|x|) = e^{-x^2/2} R(|x|),   R(a) = erfcx(a / sqrt 2) / 2
+// R is smooth and slowly varying: a degree-6 polynomial on [0, 3.9] (weighted Chebyshev fit, |error of gelu| <= 1.4e-5
+// over the whole line in fp32 arithmetic - below the rounding of the 16-bit tensor the result is stored in; beyond 3.9 the
+// polynomial's argument is clamped while the Gaussian factor keeps decaying: w(3.9) = 4.8e-5). The epilogues that use it are bound
+// by the FP32 pipe (a packed FFMA2 occupies it for two cycles): 12 FMA-class operations + 1 MUFU per element.
+__device__ __forceinline__ f32x2 gelu_poly2(f32x2 x) {
   const f32x2 ax = x & 0x7fffffff7fffffffull;
-  float d0, d1, t0, t1, e0, e1;
-  upk2(fma2(ax, pk2(0.3275911f * 0.70710678118654752440f), pk2(1.f)), d0, d1);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  float a0, a1, d0, d1, e0, e1;
+  upk2(ax, a0, a1);
+  const f32x2 ac = pk2(fminf(a0, 3.9f), fminf(a1, 3.9f));
   upk2(mul2(mul2(x, pk2(-0.5f * 1.4426950408889634f)), x), d0, d1);       // -x^2/2 * log2(e)
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(d0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(d1));
-  const f32x2 t = pk2(t0, t1);
-  f32x2 poly = fma2(pk2(-0.5f * 1.061405429f), t, pk2(0.5f * 1.453152027f));   // -P(t)/2
-  poly = fma2(poly, t, pk2(-0.5f * 1.421413741f));
-  poly = fma2(poly, t, pk2(0.5f * 0.284496736f));
-  poly = fma2(poly, t, pk2(-0.5f * 0.254829592f));
-  const f32x2 u = fma2(mul2(poly, t), pk2(e0, e1), pk2(0.5f));           // 1/2 - w
+  f32x2 r = fma2(pk2(-3.678974754e-04f), ac, pk2(5.024928134e-03f));          // -R(a), Horner
+  r = fma2(r, ac, pk2(-2.949506603e-02f));
+  r = fma2(r, ac, pk2(1.007441282e-01f));
+  r = fma2(r, ac, pk2(-2.319642752e-01f));
+  r = fma2(r, ac, pk2(3.940120637e-01f));
+  r = fma2(r, ac, pk2(-4.995374084e-01f));
+  const f32x2 u = fma2(r, pk2(e0, e1), pk2(0.5f));                          // 1/2 - w
   return fma2(ax, u, mul2(x, pk2(0.5f)));
 }
 __device__ __forceinline__ f32x2 act_tc2(f32x2 v, int act) {
   if (act == AVDF_ACT_RELU) { float a, b; upk2(v, a, b); return pk2(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
-  if (act == AVDF_ACT_GELU) return gelu_fast2(v);
+  if (act == AVDF_ACT_GELU) return gelu_poly2(v);
   return v;
 }
 __device__ __forceinline__ float act_tc(float v, int act) {
