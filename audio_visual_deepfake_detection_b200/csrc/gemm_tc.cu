@@ -68,7 +68,7 @@ struct Params {
   SegInfo seg;
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
   int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
-  int n_out, c_in, taps, stride, bn, n_tiles_n, n_tiles_m, total_tiles;
+  int n_out, c_in, taps, stride, tap_off, bn, n_tiles_n, n_tiles_m, total_tiles;
   int ws, ws_groups, ws_per;                 // weight-stationary: (segment, n-tile) groups, CTAs per group
   unsigned idesc;
   EpiParams epi;
@@ -106,6 +106,9 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
 // MODE >= 0 fixes the epilogue variant at compile time (bit 0 LayerNorm, bits 1-2 activation, bit 3 residual,
 // bit 4 positional encoding) so the epilogue carries no dead branches; MODE < 0 reads the flags at run time.
 constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (pe ? 16 : 0); }
+// bit 5: the LayerNorm follows the residual step (avdf_conv_gemm_args.ln_after_residual): attention projection + LN2 in
+// one launch. Only instantiated for the wide eight-epilogue-warp configuration with both outputs.
+constexpr int MODE_POSTLN = mode_of(true, AVDF_ACT_NONE, true, false) | 32;
 
 // OUTK >= 0 fixes which outputs exist: bit 0 fp32, bit 1 16-bit copy, bit 2 the 16-bit copy is fp16 (else bf16).
 // CFG (compile-time, so that the streaming variants carry none of the other configurations' state):
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
           tma_load_2d(smem_u32(smem_b + kb * b_stage), &p.w_map, wfull_bar, kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
       }
       for (int tap = 0; tap < p.taps; ++tap) {
-        const int d = tap - (p.taps >> 1);
+        const int d = tap - p.tap_off;
         int par = 0, dt = d;
         if (p.stride == 2) { par = d & 1; dt = (d - par) / 2; }
         for (int kb = 0; kb < kb_per_tap; ++kb) {
@@ -271,6 +274,8 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
     const uint32_t res_bar1 = bar_base + 8u * (2 * MAX_STAGES + 13 + wi);   // second residual tile (in-place fp32 path)
     const int chunks = (p.bn >> 5) / (EPI_WARPS / 4);     // 32-column chunks this warp handles: [ch0, ch1)
     const int ch0 = team * chunks, ch1 = ch0 + chunks;
+    constexpr bool POSTLN = MODE >= 0 && (MODE & 32) != 0;
+    static_assert(!POSTLN || CFG == 2, "the post-residual LayerNorm runs in the wide eight-warp configuration");
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
     const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
     const bool has_pe = MODE < 0 ? (e.pe != nullptr) : ((MODE & 16) != 0);
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
       //      the very tile the result leaves from (updated in place by the thread that owns the row), so the two 4 KB
       //      tiles of this warp double-buffer the chunks: the residual of chunk c + 1 is in flight while chunk c is computed
       //      (with one residual tile its ~1 us load latency was exposed on every 32-column chunk: the top stall in ncu)
-      constexpr bool RES32_OK = MODE >= 0 && OUTK == 1 && (MODE & 8) != 0 && (MODE & 16) == 0;
+      constexpr bool RES32_OK = (MODE >= 0 && OUTK == 1 && (MODE & 8) != 0 && (MODE & 16) == 0) || POSTLN;
       auto fetch_residual_into = [&](int ch) {    // chunk ch -> tile ch & 1 (lane 0; the tile's previous store has been read)
         const uint32_t bar = (ch & 1) ? res_bar1 : res_bar;
         mbar_arrive_expect_tx(bar, 4096);
@@ -353,6 +358,113 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
       float mean = 0.f, rstd = 1.f;
+      if constexpr (POSTLN) {
+        // ---- attention projection + LN2: pass 1 builds the residual stream y = residual * mask + gamma * ((acc + bias) *
+        //      mask) chunk by chunk in the tile its residual block arrived in (as above), sends it out (fp32), writes it
+        //      BACK over the accumulator (tcgen05.st) and sums y, y^2; pass 2 re-reads y from TMEM, normalises and emits
+        //      the 16-bit operand of the MLP through the wide 64-column boxes
+        float s = 0.f, ss = 0.f;
+        uint32_t vr[32];
+        tmem_ld32_issue(taddr + ch0 * 32, vr);
+        for (int ch = ch0; ch < ch1; ++ch) {
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vr[i]);
+          if (ch + 1 < ch1) tmem_ld32_issue(taddr + (ch + 1) * 32, vr);
+          const int cl = ch * 32;
+          unsigned char* tb = t32 + ((ch & 1) << 12);
+          if (ch > ch0 && ch + 1 < ch1 && ep_leader) {
+            tma_store_wait_read();
+            fetch_residual_into(ch + 1);
+          }
+          if (ch & 1) { mbar_wait(res_bar1, res_phase1); res_phase1 ^= 1; }
+          else { mbar_wait(res_bar, res_phase); res_phase ^= 1; }
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + cl);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gam + cl);
+          uint32_t yb[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* slot = reinterpret_cast<float4*>(tb + lane * 128 + ((j ^ sw7) << 4));
+            const float4 rv = *slot;
+            const float4 bb = b4[j], gg = g4[j];
+            const float4 y = make_float4(fmaf(gg.x, (x[4 * j] + bb.x) * mk, rv.x * mk), fmaf(gg.y, (x[4 * j + 1] + bb.y) * mk, rv.y * mk),
+                                         fmaf(gg.z, (x[4 * j + 2] + bb.z) * mk, rv.z * mk), fmaf(gg.w, (x[4 * j + 3] + bb.w) * mk, rv.w * mk));
+            *slot = y;
+            s += (y.x + y.y) + (y.z + y.w);
+            ss = fmaf(y.x, y.x, ss); ss = fmaf(y.y, y.y, ss); ss = fmaf(y.z, y.z, ss); ss = fmaf(y.w, y.w, ss);
+            yb[4 * j] = __float_as_uint(y.x); yb[4 * j + 1] = __float_as_uint(y.y); yb[4 * j + 2] = __float_as_uint(y.z); yb[4 * j + 3] = __float_as_uint(y.w);
+          }
+          tmem_st32(taddr + ch * 32, yb);
+          fence_async_smem();
+          __syncwarp();
+          if (ep_leader) {
+            tma_store_3d(&p.o32_map[tc_.seg], smem_u32(tb), tc_.n0 + cl, wt, wb);
+            tma_store_commit();
+          }
+        }
+        {                                         // the other half of the row's columns belongs to the partner warp
+          float2* part = reinterpret_cast<float2*>(part_smem) + (it & 1) * 256;
+          part[team * 128 + q * 32 + lane] = make_float2(s, ss);
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          const float2 pa = part[q * 32 + lane], pb = part[128 + q * 32 + lane];
+          s = pa.x + pb.x; ss = pa.y + pb.y;
+        }
+        mean = s / (float)p.bn;
+        rstd = rsqrtf(fmaxf(ss / (float)p.bn - mean * mean, 0.f) + 1e-5f);
+        tmem_st_wait();
+        const f32x2 nmean2 = pk2(-mean), rstd2 = pk2(rstd);
+        int tsel = 0;                             // pass 1 left its older store in tile 0, the younger one in tile 1
+        for (int ch = ch0; ch < ch1; ch += 2) {
+          uint32_t va[32], vb[32];
+          tmem_ld32_issue(taddr + ch * 32, va);
+          tmem_ld32_issue(taddr + (ch + 1) * 32, vb);
+          tmem_ld_wait();
+          if (ch + 2 >= ch1) {                     // all TMEM reads of this warp done: release the accumulator
+            tcgen05_fence_before();
+            __syncwarp();
+            if (ep_leader) mbar_arrive(tempty_bar(acc));
+          }
+          unsigned char* tw = t32 + (tsel << 12);
+          tsel ^= 1;
+          if (ep_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cl = (ch + half) * 32;
+            const float4* w4 = reinterpret_cast<const float4*>(s_lnw + cl);
+            const float4* l4 = reinterpret_cast<const float4*>(s_lnb + cl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t* vv = half == 0 ? va : vb;
+              f32x2 y[4];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const float4 ww = w4[2 * j + u], ll = l4[2 * j + u];
+                y[2 * u] = fma2(mul2(add2(pk2(__uint_as_float(vv[8 * j + 4 * u]), __uint_as_float(vv[8 * j + 4 * u + 1])), nmean2), rstd2), pk2(ww.x, ww.y), pk2(ll.x, ll.y));
+                y[2 * u + 1] = fma2(mul2(add2(pk2(__uint_as_float(vv[8 * j + 4 * u + 2]), __uint_as_float(vv[8 * j + 4 * u + 3])), nmean2), rstd2), pk2(ww.z, ww.w), pk2(ll.z, ll.w));
+              }
+              uint4 uo;
+              float f0, f1;
+              if (o16_f16) {
+                upk2(y[0], f0, f1); uo.x = pack_f16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_f16x2(f0, f1);
+                upk2(y[2], f0, f1); uo.z = pack_f16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_f16x2(f0, f1);
+              } else {
+                upk2(y[0], f0, f1); uo.x = pack_bf16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_bf16x2(f0, f1);
+                upk2(y[2], f0, f1); uo.z = pack_bf16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_bf16x2(f0, f1);
+              }
+              *reinterpret_cast<uint4*>(tw + lane * 128 + (((half * 4 + j) ^ sw7) << 4)) = uo;
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (ep_leader) {
+            tma_store_3d(&p.o16w_map[tc_.seg], smem_u32(tw), tc_.n0 + ch * 32, wt, wb);
+            tma_store_commit();
+          }
+        }
+        continue;                                   // next tile
+      }
       if (has_ln) {                               // row statistics over all bn columns (this thread owns the whole row)
         float s = 0.f, ss = 0.f;
         for (int ch = ch0; ch < ch1; ++ch) {
@@ -642,6 +754,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   fill_epi(a, p.epi);
   p.dbg = g_dbg;
   p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.bn = bn;
+  p.tap_off = a->tap_mode ? 0 : (a->taps >> 1);
   p.n_tiles_n = a->n_out / bn;
   int tiles = 0;
   for (int s = 0; s < a->n_seg; ++s) {
@@ -671,7 +784,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
           {&p.o32_map[s], a->out_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B},
           {&p.o16_map[s], a->out_h, a->out_h_dtype == AVDF_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_64B},
           {&p.res_map[s], a->residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, CU_TENSOR_MAP_SWIZZLE_128B}};
-      if (a->out_h && !a->out_f32 && bn % 64 == 0) {     // wide 16-bit box
+      if (a->out_h && (!a->out_f32 || a->ln_after_residual) && bn % 64 == 0) {     // wide 16-bit box
         cuuint64_t odims[3] = {(cuuint64_t)a->n_out, (cuuint64_t)T, (cuuint64_t)a->batch};
         cuuint64_t ostr[2] = {(cuuint64_t)a->n_out * 2, (cuuint64_t)a->o_rows_per_video * a->n_out * 2};
         cuuint32_t obox[3] = {64u, (cuuint32_t)tw, (cuuint32_t)bw};
@@ -737,7 +850,8 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     X(mode_of(true, AVDF_ACT_RELU, false, false), 6) X(mode_of(true, AVDF_ACT_RELU, false, false), 2)             \
     X(mode_of(true, AVDF_ACT_RELU, false, false), 1) X(mode_of(true, AVDF_ACT_RELU, false, true), 1)              \
     X(mode_of(false, AVDF_ACT_NONE, false, false), 1) X(mode_of(false, AVDF_ACT_NONE, true, false), 1)            \
-    X(mode_of(false, AVDF_ACT_NONE, true, false), 7) X(mode_of(false, AVDF_ACT_NONE, true, false), 3)
+    X(mode_of(false, AVDF_ACT_NONE, true, false), 7) X(mode_of(false, AVDF_ACT_NONE, true, false), 3)           \
+    X(MODE_POSTLN, 7) X(MODE_POSTLN, 3)
 #define AVDF_SET_SMEM_WS(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
 #define AVDF_SET_SMEM_W8(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, W8_SMEM_BYTES));
     AVDF_SET_SMEM(-1, -1)
@@ -756,7 +870,10 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   const int grid = ws ? ws_groups * ws_per : (p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm);
   const bool w8 = !ws && bn == MAX_BN && g_w8;
   const int smem_bytes = ws ? WS_SMEM_BYTES : (w8 ? W8_SMEM_BYTES : smem_bytes_of(bn));
-  const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr);
+  const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr) | (a->ln_after_residual ? 32 : 0);
+  if (a->ln_after_residual) {
+    AVDF_CHECK_ARG(w8 && a->n_out == MAX_BN, "ln_after_residual needs n_out = 256 and the eight-warp wide configuration");
+  }
   const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
   bool launched = false;
   cudaError_t lerr = cudaSuccess;
@@ -769,6 +886,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
 #undef AVDF_LAUNCH
 #undef AVDF_LAUNCH_WS
 #undef AVDF_LAUNCH_W8
+  if (!launched && a->ln_after_residual) { set_error("avdf_conv_gemm: no ln_after_residual instantiation for this output combination"); return AVDF_ERR_UNSUPPORTED; }
   if (!launched) {
     if (ws) lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1, 1>, grid, WS_THREADS, smem_bytes, st, p);
     else if (w8) lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1, 2>, grid, WS_THREADS, smem_bytes, st, p);

@@ -43,6 +43,20 @@ def sinusoid_table(n_pos, d):
     return tab.astype(np.float32)
 
 
+def up_weight(w_t):
+    """ConvTranspose1d(k=3, stride=2, padding=1, output_padding=1) weight [c_in, c_out, 3] (blocks.py:1443-1468) -> the
+    [2*c_out, 2*c_in] matrix of the equivalent forward-tap GEMM (avdf_conv_gemm tap_mode 1, taps at x[t], x[t+1]):
+        out[2t]   = W[:, :, 1]^T x[t]                       (rows [0, c_out):        tap 0 = W1, tap 1 = 0)
+        out[2t+1] = W[:, :, 2]^T x[t] + W[:, :, 0]^T x[t+1]   (rows [c_out, 2 c_out):  tap 0 = W2, tap 1 = W0)
+    so that GEMM row t, viewed as [2, c_out], is the pair of output positions (2t, 2t+1); x[T] reads as zero."""
+    w = w_t.detach().to(torch.float32)
+    ci, co, k = w.shape
+    assert k == 3
+    even = torch.cat([w[:, :, 1].t(), torch.zeros(co, ci)], dim=1)
+    odd = torch.cat([w[:, :, 2].t(), w[:, :, 0].t()], dim=1)
+    return torch.cat([even, odd], dim=0).contiguous()
+
+
 class PackedWeights:
     """Reference state_dict -> device tensors in the kernels' layouts.
 
@@ -141,6 +155,7 @@ class LocalizationEngine:
         # AVDF_FUSED_MLP_MIN_ROWS sets the smallest level (rows = batch * t) that uses it.
         self.fused_mlp = os.environ.get("AVDF_FUSED_MLP", "1") != "0"
         self.fused_mlp_min_rows = int(os.environ.get("AVDF_FUSED_MLP_MIN_ROWS", "0"))
+        self.fuse_ln2 = os.environ.get("AVDF_FUSE_LN2", "1") != "0"    # LN2 in the attention projection's epilogue (A/B switch)
         self.C = c["embd_dim"]
         self.n_head = c["n_head"]
         self.c_in = c["video_input_dim"] + c["audio_input_dim"]
@@ -257,7 +272,8 @@ class LocalizationEngine:
 
     # ------------------------------------------------------------------ building blocks
     def _gemm(self, a, wkey, *, B, taps=1, stride=1, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
-              act=ops.ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_act=None):
+              act=ops.ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_act=None, ln_after_residual=False,
+              tap_mode=0):
         w = self.w.dense(wkey, a.dtype) if isinstance(wkey, str) else self.w.stack_dense(wkey, a.dtype)
         n_out, k = w.shape
         if not isinstance(wkey, str):
@@ -270,12 +286,14 @@ class LocalizationEngine:
                 out_f32 = out_act
             else:
                 out_h = out_act
+        if ln_after_residual:
+            assert out_h is not None and out_f32 is not None
         ws = None
         if a.dtype == torch.float32:
             ws = self.workspace(B * o_rows * n_out * 4)
         ops.conv_gemm(a, w, taps=taps, stride=stride, batch=B, c_in=c_in, n_out=n_out, segs=segs, a_rows=a_rows,
                       o_rows=o_rows, bias=bias, row_mask=row_mask, ln=ln, act=act, pe=pe, residual=residual, gamma=gamma,
-                      out_f32=out_f32, out_h=out_h, workspace=ws)
+                      out_f32=out_f32, out_h=out_h, workspace=ws, ln_after_residual=ln_after_residual, tap_mode=tap_mode)
 
     def _attn_and_mlp(self, pre, B, T, mask, skip, window, out_name, want_act_copy, pyr=None):
         """Shared tail of TransformerBlock / MutilModelTransformerBlock after the dwconv+LN stage:
@@ -294,8 +312,16 @@ class LocalizationEngine:
         y = self.buf("y", (B, T, C), torch.float32)
         ga = w.vec(pre + ".drop_path_attn.scale") if w.has(pre + ".drop_path_attn.scale") else None
         gm = w.vec(pre + ".drop_path_mlp.scale") if w.has(pre + ".drop_path_mlp.scale") else None
-        self._gemm(att, f"{pre}.attn.proj.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.attn.proj.bias"),
-                   row_mask=mask, residual=skip, gamma=ga, out_f32=y)
+        l2 = self.buf("ln2", (B, T, C), self.adt)
+        # 16-bit path: LN2 (blocks.py:1311) runs in the projection's epilogue (ln_after_residual): y is normalised while it is
+        # still in TMEM - one launch and one fp32 round trip of the residual stream less per block
+        fuse_ln2 = self.fuse_ln2 and self.adt != torch.float32 and C == 256
+        if fuse_ln2:
+            self._gemm(att, f"{pre}.attn.proj.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.attn.proj.bias"),
+                       row_mask=mask, residual=skip, gamma=ga, out_f32=y, out_act=l2, ln=w.ln(pre + ".ln2"), ln_after_residual=True)
+        else:
+            self._gemm(att, f"{pre}.attn.proj.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.attn.proj.bias"),
+                       row_mask=mask, residual=skip, gamma=ga, out_f32=y)
         out = self.buf(out_name, (B, T, C), torch.float32)
         out_act = None
         fused = self.fused_mlp and self.adt != torch.float32 and C == 256 and B * T >= self.fused_mlp_min_rows
@@ -303,8 +329,8 @@ class LocalizationEngine:
             # pyr = (pyramid buffer [B, P, C], first row of this level): the 16-bit copy goes straight into the operand of
             # the single FPN lateral launch (fused-MLP path only)
             out_act = pyr[0] if (pyr is not None and fused) else self.buf(out_name + "_act", (B, T, C), self.adt)
-        l2 = self.buf("ln2", (B, T, C), self.adt)
-        ops.ln_rows(y, *w.ln(pre + ".ln2"), l2, B * T)
+        if not fuse_ln2:
+            ops.ln_rows(y, *w.ln(pre + ".ln2"), l2, B * T)
         if fused:
             # one launch: the [B*T, 4C] activations stay in shared memory / TMEM (csrc/mlp_fused.cu). (Folding LN2 into
             # the kernel was tried - two spare warps normalising the next 128-row tile straight into the operand

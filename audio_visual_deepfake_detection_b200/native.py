@@ -62,6 +62,7 @@ class ConvGemmArgs(Structure):
         ("pe", c_void_p), ("residual", c_void_p), ("gamma", c_void_p),
         ("out_f32", c_void_p), ("out_h", c_void_p), ("out_h_dtype", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("ln_after_residual", c_int32), ("tap_mode", c_int32),
     ]
 
 
@@ -133,7 +134,7 @@ def lib():
         if name not in ("avdf_last_error", "avdf_nms_workspace_bytes", "avdf_postprocess_workspace_bytes",
                         "avdf_conv_gemm_workspace_bytes", "avdf_abi_version"):
             fn.restype = c_int32
-    if L.avdf_abi_version() != 1:
+    if L.avdf_abi_version() != 2:
         raise AvdfError("libavdf_sm100.so ABI version mismatch")
     _lib = L
     return L

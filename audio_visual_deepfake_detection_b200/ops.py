@@ -195,7 +195,8 @@ def postprocess_workspace_bytes(batch, cand_cap):
 
 # ---------------------------------------------------------------------------- conv GEMM
 def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
-              act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_h=None, workspace=None):
+              act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_h=None, workspace=None,
+              ln_after_residual=False, tap_mode=0):
     """segs: list of (t_out, a_row, o_row[, w_row]) per segment. a: [batch, a_rows, c_in]; w: [n_w_rows, taps*c_in]
     (same dtype as a: fp32 -> CUDA-core parity path, bf16 / fp16 -> tcgen05 path). Outputs [batch, o_rows, n_out]:
     out_f32 and/or out_h (a bf16 or fp16 copy)."""
@@ -218,6 +219,7 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
         _chk(ln[0], torch.float32, "ln_w"); _chk(ln[1], torch.float32, "ln_b")
         g.ln_w, g.ln_b = ln[0].data_ptr(), ln[1].data_ptr()
     g.act = act
+    g.ln_after_residual, g.tap_mode = int(bool(ln_after_residual)), int(tap_mode)
     g.pe = pe.data_ptr() if pe is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.gamma = gamma.data_ptr() if gamma is not None else None

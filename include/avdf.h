@@ -56,7 +56,7 @@ extern "C" {
 #define AVDF_API
 #endif
 
-#define AVDF_ABI_VERSION 1
+#define AVDF_ABI_VERSION 2
 #define AVDF_MAX_LEVELS 8
 #define AVDF_MAX_SEGS 1024
 
@@ -148,7 +148,8 @@ AVDF_API int avdf_postprocess(const avdf_postprocess_args* args, void* stream);
  * pyramid (shared weights) or independent problems stacked along the rows with their own weight block (seg_w_row):
  * e.g. the q, k, v projections of one attention block in a single launch.
  * epi(v): v += bias[n]; v *= mask[row]; v = LN_n(v) * ln_w + ln_b; v = act(v); v += pe[t, n] * mask[row];
- *         v = residual[row, n] * mask[row] + gamma[n] * v            (each step only if its pointer is set)
+ *         v = residual[row, n] * mask[row] + gamma[n] * v            (each step only if its pointer is set;
+ *         ln_after_residual moves the LayerNorm behind the residual step, see the field below)
  * dtype F32 -> fp32 CUDA-core path (parity mode); BF16 / F16 -> TMA + tcgen05 tensor-core path (A and W in that
  * 16-bit format, fp32 accumulate in TMEM). out_h (optional) receives a 16-bit copy in out_h_dtype (BF16 | F16). */
 typedef struct avdf_conv_gemm_args {
@@ -167,6 +168,15 @@ typedef struct avdf_conv_gemm_args {
   const float* pe; const float* residual; const float* gamma;
   float* out_f32; void* out_h; int32_t out_h_dtype;   /* [batch, o_rows_per_video, n_out] */
   void* workspace; size_t workspace_bytes;
+  /* ln_after_residual != 0 (16-bit path, n_out = 256, residual + ln_w + out_f32 + out_h all set): the LayerNorm is applied
+   * AFTER the residual step instead of before it - out_f32 receives y = residual * mask + gamma * ((acc + bias) * mask)
+   * (the block's residual stream, blocks.py:1309-1310 / 868-869) and out_h receives LN(y) * ln_w + ln_b, the operand of
+   * the block's MLP (blocks.py:1311): the attention projection and LN2 in one launch. act must be NONE, pe NULL. */
+  int32_t ln_after_residual;
+  /* tap_mode 0: taps centred on the output position (offsets j - taps/2, MaskedConv1D); 1: forward taps (offsets
+   * 0 .. taps-1, stride 1 only): the row pair (x[t], x[t+1]) a stride-2 ConvTranspose1d(k=3, padding=1, output_padding=1)
+   * reads for its outputs 2t and 2t+1 (blocks.py:1443-1491) - see libs/modeling/engine.py `up_block` */
+  int32_t tap_mode;
 } avdf_conv_gemm_args;            /* host struct */
 AVDF_API size_t avdf_conv_gemm_workspace_bytes(const avdf_conv_gemm_args* args);
 AVDF_API int avdf_conv_gemm(const avdf_conv_gemm_args* args, void* stream);

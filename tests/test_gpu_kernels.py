@@ -605,6 +605,63 @@ def test_conv_gemm_wide_tiles_eight_epilogue_warps(case):
         assert rel_err(outs[1][0], outs[0][0]) < 2e-6
 
 
+@pytest.mark.parametrize("adt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("B,T", [(3, 96), (170, 128), (5, 24)])
+def test_conv_gemm_ln_after_residual(B, T, adt):
+    """Attention projection + LN2 in one launch (ln_after_residual): out_f32 = the residual stream, bit-equal to the
+    plain residual launch; out_h = LayerNorm of it (blocks.py:1309-1311), against torch and against avdf_ln_rows."""
+    rng = np.random.RandomState(B * 7 + T)
+    C = 256
+    x = torch.from_numpy(rng.standard_normal((B, T, C)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((C, C, 1)) / math.sqrt(C)).astype(np.float32))
+    bias = torch.from_numpy(rng.normal(0, 0.3, C).astype(np.float32))
+    ln = _ln_params(rng, C)
+    res = torch.from_numpy(rng.standard_normal((B, T, C)).astype(np.float32) * 2 + 0.5)
+    gamma = torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32))
+    valid = rng.randint(T // 2, T + 1, B); valid[0] = T
+    mask = (np.arange(T)[None] < valid[:, None])
+    y_want = _conv_ref(x.to(adt).float(), w.to(adt).float(), bias, 1, 1, torch.from_numpy(mask), None, ops.ACT_NONE, None, res, gamma)
+    l_want = model_ref.channel_ln(y_want.permute(0, 2, 1), ln[0], ln[1]).permute(0, 2, 1)
+    wp = w.reshape(C, C).contiguous()
+    kw = dict(taps=1, stride=1, batch=B, c_in=C, n_out=C, segs=[(T, 0, 0)], a_rows=T, o_rows=T, bias=dev(bias),
+              row_mask=dev(mask.astype(np.uint8)), residual=dev(res), gamma=dev(gamma))
+    y_plain = torch.zeros((B, T, C), device=DEV)
+    ops.conv_gemm(dev(x, adt), dev(wp, adt), out_f32=y_plain, **kw)
+    y = torch.zeros((B, T, C), device=DEV)
+    l2 = torch.zeros((B, T, C), dtype=adt, device=DEV)
+    ops.conv_gemm(dev(x, adt), dev(wp, adt), out_f32=y, out_h=l2, ln=(dev(ln[0]), dev(ln[1])), ln_after_residual=True, **kw)
+    l_rows = torch.zeros((B * T, C), dtype=adt, device=DEV)
+    ops.ln_rows(y.view(B * T, C), dev(ln[0]), dev(ln[1]), l_rows, B * T)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain)
+    assert rel_err(y.cpu(), y_want) < 2e-4
+    assert rel_err(l2.float().cpu(), l_want) < (5e-3 if adt == torch.float16 else 1e-2)
+    # against the separate LayerNorm kernel: only the summation order of the statistics and the last 16-bit ulp differ
+    d = (l2.float() - l_rows.view(B, T, C).float()).abs().max().item()
+    assert d <= (4e-3 if adt == torch.float16 else 4e-2), d
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+def test_conv_gemm_forward_taps_is_conv_transpose(mode):
+    """tap_mode 1 (taps at offsets 0, +1): with the weight blocks of `engine.up_weight` one launch computes
+    ConvTranspose1d(k=3, stride=2, padding=1, output_padding=1) (blocks.py:1443-1491): output row t of width 2*c_out
+    holds the transposed conv's outputs 2t and 2t+1."""
+    rng = np.random.RandomState(5)
+    B, T, cin, cout = 3, 48, 128, 64
+    x = torch.from_numpy(rng.standard_normal((B, T, cin)).astype(np.float32))
+    wt = torch.from_numpy((rng.standard_normal((cin, cout, 3)) / math.sqrt(cin * 2)).astype(np.float32))   # ConvTranspose1d layout
+    bias = torch.from_numpy(rng.normal(0, 0.3, cout).astype(np.float32))
+    adt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[mode]
+    want = F.conv_transpose1d(x.to(adt).float().permute(0, 2, 1), wt.to(adt).float(), bias, stride=2, padding=1, output_padding=1).permute(0, 2, 1)
+    from audio_visual_deepfake_detection_b200.libs.modeling.engine import up_weight
+    wg = up_weight(wt)                                                    # [2*cout, 2*cin]
+    out = torch.zeros((B, T, 2 * cout), device=DEV)
+    ops.conv_gemm(dev(x, adt), dev(wg, adt), taps=2, stride=1, batch=B, c_in=cin, n_out=2 * cout, segs=[(T, 0, 0)], a_rows=T, o_rows=T,
+                  bias=dev(torch.cat([bias, bias])), out_f32=out, tap_mode=1)
+    torch.cuda.synchronize()
+    assert rel_err(out.view(B, 2 * T, cout).cpu(), want) < (2e-5 if mode == "fp32" else 2e-4)
+
+
 def test_attention_stacked_qkv_and_interleaved_dwconv():
     rng = np.random.RandomState(10)
     B, T, C = 3, 80, 256
