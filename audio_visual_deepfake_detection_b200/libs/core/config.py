@@ -92,7 +92,8 @@ def load_config_for(model_name, overrides=None):
     """The shipped yaml for a meta-arch name (configs/), with dotted-key
     overrides such as {'dataset.video_input_dim': 0, 'test_cfg.nms_method': 'soft'}."""
     fname = {"AVLocPointTransformerRecoveryNoNormNorecon": "deepfake_exp12_test.yaml",
-             "AVLocPointTransformerRecoveryNoNormNoreconTHE": "deepfake_exp13_test.yaml"}[model_name]
+             "AVLocPointTransformerRecoveryNoNormNoreconTHE": "deepfake_exp13_test.yaml",
+             "AVLocPointTransformerRecoveryNoNorm": "deepfake_exp5_test.yaml"}[model_name]
     cfg = load_config(os.path.join(CONFIG_DIR, fname))
     for key, val in (overrides or {}).items():
         node = cfg

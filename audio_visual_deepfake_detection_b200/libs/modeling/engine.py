@@ -29,7 +29,7 @@ import torch
 
 from ... import ops
 from ...native import AvdfError
-from .spec import EXP13, state_dict_spec
+from .spec import EXP5, EXP13, state_dict_spec
 
 
 def sinusoid_table(n_pos, d):
@@ -143,6 +143,7 @@ class LocalizationEngine:
         self.cfg = c
         self.name = model_name
         self.exp13 = model_name == EXP13
+        self.recon = model_name == EXP5      # live Expansion: its output is embedded and becomes K of resselfattention
         self.device = torch.device(device)
         self.precision = precision
         # in_dt: format of the raw feature tensor (unbounded values -> bf16 range); adt: format of every
@@ -186,7 +187,7 @@ class LocalizationEngine:
         if self.num_classes != 1:
             raise AvdfError("the fused postprocess handles num_classes == 1 (the shipped configs)")
         missing = [k for k in state_dict_spec(c, model_name) if (k not in state_dict and "module." + k not in state_dict)
-                   and not k.startswith("interpolator.expansion.") and not k.startswith("segmentandCls.bn1")]
+                   and not (k.startswith("interpolator.expansion.") and not self.recon) and not k.startswith("segmentandCls.bn1")]
         if missing:
             raise KeyError("state_dict is missing %d tensors, e.g. %s" % (len(missing), missing[:3]))
         self.w = PackedWeights(state_dict, self.device)
@@ -242,13 +243,20 @@ class LocalizationEngine:
             v = np.asarray(key[0], dtype=np.int64)[:, None]
             lv = [((np.arange(n)[None, :] * s) < v).astype(np.uint8) for n, s in zip(lens, self.strides)]
             pyr = np.concatenate(lv, axis=1)
-            flat = np.concatenate([pyr.reshape(-1)] + [a.reshape(-1) for a in lv])
+            # masks of the Expansion (UpBlock: nearest up-sampling of the coarsest Contraction mask, blocks.py:1480-1484):
+            # up_l[b, t] = mask_last[b, t >> (last - l)]
+            last = len(lens) - 1
+            up = [lv[last][:, np.arange(n) >> (last - l)] for l, n in enumerate(lens)] if self.recon else []
+            flat = np.concatenate([pyr.reshape(-1)] + [a.reshape(-1) for a in lv] + [np.ascontiguousarray(a).reshape(-1) for a in up])
             dev = torch.from_numpy(flat).to(self.device)
             B, P = len(valid), sum(lens)
             out = {"pyr": dev[: B * P].view(B, P)}
             off = B * P
             for l, n in enumerate(lens):
                 out[l] = dev[off: off + B * n].view(B, n)
+                off += B * n
+            for l, n in enumerate(lens if self.recon else []):
+                out["up%d" % l] = dev[off: off + B * n].view(B, n)
                 off += B * n
             if len(self._mask_cache) > 64:
                 self._mask_cache.clear()
@@ -367,9 +375,10 @@ class LocalizationEngine:
                          out_rows=3 * To, out_row_offsets=[0, To, 2 * To], skip_out=skip if stride == 2 else None)
         return self._attn_and_mlp(pre, B, To, mask, skip, window, out_name, want_act_copy, pyr)
 
-    def mm_block(self, pre, xq, kv, B, Tq, Tkv, masks, level, window, out_name, want_act_copy=False, pyr=None):
+    def mm_block(self, pre, xq, kv, B, Tq, Tkv, masks, level, window, out_name, want_act_copy=False, pyr=None, xk=None):
         """MutilModelTransformerBlock.forward (blocks.py:866-876): q from xq [B,Tq,C]; k,v from kv [B,Tkv,C]
-        nearest-resampled to Tq (backbones.py:487,490)."""
+        nearest-resampled to Tq (backbones.py:487,490). xk (same length as xq): a separate source for the K stream - the
+        embedded reconstruction of the exp5-style arch (backbones.py:469)."""
         C, w = self.C, self.w
         mask = masks[level]
         qkvn = self.buf("qkvn", (B, 3 * Tq, C), self.adt)
@@ -377,7 +386,12 @@ class LocalizationEngine:
         dws = [w.dw(f"{pre}.attn.{n}_conv.conv.weight") for n in names]
         lno = [w.ln(f"{pre}.attn.{n}_norm") for n in names]
         lni = [w.ln(pre + ".lnq"), w.ln(pre + ".lnk"), w.ln(pre + ".lnv")]
-        if kv is xq:
+        if xk is not None:
+            assert kv is xq and Tkv == Tq
+            for i, src in enumerate((xq, xk, xq)):
+                ops.ln_dwconv_ln(src, batch=B, t_src=Tq, t_virt=Tq, shift=0, stride=1, mask_out=mask, ln_in=lni[i:i + 1],
+                                 dw=dws[i:i + 1], ln_out=lno[i:i + 1], outs=[qkvn], out_rows=3 * Tq, out_row_offsets=[i * Tq])
+        elif kv is xq:
             ops.ln_dwconv_ln(xq, batch=B, t_src=Tq, t_virt=Tq, shift=0, stride=1, mask_out=mask, ln_in=lni, dw=dws,
                              ln_out=lno, outs=[qkvn] * 3, out_rows=3 * Tq, out_row_offsets=[0, Tq, 2 * Tq])
         else:
@@ -420,7 +434,36 @@ class LocalizationEngine:
             ops.vcls_exp12(z, w.dense_t("interpolator.conv0.0.weight"), w.dense_t("interpolator.conv1.weight"),
                            *w.ln("interpolator.bn1"), w.vec("interpolator.conv2.weight"), w.vec("interpolator.conv2.bias"),
                            vcls, batch=B, t=T)
+        self._contracted = z          # [B, T_last, C]: the Expansion's input (exp5-style arch)
         return vcls
+
+    def expansion(self, z, B, masks):
+        """Expansion.forward (blocks.py:1568-1590): 5 x UpBlock = ConvTranspose1d(k3, s2, p1, output_padding 1) + bias ->
+        * up-sampled mask -> InstanceNorm1d -> LeakyReLU(0.2) (blocks.py:1519-1541; `last` is False: DeepInterpolator builds
+        Expansion(tanh=False)). A transposed conv with these parameters is the forward-tap GEMM of `up_weight`: row t of
+        the [B, T, 2 c_out] result is the output pair (2t, 2t+1), i.e. the result IS [B, 2T, c_out]. Returns the
+        reconstruction [B, L, c_in] in the raw-feature operand format (it goes through the same embedding weights)."""
+        w = self.w
+        last = self.n_levels - 1
+        T = z.shape[1]
+        for i in range(5):
+            key = f"interpolator.expansion.up_{i + 1}.conv_transpose.conv"
+            ck = ("up", key, z.dtype)
+            if ck not in w._cache:
+                w._cache[ck] = up_weight(w.sd[key + ".weight"]).to(self.device).to(z.dtype).contiguous()
+                w._cache[("upb", key)] = torch.cat([w.vec(key + ".bias")] * 2).contiguous()
+            wg, bias2 = w._cache[ck], w._cache[("upb", key)]
+            co = wg.shape[0] // 2
+            raw = self.buf("vc_raw", (B, T * 2 * co), torch.float32)
+            ws = self.workspace(B * T * 2 * co * 4) if z.dtype == torch.float32 else None
+            ops.conv_gemm(z, wg, taps=2, stride=1, batch=B, c_in=z.shape[2], n_out=2 * co, segs=[(T, 0, 0)], a_rows=T, o_rows=T,
+                          bias=bias2, row_mask=masks["up%d" % (last - i)], out_f32=raw, workspace=ws, tap_mode=1)
+            T *= 2
+            out_dt = self.in_dt if i == 4 else self.adt
+            z = self.buf("up_z%d" % (i & 1) if i < 4 else "reco", (B, T * co), out_dt)
+            ops.instnorm_lrelu(raw.view(B, T, co), z.view(B, T, co), batch=B, t=T, channels=co)
+            z = z.view(B, T, co)
+        return z
 
     def forward_dense(self, x_act, valid):
         """x_act: [B, L, c_in] in `self.in_dt` (token-major), valid: host list of valid lengths.
@@ -435,24 +478,34 @@ class LocalizationEngine:
         masks = self.masks(valid, L)
         vcls = self.video_cls(x_act, B, L, masks)
         # ---- embedding (backbones.py:437-465), once
-        h = x_act
         n_embd = self.arch[0]
-        x = None
-        for i in range(n_embd):
-            last = i == n_embd - 1
-            ln = w.ln(f"backbone.embd_norm.{i}") if w.has(f"backbone.embd_norm.{i}.weight") else None
-            bias = w.vec(f"backbone.embd.{i}.conv.bias") if w.has(f"backbone.embd.{i}.conv.bias") else None
-            kw = dict(B=B, taps=3, segs=[(L, 0, 0)], a_rows=L, o_rows=L, bias=bias, row_mask=masks[0], ln=ln, act=ops.ACT_RELU)
-            if last:
-                x = self.buf("x_embd", (B, L, C), torch.float32)
-                self._gemm(h, f"backbone.embd.{i}.conv.weight", pe=self.pe(L) if self.cfg["use_abs_pe"] else None, out_f32=x, **kw)
-            else:
-                e = self.buf("embd%d" % i, (B, L, C), adt)
-                self._gemm(h, f"backbone.embd.{i}.conv.weight", out_act=e, **kw)
-                h = e
+
+        def embed(h, out_name):
+            x_ = None
+            for i in range(n_embd):
+                last = i == n_embd - 1
+                ln = w.ln(f"backbone.embd_norm.{i}") if w.has(f"backbone.embd_norm.{i}.weight") else None
+                bias = w.vec(f"backbone.embd.{i}.conv.bias") if w.has(f"backbone.embd.{i}.conv.bias") else None
+                kw = dict(B=B, taps=3, segs=[(L, 0, 0)], a_rows=L, o_rows=L, bias=bias, row_mask=masks[0], ln=ln, act=ops.ACT_RELU)
+                if last:
+                    x_ = self.buf(out_name, (B, L, C), torch.float32)
+                    self._gemm(h, f"backbone.embd.{i}.conv.weight", pe=self.pe(L) if self.cfg["use_abs_pe"] else None, out_f32=x_, **kw)
+                else:
+                    e = self.buf("embd%d" % i, (B, L, C), adt)
+                    self._gemm(h, f"backbone.embd.{i}.conv.weight", out_act=e, **kw)
+                    h = e
+            return x_
+
+        x = embed(x_act, "x_embd")
         # ---- backbone (backbones.py:467-495)
         w0 = self.win[0]
-        x, _ = self.mm_block("backbone.resselfattention", x, x, B, L, L, masks, 0, w0, "x_res")
+        if self.recon:
+            # exp5-style: K of resselfattention = the embedded reconstruction (av_fd_meta_arch.py:346-348, backbones.py:469);
+            # norm_x is identical to x (DeepInterpolator(norm=False)) and never used
+            reco_e = embed(self.expansion(self._contracted, B, masks), "reco_embd")
+            x, _ = self.mm_block("backbone.resselfattention", x, x, B, L, L, masks, 0, w0, "x_res", xk=reco_e)
+        else:
+            x, _ = self.mm_block("backbone.resselfattention", x, x, B, L, L, masks, 0, w0, "x_res")
         for i in range(self.arch[1]):
             x, _ = self.transformer_block(f"backbone.stem.{i}", x, B, L, masks, 0, 1, w0, "x_stem%d" % i)
         lh, lh_act = x, None

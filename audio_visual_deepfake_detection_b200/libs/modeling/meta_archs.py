@@ -27,7 +27,7 @@ from ... import ops
 from ...native import AvdfError
 from .engine import LocalizationEngine
 from .models import register_backbone, register_generator, register_meta_arch, register_neck
-from .spec import EXP12, EXP13, state_dict_spec
+from .spec import EXP5, EXP12, EXP13, state_dict_spec
 
 
 def _on_model_device(fn):
@@ -357,6 +357,13 @@ class GraphedPass:
 class AVPtTransformerRecovery(_LocalizationBase):
     """exp12: video-level branch = DeepInterpolator (Contraction + classifier), av_fd_no_recon.py:318."""
     MODEL_NAME = EXP12
+
+
+@register_meta_arch(EXP5)
+class AVPtTransformerRecoveryRecon(_LocalizationBase):
+    """exp5-style: DeepInterpolator with its Expansion live - the reconstruction is embedded and attended to as K by
+    backbone.resselfattention (av_fd_meta_arch.py:162, 346-348; blocks.py:1568-1590)."""
+    MODEL_NAME = EXP5
 
 
 @register_meta_arch(EXP13)

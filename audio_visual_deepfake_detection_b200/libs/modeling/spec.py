@@ -1,4 +1,4 @@
-"""Parameter inventory of the two meta-archs on the hot path.
+"""Parameter inventory of the meta-archs on the hot path.
 
 `state_dict_spec` lists every tensor name/shape a reference checkpoint holds
 for `AVLocPointTransformerRecoveryNoNormNorecon` (exp12,
@@ -12,6 +12,9 @@ from collections import OrderedDict
 
 EXP12 = "AVLocPointTransformerRecoveryNoNormNorecon"
 EXP13 = "AVLocPointTransformerRecoveryNoNormNoreconTHE"
+# exp5-style: same modules as exp12, but the DeepInterpolator's Expansion is LIVE - its reconstruction of the input is
+# embedded and feeds the K stream of backbone.resselfattention (libs/modeling/av_fd_meta_arch.py:162, 346-348)
+EXP5 = "AVLocPointTransformerRecoveryNoNorm"
 
 
 def _ln(spec, name, c):
@@ -100,7 +103,7 @@ def state_dict_spec(model_cfg: dict, model_name: str) -> "OrderedDict[str, tuple
                 spec[f"reg_head.scale.{i}.scale"] = ()
         _conv(spec, f"{head}.{last}.conv", n_out, H, hk, True)
     # video-level branch
-    if model_name == EXP12:       # DeepInterpolator(input_dim, embd_dim), blocks.py:1593-1606
+    if model_name in (EXP12, EXP5):   # DeepInterpolator(input_dim, embd_dim), blocks.py:1593-1606
         dims = [n_in, C, 2 * C, 4 * C, 8 * C, C]          # Contraction, blocks.py:1546-1551
         for i in range(5):
             _conv(spec, f"interpolator.contraction.down_{i + 1}.conv_block.conv", dims[i + 1], dims[i], 3, True)

@@ -86,7 +86,8 @@ def synthetic_streams(duration: float, seed: int, video_dim=256, byola_dim=2048,
     out = {}
     if video_dim:
         out["video"] = rng.standard_normal((t_v, video_dim)).astype(np.float32)
-    out["byola"] = np.abs(rng.standard_normal((t_b, byola_dim))).astype(np.float32)
+    if byola_dim:
+        out["byola"] = np.abs(rng.standard_normal((t_b, byola_dim))).astype(np.float32)
     out["emo"] = rng.standard_normal((t_e, emo_dim)).astype(np.float32)
     return out
 
@@ -103,6 +104,7 @@ def tinydataset_streams(index: int, seed: int, video_dim=256, byola_dim=2048, em
     out = {}
     if video_dim:
         out["video"] = rng.standard_normal((vf, video_dim)).astype(np.float32)
-    out["byola"] = np.abs(rng.standard_normal((t_b, byola_dim))).astype(np.float32)
+    if byola_dim:
+        out["byola"] = np.abs(rng.standard_normal((t_b, byola_dim))).astype(np.float32)
     out["emo"] = rng.standard_normal((t_e, emo_dim)).astype(np.float32)
     return duration, out

@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 import ref_harness as rh                                  # noqa: E402
 import interp_ref                                         # noqa: E402
-from audio_visual_deepfake_detection_b200.libs.modeling.spec import EXP12, EXP13   # noqa: E402
+from audio_visual_deepfake_detection_b200.libs.modeling.spec import EXP5, EXP12, EXP13   # noqa: E402
 from audio_visual_deepfake_detection_b200.libs.utils import synthetic as syn        # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -37,7 +37,11 @@ MODEL_CASES = {
     "exp12": (EXP12, {}, True, 0),
     "exp13": (EXP13, {}, True, 0),
     "audio_only": (EXP12, {"dataset.video_input_dim": 0}, False, 3),
+    # exp5-style arch with a live reconstruction branch: visual stream + emotion2vec, no BYOL-A
+    "exp5": (EXP5, {}, "video+emo", 5),
 }
+# the reference yaml each case is built from (None: configs_test/deepfake_exp12_test.yaml)
+REF_CONFIG = {"exp13": "configs_train/deepfake_exp13.yaml", "exp5": "configs_train/deepfake_exp5.yaml"}
 # (duration, seed, mode): 'interp' = dataset path (T=768, all-true mask);
 # 'ragged' = feats shorter than max_seq_len fed as-is (masked tail);
 VIDEO_CASES = [(4.03, 100, "interp"), (9.04, 101, "interp"), (26.37, 102, "interp"), (7.42, 103, "ragged")]
@@ -53,7 +57,7 @@ def sweep_inputs(n, seed):
 
 
 def make_item(duration, seed, mode, use_video, max_seq_len=768):
-    st = syn.synthetic_streams(duration, seed, video_dim=256 if use_video else 0)
+    st = syn.synthetic_streams(duration, seed, video_dim=256 if use_video else 0, byola_dim=0 if use_video == "video+emo" else 2048)
     if mode == "interp":
         return interp_ref.dataset_item(st, duration, f"vid{seed}", max_seq_len)
     # ragged: resample every stream to a short common length and do NOT upsample to max_seq_len
@@ -131,7 +135,7 @@ def gen_interp():
 def gen_models():
     for case, (model_name, overrides, use_video, wseed) in MODEL_CASES.items():
         # exp13 has no test yaml in the reference; its own (training) yaml carries the test_cfg
-        cfg_path = os.path.join(rh.REF_ROOT, "configs_train/deepfake_exp13.yaml") if model_name == EXP13 else None
+        cfg_path = os.path.join(rh.REF_ROOT, REF_CONFIG[case]) if case in REF_CONFIG else None
         cfg, model = rh.build_reference_model(config_path=cfg_path, model_name=model_name, overrides=overrides)
         sd = syn.synthetic_state_dict(cfg["model"], model_name, seed=wseed)
         model.load_state_dict(sd, strict=True)
@@ -165,7 +169,11 @@ def gen_models():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    gen_nms()
-    gen_interp()
+    only = sys.argv[1:]                 # e.g. `python oracle/make_golden.py exp5`: only these model cases
+    if only:
+        MODEL_CASES = {k: v for k, v in MODEL_CASES.items() if k in only}
+    else:
+        gen_nms()
+        gen_interp()
     gen_models()
     print("golden fixtures written to", OUT)

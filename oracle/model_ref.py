@@ -151,6 +151,8 @@ class OracleModel:
         self.sd = {k[7:] if k.startswith("module.") else k: v.detach().to(torch.float32).cpu()
                    for k, v in state_dict.items()}
         self.exp13 = model_name.endswith("THE")
+        # exp5-style arch (libs/modeling/av_fd_meta_arch.py:162): the Expansion's reconstruction is live
+        self.recon = model_name == "AVLocPointTransformerRecoveryNoNorm"
         c = model_cfg
         self.n_head = c["n_head"]
         self.C = c["embd_dim"]
@@ -230,14 +232,12 @@ class OracleModel:
         return self._mlp_and_residual(pre, xq, a, om), om
 
     # ---- backbone -----------------------------------------------------------
-    def backbone(self, x: Tensor, mask: Tensor, taps: Optional[dict] = None):
-        """ConvHRLRFullResSelfAttTransformerBackboneRevised.forward,
-        backbones.py:413-495. norm_x is dead, reco_x == x in the Norecon archs,
-        so the embedding is evaluated once (identical values)."""
+    def _embed(self, x: Tensor, mask: Tensor) -> Tensor:
+        """Embedding convs + LN + ReLU + absolute PE, backbones.py:437-465."""
         T = x.shape[-1]
         for i in range(self.arch[0]):
-            x, mask = masked_conv1d(x, mask, self.p(f"backbone.embd.{i}.conv.weight"),
-                                    self.sd.get(f"backbone.embd.{i}.conv.bias"))
+            x, _ = masked_conv1d(x, mask, self.p(f"backbone.embd.{i}.conv.weight"),
+                                 self.sd.get(f"backbone.embd.{i}.conv.bias"))
             if self.has(f"backbone.embd_norm.{i}.weight"):
                 x = self.ln(x, f"backbone.embd_norm.{i}")
             x = torch.relu(x)
@@ -246,10 +246,21 @@ class OracleModel:
             if T >= self.max_seq_len:
                 pe = F.interpolate(pe, T, mode="linear", align_corners=False)
             x = x + pe[:, :, :T] * mask.to(x.dtype)
+        return x
+
+    def backbone(self, x: Tensor, mask: Tensor, taps: Optional[dict] = None, reco: Optional[Tensor] = None):
+        """ConvHRLRFullResSelfAttTransformerBackboneRevised.forward,
+        backbones.py:413-495. norm_x is dead; reco_x == x in the Norecon archs,
+        so their embedding is evaluated once (identical values). In the exp5-style
+        arch `reco` (the Expansion's output) is embedded with the same weights and is
+        the K stream of resselfattention (backbones.py:469)."""
+        reco_e = self._embed(reco, mask) if reco is not None else None
+        x = self._embed(x, mask)
         if taps is not None:
             taps["embd"] = x
         w0 = self.win[0]
-        x, _ = self.mm_block("backbone.resselfattention", x, mask, x, mask, x, mask, w0)
+        xk = reco_e if reco_e is not None else x
+        x, _ = self.mm_block("backbone.resselfattention", x, mask, xk, mask, x, mask, w0)
         if taps is not None:
             taps["res"] = x
         for i in range(self.arch[1]):
@@ -318,12 +329,28 @@ class OracleModel:
         y, m = masked_conv1d(x, m, self.p(pre + ".conv_block.conv.weight"), self.p(pre + ".conv_block.conv.bias"), stride)
         return F.leaky_relu(instance_norm_t(y), 0.2), m
 
+    def expansion(self, z: Tensor, m: Tensor) -> Tensor:
+        """Expansion.forward, blocks.py:1568-1590: 5 x UpBlock (blocks.py:1519-1541) =
+        ConvTranspose1d(k3, stride 2, padding 1, output_padding 1) * nearest-upsampled
+        mask (blocks.py:1472-1491) -> InstanceNorm1d -> LeakyReLU(0.2); `last` is
+        False everywhere (DeepInterpolator passes tanh=False, blocks.py:1599)."""
+        for i in range(1, 6):
+            pre = f"interpolator.expansion.up_{i}.conv_transpose.conv"
+            y = F.conv_transpose1d(z, self.p(pre + ".weight"), self.p(pre + ".bias"), stride=2, padding=1, output_padding=1)
+            m = F.interpolate(m.to(y.dtype), size=y.shape[-1], mode="nearest")
+            y = y * m
+            m = m.bool()
+            z = F.leaky_relu(instance_norm_t(y), 0.2)
+        return z
+
     def video_cls_exp12(self, x: Tensor, mask: Tensor) -> Tensor:
         """DeepInterpolator.forward with norm=False, blocks.py:1627-1638; the
-        Expansion output is discarded by the caller (av_fd_no_recon.py:346)."""
+        Expansion output is discarded by the Norecon callers (av_fd_no_recon.py:346)
+        and kept (self._reco) for the exp5-style arch (av_fd_meta_arch.py:346)."""
         z, m = x, mask
         for i in range(1, 6):
             z, m = self._down_block(f"interpolator.contraction.down_{i}", z, m, 2)
+        self._reco = self.expansion(z, m) if self.recon else None
         g = F.conv1d(z, self.p("interpolator.conv0.0.weight"))
         g = F.leaky_relu(instance_norm_t(g), 0.2)
         pooled = torch.cat([g.max(dim=2).values, g.mean(dim=2)], dim=1)          # [B, 2C]
@@ -350,7 +377,7 @@ class OracleModel:
         """x [B, C_in, T] fp32, mask [B, 1, T] bool -> (logits[l] [B,1,T_l],
         offsets[l] [B,2,T_l], masks[l] [B,1,T_l], video_cls [B,1])."""
         vcls = self.video_cls_exp13(x, mask) if self.exp13 else self.video_cls_exp12(x, mask)
-        feats, masks = self.backbone(x, mask, taps)
+        feats, masks = self.backbone(x, mask, taps, reco=self._reco if self.recon else None)
         if taps is not None:
             taps["feats"] = feats
         fpn, masks = self.neck(feats, masks)

@@ -18,14 +18,15 @@ from audio_visual_deepfake_detection_b200.libs.utils import synthetic as syn
 def make_videos(n_videos, use_video, seed0=5000, include_tiny=True):
     """The 12 tinydataset-shaped clips (BASELINE.json configs[0]) followed by AV-Deepfake1M-length clips."""
     raw = []
+    byola = 0 if use_video == "video+emo" else 2048          # the exp5-style case: visual stream + emotion2vec only
     if include_tiny:
         for i in range(min(n_videos, len(syn.TINYDATASET_SHAPES))):
-            d, st = syn.tinydataset_streams(i, seed0 + i, video_dim=256 if use_video else 0)
+            d, st = syn.tinydataset_streams(i, seed0 + i, video_dim=256 if use_video else 0, byola_dim=byola)
             raw.append({"video_id": "tiny%02d" % i, "duration": d, "streams": st})
     durs = syn.sample_durations(max(0, n_videos - len(raw)), seed=seed0)
     for j, d in enumerate(durs):
         raw.append({"video_id": "syn%04d" % j, "duration": float(d),
-                    "streams": syn.synthetic_streams(float(d), seed0 + 100 + j, video_dim=256 if use_video else 0)})
+                    "streams": syn.synthetic_streams(float(d), seed0 + 100 + j, video_dim=256 if use_video else 0, byola_dim=byola)})
     return raw
 
 

@@ -10,7 +10,7 @@ import torch
 
 from audio_visual_deepfake_detection_b200 import native
 from audio_visual_deepfake_detection_b200.libs.core import load_config_for
-from audio_visual_deepfake_detection_b200.libs.modeling import EXP12, EXP13, make_meta_arch, state_dict_spec
+from audio_visual_deepfake_detection_b200.libs.modeling import EXP5, EXP12, EXP13, make_meta_arch, state_dict_spec
 from audio_visual_deepfake_detection_b200.libs.modeling import models as registry
 from audio_visual_deepfake_detection_b200.libs.utils import synthetic as syn
 
@@ -47,11 +47,11 @@ def test_argument_errors_are_codes_not_crashes():
 
 
 def test_registries_and_state_dict_contract():
-    assert set(registry.meta_archs) >= {EXP12, EXP13}
+    assert set(registry.meta_archs) >= {EXP5, EXP12, EXP13}
     assert "convHRLRFullResSelfAttTransformerRevised" in registry.backbones and "fpn" in registry.necks and "point" in registry.generators
     with pytest.raises(KeyError):
         make_meta_arch("LocPointTransformer")
-    for name, n_tensors in ((EXP12, 608), (EXP13, 599)):          # tensors in the reference checkpoints
+    for name, n_tensors in ((EXP12, 608), (EXP13, 599), (EXP5, 608)):          # tensors in the reference checkpoints
         cfg = load_config_for(name)
         assert len(state_dict_spec(cfg["model"], name)) == n_tensors
         model = make_meta_arch(cfg["model_name"], **cfg["model"])

@@ -24,7 +24,7 @@ N_VIDEOS = int(os.environ.get("AVDF_PARITY_VIDEOS", "256"))
 
 
 @pytest.mark.parametrize("weights", ["dense", "sparse"])
-@pytest.mark.parametrize("case", ["audio_only", "exp12", "exp13"])
+@pytest.mark.parametrize("case", ["audio_only", "exp12", "exp13", "exp5"])
 def test_final_sets_batch32_mixed(case, weights):
     """weights: "dense" = the golden fixtures' synthetic weights (~1000 of 1512 points above 0.2: a stress case in which
     the reference itself sits within 1e-5..1e-3 of a threshold in every video); "sparse" = cls prior -7: a handful of
