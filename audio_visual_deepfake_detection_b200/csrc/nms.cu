@@ -15,6 +15,7 @@
 //     below min_score";
 //   * the gaussian weight uses a restatement of glibc's expf (double polynomial + table),
 //     which is what std::exp(float) resolves to in the reference build.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace avdf {
@@ -286,6 +287,210 @@ nms_standalone_kernel(const float* __restrict__ segs, const float* __restrict__ 
     }
   }
   if (threadIdx.x == 0) *out_count = k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large candidate lists (n > NMS_SMEM_CAP: the 10k / 100k points of the NMS sweep): one CLUSTER of NMS_CL CTAs. The
+// reference's working arrays are distributed by POSITION - position p lives in CTA p / S at offset p % S of that CTA's
+// shared memory - so every pick is: local argmax over the CTA's slice -> the CTA's best (with the candidate's data) is
+// written into every CTA's exchange table through distributed shared memory -> barrier.cluster -> every CTA reduces the
+// NMS_CL records to the same global pick and decays / suppresses its own slice. The soft-NMS bookkeeping (swap the pick
+// to the front, swap failed candidates with the last one and shrink, nms_cpu.cpp:105-157) is emulated exactly as in
+// soft_nms_block above: fail counts are exchanged the same way, holes are ranked through a cluster-wide prefix, the hole
+// list lives in the global workspace, survivors beyond the new end are moved into the holes with remote stores.
+// One CTA walking a 100k list from global memory takes ~70-80 us per pick; here a pick costs 2-4 cluster barriers.
+// ---------------------------------------------------------------------------------------------
+constexpr int NMS_CL = 16;                      // CTAs per cluster (non-portable size: needs the launch attribute)
+constexpr int NMS_CL_SLICE_MAX = 11264;         // positions per CTA: 5 arrays x 4 B x 11264 = 220 KB
+struct ClRec { float s; int pos; float x1, x2, ar; int id; };       // a CTA's best candidate (pos < 0: none)
+struct ClSwap { float x1, x2, sc, ar; int id; int pad; };            // the element at position i (it moves to the pick's slot)
+struct ClShared {
+  ClRec rec[2][NMS_CL];
+  ClSwap swp[2];
+  int cnt[NMS_CL];
+};
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cl_map(uint32_t addr, int rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cl_st(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+nms_cluster_kernel(const float* __restrict__ segs, const float* __restrict__ scores, int n, int S,
+                   float thr, float sigma, float min_score, int method /* -1 = hard */, int max_num,
+                   float* dets, long long* out_idx, int* out_count, int* hole /* global, n ints */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ NmsShared sh;
+  __shared__ ClShared cs;
+  float* x1 = reinterpret_cast<float*>(smem_raw);
+  float* x2 = x1 + S; float* sc = x2 + S; float* ar = sc + S;
+  int* id = reinterpret_cast<int*>(ar + S);
+  const int rank = cl_rank();
+  const int base = rank * S;                       // first position of this CTA's slice
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = threadIdx.x; o < S; o += NMS_THREADS) {
+    const int p = base + o;
+    if (p < n) {
+      float a = segs[2 * p], b = segs[2 * p + 1];
+      x1[o] = a; x2[o] = b; sc[o] = scores[p];
+      ar[o] = __fadd_rn(__fsub_rn(b, a), 1e-6f);
+      id[o] = p;
+    }
+  }
+  __syncthreads();
+  // publish this CTA's best candidate (threads 0..NMS_CL-1: one remote CTA each)
+  auto publish_best = [&](const Best& b, int buf) {
+    if (threadIdx.x < NMS_CL) {
+      ClRec r; r.s = b.s; r.pos = b.pos;
+      if (b.pos >= 0) { const int o = b.pos - base; r.x1 = x1[o]; r.x2 = x2[o]; r.ar = ar[o]; r.id = id[o]; }
+      else { r.x1 = r.x2 = r.ar = 0.f; r.id = 0; }
+      const uint32_t dst = cl_map(smem_addr_u32(&cs.rec[buf][rank]), (int)threadIdx.x);
+      cl_st(dst, __float_as_uint(r.s)); cl_st(dst + 4, (uint32_t)r.pos); cl_st(dst + 8, __float_as_uint(r.x1));
+      cl_st(dst + 12, __float_as_uint(r.x2)); cl_st(dst + 16, __float_as_uint(r.ar)); cl_st(dst + 20, (uint32_t)r.id);
+    }
+  };
+  auto global_best = [&](int buf) -> ClRec {      // the same record in every thread of every CTA
+    ClRec g = cs.rec[buf][0];
+#pragma unroll
+    for (int c = 1; c < NMS_CL; ++c) {
+      const ClRec r = cs.rec[buf][c];
+      if (r.pos >= 0 && (g.pos < 0 || r.s > g.s || (r.s == g.s && r.pos < g.pos))) g = r;
+    }
+    return g;
+  };
+  int k = 0;
+  if (method < 0) {
+    // ---- hard NMS (nms_cpu.cpp:19-58): greedy over descending score, ties by ascending index; id < 0 = suppressed
+    int slot = 0, buf = 0;
+    const int cnt_own = min(S, n - base);
+    while (max_num <= 0 || k < max_num) {
+      Best b; b.pos = -1; b.s = 0.f; b.tie = 0;
+      for (int o = threadIdx.x; o < cnt_own; o += NMS_THREADS)
+        if (id[o] >= 0 && better(sc[o], base + o, b)) { b.s = sc[o]; b.tie = base + o; b.pos = base + o; }
+      b = block_best(b, sh.best, slot);
+      slot ^= 1;
+      publish_best(b, buf);
+      cl_sync();
+      const ClRec g = global_best(buf);
+      buf ^= 1;
+      if (g.pos < 0) break;
+      if (rank == 0 && threadIdx.x == 0) out_idx[k] = g.pos;
+      for (int o = threadIdx.x; o < cnt_own; o += NMS_THREADS) {
+        if (id[o] < 0) continue;
+        if (base + o == g.pos) { id[o] = ~id[o]; continue; }
+        float ovr = ovr_eps(g.x1, g.x2, g.ar, x1[o], x2[o], ar[o]);
+        if (ovr >= thr) id[o] = ~id[o];
+      }
+      __syncthreads();
+      ++k;
+    }
+  } else {
+    // ---- soft NMS (nms_cpu.cpp:67-160), positions [0, nsegs) distributed over the cluster
+    int nsegs = n, slot = 0, sslot = 0;
+    int i = 0;
+    for (; i < nsegs; ++i) {
+      if (max_num > 0 && i >= max_num) break;
+      const int hi = min(nsegs, base + S);       // this CTA's positions are [base, hi)
+      // 1. first maximum in position order over [i, nsegs): local part, then the exchange
+      Best b; b.pos = -1; b.s = 0.f; b.tie = 0;
+      for (int p = max(i, base) + threadIdx.x; p < hi; p += NMS_THREADS)
+        if (better(sc[p - base], p, b)) { b.s = sc[p - base]; b.tie = p; b.pos = p; }
+      b = block_best(b, sh.best, slot);
+      slot ^= 1;
+      publish_best(b, 0);
+      if (i >= base && i < base + S && threadIdx.x >= 32 && threadIdx.x < 32 + NMS_CL) {   // the owner of position i
+        const int o = i - base;
+        const uint32_t dst = cl_map(smem_addr_u32(&cs.swp[0]), (int)threadIdx.x - 32);
+        cl_st(dst, __float_as_uint(x1[o])); cl_st(dst + 4, __float_as_uint(x2[o])); cl_st(dst + 8, __float_as_uint(sc[o]));
+        cl_st(dst + 12, __float_as_uint(ar[o])); cl_st(dst + 16, (uint32_t)id[o]);
+      }
+      cl_sync();
+      const ClRec g = global_best(0);
+      const ClSwap o_ = cs.swp[0];
+      const int mp = g.pos;
+      if (rank == 0 && threadIdx.x == 0) {
+        dets[3 * i + 0] = g.x1; dets[3 * i + 1] = g.x2; dets[3 * i + 2] = g.s;
+        out_idx[i] = g.id;
+      }
+      // 3. decay every position in (i, nsegs); the slot mp now holds the old element i
+      int nfail = 0;
+      for (int p = max(i + 1, base) + threadIdx.x; p < hi; p += NMS_THREADS) {
+        const int o = p - base;
+        float jx1, jx2, jsc, jar;
+        if (p == mp) {
+          jx1 = o_.x1; jx2 = o_.x2; jsc = o_.sc; jar = o_.ar;
+          x1[o] = o_.x1; x2[o] = o_.x2; ar[o] = o_.ar; id[o] = o_.id;
+        } else {
+          jx1 = x1[o]; jx2 = x2[o]; jsc = sc[o]; jar = ar[o];
+        }
+        float ovr = ovr_eps(g.x1, g.x2, g.ar, jx1, jx2, jar);
+        float weight = 1.f;
+        if (method == 0) { if (ovr >= thr) weight = 0.f; }
+        else if (method == 1) { if (ovr >= thr) weight = __fsub_rn(1.f, ovr); }
+        else if (method == 2) { weight = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), sigma)); }
+        jsc = __fmul_rn(jsc, weight);
+        sc[o] = jsc;
+        nfail += (jsc < min_score) ? 1 : 0;
+      }
+      const int Fc = block_sum(nfail, sh.sum, sslot);   // barrier inside: decay writes are visible in the CTA
+      sslot ^= 1;
+      if (threadIdx.x < NMS_CL) cl_st(cl_map(smem_addr_u32(&cs.cnt[rank]), (int)threadIdx.x), (uint32_t)Fc);
+      cl_sync();
+      int F = 0, before = 0;
+#pragma unroll
+      for (int c = 0; c < NMS_CL; ++c) { const int v = cs.cnt[c]; F += v; before += (c < rank) ? v : 0; }
+      if (F == 0) continue;                            // (uniform over the cluster)
+      // 4. "swap with last, shrink": holes = failed positions below the new end, ranked in ascending order; the k-th hole
+      //    receives the k-th survivor counted from the old end backwards
+      const int lo = max(i + 1, base), L = max(hi - lo, 0), new_n = nsegs - F;
+      const int chunk = (L + NMS_THREADS - 1) / NMS_THREADS;
+      const int cb = lo + threadIdx.x * chunk;
+      const int ce = min(cb + chunk, hi);
+      int cnt = 0;
+      for (int p = cb; p < ce; ++p) cnt += (sc[p - base] < min_score) ? 1 : 0;
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) sh.scan[w] = inc;
+      __syncthreads();
+      int wbase = before;
+      for (int q = 0; q < w; ++q) wbase += sh.scan[q];
+      int run = wbase + inc - cnt;                     // failures strictly before this chunk, over the whole list
+      for (int p = cb; p < ce; ++p) {
+        const bool fail = sc[p - base] < min_score;
+        if (fail && p < new_n) hole[run] = p;
+        run += fail ? 1 : 0;
+      }
+      cl_sync();                                       // the hole list (global memory) is complete
+      run = wbase + inc - cnt;
+      for (int p = cb; p < ce; ++p) {
+        const int o = p - base;
+        const bool fail = sc[o] < min_score;
+        run += fail ? 1 : 0;                           // inclusive failure count through p
+        if (!fail && p >= new_n) {
+          const int rank_desc = (nsegs - 1 - p) - (F - run);
+          const int dst = __ldcg(hole + rank_desc);    // (written by another SM: bypass L1)
+          const int dr = dst / S, dof = dst - dr * S;
+          cl_st(cl_map(smem_addr_u32(x1 + dof), dr), __float_as_uint(x1[o]));
+          cl_st(cl_map(smem_addr_u32(x2 + dof), dr), __float_as_uint(x2[o]));
+          cl_st(cl_map(smem_addr_u32(sc + dof), dr), __float_as_uint(sc[o]));
+          cl_st(cl_map(smem_addr_u32(ar + dof), dr), __float_as_uint(ar[o]));
+          cl_st(cl_map(smem_addr_u32(id + dof), dr), (uint32_t)id[o]);
+        }
+      }
+      cl_sync();                                       // moves have landed before the next argmax
+      nsegs = new_n;
+    }
+    k = i;
+  }
+  if (rank == 0 && threadIdx.x == 0) *out_count = k;
+  cl_sync();                                           // no CTA exits while its shared memory may still be written remotely
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -561,6 +766,15 @@ static size_t nms_smem_bytes() { return (size_t)NMS_SMEM_CAP * 6 * sizeof(float)
 
 using namespace avdf;
 
+static bool g_nms_cluster = !(getenv("AVDF_NMS_CLUSTER") && atoi(getenv("AVDF_NMS_CLUSTER")) == 0);
+// Debug / test hook: lists longer than the shared-memory capacity run on a cluster of CTAs (1, default) or on one CTA from
+// the global workspace (0). Returns the previous setting.
+extern "C" __attribute__((visibility("default"))) int avdf_debug_nms_cluster(int on) {
+  const int prev = g_nms_cluster ? 1 : 0;
+  g_nms_cluster = on != 0;
+  return prev;
+}
+
 extern "C" size_t avdf_nms_workspace_bytes(int32_t n) {
   return n > NMS_SMEM_CAP ? (size_t)n * 6 * sizeof(float) : 0;
 }
@@ -575,6 +789,28 @@ static int launch_standalone(const float* segs, const float* scores, int32_t n, 
   AVDF_CHECK_ARG(segs && scores && out_idx, "null pointer");
   const int use_gws = n > NMS_SMEM_CAP;
   if (use_gws) AVDF_CHECK_ARG(ws != nullptr && ws_bytes >= avdf_nms_workspace_bytes(n), "workspace too small");
+  if (use_gws && g_nms_cluster && n <= NMS_CL * NMS_CL_SLICE_MAX) {
+    // one cluster of NMS_CL CTAs, the working arrays distributed over their shared memory
+    const int S = ((n + NMS_CL - 1) / NMS_CL + 31) / 32 * 32;
+    const size_t smem = (size_t)S * 5 * sizeof(float);
+    static avdf::DeviceOnce once;
+    const int dev = avdf::current_device();
+    if (!once.done(dev)) {
+      AVDF_CUDA(cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NMS_CL_SLICE_MAX * 5 * sizeof(float))));
+      AVDF_CUDA(cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      once.mark(dev);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(NMS_CL); cfg.blockDim = dim3(NMS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NMS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, segs, scores, (int)n, S, thr, sigma, min_score, method, (int)max_num,
+                                             dets, reinterpret_cast<long long*>(out_idx), out_count, reinterpret_cast<int*>(ws));
+    if (e != cudaSuccess) { set_error("nms_cluster_kernel: launch failed: %s", cudaGetErrorString(e)); return AVDF_ERR_CUDA; }
+    return check_launch("nms_cluster_kernel");
+  }
   AVDF_SMEM_ATTR_ONCE(nms_standalone_kernel, nms_smem_bytes());
   nms_standalone_kernel<<<1, NMS_THREADS, use_gws ? 0 : nms_smem_bytes(), st>>>(
       segs, scores, n, thr, sigma, min_score, method, max_num, dets, reinterpret_cast<long long*>(out_idx),

@@ -276,7 +276,27 @@ def nms_sweep(dev):
             cpu_ms = 1000.0 * (time.perf_counter() - t0)
             res[kind] = {"gpu_us": gpu_us, "cpu_ms": cpu_ms, "picks": int(len(want)),
                          "bit_equal": bool(np.array_equal(got.cpu().numpy(), want))}
+            if n <= 1512:
+                # the product's shape: ONE launch of the fused postprocess kernel over a batch of videos, one CTA per video
+                # (NMS + voting + the final sort, max_seg_num 100 like the shipped test_cfg) - 148 copies of this list
+                B = 148
+                cs = d_s[None].repeat(B, 1, 1).contiguous(); cc = d_p[None].repeat(B, 1).contiguous()
+                cn = torch.full((B,), n, dtype=torch.int32, device=dev)
+                osg = torch.zeros((B, 100, 2), device=dev); osc = torch.zeros((B, 100), device=dev)
+                ocn = torch.zeros(B, dtype=torch.int32, device=dev)
+                bf = lambda: ops.postprocess(B, cand_segs=cs, cand_scores=cc, cand_count=cn, iou_threshold=0.1, min_score=0.2, sigma=0.75,   # noqa: E731
+                                             voting_thresh=0.9, max_seg_num=100, use_soft_nms=(kind == "soft"), out_segs=osg,
+                                             out_scores=osc, out_count=ocn)
+                bf(); torch.cuda.synchronize()
+                e0.record()
+                for _ in range(10):
+                    bf()
+                e1.record(); torch.cuda.synchronize()
+                res[kind]["batched_148_videos_us_per_video"] = 1000.0 * e0.elapsed_time(e1) / 10 / B
         out[str(n)] = res
+    out["note"] = ("gpu_us: one list per launch, full pick list like nms_1d_cpu (N <= 6144: one CTA in shared memory; larger: a cluster of "
+                   "16 CTAs, the working arrays distributed over their shared memory); batched_148_videos_us_per_video: the fused "
+                   "postprocess kernel, one CTA per video, 100 picks + voting; cpu_ms: oracle/nms_ref.c (port of nms_cpu.cpp), one core")
     return out
 
 
