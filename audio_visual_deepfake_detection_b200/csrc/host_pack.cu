@@ -172,10 +172,23 @@ extern "C" int avdf_h2d_gather(const void* const* src, void* const* dst, const s
   AVDF_CHECK_ARG(n >= 0, "n >= 0");
   AVDF_CHECK_ARG(n == 0 || (src && dst && nbytes), "null span arrays");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  for (int i = 0; i < n; ++i) {
-    if (nbytes[i] == 0) continue;
+  // Spans that follow each other in BOTH address spaces are sent as one copy: a batch collated stream-major in one pinned
+  // block (libs/datasets collate_pinned) leaves as one copy per stream instead of one per video and stream - measured on
+  // the PCIe Gen5 link of the bench box: 46.9 GB/s with 96 copies of ~0.8 MB per batch, 55.3 GB/s with one (scripts/h2d_ceiling.py)
+  int i = 0;
+  while (i < n) {
+    if (nbytes[i] == 0) { ++i; continue; }
     AVDF_CHECK_ARG(src[i] && dst[i], "null span pointer");
-    AVDF_CUDA(cudaMemcpyAsync(dst[i], src[i], nbytes[i], cudaMemcpyHostToDevice, st));
+    const char* s0 = static_cast<const char*>(src[i]);
+    char* d0 = static_cast<char*>(dst[i]);
+    size_t len = nbytes[i];
+    int j = i + 1;
+    while (j < n && (nbytes[j] == 0 || (static_cast<const char*>(src[j]) == s0 + len && static_cast<char*>(dst[j]) == d0 + len))) {
+      len += nbytes[j];
+      ++j;
+    }
+    AVDF_CUDA(cudaMemcpyAsync(d0, s0, len, cudaMemcpyHostToDevice, st));
+    i = j;
   }
   return AVDF_OK;
 }

@@ -19,7 +19,7 @@
 namespace avdf {
 
 struct InterpParams {
-  const float* src[3];         // packed rows of all videos, per stream: [sum_b T_s(b), C_s]
+  const void* src[3];          // packed rows of all videos, per stream: [sum_b T_s(b), C_s], fp32 or bf16 (16-bit feature shards)
   const int* row_off[3];       // [B+1] prefix offsets (rows) per stream
   int c[3];                    // channels per stream (0 = stream absent)
   int c_off[3];                // channel offset in the concatenated output
@@ -33,7 +33,7 @@ struct InterpParams {
 // sources per 32-video batch, which is what bounded the kernel at 45 % of the HBM roofline.)
 constexpr int INTERP_ROWS = 16;
 
-template <typename OutT>
+template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256) interp_concat_kernel(const InterpParams p, OutT* __restrict__ out) {
   const int groups_per_row = p.c_total >> 3;
   const int chunks_per_video = (p.t_out + INTERP_ROWS - 1) / INTERP_ROWS;
@@ -50,12 +50,12 @@ __global__ void __launch_bounds__(256) interp_concat_kernel(const InterpParams p
     const int r0 = p.row_off[s][b];
     const int t_in = p.row_off[s][b + 1] - r0;
     const int cstride = p.c[s];
-    const float* base = p.src[s] + (size_t)r0 * cstride + cs;
+    const InT* base = static_cast<const InT*>(p.src[s]) + (size_t)r0 * cstride + cs;
     OutT* orow = out + ((size_t)b * p.t_out + t_first) * p.c_total + ch;
     if (t_in == p.t_out) {
       for (int t = t_first; t < t_end; ++t, orow += p.c_total) {
         float v[8];
-        Row8<float>::load(base + (size_t)t * cstride, v);
+        Row8<InT>::load(base + (size_t)t * cstride, v);
         Row8<OutT>::store(orow, v);
       }
       continue;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) interp_concat_kernel(const InterpParams p
 #pragma unroll
           for (int k = 0; k < 8; ++k) a[k] = c[k];
         } else {
-          Row8<float>::load(base + (size_t)i0 * cstride, a);
+          Row8<InT>::load(base + (size_t)i0 * cstride, a);
         }
         h0 = i0;
       }
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) interp_concat_kernel(const InterpParams p
 #pragma unroll
           for (int k = 0; k < 8; ++k) c[k] = a[k];
         } else {
-          Row8<float>::load(base + (size_t)i1 * cstride, c);
+          Row8<InT>::load(base + (size_t)i1 * cstride, c);
         }
         h1 = i1;
       }
@@ -135,7 +135,16 @@ extern "C" int avdf_interp_concat(const float* video, const float* byola, const 
                                   const int32_t* video_off, const int32_t* byola_off, const int32_t* emo_off,
                                   int32_t batch, int32_t c_video, int32_t c_byola, int32_t c_emo, int32_t t_out,
                                   void* out, int32_t out_dtype, void* stream) {
+  return avdf_interp_concat_in(video, byola, emo, AVDF_DTYPE_F32, video_off, byola_off, emo_off, batch, c_video, c_byola, c_emo, t_out,
+                               out, out_dtype, stream);
+}
+
+extern "C" int avdf_interp_concat_in(const void* video, const void* byola, const void* emo, int32_t in_dtype,
+                                     const int32_t* video_off, const int32_t* byola_off, const int32_t* emo_off,
+                                     int32_t batch, int32_t c_video, int32_t c_byola, int32_t c_emo, int32_t t_out,
+                                     void* out, int32_t out_dtype, void* stream) {
   AVDF_CHECK_ARG(batch >= 0 && t_out > 0, "bad batch / t_out");
+  AVDF_CHECK_ARG(in_dtype == AVDF_DTYPE_F32 || in_dtype == AVDF_DTYPE_BF16, "in_dtype must be F32 or BF16");
   AVDF_CHECK_ARG(c_video >= 0 && c_byola >= 0 && c_emo >= 0, "negative channel count");
   AVDF_CHECK_ARG((c_video % 8 | c_byola % 8 | c_emo % 8) == 0, "channel counts must be multiples of 8");
   AVDF_CHECK_ARG(c_video + c_byola + c_emo > 0, "no stream");
@@ -158,6 +167,10 @@ extern "C" int avdf_interp_concat(const float* video, const float* byola, const 
   int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);   // grid-stride, 16 CTAs of 256 per SM
   if (grid < 1) grid = 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  AVDF_DISPATCH_DTYPE(out_dtype, OutT, (interp_concat_kernel<OutT><<<grid, 256, 0, st>>>(p, reinterpret_cast<OutT*>(out))));
+  if (in_dtype == AVDF_DTYPE_F32) {
+    AVDF_DISPATCH_DTYPE(out_dtype, OutT, (interp_concat_kernel<float, OutT><<<grid, 256, 0, st>>>(p, reinterpret_cast<OutT*>(out))));
+  } else {
+    AVDF_DISPATCH_DTYPE(out_dtype, OutT, (interp_concat_kernel<__nv_bfloat16, OutT><<<grid, 256, 0, st>>>(p, reinterpret_cast<OutT*>(out))));
+  }
   return check_launch("interp_concat_kernel");
 }

@@ -234,12 +234,14 @@ class _LocalizationBase(nn.Module):
             if n not in chunk[0]["streams"]:
                 packed["streams"].append(None); packed["offs"].append(None)
                 continue
-            arrs = [c["streams"][n].numpy() if torch.is_tensor(c["streams"][n]) else np.asarray(c["streams"][n], dtype=np.float32)
-                    for c in chunk]
+            from .streaming import _stream_array
+            arrs = [_stream_array(c["streams"][n]) for c in chunk]              # fp32, or uint16 = bf16 feature shards
             off = np.zeros(B + 1, np.int32)
             off[1:] = np.cumsum([a.shape[0] for a in arrs])
-            host = torch.empty((int(off[-1]), arrs[0].shape[1]), dtype=torch.float32, pin_memory=torch.cuda.is_available())
-            np.concatenate(arrs, axis=0, out=host.numpy())
+            shard16 = arrs[0].dtype == np.uint16
+            host = torch.empty((int(off[-1]), arrs[0].shape[1]), dtype=torch.bfloat16 if shard16 else torch.float32,
+                               pin_memory=torch.cuda.is_available())
+            np.concatenate(arrs, axis=0, out=host.view(torch.int16).numpy().view(np.uint16) if shard16 else host.numpy())
             packed["streams"].append(host)
             packed["offs"].append(torch.from_numpy(off))
         meta = np.empty((4, B), np.float32)

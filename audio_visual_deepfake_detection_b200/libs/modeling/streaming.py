@@ -25,6 +25,45 @@ from ... import native
 STREAMS = ("video", "byola", "emo")
 
 
+def bf16_shard(a):
+    """fp32 array -> the opt-in 16-bit feature-shard format: bf16 bit patterns (round to nearest even) in a uint16 array of
+    the same shape. Arrays of this dtype are accepted wherever raw streams are (`model.stream`, `forward_streams`,
+    `collate_pinned`): half the host -> device bytes per video; the GPU resampling reads bf16 and computes in fp32."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+def _stream_array(x):
+    """numpy view of a raw-stream array: fp32, or uint16 holding bf16 bits (torch.bfloat16 tensors are viewed as such)."""
+    if torch.is_tensor(x):
+        x = x.view(torch.int16).numpy().view(np.uint16) if x.dtype == torch.bfloat16 else x.numpy()
+    x = np.asarray(x)
+    return x if x.dtype == np.uint16 else np.asarray(x, dtype=np.float32)
+
+
+def collate_pinned(chunk):
+    """A batch of raw-stream items ({video_id, duration, streams: {name: [T, C] fp32}}) re-homed in ONE page-locked block,
+    laid out stream-major (every video's rows of stream 0, then stream 1, ...) - the layout the interp/concat kernel reads on
+    the device. `StreamRunner` recognises page-locked sources and copies them where they are; with this layout a batch
+    leaves as one host->device copy per stream (avdf_h2d_gather merges adjacent spans). This is the collate step of a
+    loader that feeds `model.stream()` (the reference collates in DataLoader workers and pins per tensor,
+    libs/datasets/datasets.py:27-43)."""
+    names = [n for n in STREAMS if n in chunk[0]["streams"]]
+    arrs = {n: [_stream_array(c["streams"][n]) for c in chunk] for n in names}
+    dt = arrs[names[0]][0].dtype                   # float32, or uint16 = bf16 shards (bf16_shard)
+    total = sum(a.size for n in names for a in arrs[n])
+    block = torch.empty(total, dtype=torch.float32 if dt == np.float32 else torch.int16, pin_memory=torch.cuda.is_available()).numpy().view(dt)
+    pos, views = 0, [dict() for _ in chunk]
+    for n in names:
+        for b, a in enumerate(arrs[n]):
+            v = block[pos:pos + a.size].reshape(a.shape)
+            v[...] = a
+            views[b][n] = v
+            pos += a.size
+    return [{**c, "streams": views[b]} for b, c in enumerate(chunk)]
+
+
 def video_meta(c, t_first, L, feat_stride=1, num_frames=1):
     """(feat_stride, 0.5 * feat_num_frames, fps, duration) of one raw-stream item as fp32, i.e. the scalars
     av_fd_no_recon.py:860-865 feeds into its fp32 tensor expression. An item that carries the dataset's own
@@ -53,7 +92,7 @@ class _Slot:
         self.ids, self.B, self.busy = None, 0, False
         self.direct = None                    # (src, device dst, nbytes, n, keep-alive) of a batch whose arrays are pinned
 
-    def ensure(self, rows, chans, max_batch, K, device, seconds):
+    def ensure(self, rows, chans, max_batch, K, device, seconds, dtype=torch.float32):
         """Staging capacity. The captured graph holds the device staging pointers, so growing them forces a
         re-capture: size them once for a full batch of MAX_SECONDS-long videos at this stream's frame rate (the
         AV-Deepfake1M test split tops out at 33 s) and grow (x1.5) only if a batch still exceeds that."""
@@ -62,12 +101,12 @@ class _Slot:
         for s in range(3):
             if chans[s] == 0:
                 continue
-            if self.host[s] is None or rows[s] > self.cap[s]:
+            if self.host[s] is None or rows[s] > self.cap[s] or self.host[s].dtype != dtype:
                 rate = rows[s] / max(seconds, 1e-3)                       # rows per second of video for this stream
                 want = int(max_batch * MAX_SECONDS * rate * 1.05) + 64 if self.host[s] is None else 0
                 self.cap[s] = max(want, int(rows[s] * 1.5) + 64)
-                self.host[s] = torch.empty((self.cap[s], chans[s]), dtype=torch.float32, pin_memory=True)
-                self.dev[s] = torch.empty((self.cap[s], chans[s]), dtype=torch.float32, device=device)
+                self.host[s] = torch.empty((self.cap[s], chans[s]), dtype=dtype, pin_memory=True)
+                self.dev[s] = torch.empty((self.cap[s], chans[s]), dtype=dtype, device=device)
                 grown = True
         if not hasattr(self, "h_off"):
             self.h_off = torch.zeros((3, max_batch + 1), dtype=torch.int32, pin_memory=True)
@@ -124,15 +163,17 @@ class StreamRunner:
         eng, L = self.eng, self.eng.max_seq_len
         B = len(chunk)
         present = [n in chunk[0]["streams"] for n in STREAMS]
-        arrs = [[np.asarray(c["streams"][n].numpy() if torch.is_tensor(c["streams"][n]) else c["streams"][n]) for c in chunk]
-                if p else None for n, p in zip(STREAMS, present)]
+        arrs = [[_stream_array(c["streams"][n]) for c in chunk] if p else None for n, p in zip(STREAMS, present)]
+        np_dt = next(al[0].dtype for al in arrs if al)            # float32, or uint16 = bf16 feature shards
+        item = np_dt.itemsize
         rows = [sum(a.shape[0] for a in al) if al else 0 for al in arrs]
         chans = [al[0].shape[1] if al else 0 for al in arrs]
         if sum(chans) != eng.c_in:
             raise ValueError("streams carry %d channels, the model expects %d" % (sum(chans), eng.c_in))
         K = int(eng.test_cfg["max_seg_num"])
         with self.cuda_lock:
-            slot.ensure(rows, chans, eng.max_batch, K, eng.device, sum(float(c["duration"]) for c in chunk))
+            slot.ensure(rows, chans, eng.max_batch, K, eng.device, sum(float(c["duration"]) for c in chunk),
+                        torch.float32 if item == 4 else torch.bfloat16)
         off = slot.h_off.numpy()
         src, dst, nbytes = [], [], []
         for s in range(3):
@@ -140,10 +181,12 @@ class StreamRunner:
                 continue
             off[s, 0] = 0
             off[s, 1:B + 1] = np.cumsum([a.shape[0] for a in arrs[s]])
-            base, row_bytes = slot.host[s].data_ptr(), chans[s] * 4
+            base, row_bytes = slot.host[s].data_ptr(), chans[s] * item
             for b, a in enumerate(arrs[s]):
-                if a.dtype != np.float32 or not a.flags.c_contiguous:       # the .npy files are fp32 row-major; anything else is converted
-                    a = arrs[s][b] = np.ascontiguousarray(a, dtype=np.float32)
+                if a.dtype != np_dt:
+                    raise ValueError("a batch mixes fp32 streams and 16-bit shards")
+                if not a.flags.c_contiguous:                                   # the .npy files are row-major; anything else is converted
+                    a = arrs[s][b] = np.ascontiguousarray(a)
                 if a.shape[1] != chans[s]:
                     raise ValueError("stream %s: video %d has %d channels, the batch has %d" % (STREAMS[s], b, a.shape[1], chans[s]))
                 src.append(a.ctypes.data); dst.append(base + int(off[s, b]) * row_bytes); nbytes.append(a.nbytes)
@@ -158,7 +201,7 @@ class StreamRunner:
             for s in range(3):
                 if arrs[s] is None:
                     continue
-                dbase, row_bytes = slot.dev[s].data_ptr(), chans[s] * 4
+                dbase, row_bytes = slot.dev[s].data_ptr(), chans[s] * item
                 dev_dst += [dbase + int(off[s, b]) * row_bytes for b in range(B)]
             slot.direct = (c_src, (ctypes.c_void_p * n)(*dev_dst), c_n, n, arrs)      # arrs: keeps the sources alive
             self.n_direct += 1
@@ -173,7 +216,7 @@ class StreamRunner:
         vidx = slot.h_vidx.numpy()
         for b, c in enumerate(chunk):
             vidx[b] = int(c.get("index", b))
-        slot.rows, slot.chans, slot.B, slot.ids = rows, chans, B, [c["video_id"] for c in chunk]
+        slot.rows, slot.chans, slot.B, slot.ids, slot.item = rows, chans, B, [c["video_id"] for c in chunk], item
 
     def _launch(self, slot):
         with torch.cuda.device(self.eng.device):      # the caller's thread may have another device selected
@@ -191,7 +234,7 @@ class StreamRunner:
             if slot.chans[s]:
                 if slot.direct is None:
                     slot.dev[s][:slot.rows[s]].copy_(slot.host[s][:slot.rows[s]], non_blocking=True)
-                nbytes += slot.rows[s] * slot.chans[s] * 4
+                nbytes += slot.rows[s] * slot.chans[s] * slot.item
         slot.d_off.copy_(slot.h_off, non_blocking=True)
         slot.d_meta.copy_(slot.h_meta, non_blocking=True)
         if self.records is not None:
@@ -204,7 +247,7 @@ class StreamRunner:
             staged["records"], staged["vidx"] = self.records, slot.d_vidx[:B]
         if self.use_graph and B == eng.max_batch:
             # the test-time config and the record ring are baked into the captured launches
-            key = (B, self.model.test_key(), None if self.records is None else self.records[0].data_ptr())
+            key = (B, self.model.test_key(), None if self.records is None else self.records[0].data_ptr(), slot.item)
             g = slot.graphs.get(key)
             if g is None:
                 with self.cuda_lock:

@@ -20,7 +20,7 @@ ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 # every symbol include/avdf.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "avdf_abi_version", "avdf_last_error", "avdf_device_info", "avdf_interp_concat", "avdf_pack_feats",
+    "avdf_abi_version", "avdf_last_error", "avdf_device_info", "avdf_interp_concat", "avdf_interp_concat_in", "avdf_pack_feats",
     "avdf_nms_workspace_bytes", "avdf_nms_hard", "avdf_nms_soft",
     "avdf_postprocess_workspace_bytes", "avdf_postprocess",
     "avdf_conv_gemm_workspace_bytes", "avdf_conv_gemm", "avdf_mlp_fused", "avdf_ln_dwconv_ln", "avdf_attention",
@@ -104,6 +104,7 @@ def lib():
     L.avdf_last_error.restype = c_char_p
     L.avdf_device_info.argtypes = [POINTER(c_int32)] * 3
     L.avdf_interp_concat.argtypes = [c_void_p] * 6 + [c_int32] * 5 + [c_void_p, c_int32, c_void_p]
+    L.avdf_interp_concat_in.argtypes = [c_void_p] * 3 + [c_int32] + [c_void_p] * 3 + [c_int32] * 5 + [c_void_p, c_int32, c_void_p]
     L.avdf_pack_feats.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]
     L.avdf_nms_workspace_bytes.restype = c_size_t
     L.avdf_nms_workspace_bytes.argtypes = [c_int32]

@@ -85,21 +85,25 @@ def _levels(level_len):
 
 # ---------------------------------------------------------------------------- K1
 def interp_concat(streams, offsets, t_out, out):
-    """streams: (video|None, byola|None, emo|None) packed [sum_T, C_s] fp32;
+    """streams: (video|None, byola|None, emo|None) packed [sum_T, C_s], all fp32 or all bf16 (16-bit feature shards);
     offsets: matching int32 [B+1] row prefix tensors; out [B, t_out, C_total]."""
     L = nv.lib()
     ptrs, offs, cs = [], [], []
     batch = None
+    in_dt = next(s.dtype for s in streams if s is not None)
+    if in_dt not in (torch.float32, torch.bfloat16):
+        raise TypeError("streams must be fp32 or bf16")
     for s, o in zip(streams, offsets):
         if s is None:
             ptrs.append(None); offs.append(None); cs.append(0)
             continue
-        _chk(s, torch.float32, "stream"); _chk(o, torch.int32, "offsets")
+        _chk(s, in_dt, "stream"); _chk(o, torch.int32, "offsets")
         ptrs.append(nv.ptr(s)); offs.append(nv.ptr(o)); cs.append(s.shape[1])
         batch = o.numel() - 1
     _chk(out, None, "out")
     assert out.shape == (batch, t_out, sum(cs)), (out.shape, batch, t_out, cs)
-    _call("avdf_interp_concat", L.avdf_interp_concat, (ptrs[0], ptrs[1], ptrs[2], offs[0], offs[1], offs[2], batch, cs[0], cs[1], cs[2],
+    _call("avdf_interp_concat", L.avdf_interp_concat_in, (ptrs[0], ptrs[1], ptrs[2], DTYPE_F32 if in_dt == torch.float32 else DTYPE_BF16,
+                                  offs[0], offs[1], offs[2], batch, cs[0], cs[1], cs[2],
                                   t_out, nv.ptr(out), _dt(out), _stream(),), launches=1, work={"bytes": _nbytes(*[t for t in streams if t is not None]) + _nbytes(out)})
     return out
 

@@ -85,23 +85,10 @@ def make_raw_batches(n_batches, use_video, seed0):
 
 
 def pin_batches(batches):
-    """The same batches with every stream array living in page-locked host memory (one pinned block per batch, numpy views)."""
-    import torch
-    out = []
-    for chunk in batches:
-        total = sum(a.size for c in chunk for a in c["streams"].values())
-        block = torch.empty(total, dtype=torch.float32, pin_memory=True).numpy()
-        pos, new_chunk = 0, []
-        for c in chunk:
-            st = {}
-            for k, a in c["streams"].items():
-                v = block[pos:pos + a.size].reshape(a.shape)
-                v[...] = a
-                st[k] = v
-                pos += a.size
-            new_chunk.append({**c, "streams": st})
-        out.append(new_chunk)
-    return out
+    """The same batches with every stream array living in page-locked host memory: one pinned block per batch, collated
+    stream-major by the product's loader-side helper (libs/modeling/streaming.py collate_pinned)."""
+    from audio_visual_deepfake_detection_b200.libs.modeling.streaming import collate_pinned
+    return [collate_pinned(chunk) for chunk in batches]
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -421,7 +408,15 @@ def measure_workload(args, workload, steps, rank, world, local, dist, full):
         return world * n_out / float(dt.item()), runner.h2d_bytes // steps, runner.d2h_bytes // steps
     e2e_pageable = e2e_leg(raw)[0] if full else None
     e2e_value, h2d_step, d2h_step = e2e_leg(pin_batches(raw))
+    # (3) the opt-in 16-bit feature-shard format (streaming.bf16_shard: the raw streams stored as bf16): half the bytes over PCIe
+    e2e_shard = None
+    if full:
+        from audio_visual_deepfake_detection_b200.libs.modeling.streaming import bf16_shard
+        shard = [[{**c, "streams": {k: bf16_shard(a) for k, a in c["streams"].items()}} for c in chunk] for chunk in raw]
+        v_, h_, _ = e2e_leg(pin_batches(shard))
+        e2e_shard = {"value": v_, "h2d_bytes_per_step": h_}
     res = {"value": value, "ms": ms, "launches": launches, "clocks": clocks, "e2e": e2e_value, "e2e_pageable": e2e_pageable,
+           "e2e_shard": e2e_shard,
            "h2d": h2d_step, "d2h": d2h_step, "desc": desc, "cfg": cfg, "name": name, "n_lanes": n_lanes, "h2d_batch": h2d}
     if not full:
         return res, None
@@ -539,10 +534,13 @@ def run_ours(args):
                            "parallelism": "videos sharded over %d rank(s); one all-gather of result records per run" % world,
                            "gflop_per_video": gflop},
                 "e2e": {"value": r["e2e"], "unit": "videos/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                        "inputs": "host numpy arrays in pinned memory, copied H2D where they are (model.stream)",
+                        "inputs": "host numpy arrays in pinned memory (one block per batch, collated stream-major: collate_pinned), copied H2D where they are (model.stream)",
                         "pageable_inputs_value": r["e2e_pageable"],
                         "pageable_inputs_note": "same call on pageable numpy arrays: one host gather (avdf_host_pack) into pinned "
-                                                "staging per batch first; bounded by the host cores all ranks share"},
+                                                "staging per batch first; bounded by the host cores all ranks share",
+                        "bf16_shards": r["e2e_shard"],
+                        "bf16_shards_note": "same call on the opt-in 16-bit feature-shard format (raw streams stored as bf16, pinned, collated): "
+                                            "half the PCIe bytes; tests/test_gpu_model.py::test_bf16_feature_shards_and_collated_pinned_batches"},
                 "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": r["roof"],
                 "step_roofline": {"tensor_frac": (r["value"] / world) * gflop * 1e9 / (r["peak_tf"] * 1e12),
                                   "min_ms_per_batch": r["step_roof_ms"], "achieved_ms_per_batch": r["ms"] / n_batches,

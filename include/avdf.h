@@ -78,6 +78,13 @@ AVDF_API int avdf_interp_concat(const float* video, const float* byola, const fl
                        int32_t batch, int32_t c_video, int32_t c_byola, int32_t c_emo, int32_t t_out,
                        void* out, int32_t out_dtype, void* stream);
 
+/* The same with the raw streams stored as bf16 (in_dtype = AVDF_DTYPE_BF16): the opt-in 16-bit feature-shard format of the
+ * ingestion path (half the host -> device bytes per video; the interpolation arithmetic stays fp32). */
+AVDF_API int avdf_interp_concat_in(const void* video, const void* byola, const void* emo, int32_t in_dtype,
+                          const int32_t* video_off, const int32_t* byola_off, const int32_t* emo_off,
+                          int32_t batch, int32_t c_video, int32_t c_byola, int32_t c_emo, int32_t t_out,
+                          void* out, int32_t out_dtype, void* stream);
+
 /* ---- preprocessing (av_fd_no_recon.py:431-479): one video's feats [channels, t] fp32 (dataset item layout)
  * -> token-major rows out[t_padded, channels], zero-padded from t to t_padded. */
 AVDF_API int avdf_pack_feats(const float* feats_ct, int32_t channels, int32_t t, int32_t t_padded, void* out,

@@ -153,6 +153,52 @@ def test_stream_from_pinned_arrays_skips_the_staging_copy():
         assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["segments"], b["segments"]) and torch.equal(a["video_cls"], b["video_cls"])
 
 
+def test_bf16_feature_shards_and_collated_pinned_batches():
+    """The opt-in 16-bit feature-shard format (streaming.bf16_shard: bf16 bits in uint16 arrays) through model.stream, both
+    staged (pageable arrays) and direct (one pinned block per batch, collated stream-major: collate_pinned, one merged
+    host->device copy per stream): the GPU resampling of bf16 inputs is bit-identical to the fp32-input kernel fed the
+    same rounded values, and the end-to-end results are those of model() on the bf16-rounded features."""
+    from audio_visual_deepfake_detection_b200 import ops
+    from audio_visual_deepfake_detection_b200.libs.modeling.streaming import bf16_shard, collate_pinned
+    import interp_ref
+    model, use_video = build("exp12", "mixed")
+    rng = np.random.RandomState(8)
+    batches = []
+    for bi in range(3):
+        durs = rng.uniform(4.1, 14.0, size=[3, 8, 2][bi])
+        batches.append([{"video_id": f"s{bi}v{i}", "duration": float(d), "streams": syn.synthetic_streams(float(d), 2000 + 10 * bi + i)}
+                        for i, d in enumerate(durs)])
+    shard = [[{**c, "streams": {k: bf16_shard(a) for k, a in c["streams"].items()}} for c in chunk] for chunk in batches]
+    rounded = [[{**c, "streams": {k: torch.from_numpy(a).to(torch.bfloat16).float().numpy() for k, a in c["streams"].items()}}
+                for c in chunk] for chunk in batches]
+    # kernel level: bf16 in == fp32 in on the rounded values
+    pk16, pk32 = model.stage(model.pack_streams(shard[1])), model.stage(model.pack_streams(rounded[1]))
+    assert pk16["streams"][1].dtype == torch.bfloat16 and model.h2d_bytes(pk16) < 0.55 * model.h2d_bytes(pk32)
+    B, L, C = len(shard[1]), model.max_seq_len, model.engine().c_in
+    xa = torch.zeros((B, L, C), dtype=torch.bfloat16, device="cuda"); xb = torch.zeros_like(xa)
+    ops.interp_concat(pk16["streams"], pk16["offs"], L, xa)
+    ops.interp_concat(pk32["streams"], pk32["offs"], L, xb)
+    assert torch.equal(xa, xb)
+    # end to end: staged shards, direct (collated pinned) shards and fp32 streams of the rounded values agree exactly
+    runner = model.runner()
+    want = [r for out in model.stream(iter(rounded)) for r in out]
+    n0 = runner.n_direct
+    got_staged = [r for out in model.stream(iter(shard)) for r in out]
+    assert runner.n_direct == n0
+    got_direct = [r for out in model.stream(iter([collate_pinned(c) for c in shard])) for r in out]
+    assert runner.n_direct == n0 + len(shard)
+    for a, b, c in zip(want, got_staged, got_direct):
+        assert a["video_id"] == b["video_id"] == c["video_id"]
+        assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["segments"], b["segments"])
+        assert torch.equal(a["scores"], c["scores"]) and torch.equal(a["segments"], c["segments"])
+    # and they stay at the mixed-precision bar against the fp32 features (the reference's input): dense outputs
+    items32 = [interp_ref.dataset_item(c["streams"], c["duration"], c["video_id"]) for c in batches[1]]
+    items16 = [interp_ref.dataset_item(c["streams"], c["duration"], c["video_id"]) for c in rounded[1]]
+    l32, o32, _ = model.dense_outputs(items32)
+    l16, o16, _ = model.dense_outputs(items16)
+    assert max_rel(l16.numpy(), l32.numpy()) < 5e-3 and max_rel(o16.numpy(), o32.numpy()) < 5e-3
+
+
 def test_fused_mlp_path_matches_two_launch_path():
     """engine.fused_mlp routes every block's MLP through avdf_mlp_fused (one launch, hidden activations on chip). Per call
     it agrees with the two-GEMM path to ~1e-6 (tests/test_gpu_kernels.py::test_mlp_fused); over the whole network

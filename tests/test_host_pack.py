@@ -100,3 +100,21 @@ def test_h2d_gather_rejects_bad_arguments_without_touching_cuda():
     one = (ctypes.c_void_p * 1)(None)
     assert L.avdf_h2d_gather(one, one, (ctypes.c_size_t * 1)(64), 1, None) == -1   # null span with a non-zero size
     assert L.avdf_h2d_gather(one, one, (ctypes.c_size_t * 1)(0), 1, None) == 0     # empty spans are skipped
+
+
+def test_bf16_shard_is_round_to_nearest_even():
+    """streaming.bf16_shard (the opt-in 16-bit feature-shard format) produces torch's bf16 bit patterns."""
+    import torch
+    from audio_visual_deepfake_detection_b200.libs.modeling.streaming import bf16_shard, collate_pinned
+    rng = np.random.RandomState(0)
+    x = (rng.standard_normal((257, 64)) * np.exp(rng.uniform(-20, 20, (257, 64)))).astype(np.float32)
+    x[0, :4] = [0.0, -0.0, 1.00390625, 1.01171875]                 # exact ties: round to even
+    want = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(bf16_shard(x), want)
+    chunk = [{"video_id": "a", "duration": 5.0, "streams": {"byola": want[:10], "emo": want[10:30]}},
+             {"video_id": "b", "duration": 6.0, "streams": {"byola": want[30:50], "emo": want[50:60]}}]
+    out = collate_pinned(chunk)
+    assert out[0]["streams"]["byola"].dtype == np.uint16 and np.array_equal(out[1]["streams"]["emo"], want[50:60])
+    # stream-major, one block: every video's rows of a stream are adjacent in memory
+    a0, a1 = out[0]["streams"]["byola"], out[1]["streams"]["byola"]
+    assert a1.ctypes.data == a0.ctypes.data + a0.nbytes
