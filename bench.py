@@ -415,8 +415,41 @@ def measure_workload(args, workload, steps, rank, world, local, dist, full):
         shard = [[{**c, "streams": {k: bf16_shard(a) for k, a in c["streams"].items()}} for c in chunk] for chunk in raw]
         v_, h_, _ = e2e_leg(pin_batches(shard))
         e2e_shard = {"value": v_, "h2d_bytes_per_step": h_}
+    # (4) what the box can deliver: every rank copies one of its pinned batches host -> device back to back for ~1 s, all
+    # ranks at once, nothing else on the GPUs (scripts/h2d_ceiling.py is the stand-alone version with per-span copies)
+    ceiling = None
+    if full:
+        pk = packed[0]
+        srcs = [t for t in pk["streams"] if t is not None]
+        dsts = [torch.empty_like(t, device=dev) for t in srcs]
+        nb = sum(t.numel() * t.element_size() for t in srcs)
+        cst = torch.cuda.Stream()
+        barrier()
+        with torch.cuda.stream(cst):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(cst)
+            t0_, k_ = time.perf_counter(), 0
+            while time.perf_counter() - t0_ < 1.0:
+                for s_t, d_t in zip(srcs, dsts):
+                    d_t.copy_(s_t, non_blocking=True)
+                k_ += 1
+                if k_ % 8 == 0:
+                    cst.synchronize()
+            c1.record(cst)
+            cst.synchronize()
+        gbs = torch.tensor([k_ * nb / (c0.elapsed_time(c1) * 1e-3) / 1e9], device=dev)
+        allg = [torch.zeros_like(gbs) for _ in range(world)] if world > 1 else [gbs]
+        if world > 1:
+            dist.all_gather(allg, gbs)
+        per_rank = [round(float(g.item()), 1) for g in allg]
+        bpv = nb / BATCH
+        ceiling = {"per_rank_gbs": per_rank, "aggregate_gbs": round(sum(per_rank), 1), "bytes_per_video_fp32": bpv,
+                   "videos_per_s_fed_fp32": round(sum(per_rank) * 1e9 / bpv), "videos_per_s_fed_if_every_rank_waits_for_the_slowest": round(min(per_rank) * world * 1e9 / bpv),
+                   "note": "pinned host -> device copies only, all ranks at once, ~1 s: the host-memory / PCIe path of this box; e2e.value (fp32 "
+                           "features) cannot exceed it, bf16 shards halve the bytes"}
+        del dsts
     res = {"value": value, "ms": ms, "launches": launches, "clocks": clocks, "e2e": e2e_value, "e2e_pageable": e2e_pageable,
-           "e2e_shard": e2e_shard,
+           "e2e_shard": e2e_shard, "h2d_ceiling": ceiling,
            "h2d": h2d_step, "d2h": d2h_step, "desc": desc, "cfg": cfg, "name": name, "n_lanes": n_lanes, "h2d_batch": h2d}
     if not full:
         return res, None
@@ -538,6 +571,7 @@ def run_ours(args):
                         "pageable_inputs_value": r["e2e_pageable"],
                         "pageable_inputs_note": "same call on pageable numpy arrays: one host gather (avdf_host_pack) into pinned "
                                                 "staging per batch first; bounded by the host cores all ranks share",
+                        "h2d_ceiling": r["h2d_ceiling"],
                         "bf16_shards": r["e2e_shard"],
                         "bf16_shards_note": "same call on the opt-in 16-bit feature-shard format (raw streams stored as bf16, pinned, collated): "
                                             "half the PCIe bytes; tests/test_gpu_model.py::test_bf16_feature_shards_and_collated_pinned_batches"},
