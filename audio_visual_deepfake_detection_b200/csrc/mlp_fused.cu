@@ -25,6 +25,18 @@
 // epilogue: acc2 -> +b2, mask, gamma, + residual, thread = row in the TMEM-native layout: the residual block arrives by TMA
 // in the swizzled 4 KB tile the result leaves from (two tiles per warp, the first residual block is fetched while the
 // chunk loop still runs), global memory is touched by TMA only (rows beyond the tensor are clipped by the tensor map).
+//
+// PROJ variant (avdf_mlp_fused_args.att != NULL): the block's attention output projection and LN2 run in the same kernel
+// ("block tail": blocks.py:1223, 1309-1316 / 779, 868-872 in one launch):
+//     y   = skip * mask + gamma_a * ((att Wo^T + bo) * mask)            acc2 <- att . Wo^T (4 K slices through the weight ring)
+//     x   = LN2(y)                                                        never leaves the SM: written into the x tile in the
+//                                                                         K-major swizzled operand layout by the epilogue warps
+//     out = y * mask + gamma_m * ((GELU(x W1^T + b1) W2^T + b2) * mask)   as above, the residual y re-read through TMA
+// The att tile arrives by TMA in the (then idle) hidden + staging tiles; the projection epilogue works like the GEMM's
+// post-residual LayerNorm epilogue (gemm_tc.cu): pass 1 builds y in the tiles its residual blocks arrived in (they live in
+// the x tile's memory, free until pass 2), sends it out, writes it back over the accumulator (tcgen05.st) and sums y, y^2;
+// pass 2 re-reads y from TMEM, normalises and writes the 16-bit x tile. y makes one round trip through L2 (it is the MLP's
+// residual); the LN2 output and one launch per block are gone.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -51,13 +63,16 @@ constexpr int OFF_X = 0;                      // 4 units
 constexpr int OFF_H = OFF_X + 4 * UNIT;       // 2 units (the hidden chunk); the final epilogue reuses them as 8 x 4 KB tiles
 constexpr int OFF_STG = OFF_H + 2 * UNIT;     // 8 x 4 KB: every epilogue warp's first residual / result tile
 constexpr int OFF_RING = OFF_STG + EPI_WARPS * 4096;   // RING units
-constexpr int OFF_VEC = OFF_RING + RING * UNIT;        // b1[1024], b2[256], gamma[256]
-constexpr int OFF_BAR = OFF_VEC + (HID + 2 * C) * 4;
+constexpr int OFF_VEC = OFF_RING + RING * UNIT;        // b1[1024], b2[256], gamma[256]; PROJ: bo, gamma_a, ln2 w, ln2 b [256 each]
+constexpr int OFF_PART = OFF_VEC + (HID + 6 * C) * 4;  // PROJ: LayerNorm partial sums, [2 column halves][128 rows] float2
+constexpr int OFF_BAR = OFF_PART + 2 * BM * 8;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;       // + alignment slack
 
 struct Params {
   CUtensorMap x_map, w1_map, w2_map;   // boxes: x (64, 128), W1 (64, 64 rows: this CTA's half of a chunk), W2 (64, 128 rows)
   CUtensorMap res_map, out_map;        // fp32 [rows, 256], box (32 columns, 32 rows), swizzle 128B
+  CUtensorMap att_map, wo_map, skip_map;   // PROJ: att [rows, 256] (64, 128), Wo [256, 256] (64 K, 128 rows: this CTA's half), skip fp32 like res_map
+  const float* bo; const float* gamma_a; const float* ln2_w; const float* ln2_b;
   void* out_h;
   const float* b1; const float* b2; const float* gamma; const unsigned char* row_mask;
   int rows, tiles;
@@ -70,10 +85,10 @@ __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t;
 
 // barrier slots
 enum { B_XFULL = 0, B_XEMPTY, B_RFULL, B_REMPTY = B_RFULL + RING, B_A1FULL = B_REMPTY + RING, B_A1EMPTY = B_A1FULL + 2,
-       B_HFULL = B_A1EMPTY + 2, B_HEMPTY, B_A2FULL, B_A2EMPTY, B_RES, B_COUNT = B_RES + 2 * EPI_WARPS };
+       B_HFULL = B_A1EMPTY + 2, B_HEMPTY, B_A2FULL, B_A2EMPTY, B_ATTFULL, B_ATTEMPTY, B_RES, B_COUNT = B_RES + 2 * EPI_WARPS };
 static_assert(B_COUNT * 8 + 8 <= 512, "barrier block");
 
-template <bool F16>
+template <bool F16, bool PROJ>
 __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -84,6 +99,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
   float* s_b1 = reinterpret_cast<float*>(smem + OFF_VEC);
   float* s_b2 = s_b1 + HID;
   float* s_gam = s_b2 + C;
+  float* s_bo = s_gam + C; float* s_gama = s_bo + C; float* s_l2w = s_gama + C; float* s_l2b = s_l2w + C;   // PROJ
+  float2* s_part = reinterpret_cast<float2*>(smem + OFF_PART);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + B_COUNT);
   const uint32_t bar_base = smem_u32(bars);
@@ -105,9 +122,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.w2_map) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.res_map) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.out_map) : "memory");
+    if (PROJ) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.att_map) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.wo_map) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.skip_map) : "memory");
+    }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar(B_XFULL), 1); mbar_init(bar(B_XEMPTY), 1);
+    mbar_init(bar(B_XFULL), PROJ ? 2 * EPI_WARPS : 1); mbar_init(bar(B_XEMPTY), 1);   // PROJ: the x tile is written by the epilogue warps
+    mbar_init(bar(B_ATTFULL), 1); mbar_init(bar(B_ATTEMPTY), EPI_WARPS);
     for (int s = 0; s < RING; ++s) { mbar_init(bar(B_RFULL + s), 1); mbar_init(bar(B_REMPTY + s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar(B_A1FULL + s), 1); mbar_init(bar(B_A1EMPTY + s), 2 * GELU_WARPS); }
     mbar_init(bar(B_HFULL), 2 * GELU_WARPS); mbar_init(bar(B_HEMPTY), 1);
@@ -124,6 +147,11 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     for (int i = threadIdx.x - 128; i < C; i += GELU_WARPS * 32) {
       s_b2[i] = p.b2 ? __ldg(p.b2 + i) : 0.f;
       s_gam[i] = p.gamma ? __ldg(p.gamma + i) : 1.f;
+      if (PROJ) {
+        s_bo[i] = p.bo ? __ldg(p.bo + i) : 0.f;
+        s_gama[i] = p.gamma_a ? __ldg(p.gamma_a + i) : 1.f;
+        s_l2w[i] = __ldg(p.ln2_w + i); s_l2b[i] = __ldg(p.ln2_b + i);
+      }
     }
   }
   tcgen05_fence_before();
@@ -166,15 +194,33 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     };
     for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
       const int tile = 2 * unit + (int)rank;
-      mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);
       nu = 0;
-      MLPF_TS(0, 0);
-      if (leader) {
-        if (rank == 0) mbar_arrive_expect_tx(bar(B_XFULL), 8 * UNIT);
-        const uint32_t xb = lbar(B_XFULL);
-        for (int s = 0; s < 4; ++s) tma_load_2d_pair(smem_u32(sx + s * UNIT), &p.x_map, xb, s * 64, tile * BM);
+      if (!PROJ) {
+        mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);
+        MLPF_TS(0, 0);
+        if (leader) {
+          if (rank == 0) mbar_arrive_expect_tx(bar(B_XFULL), 8 * UNIT);
+          const uint32_t xb = lbar(B_XFULL);
+          for (int s = 0; s < 4; ++s) tma_load_2d_pair(smem_u32(sx + s * UNIT), &p.x_map, xb, s * 64, tile * BM);
+        }
+        __syncwarp();
+      } else {
+        // the att tile lands in the hidden + staging tiles (4 consecutive units), free once the previous tile's final
+        // epilogue has drained them; then the four K slices of this CTA's half of Wo go through the ring
+        mbar_wait(bar(B_ATTEMPTY), (uint32_t)(it & 1) ^ 1);
+        MLPF_TS(0, 0);
+        if (leader) {
+          if (rank == 0) mbar_arrive_expect_tx(bar(B_ATTFULL), 8 * UNIT);
+          const uint32_t ab = lbar(B_ATTFULL);
+          for (int s = 0; s < 4; ++s) tma_load_2d_pair(smem_u32(sh + s * UNIT), &p.att_map, ab, s * 64, tile * BM);
+        }
+        __syncwarp();
+        for (int sl = 0; sl < 4; ++sl) {
+          const uint32_t fb = begin_slot();
+          if (leader) tma_load_2d_pair(smem_u32(sring + stage * UNIT), &p.wo_map, fb, sl * 64, (int)rank * 128);
+          end_slot();
+        }
       }
-      __syncwarp();
       for (int u = 0; u < 2; ++u) load_w1(chunk_of(0), u);
       for (int j = 0; j < NCHUNK; ++j) {
         if (j + 1 < NCHUNK)
@@ -188,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     // 256 x 256 x 16 (each CTA holds half of the B rows at the same shared-memory offsets)
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0; int it = 0;
-    uint32_t n_a1[2] = {0, 0}, n_h = 0;
+    uint32_t n_a1[2] = {0, 0}, n_h = 0, n_a2e = 0;
     auto g1 = [&](int j) {
       const int b = j & 1;
       mbar_wait(bar(B_A1EMPTY + b), (n_a1[b] & 1) ^ 1);
@@ -214,6 +260,27 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
       ++n_a1[b];
     };
     for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
+      if (PROJ) {
+        // acc2 <- att . Wo^T: 4 ring slots x 4 instructions of 256 x 256 x 16
+        mbar_wait(bar(B_A2EMPTY), (n_a2e & 1) ^ 1); ++n_a2e;       // the previous tile's final epilogue has drained acc2
+        mbar_wait(bar(B_ATTFULL), (uint32_t)(it & 1));
+        tcgen05_fence_after();
+        for (int sl = 0; sl < 4; ++sl) {
+          mbar_wait(bar(B_RFULL + stage), phase);
+          tcgen05_fence_after();
+          if (leader) {
+            const uint64_t da = make_sw128_desc(smem_u32(sh + sl * UNIT));
+            const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_pair(tm_acc2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc2, (sl > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(bar(B_REMPTY + stage));
+            if (sl == 3) umma_commit_pair(bar(B_A2FULL));
+          }
+          __syncwarp();
+          if (++stage == RING) { stage = 0; phase ^= 1; }
+        }
+      }
       mbar_wait(bar(B_XFULL), (uint32_t)(it & 1));
       tcgen05_fence_after();
       MLPF_TS(1, 0);
@@ -223,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         if (j + 1 < NCHUNK) g1(j + 1);
         MLPF_TS(1, 2 + 4 * j);                  // G1(j+1) issued
         if (j == NCHUNK - 2 && leader) umma_commit_pair(bar(B_XEMPTY));   // every G1 of this tile is issued: x may be replaced
-        if (j == 0) { mbar_wait(bar(B_A2EMPTY), (uint32_t)(it & 1) ^ 1); tcgen05_fence_after(); }
+        if (j == 0) { mbar_wait(bar(B_A2EMPTY), (n_a2e & 1) ^ 1); ++n_a2e; tcgen05_fence_after(); }   // (PROJ: LN2 pass 2 has read y)
         mbar_wait(bar(B_HFULL), n_h & 1);
         tcgen05_fence_after();
         MLPF_TS(1, 3 + 4 * j);                  // hidden chunk j ready
@@ -267,7 +334,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     uint32_t res_phase[2] = {0, 0};
     const uint32_t a1empty_bar[2] = {lbar(B_A1EMPTY), lbar(B_A1EMPTY + 1)};
     const uint32_t hfull_bar = lbar(B_HFULL), a2empty_bar = lbar(B_A2EMPTY);
-    uint32_t n_a1[2] = {0, 0}, n_h = 0;
+    uint32_t n_a1[2] = {0, 0}, n_h = 0, n_a2f = 0;
+    const uint32_t xfull_bar = lbar(B_XFULL);
     int it = 0;
     for (int unit = unit0; unit < n_units; unit += unit_step, ++it) {
       const int tile = 2 * unit + (int)rank;
@@ -280,7 +348,109 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         mbar_arrive_expect_tx(res_bar[ch & 1], 4096);
         tma_load_2d(smem_u32((ch & 1) ? tB : tA), &p.res_map, res_bar[ch & 1], col0 + ch * 32, wrow);
       };
-      if (fin && lane == 0) fetch_residual(0);  // tA was drained at the end of the previous tile
+      if (!PROJ && fin && lane == 0) fetch_residual(0);  // tA was drained at the end of the previous tile
+      if (PROJ) {
+        // ---- attention projection epilogue + LN2 (warps = final-epilogue warps: all 8)
+        unsigned char* tX[2] = {sx + wi * 8192, sx + wi * 8192 + 4096};     // this warp's two tiles inside the (still unused) x tile
+        auto fetch_skip = [&](int ch) {
+          mbar_arrive_expect_tx(res_bar[ch & 1], 4096);
+          tma_load_2d(smem_u32(tX[ch & 1]), &p.skip_map, res_bar[ch & 1], col0 + ch * 32, wrow);
+        };
+        mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);       // the previous tile's G1s have read the x tile
+        if (lane == 0) { fetch_skip(0); fetch_skip(1); }
+        mbar_wait(bar(B_A2FULL), n_a2f & 1); ++n_a2f;
+        tcgen05_fence_after();
+        const uint32_t taddr2 = tm_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+        float s = 0.f, ss = 0.f;
+        uint32_t vr[32];
+        tmem_ld32_issue(taddr2, vr);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vr[i]);
+          if (ch + 1 < 4) tmem_ld32_issue(taddr2 + (ch + 1) * 32, vr);
+          unsigned char* tb = tX[ch & 1];
+          mbar_wait(res_bar[ch & 1], res_phase[ch & 1]);
+          res_phase[ch & 1] ^= 1;
+          const float4* b4 = reinterpret_cast<const float4*>(s_bo + col0 + ch * 32);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gama + col0 + ch * 32);
+          uint32_t yb[32];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {        // y = gamma_a * ((acc + bo) * mask) + skip * mask, in place (the GEMM epilogue's formula)
+            float4* slot = reinterpret_cast<float4*>(tb + lane * 128 + ((jj ^ sw7) << 4));
+            const float4 rv = *slot;
+            const float4 bb = b4[jj], gg = g4[jj];
+            const float4 y = make_float4(fmaf(gg.x, (x[4 * jj] + bb.x) * mk, rv.x * mk), fmaf(gg.y, (x[4 * jj + 1] + bb.y) * mk, rv.y * mk),
+                                         fmaf(gg.z, (x[4 * jj + 2] + bb.z) * mk, rv.z * mk), fmaf(gg.w, (x[4 * jj + 3] + bb.w) * mk, rv.w * mk));
+            *slot = y;
+            s += (y.x + y.y) + (y.z + y.w);
+            ss = fmaf(y.x, y.x, ss); ss = fmaf(y.y, y.y, ss); ss = fmaf(y.z, y.z, ss); ss = fmaf(y.w, y.w, ss);
+            yb[4 * jj] = __float_as_uint(y.x); yb[4 * jj + 1] = __float_as_uint(y.y); yb[4 * jj + 2] = __float_as_uint(y.z); yb[4 * jj + 3] = __float_as_uint(y.w);
+          }
+          tmem_st32(taddr2 + ch * 32, yb);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.res_map, smem_u32(tb), col0 + ch * 32, wrow);       // res_map = y: the MLP's residual
+            tma_store_commit();
+            if (ch + 2 < 4) { tma_store_wait_read(); fetch_skip(ch + 2); }
+          }
+        }
+        s_part[g * BM + r] = make_float2(s, ss);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // the two warps of this row quarter
+        const float2 pa = s_part[r], pb = s_part[BM + r];
+        const float mean = (pa.x + pb.x) * (1.f / C);
+        const float rstd = rsqrtf(fmaxf((pa.y + pb.y) * (1.f / C) - mean * mean, 0.f) + 1e-5f);
+        tmem_st_wait();
+        if (lane == 0) tma_store_wait_read();      // the y stores have read this warp's tiles
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // every warp's tiles are free: the memory becomes the x tile
+        const f32x2 nmean2 = pk2(-mean), rstd2 = pk2(rstd);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {           // pass 2: x = LN2(y) in the K-major 128B-swizzled operand layout
+          uint32_t vy[32];
+          tmem_ld32_issue(taddr2 + ch * 32, vy);
+          tmem_ld_wait();
+          if (ch == 3) {                           // y is in registers: acc2 may take G2
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a2empty_bar);
+          }
+          const int c0 = col0 + ch * 32;
+          unsigned char* xrow = sx + (c0 >> 6) * UNIT + r * 128;
+          const int slot0 = (c0 & 63) >> 3;
+          const float4* w4 = reinterpret_cast<const float4*>(s_l2w + c0);
+          const float4* l4 = reinterpret_cast<const float4*>(s_l2b + c0);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            f32x2 y[4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 ww = w4[2 * jj + u], ll = l4[2 * jj + u];
+              y[2 * u] = fma2(mul2(add2(pk2(__uint_as_float(vy[8 * jj + 4 * u]), __uint_as_float(vy[8 * jj + 4 * u + 1])), nmean2), rstd2), pk2(ww.x, ww.y), pk2(ll.x, ll.y));
+              y[2 * u + 1] = fma2(mul2(add2(pk2(__uint_as_float(vy[8 * jj + 4 * u + 2]), __uint_as_float(vy[8 * jj + 4 * u + 3])), nmean2), rstd2), pk2(ww.z, ww.w), pk2(ll.z, ll.w));
+            }
+            uint4 uo;
+            float f0, f1;
+            if (F16) {
+              upk2(y[0], f0, f1); uo.x = pack_f16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_f16x2(f0, f1);
+              upk2(y[2], f0, f1); uo.z = pack_f16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_f16x2(f0, f1);
+            } else {
+              upk2(y[0], f0, f1); uo.x = pack_bf16x2(f0, f1); upk2(y[1], f0, f1); uo.y = pack_bf16x2(f0, f1);
+              upk2(y[2], f0, f1); uo.z = pack_bf16x2(f0, f1); upk2(y[3], f0, f1); uo.w = pack_bf16x2(f0, f1);
+            }
+            *reinterpret_cast<uint4*>(xrow + (((slot0 + jj) ^ sw7) << 4)) = uo;
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(xfull_bar);
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // y is in global memory: it comes back as the MLP's residual
+          fetch_residual(0);                       // tA: the att tile it held is consumed (acc2 was complete)
+        }
+      }
       for (int j = 0; j < NCHUNK; ++j) {
         const int b = j & 1;
         mbar_wait(bar(B_A1FULL + b), n_a1[b] & 1);
@@ -337,7 +507,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
       //      c + 1 is in flight while chunk c is computed, the one of chunk c + 2 is fetched once chunk c's store has
       //      read the tile
       if (fin) {
-      mbar_wait(bar(B_A2FULL), (uint32_t)(it & 1));
+      mbar_wait(bar(B_A2FULL), n_a2f & 1); ++n_a2f;
       tcgen05_fence_after();
       if (wi == 0 && lane == 0) MLPF_TS(2, 40);
       if (lane == 0) fetch_residual(1);           // the hidden tile (tB) is free now
@@ -400,7 +570,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         }
       }
       if (wi == 0 && lane == 0) MLPF_TS(2, 41);
-      if (lane == 0) tma_store_wait_read();       // both tiles drained: tB returns to the hidden tile, tA takes the next residual
+      if (lane == 0) {
+        tma_store_wait_read();                    // both tiles drained: tB returns to the hidden tile, tA takes the next residual
+        if (PROJ) mbar_arrive(bar(B_ATTEMPTY));   // ... or, with tB, the next att tile
+      }
       }
       // every warp's tB lives in the hidden tile, which other warps overwrite in the next tile's first chunk
       asm volatile("bar.sync 1, %0;" ::"n"(GELU_WARPS * 32) : "memory");
@@ -434,9 +607,18 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   AVDF_CHECK_ARG(a->channels == C && a->hidden == HID, "avdf_mlp_fused supports channels = 256, hidden = 1024");
   AVDF_CHECK_ARG(a->dtype == AVDF_DTYPE_F16 || a->dtype == AVDF_DTYPE_BF16, "dtype must be a 16-bit type");
   AVDF_CHECK_ARG(a->rows >= 0, "rows must be >= 0");
-  AVDF_CHECK_ARG(a->x && a->w1 && a->w2 && a->residual && a->out, "null pointer");
-  AVDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w1) | reinterpret_cast<uintptr_t>(a->w2) |
-                   reinterpret_cast<uintptr_t>(a->residual) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0, "pointers must be 16-byte aligned");
+  const bool proj = a->att != nullptr;
+  AVDF_CHECK_ARG(a->w1 && a->w2 && a->out, "null pointer");
+  if (proj) {
+    AVDF_CHECK_ARG(a->w_o && a->ln2_w && a->ln2_b && a->skip && a->y, "block tail: w_o, ln2_w, ln2_b, skip and y are required");
+    AVDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->att) | reinterpret_cast<uintptr_t>(a->w_o) | reinterpret_cast<uintptr_t>(a->skip) |
+                     reinterpret_cast<uintptr_t>(a->y)) & 15) == 0, "pointers must be 16-byte aligned");
+    AVDF_CHECK_ARG(GELU_WARPS == EPI_WARPS, "block tail needs the eight-warp build");
+  } else {
+    AVDF_CHECK_ARG(a->x && a->residual, "null pointer");
+  }
+  AVDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(proj ? a->att : a->x) | reinterpret_cast<uintptr_t>(a->w1) | reinterpret_cast<uintptr_t>(a->w2) |
+                   reinterpret_cast<uintptr_t>(proj ? a->y : a->residual) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0, "pointers must be 16-byte aligned");
   if (a->rows == 0) return AVDF_OK;
   tc::EncodeFn encode = tc::get_encode();
   if (!encode) { set_error("avdf_mlp_fused: cuTensorMapEncodeTiled not available from the driver"); return AVDF_ERR_CUDA; }
@@ -456,10 +638,16 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
     return AVDF_OK;
   };
   int rc;
-  if ((rc = enc2(&p.x_map, dt, 2, a->x, C, a->rows, 64, 128, "x"))) return rc;
+  if (!proj && (rc = enc2(&p.x_map, dt, 2, a->x, C, a->rows, 64, 128, "x"))) return rc;
+  if (proj) {
+    if ((rc = enc2(&p.att_map, dt, 2, a->att, C, a->rows, 64, 128, "att"))) return rc;
+    if ((rc = enc2(&p.wo_map, dt, 2, a->w_o, C, C, 64, 128, "w_o"))) return rc;
+    if ((rc = enc2(&p.skip_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->skip, C, a->rows, 32, 32, "skip"))) return rc;
+    p.bo = a->b_o; p.gamma_a = a->gamma_attn; p.ln2_w = a->ln2_w; p.ln2_b = a->ln2_b;
+  }
   if ((rc = enc2(&p.w1_map, dt, 2, a->w1, C, HID, 64, 64, "w1"))) return rc;
   if ((rc = enc2(&p.w2_map, dt, 2, a->w2, HID, C, 64, 128, "w2"))) return rc;
-  if ((rc = enc2(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->residual, C, a->rows, 32, 32, "residual"))) return rc;
+  if ((rc = enc2(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, proj ? a->y : a->residual, C, a->rows, 32, 32, "residual"))) return rc;
   if ((rc = enc2(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, C, a->rows, 32, 32, "out"))) return rc;
   p.out_h = a->out_h;
   p.oh_t = a->out_h_t; p.oh_pitch = a->out_h_pitch; p.oh_row0 = a->out_h_row0;
@@ -475,14 +663,19 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(128 >> 3) << 17) | m_field;
   p.idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(256 >> 3) << 17) | m_field;
   const int sms = device_sm_count();
-  AVDF_SMEM_ATTR_ONCE(mlp_fused_kernel<true>, SMEM_BYTES);
-  AVDF_SMEM_ATTR_ONCE(mlp_fused_kernel<false>, SMEM_BYTES);
+  AVDF_SMEM_ATTR_ONCE((mlp_fused_kernel<true, false>), SMEM_BYTES);
+  AVDF_SMEM_ATTR_ONCE((mlp_fused_kernel<false, false>), SMEM_BYTES);
+  AVDF_SMEM_ATTR_ONCE((mlp_fused_kernel<true, true>), SMEM_BYTES);
+  AVDF_SMEM_ATTR_ONCE((mlp_fused_kernel<false, true>), SMEM_BYTES);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // clusters of two CTAs (one TPC); a pair walks pairs of 128-row tiles
   const int units = (p.tiles + 1) / 2, max_pairs = sms / 2;
   const int grid = 2 * (units < max_pairs ? units : max_pairs);
-  const cudaError_t lerr = f16 ? launch_pdl_cluster(mlp_fused_kernel<true>, grid, THREADS, SMEM_BYTES, st, 2, p)
-                               : launch_pdl_cluster(mlp_fused_kernel<false>, grid, THREADS, SMEM_BYTES, st, 2, p);
+  cudaError_t lerr;
+  if (proj) lerr = f16 ? launch_pdl_cluster(mlp_fused_kernel<true, true>, grid, THREADS, SMEM_BYTES, st, 2, p)
+                       : launch_pdl_cluster(mlp_fused_kernel<false, true>, grid, THREADS, SMEM_BYTES, st, 2, p);
+  else lerr = f16 ? launch_pdl_cluster(mlp_fused_kernel<true, false>, grid, THREADS, SMEM_BYTES, st, 2, p)
+                  : launch_pdl_cluster(mlp_fused_kernel<false, false>, grid, THREADS, SMEM_BYTES, st, 2, p);
   if (lerr != cudaSuccess) { set_error("mlp_fused_kernel: launch failed: %s", cudaGetErrorString(lerr)); return AVDF_ERR_CUDA; }
   return check_launch("mlp_fused_kernel");
 }

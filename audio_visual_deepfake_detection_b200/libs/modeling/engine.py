@@ -157,6 +157,7 @@ class LocalizationEngine:
         self.fused_mlp = os.environ.get("AVDF_FUSED_MLP", "1") != "0"
         self.fused_mlp_min_rows = int(os.environ.get("AVDF_FUSED_MLP_MIN_ROWS", "0"))
         self.fuse_ln2 = os.environ.get("AVDF_FUSE_LN2", "1") != "0"    # LN2 in the attention projection's epilogue (A/B switch)
+        self.fuse_tail = os.environ.get("AVDF_FUSE_TAIL", "1") != "0"  # projection + LN2 + MLP as one launch (A/B switch)
         self.C = c["embd_dim"]
         self.n_head = c["n_head"]
         self.c_in = c["video_input_dim"] + c["audio_input_dim"]
@@ -324,7 +325,12 @@ class LocalizationEngine:
         # 16-bit path: LN2 (blocks.py:1311) runs in the projection's epilogue (ln_after_residual): y is normalised while it is
         # still in TMEM - one launch and one fp32 round trip of the residual stream less per block
         fuse_ln2 = self.fuse_ln2 and self.adt != torch.float32 and C == 256
-        if fuse_ln2:
+        fused = self.fused_mlp and self.adt != torch.float32 and C == 256 and B * T >= self.fused_mlp_min_rows
+        # block tail: projection + LN2 + MLP in ONE launch (csrc/mlp_fused.cu, PROJ variant): the LN2 output never leaves the SM
+        fuse_tail = self.fuse_tail and fuse_ln2 and fused
+        if fuse_tail:
+            pass
+        elif fuse_ln2:
             self._gemm(att, f"{pre}.attn.proj.weight", B=B, segs=seg, a_rows=T, o_rows=T, bias=w.vec(f"{pre}.attn.proj.bias"),
                        row_mask=mask, residual=skip, gamma=ga, out_f32=y, out_act=l2, ln=w.ln(pre + ".ln2"), ln_after_residual=True)
         else:
@@ -332,7 +338,6 @@ class LocalizationEngine:
                        row_mask=mask, residual=skip, gamma=ga, out_f32=y)
         out = self.buf(out_name, (B, T, C), torch.float32)
         out_act = None
-        fused = self.fused_mlp and self.adt != torch.float32 and C == 256 and B * T >= self.fused_mlp_min_rows
         if want_act_copy and self.adt != torch.float32:
             # pyr = (pyramid buffer [B, P, C], first row of this level): the 16-bit copy goes straight into the operand of
             # the single FPN lateral launch (fused-MLP path only)
@@ -344,9 +349,12 @@ class LocalizationEngine:
             # the kernel was tried - two spare warps normalising the next 128-row tile straight into the operand
             # layout - and measured slower, 14.7k vs 15.9k videos/s: ~10 us per tile that cannot be hidden because the
             # x tile cannot be double-buffered in 227 KB. LN2 stays a separate 9 us launch.)
-            ops.mlp_fused(l2, w.dense(f"{pre}.mlp.0.weight", self.adt), w.vec(f"{pre}.mlp.0.bias"),
+            proj = None
+            if fuse_tail:
+                proj = (att, w.dense(f"{pre}.attn.proj.weight", self.adt), w.vec(f"{pre}.attn.proj.bias"), ga, w.ln(pre + ".ln2"), skip, y)
+            ops.mlp_fused(None if fuse_tail else l2, w.dense(f"{pre}.mlp.0.weight", self.adt), w.vec(f"{pre}.mlp.0.bias"),
                           w.dense(f"{pre}.mlp.3.weight", self.adt), w.vec(f"{pre}.mlp.3.bias"),
-                          row_mask=mask, residual=y, gamma=gm, out=out, out_h=out_act,
+                          row_mask=mask, residual=y, gamma=gm, out=out, out_h=out_act, proj=proj,
                           out_h_level=(T, pyr[0].shape[1], pyr[1]) if (pyr is not None and out_act is not None) else None)
             return out, out_act
         h = self.buf("mlp_h", (B, T, 4 * C), self.adt)

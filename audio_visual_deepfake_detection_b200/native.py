@@ -84,6 +84,8 @@ class MlpFusedArgs(Structure):
         ("x", c_void_p), ("w1", c_void_p), ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p),
         ("row_mask", c_void_p), ("residual", c_void_p), ("gamma", c_void_p), ("out", c_void_p), ("out_h", c_void_p),
         ("out_h_t", c_int32), ("out_h_pitch", c_int32), ("out_h_row0", c_int32),
+        ("att", c_void_p), ("w_o", c_void_p), ("b_o", c_void_p), ("gamma_attn", c_void_p), ("ln2_w", c_void_p), ("ln2_b", c_void_p),
+        ("skip", c_void_p), ("y", c_void_p),
     ]
 
 

@@ -226,6 +226,18 @@ typedef struct avdf_mlp_fused_args {
   int32_t out_h_t, out_h_pitch, out_h_row0;   /* 0: the copy is dense [rows, channels]; else rows = batch * out_h_t and row
                                                * b * out_h_t + t goes to row b * out_h_pitch + out_h_row0 + t (one level of
                                                * a [batch, P, channels] pyramid buffer, necks.py:62-93's input) */
+  /* "block tail" (att != NULL): the attention output projection and LN2 of the block run in the same launch
+   * (blocks.py:1223, 1309-1316 / 779, 868-872):
+   *   y = skip * mask + gamma_attn * ((att w_o^T + b_o) * mask);  x = LN(y) * ln2_w + ln2_b (16-bit, never leaves the SM);
+   *   out = y * mask + gamma * ((GELU(x w1^T + b1) w2^T + b2) * mask)
+   * x and residual are ignored; y [rows, channels] fp32 is written (and read back as the MLP's residual). Equivalent to
+   * avdf_conv_gemm(ln_after_residual) followed by the plain avdf_mlp_fused. */
+  const void* att;               /* [rows, channels] 16-bit (dtype) or NULL */
+  const void* w_o; const float* b_o;   /* [channels, channels], [channels] */
+  const float* gamma_attn;       /* [channels] or NULL */
+  const float* ln2_w; const float* ln2_b;   /* [channels] */
+  const float* skip;             /* [rows, channels] fp32: the block's input (or its max-pooled copy) */
+  float* y;                      /* [rows, channels] fp32 */
 } avdf_mlp_fused_args;
 AVDF_API int avdf_mlp_fused(const avdf_mlp_fused_args* args, void* stream);
 

@@ -719,6 +719,45 @@ def test_mlp_fused(rows, dt):
     assert rel_err(out.cpu(), out2.view(rows, C).cpu()) < 2e-4
 
 
+@pytest.mark.parametrize("rows", [128, 300, 32 * 96, 32 * 768])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_block_tail_projection_ln2_mlp_in_one_launch(rows, dt):
+    """avdf_mlp_fused with att != NULL (attention projection + LN2 + MLP of a block in one launch) against the two launches
+    it replaces: conv_gemm(ln_after_residual) + mlp_fused. y is bit-equal; out differs only through last-bit differences of
+    the 16-bit LN2 operand (the statistics are summed in another order)."""
+    rng = np.random.RandomState(rows + (1 if dt == torch.float16 else 2))
+    C, H = 256, 1024
+    att = dev(torch.from_numpy(rng.standard_normal((rows, C)).astype(np.float32)), dt)
+    wo = dev(torch.from_numpy((rng.standard_normal((C, C)) / math.sqrt(C)).astype(np.float32)), dt)
+    bo = dev(torch.from_numpy(rng.normal(0, 0.3, C).astype(np.float32)))
+    ga = dev(torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)))
+    ln2 = tuple(dev(t) for t in _ln_params(rng, C))
+    skip = dev(torch.from_numpy((rng.standard_normal((rows, C)) * 2 + 0.5).astype(np.float32)))
+    w1 = dev(torch.from_numpy((rng.standard_normal((H, C)) / 16).astype(np.float32)), dt)
+    w2 = dev(torch.from_numpy((rng.standard_normal((C, H)) / 32).astype(np.float32)), dt)
+    b1 = dev(torch.from_numpy(rng.standard_normal(H).astype(np.float32)))
+    b2 = dev(torch.from_numpy(rng.standard_normal(C).astype(np.float32)))
+    gm = dev(torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)))
+    mask_np = (rng.uniform(size=rows) > 0.15).astype(np.uint8); mask_np[:3] = 1
+    mask = dev(torch.from_numpy(mask_np))
+    # reference: two launches
+    y_ref = torch.zeros((rows, C), device=DEV); l2 = torch.zeros((rows, C), dtype=dt, device=DEV); out_ref = torch.zeros((rows, C), device=DEV)
+    ops.conv_gemm(att.view(1, rows, C), wo, taps=1, batch=1, c_in=C, n_out=C, segs=[(rows, 0, 0)], a_rows=rows, o_rows=rows, bias=bo,
+                  row_mask=mask.view(1, rows), residual=skip.view(1, rows, C), gamma=ga, out_f32=y_ref.view(1, rows, C), out_h=l2.view(1, rows, C),
+                  ln=ln2, ln_after_residual=True)
+    ops.mlp_fused(l2, w1, b1, w2, b2, row_mask=mask, residual=y_ref, gamma=gm, out=out_ref)
+    # one launch
+    y = torch.zeros((rows, C), device=DEV); out = torch.zeros((rows, C), device=DEV)
+    ops.mlp_fused(None, w1, b1, w2, b2, row_mask=mask, residual=None, gamma=gm, out=out, proj=(att, wo, bo, ga, ln2, skip, y))
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    assert rel_err(out.cpu(), out_ref.cpu()) < (2e-3 if dt == torch.float16 else 1.5e-2)
+    # and against plain torch on the same 16-bit operands
+    mk_t = torch.from_numpy(mask_np.astype(np.float32))[:, None]
+    yt = skip.cpu() * mk_t + ga.cpu() * ((att.float().cpu() @ wo.float().cpu().t() + bo.cpu()) * mk_t)
+    assert rel_err(y.cpu(), yt) < 2e-4
+
+
 def test_mlp_fused_16bit_copy_into_pyramid_level():
     """out_h: the 16-bit copy of the fused MLP's result, dense or scattered into one level of a [batch, P, C] pyramid
     buffer (the operand of the single FPN lateral launch)."""
