@@ -41,7 +41,7 @@ WORKLOADS = {
     "av13": ("exp13", {}, True, "audio-visual fused exp13-arch localization (SegmentandCls branch), batch 32"),
 }
 BATCH = 32
-TRAFFIC_FILE = "r1_j_step_traffic.json"    # per-kernel DRAM bytes of one pass (ncu pass, see profiles/README.md)
+TRAFFIC_FILE = "r2_i_step_traffic.json"    # per-kernel DRAM bytes of one pass (ncu pass, see profiles/README.md)
 PIPE_FILE = "r2_tensor_pipe.json"          # sm__pipe_tensor_cycles_active per kernel from the committed ncu --set full page
 N_POOL = 8              # distinct resident input batches rotated through the timed region (8 x ~75 MB > 126 MB L2)
 
