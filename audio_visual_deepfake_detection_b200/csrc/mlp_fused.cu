@@ -31,12 +31,15 @@
 //     y   = skip * mask + gamma_a * ((att Wo^T + bo) * mask)            acc2 <- att . Wo^T (4 K slices through the weight ring)
 //     x   = LN2(y)                                                        never leaves the SM: written into the x tile in the
 //                                                                         K-major swizzled operand layout by the epilogue warps
-//     out = y * mask + gamma_m * ((GELU(x W1^T + b1) W2^T + b2) * mask)   as above, the residual y re-read through TMA
+//     out = (y + GELU(x W1^T + b1) W2'^T + b2') * mask                     W2' = diag(gamma_m) W2, b2' = gamma_m b2 (folded by the
+//                                                                         caller): y STAYS in the accumulator and the G2
+//                                                                         instructions accumulate on top of it
 // The att tile arrives by TMA in the (then idle) hidden + staging tiles; the projection epilogue works like the GEMM's
 // post-residual LayerNorm epilogue (gemm_tc.cu): pass 1 builds y in the tiles its residual blocks arrived in (they live in
 // the x tile's memory, free until pass 2), sends it out, writes it back over the accumulator (tcgen05.st) and sums y, y^2;
-// pass 2 re-reads y from TMEM, normalises and writes the 16-bit x tile. y makes one round trip through L2 (it is the MLP's
-// residual); the LN2 output and one launch per block are gone.
+// pass 2 re-reads y from TMEM, normalises and writes the 16-bit x tile. Neither y nor the LN2 output leaves the SM: per 128
+// rows the kernel reads skip (128 KB) + att (64 KB) and writes out (128 KB) - the fp32 residual stream's minimum - where the
+// separate launches moved y out and in twice more. (y is also stored when the caller passes a y pointer: tests.)
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -73,6 +76,7 @@ struct Params {
   CUtensorMap res_map, out_map;        // fp32 [rows, 256], box (32 columns, 32 rows), swizzle 128B
   CUtensorMap att_map, wo_map, skip_map;   // PROJ: att [rows, 256] (64, 128), Wo [256, 256] (64 K, 128 rows: this CTA's half), skip fp32 like res_map
   const float* bo; const float* gamma_a; const float* ln2_w; const float* ln2_b;
+  int y_store;                         // PROJ: also store y through res_map (0: y never leaves the SM)
   void* out_h;
   const float* b1; const float* b2; const float* gamma; const unsigned char* row_mask;
   int rows, tiles;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
             const uint64_t db = make_sw128_desc(smem_u32(sring + stage * UNIT));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_pair(tm_acc2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc2, (j > 0 || sl > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_pair(tm_acc2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc2, (PROJ || j > 0 || sl > 0 || k > 0) ? 1u : 0u);   // PROJ: on top of y
             umma_commit_pair(bar(B_REMPTY + stage));
           }
           __syncwarp();
@@ -358,8 +362,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         };
         mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);       // the previous tile's G1s have read the x tile
         if (lane == 0) { fetch_skip(0); fetch_skip(1); }
+        if (wi == 0 && lane == 0) MLPF_TS(2, 42);              // skip tiles requested
         mbar_wait(bar(B_A2FULL), n_a2f & 1); ++n_a2f;
         tcgen05_fence_after();
+        if (wi == 0 && lane == 0) MLPF_TS(2, 43);              // projection accumulator complete
         const uint32_t taddr2 = tm_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
         float s = 0.f, ss = 0.f;
         uint32_t vr[32];
@@ -372,6 +378,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
           for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vr[i]);
           if (ch + 1 < 4) tmem_ld32_issue(taddr2 + (ch + 1) * 32, vr);
           unsigned char* tb = tX[ch & 1];
+          if (ch >= 1 && ch + 1 < 4 && lane == 0) {     // tile (ch + 1) & 1 held chunk ch - 1 (its optional store was issued one chunk ago)
+            if (p.y_store) tma_store_wait_read();
+            fetch_skip(ch + 1);
+          }
           mbar_wait(res_bar[ch & 1], res_phase[ch & 1]);
           res_phase[ch & 1] ^= 1;
           const float4* b4 = reinterpret_cast<const float4*>(s_bo + col0 + ch * 32);
@@ -389,22 +399,26 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
             ss = fmaf(y.x, y.x, ss); ss = fmaf(y.y, y.y, ss); ss = fmaf(y.z, y.z, ss); ss = fmaf(y.w, y.w, ss);
             yb[4 * jj] = __float_as_uint(y.x); yb[4 * jj + 1] = __float_as_uint(y.y); yb[4 * jj + 2] = __float_as_uint(y.z); yb[4 * jj + 3] = __float_as_uint(y.w);
           }
-          tmem_st32(taddr2 + ch * 32, yb);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&p.res_map, smem_u32(tb), col0 + ch * 32, wrow);       // res_map = y: the MLP's residual
-            tma_store_commit();
-            if (ch + 2 < 4) { tma_store_wait_read(); fetch_skip(ch + 2); }
+          tmem_st32(taddr2 + ch * 32, yb);        // y replaces the projection in the accumulator: the LayerNorm pass and G2 build on it
+          if (p.y_store) {                        // (optional copy of y for the caller)
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.res_map, smem_u32(tb), col0 + ch * 32, wrow);
+              tma_store_commit();
+            }
+          } else {
+            __syncwarp();                         // every lane has read the tile
           }
         }
+        if (wi == 0 && lane == 0) MLPF_TS(2, 44);              // pass 1 done (y stored, written back to TMEM)
         s_part[g * BM + r] = make_float2(s, ss);
         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // the two warps of this row quarter
         const float2 pa = s_part[r], pb = s_part[BM + r];
         const float mean = (pa.x + pb.x) * (1.f / C);
         const float rstd = rsqrtf(fmaxf((pa.y + pb.y) * (1.f / C) - mean * mean, 0.f) + 1e-5f);
         tmem_st_wait();
-        if (lane == 0) tma_store_wait_read();      // the y stores have read this warp's tiles
+        if (p.y_store && lane == 0) tma_store_wait_read();      // the y stores have read this warp's tiles
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // every warp's tiles are free: the memory becomes the x tile
         const f32x2 nmean2 = pk2(-mean), rstd2 = pk2(rstd);
 #pragma unroll 1
@@ -445,11 +459,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(xfull_bar);
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // y is in global memory: it comes back as the MLP's residual
-          fetch_residual(0);                       // tA: the att tile it held is consumed (acc2 was complete)
-        }
+        if (wi == 0 && lane == 0) MLPF_TS(2, 45);              // pass 2 done: the x tile is written
+        if (lane == 0) mbar_arrive_cluster(xfull_bar);
       }
       for (int j = 0; j < NCHUNK; ++j) {
         const int b = j & 1;
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
       mbar_wait(bar(B_A2FULL), n_a2f & 1); ++n_a2f;
       tcgen05_fence_after();
       if (wi == 0 && lane == 0) MLPF_TS(2, 40);
-      if (lane == 0) fetch_residual(1);           // the hidden tile (tB) is free now
+      if (!PROJ && lane == 0) fetch_residual(1);  // the hidden tile (tB) is free now
       const uint32_t taddr2 = tm_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
       // optional 16-bit copy of the result (the operand of the FPN lateral conv / the next level's block): same dtype as x;
       // rows leave transposed (lane = column) as 64-byte row pieces
@@ -534,9 +545,26 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
           if (lane == 0) mbar_arrive_cluster(a2empty_bar);
         }
         unsigned char* tb = (ch & 1) ? tB : tA;
+        const float4* b4 = reinterpret_cast<const float4*>(s_b2 + col0 + ch * 32);
+        if (PROJ) {
+          // the accumulator already holds y + the MLP (b2 / W2 pre-scaled by the caller): (acc + b2') * mask
+          if (ch >= 2) {                          // this tile's previous store (chunk ch - 2) has read it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 bb = b4[jj];
+            *reinterpret_cast<float4*>(tb + lane * 128 + ((jj ^ sw7) << 4)) =
+                make_float4((x[4 * jj] + bb.x) * mk, (x[4 * jj + 1] + bb.y) * mk, (x[4 * jj + 2] + bb.z) * mk, (x[4 * jj + 3] + bb.w) * mk);
+          }
+        } else {
+        if (ch >= 1 && ch + 1 < 4 && lane == 0) {   // tile (ch + 1) & 1 held chunk ch - 1: its store was issued one chunk ago
+          tma_store_wait_read();
+          fetch_residual(ch + 1);
+        }
         mbar_wait(res_bar[ch & 1], res_phase[ch & 1]);
         res_phase[ch & 1] ^= 1;
-        const float4* b4 = reinterpret_cast<const float4*>(s_b2 + col0 + ch * 32);
         const float4* g4 = reinterpret_cast<const float4*>(s_gam + col0 + ch * 32);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {          // residual * mask + gamma * ((acc + b2) * mask), in place
@@ -545,6 +573,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
           const float4 bb = b4[jj], gg = g4[jj];
           *slot = make_float4(fmaf(rv.x, mk, gg.x * ((x[4 * jj] + bb.x) * mk)), fmaf(rv.y, mk, gg.y * ((x[4 * jj + 1] + bb.y) * mk)),
                               fmaf(rv.z, mk, gg.z * ((x[4 * jj + 2] + bb.z) * mk)), fmaf(rv.w, mk, gg.w * ((x[4 * jj + 3] + bb.w) * mk)));
+        }
         }
         fence_async_smem();
         __syncwarp();
@@ -563,10 +592,6 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
             if (rr < nrow) outh_base[(size_t)dr * C + ch * 32] = hb;
           }
           __syncwarp();
-        }
-        if (ch + 2 < 4 && lane == 0) {            // refill this tile with the residual of chunk ch + 2
-          tma_store_wait_read();
-          fetch_residual(ch + 2);
         }
       }
       if (wi == 0 && lane == 0) MLPF_TS(2, 41);
@@ -610,7 +635,8 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   const bool proj = a->att != nullptr;
   AVDF_CHECK_ARG(a->w1 && a->w2 && a->out, "null pointer");
   if (proj) {
-    AVDF_CHECK_ARG(a->w_o && a->ln2_w && a->ln2_b && a->skip && a->y, "block tail: w_o, ln2_w, ln2_b, skip and y are required");
+    AVDF_CHECK_ARG(a->w_o && a->ln2_w && a->ln2_b && a->skip, "block tail: w_o, ln2_w, ln2_b and skip are required");
+    AVDF_CHECK_ARG(a->gamma == nullptr, "block tail: fold the MLP's scale into w2 / b2 (gamma must be NULL)");
     AVDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->att) | reinterpret_cast<uintptr_t>(a->w_o) | reinterpret_cast<uintptr_t>(a->skip) |
                      reinterpret_cast<uintptr_t>(a->y)) & 15) == 0, "pointers must be 16-byte aligned");
     AVDF_CHECK_ARG(GELU_WARPS == EPI_WARPS, "block tail needs the eight-warp build");
@@ -618,7 +644,7 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
     AVDF_CHECK_ARG(a->x && a->residual, "null pointer");
   }
   AVDF_CHECK_ARG(((reinterpret_cast<uintptr_t>(proj ? a->att : a->x) | reinterpret_cast<uintptr_t>(a->w1) | reinterpret_cast<uintptr_t>(a->w2) |
-                   reinterpret_cast<uintptr_t>(proj ? a->y : a->residual) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0, "pointers must be 16-byte aligned");
+                   reinterpret_cast<uintptr_t>(proj ? nullptr : a->residual) | reinterpret_cast<uintptr_t>(a->out)) & 15) == 0, "pointers must be 16-byte aligned");
   if (a->rows == 0) return AVDF_OK;
   tc::EncodeFn encode = tc::get_encode();
   if (!encode) { set_error("avdf_mlp_fused: cuTensorMapEncodeTiled not available from the driver"); return AVDF_ERR_CUDA; }
@@ -647,7 +673,8 @@ extern "C" int avdf_mlp_fused(const avdf_mlp_fused_args* a, void* stream) {
   }
   if ((rc = enc2(&p.w1_map, dt, 2, a->w1, C, HID, 64, 64, "w1"))) return rc;
   if ((rc = enc2(&p.w2_map, dt, 2, a->w2, HID, C, 64, 128, "w2"))) return rc;
-  if ((rc = enc2(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, proj ? a->y : a->residual, C, a->rows, 32, 32, "residual"))) return rc;
+  p.y_store = (proj && a->y) ? 1 : 0;
+  if ((!proj || a->y) && (rc = enc2(&p.res_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, proj ? a->y : a->residual, C, a->rows, 32, 32, "residual"))) return rc;
   if ((rc = enc2(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->out, C, a->rows, 32, 32, "out"))) return rc;
   p.out_h = a->out_h;
   p.oh_t = a->out_h_t; p.oh_pitch = a->out_h_pitch; p.oh_row0 = a->out_h_row0;

@@ -350,11 +350,20 @@ class LocalizationEngine:
             # layout - and measured slower, 14.7k vs 15.9k videos/s: ~10 us per tile that cannot be hidden because the
             # x tile cannot be double-buffered in 227 KB. LN2 stays a separate 9 us launch.)
             proj = None
+            w2, b2, g2 = w.dense(f"{pre}.mlp.3.weight", self.adt), w.vec(f"{pre}.mlp.3.bias"), gm
             if fuse_tail:
-                proj = (att, w.dense(f"{pre}.attn.proj.weight", self.adt), w.vec(f"{pre}.attn.proj.bias"), ga, w.ln(pre + ".ln2"), skip, y)
+                # y stays in the accumulator and the second GEMM accumulates on top of it: the MLP's AffineDropPath scale
+                # (blocks.py:1316) is folded into W2 / b2 once, in fp32, before the 16-bit rounding of the weights
+                proj = (att, w.dense(f"{pre}.attn.proj.weight", self.adt), w.vec(f"{pre}.attn.proj.bias"), ga, w.ln(pre + ".ln2"), skip, None)
+                if gm is not None:
+                    ck = ("tail", pre, self.adt)
+                    if ck not in w._cache:
+                        w32 = w.sd[f"{pre}.mlp.3.weight"].detach().to(torch.float32).reshape(C, -1).to(self.device)
+                        w._cache[ck] = ((w32 * gm[:, None]).to(self.adt).contiguous(), (b2 * gm).contiguous())
+                    w2, b2 = w._cache[ck]
+                    g2 = None
             ops.mlp_fused(None if fuse_tail else l2, w.dense(f"{pre}.mlp.0.weight", self.adt), w.vec(f"{pre}.mlp.0.bias"),
-                          w.dense(f"{pre}.mlp.3.weight", self.adt), w.vec(f"{pre}.mlp.3.bias"),
-                          row_mask=mask, residual=y, gamma=gm, out=out, out_h=out_act, proj=proj,
+                          w2, b2, row_mask=mask, residual=y, gamma=g2, out=out, out_h=out_act, proj=proj,
                           out_h_level=(T, pyr[0].shape[1], pyr[1]) if (pyr is not None and out_act is not None) else None)
             return out, out_act
         h = self.buf("mlp_h", (B, T, 4 * C), self.adt)

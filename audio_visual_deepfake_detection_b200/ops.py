@@ -246,12 +246,13 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
 def mlp_fused(x, w1, b1, w2, b2, *, row_mask, residual, gamma, out, out_h=None, out_h_level=None, proj=None):
     """out = residual*mask + gamma * ((GELU(x w1^T + b1) w2^T + b2) * mask); x [..., 256] fp16|bf16, w1 [1024, 256],
     w2 [256, 1024] of the same dtype, residual / out fp32 [..., 256]. One launch; the hidden activations stay on chip.
-    proj = (att, w_o, b_o, gamma_attn, (ln2_w, ln2_b), skip, y): the block tail - the attention projection and LN2 in the
-    same launch; x may be None then (its dtype is att's), residual is ignored (it is y)."""
+    proj = (att, w_o, b_o, gamma_attn, (ln2_w, ln2_b), skip, y | None): the block tail - the attention projection and LN2 in
+    the same launch, the residual stream y kept in the accumulator: w2 / b2 must come pre-scaled by the MLP's scale and
+    gamma must be None; x may be None (its dtype is att's), residual is ignored."""
     L = nv.lib()
     if proj is not None:
         x = proj[0] if x is None else x
-        residual = proj[6]
+        residual = proj[5]                 # (placeholder for the checks below: the kernel ignores it)
     _chk(x, None, "x"); _chk(w1, x.dtype, "w1"); _chk(w2, x.dtype, "w2")
     _chk(b1, torch.float32, "b1"); _chk(b2, torch.float32, "b2"); _chk(gamma, torch.float32, "gamma")
     _chk(row_mask, torch.uint8, "row_mask"); _chk(residual, torch.float32, "residual"); _chk(out, torch.float32, "out")
@@ -275,13 +276,15 @@ def mlp_fused(x, w1, b1, w2, b2, *, row_mask, residual, gamma, out, out_h=None, 
         att, w_o, b_o, ga, ln2, skip, y = proj
         _chk(att, x.dtype, "att"); _chk(w_o, x.dtype, "w_o"); _chk(b_o, torch.float32, "b_o"); _chk(ga, torch.float32, "gamma_attn")
         _chk(ln2[0], torch.float32, "ln2_w"); _chk(ln2[1], torch.float32, "ln2_b"); _chk(skip, torch.float32, "skip"); _chk(y, torch.float32, "y")
-        assert att.numel() == rows * C and skip.numel() == rows * C and y.numel() == rows * C and w_o.shape == (C, C)
-        a.att, a.w_o, a.skip, a.y = att.data_ptr(), w_o.data_ptr(), skip.data_ptr(), y.data_ptr()
+        assert att.numel() == rows * C and skip.numel() == rows * C and (y is None or y.numel() == rows * C) and w_o.shape == (C, C)
+        assert gamma is None, "block tail: fold the MLP's scale into w2 / b2"
+        a.att, a.w_o, a.skip = att.data_ptr(), w_o.data_ptr(), skip.data_ptr()
+        a.y = y.data_ptr() if y is not None else None
         a.b_o = b_o.data_ptr() if b_o is not None else None
         a.gamma_attn = ga.data_ptr() if ga is not None else None
         a.ln2_w, a.ln2_b = ln2[0].data_ptr(), ln2[1].data_ptr()
         flops += 2.0 * rows * C * C
-        nbytes += rows * C * 8 + C * C * x.element_size()        # + skip in, y out (y's re-read and x are on-chip / L2 traffic of the same launch)
+        nbytes += C * C * x.element_size() - rows * C * x.element_size()   # att in instead of x in (+ skip in counted as the residual), + Wo
     _call("avdf_mlp_fused", L.avdf_mlp_fused, (ctypes.byref(a), _stream(),), launches=1,
           work={"flops": flops, "bytes": nbytes, "m": rows, "n": C, "k": H})
     return out

@@ -229,15 +229,17 @@ typedef struct avdf_mlp_fused_args {
   /* "block tail" (att != NULL): the attention output projection and LN2 of the block run in the same launch
    * (blocks.py:1223, 1309-1316 / 779, 868-872):
    *   y = skip * mask + gamma_attn * ((att w_o^T + b_o) * mask);  x = LN(y) * ln2_w + ln2_b (16-bit, never leaves the SM);
-   *   out = y * mask + gamma * ((GELU(x w1^T + b1) w2^T + b2) * mask)
-   * x and residual are ignored; y [rows, channels] fp32 is written (and read back as the MLP's residual). Equivalent to
-   * avdf_conv_gemm(ln_after_residual) followed by the plain avdf_mlp_fused. */
+   *   out = (y + GELU(x w1^T + b1) w2^T + b2) * mask
+   * y stays in the tensor-memory accumulator and the second GEMM accumulates on top of it, so the MLP's AffineDropPath
+   * scale must be FOLDED by the caller: pass w2 = diag(scale) w2, b2 = scale * b2 and gamma = NULL. x and residual are
+   * ignored; y (optional, may be NULL) receives a copy of the residual stream between the two halves of the block.
+   * Equivalent to avdf_conv_gemm(ln_after_residual) followed by the plain avdf_mlp_fused. */
   const void* att;               /* [rows, channels] 16-bit (dtype) or NULL */
   const void* w_o; const float* b_o;   /* [channels, channels], [channels] */
   const float* gamma_attn;       /* [channels] or NULL */
   const float* ln2_w; const float* ln2_b;   /* [channels] */
   const float* skip;             /* [rows, channels] fp32: the block's input (or its max-pooled copy) */
-  float* y;                      /* [rows, channels] fp32 */
+  float* y;                      /* [rows, channels] fp32 or NULL */
 } avdf_mlp_fused_args;
 AVDF_API int avdf_mlp_fused(const avdf_mlp_fused_args* args, void* stream);
 

@@ -746,12 +746,18 @@ def test_block_tail_projection_ln2_mlp_in_one_launch(rows, dt):
                   row_mask=mask.view(1, rows), residual=skip.view(1, rows, C), gamma=ga, out_f32=y_ref.view(1, rows, C), out_h=l2.view(1, rows, C),
                   ln=ln2, ln_after_residual=True)
     ops.mlp_fused(l2, w1, b1, w2, b2, row_mask=mask, residual=y_ref, gamma=gm, out=out_ref)
-    # one launch
-    y = torch.zeros((rows, C), device=DEV); out = torch.zeros((rows, C), device=DEV)
-    ops.mlp_fused(None, w1, b1, w2, b2, row_mask=mask, residual=None, gamma=gm, out=out, proj=(att, wo, bo, ga, ln2, skip, y))
+    # one launch: y stays in the accumulator, so the MLP's scale is folded into W2 / b2 by the caller (fp32, before the rounding)
+    w2f = dev((w2.float().cpu() * gm.cpu()[:, None]), dt)
+    b2f = (b2 * gm).contiguous()
+    y = torch.zeros((rows, C), device=DEV); out = torch.zeros((rows, C), device=DEV); out_noy = torch.zeros((rows, C), device=DEV)
+    ops.mlp_fused(None, w1, b1, w2f, b2f, row_mask=mask, residual=None, gamma=None, out=out, proj=(att, wo, bo, ga, ln2, skip, y))
+    ops.mlp_fused(None, w1, b1, w2f, b2f, row_mask=mask, residual=None, gamma=None, out=out_noy, proj=(att, wo, bo, ga, ln2, skip, None))
     torch.cuda.synchronize()
-    assert torch.equal(y, y_ref)
+    assert torch.equal(y, y_ref)                 # the optional copy of the residual stream
+    assert torch.equal(out, out_noy)             # storing it or not changes nothing
     assert rel_err(out.cpu(), out_ref.cpu()) < (2e-3 if dt == torch.float16 else 1.5e-2)
+    with pytest.raises(AssertionError):          # an unfolded scale is refused
+        ops.mlp_fused(None, w1, b1, w2, b2, row_mask=mask, residual=None, gamma=gm, out=out, proj=(att, wo, bo, ga, ln2, skip, None))
     # and against plain torch on the same 16-bit operands
     mk_t = torch.from_numpy(mask_np.astype(np.float32))[:, None]
     yt = skip.cpu() * mk_t + ga.cpu() * ((att.float().cpu() @ wo.float().cpu().t() + bo.cpu()) * mk_t)
