@@ -89,7 +89,8 @@ __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t;
 
 // barrier slots
 enum { B_XFULL = 0, B_XEMPTY, B_RFULL, B_REMPTY = B_RFULL + RING, B_A1FULL = B_REMPTY + RING, B_A1EMPTY = B_A1FULL + 2,
-       B_HFULL = B_A1EMPTY + 2, B_HEMPTY, B_A2FULL, B_A2EMPTY, B_ATTFULL, B_ATTEMPTY, B_RES, B_COUNT = B_RES + 2 * EPI_WARPS };
+       B_HFULL = B_A1EMPTY + 2, B_HEMPTY, B_A2FULL, B_A2EMPTY, B_ATTFULL, B_ATTEMPTY, B_RES, B_RES2 = B_RES + 2 * EPI_WARPS,
+       B_COUNT = B_RES2 + 2 * EPI_WARPS };
 static_assert(B_COUNT * 8 + 8 <= 512, "barrier block");
 
 template <bool F16, bool PROJ>
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
     for (int s = 0; s < 2; ++s) { mbar_init(bar(B_A1FULL + s), 1); mbar_init(bar(B_A1EMPTY + s), 2 * GELU_WARPS); }
     mbar_init(bar(B_HFULL), 2 * GELU_WARPS); mbar_init(bar(B_HEMPTY), 1);
     mbar_init(bar(B_A2FULL), 1); mbar_init(bar(B_A2EMPTY), 2 * EPI_WARPS);
-    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(bar(B_RES + s), 1);
+    for (int s = 0; s < 4 * EPI_WARPS; ++s) mbar_init(bar(B_RES + s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {       // one warp of EACH CTA of the pair
@@ -355,10 +356,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
       if (!PROJ && fin && lane == 0) fetch_residual(0);  // tA was drained at the end of the previous tile
       if (PROJ) {
         // ---- attention projection epilogue + LN2 (warps = final-epilogue warps: all 8)
-        unsigned char* tX[2] = {sx + wi * 8192, sx + wi * 8192 + 4096};     // this warp's two tiles inside the (still unused) x tile
+        // the skip blocks of the four chunks: two tiles inside the (still unused) x tile, requested right away, and - once the
+        // projection has consumed the att tile - this warp's staging tile and its slice of the hidden tile
+        unsigned char* tX[4] = {sx + wi * 8192, sx + wi * 8192 + 4096, tA, tB};
+        const uint32_t sk_bar[4] = {res_bar[0], res_bar[1], bar(B_RES2 + 2 * wi), bar(B_RES2 + 2 * wi + 1)};
         auto fetch_skip = [&](int ch) {
-          mbar_arrive_expect_tx(res_bar[ch & 1], 4096);
-          tma_load_2d(smem_u32(tX[ch & 1]), &p.skip_map, res_bar[ch & 1], col0 + ch * 32, wrow);
+          mbar_arrive_expect_tx(sk_bar[ch], 4096);
+          tma_load_2d(smem_u32(tX[ch]), &p.skip_map, sk_bar[ch], col0 + ch * 32, wrow);
         };
         mbar_wait(bar(B_XEMPTY), (uint32_t)(it & 1) ^ 1);       // the previous tile's G1s have read the x tile
         if (lane == 0) { fetch_skip(0); fetch_skip(1); }
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         mbar_wait(bar(B_A2FULL), n_a2f & 1); ++n_a2f;
         tcgen05_fence_after();
         if (wi == 0 && lane == 0) MLPF_TS(2, 43);              // projection accumulator complete
+        if (lane == 0) { fetch_skip(2); fetch_skip(3); }        // the att tile is consumed
         const uint32_t taddr2 = tm_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
         float s = 0.f, ss = 0.f;
         uint32_t vr[32];
@@ -377,13 +382,9 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vr[i]);
           if (ch + 1 < 4) tmem_ld32_issue(taddr2 + (ch + 1) * 32, vr);
-          unsigned char* tb = tX[ch & 1];
-          if (ch >= 1 && ch + 1 < 4 && lane == 0) {     // tile (ch + 1) & 1 held chunk ch - 1 (its optional store was issued one chunk ago)
-            if (p.y_store) tma_store_wait_read();
-            fetch_skip(ch + 1);
-          }
-          mbar_wait(res_bar[ch & 1], res_phase[ch & 1]);
-          res_phase[ch & 1] ^= 1;
+          unsigned char* tb = tX[ch];
+          if (ch < 2) { mbar_wait(sk_bar[ch], res_phase[ch]); res_phase[ch] ^= 1; }
+          else mbar_wait(sk_bar[ch], (uint32_t)(it & 1));
           const float4* b4 = reinterpret_cast<const float4*>(s_bo + col0 + ch * 32);
           const float4* g4 = reinterpret_cast<const float4*>(s_gama + col0 + ch * 32);
           uint32_t yb[32];
