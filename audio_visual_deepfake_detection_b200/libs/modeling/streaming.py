@@ -7,7 +7,7 @@ Per batch of <= max_batch videos:
   H2D    (copy engine)   pinned -> static device staging buffers, asynchronous on the compute stream
   GPU                    the whole pass (interp/concat -> model -> decode -> NMS) replayed as ONE CUDA graph
   D2H                    fixed-size results -> pinned host, then an event
-n_slots (default 10, env AVDF_STREAM_SLOTS; measured 6 -> 10: 13.5k -> 15.5k videos/s end to end) staging slots rotate: one is being packed while up to n_slots-1 batches are in flight on the
+n_slots (default 6, env AVDF_STREAM_SLOTS; round 2, one GPU: 4 / 6 / 10 slots = 17.7k / 19.5k / 19.1k videos/s end to end) staging slots rotate: one is being packed while up to n_slots-1 batches are in flight on the
 GPU, each on its own stream and engine lane (buffer set), so copies and kernels of consecutive batches overlap. This replaces the
 reference's DataLoader workers (which run F.interpolate on the CPU, libs/datasets/deepfake_video_audio.py:513-547)
 plus the per-video `.to(device)` / `.cpu()` of libs/modeling/av_fd_no_recon.py:476-477, 841-846.
@@ -125,7 +125,7 @@ class _Slot:
 
 class StreamRunner:
     def __init__(self, model, n_slots=None, n_threads=None):
-        n_slots = n_slots or int(os.environ.get("AVDF_STREAM_SLOTS", "10"))
+        n_slots = n_slots or int(os.environ.get("AVDF_STREAM_SLOTS", "6"))      # batches in flight (measured 4 / 6 / 8 / 10 / 14: 17.7k / 19.6k / 19.3k / 19.1k / 19.1k videos/s)
         self.model = model
         self.eng = model.engine()
         with torch.cuda.device(self.eng.device):
