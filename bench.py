@@ -39,6 +39,8 @@ WORKLOADS = {
               "audio-only (BYOL-A 2048 + Emotion2Vec 768) exp12-arch localization, synthetic AV-Deepfake1M-length sequences, batch 32"),
     "av12": ("exp12", {}, True, "audio-visual fused exp12-arch localization (3072 ch), batch 32"),
     "av13": ("exp13", {}, True, "audio-visual fused exp13-arch localization (SegmentandCls branch), batch 32"),
+    # the exp5-style arch (live reconstruction branch), visual stream + emotion2vec (1024 ch) like its yaml
+    "av5": ("exp5", {}, "video+emo", "audio-visual exp5-style localization with the live reconstruction branch (1024 ch), batch 32"),
 }
 BATCH = 32
 TRAFFIC_FILE = "r2_i_step_traffic.json"    # per-kernel DRAM bytes of one pass (ncu pass, see profiles/README.md)
@@ -46,7 +48,7 @@ PIPE_FILE = "r2_tensor_pipe.json"          # sm__pipe_tensor_cycles_active per k
 N_POOL = 8              # distinct resident input batches rotated through the timed region (8 x ~75 MB > 126 MB L2)
 
 
-def flops_per_video(cfg_model, exp13):
+def flops_per_video(cfg_model, exp13, recon=False):
     """Algorithmic FLOPs per video (embedding once, dead Expansion dropped)."""
     cin = cfg_model["video_input_dim"] + cfg_model["audio_input_dim"]
     C, T = cfg_model["embd_dim"], cfg_model["max_seq_len"]
@@ -60,14 +62,17 @@ def flops_per_video(cfg_model, exp13):
     else:
         dims = [cin, C, 2 * C, 4 * C, 8 * C, C]
         vc = sum(2 * (T >> (i + 1)) * dims[i + 1] * 3 * dims[i] for i in range(5))
+    if recon:       # exp5-style: the Expansion (ConvTranspose1d k3: 3 taps per input position, blocks.py:1568-1590) + a second embedding pass
+        up = [C, 2048, 1024, 512, 256, cin]
+        vc += sum(2 * (T >> (5 - i)) * up[i] * 3 * up[i + 1] for i in range(5)) + embed
     return embed + blocks + fpn + heads + vc
 
 
 def build_cfg(workload):
     from audio_visual_deepfake_detection_b200.libs.core import load_config_for
-    from audio_visual_deepfake_detection_b200.libs.modeling import EXP12, EXP13
+    from audio_visual_deepfake_detection_b200.libs.modeling import EXP5, EXP12, EXP13
     key, overrides, use_video, desc = WORKLOADS[workload]
-    name = EXP12 if key == "exp12" else EXP13
+    name = {"exp12": EXP12, "exp13": EXP13, "exp5": EXP5}[key]
     # the metric is quoted with soft-NMS (BASELINE.json); the shipped yaml resolves to hard
     cfg = load_config_for(name, dict(overrides, **{"test_cfg.nms_method": "soft"}))
     return cfg, name, use_video, desc
@@ -80,7 +85,8 @@ def make_raw_batches(n_batches, use_video, seed0):
     for i in range(n_batches):
         out.append([{"video_id": "v%06d" % (seed0 * 100000 + i * BATCH + j), "duration": float(durs[i * BATCH + j]),
                      "streams": syn.synthetic_streams(float(durs[i * BATCH + j]), seed0 * 100000 + i * BATCH + j,
-                                                      video_dim=256 if use_video else 0)} for j in range(BATCH)])
+                                                      video_dim=256 if use_video else 0,
+                                                      byola_dim=0 if use_video == "video+emo" else 2048)} for j in range(BATCH)])
     return out
 
 
@@ -548,7 +554,7 @@ def run_ours(args):
     r, model = measure_workload(args, args.workload, args.steps, rank, world, local, dist, full=True)
     cfg, name = r["cfg"], r["name"]
     n_batches = args.steps * BATCHES_PER_STEP
-    gflop = flops_per_video(cfg["model"], name.endswith("THE")) / 1e9
+    gflop = flops_per_video(cfg["model"], name.endswith("THE"), name.endswith("NoNorm")) / 1e9
 
     line = None
     if rank == 0:
@@ -609,12 +615,12 @@ def run_ours(args):
             del model
             torch.cuda.empty_cache()
             extra = {}
-            for wl in ("av12", "av13"):
+            for wl in ("av12", "av13", "av5"):
                 if wl == args.workload:
                     continue
                 rr, _ = measure_workload(args, wl, max(2, args.steps // 4), rank, world, local, dist, full=False)
                 extra[wl] = {"workload": rr["desc"], "value": rr["value"], "unit": "videos/s", "e2e": rr["e2e"], "steps": max(2, args.steps // 4),
-                             "gflop_per_video": flops_per_video(rr["cfg"]["model"], rr["name"].endswith("THE")) / 1e9}
+                             "gflop_per_video": flops_per_video(rr["cfg"]["model"], rr["name"].endswith("THE"), rr["name"].endswith("NoNorm")) / 1e9}
                 torch.cuda.empty_cache()
             extra["nms_sweep"] = nms_sweep(dev)
             line["extra"] = extra
@@ -655,7 +661,7 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "fp32"])
     ap.add_argument("--ref-videos", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the av12 / av13 / NMS-sweep extras of the single-GPU line")
+    ap.add_argument("--no-extra", action="store_true", help="skip the av12 / av13 / av5 / NMS-sweep extras of the single-GPU line")
     ap.add_argument("--lanes", type=int, default=8, help="batches in flight at once (each on its own stream and buffer set)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event timings of one step to this json")
