@@ -806,10 +806,15 @@ static int launch_standalone(const float* segs, const float* scores, int32_t n, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NMS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, segs, scores, (int)n, S, thr, sigma, min_score, method, (int)max_num,
-                                             dets, reinterpret_cast<long long*>(out_idx), out_count, reinterpret_cast<int*>(ws));
-    if (e != cudaSuccess) { set_error("nms_cluster_kernel: launch failed: %s", cudaGetErrorString(e)); return AVDF_ERR_CUDA; }
-    return check_launch("nms_cluster_kernel");
+    // a device (or partition) that cannot co-schedule NMS_CL such CTAs in one cluster takes the single-CTA path below
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, nms_cluster_kernel, &cfg) != cudaSuccess) { max_clusters = 0; (void)cudaGetLastError(); }
+    if (max_clusters >= 1) {
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, segs, scores, (int)n, S, thr, sigma, min_score, method, (int)max_num,
+                                               dets, reinterpret_cast<long long*>(out_idx), out_count, reinterpret_cast<int*>(ws));
+      if (e != cudaSuccess) { set_error("nms_cluster_kernel: launch failed: %s", cudaGetErrorString(e)); return AVDF_ERR_CUDA; }
+      return check_launch("nms_cluster_kernel");
+    }
   }
   AVDF_SMEM_ATTR_ONCE(nms_standalone_kernel, nms_smem_bytes());
   nms_standalone_kernel<<<1, NMS_THREADS, use_gws ? 0 : nms_smem_bytes(), st>>>(
