@@ -1440,6 +1440,53 @@ extern "C" int avdf_head_final(const void* cls_feat, const void* reg_feat, int32
   return check_launch("head_final_kernel");
 }
 
+// Heads from per-tap partial sums (avdf_conv_gemm dot_out of the last tower layers): one thread per pyramid row adds the
+// three taps of its neighbours inside the level, bias, mask, Scale and ReLU (av_fd_no_recon.py:82-89, 152-159).
+namespace avdf {
+__global__ void __launch_bounds__(256) head_combine_kernel(const HeadParams p, const float* __restrict__ cd, const float* __restrict__ rd) {
+  const long long rows = (long long)p.B * p.P;
+  const float cb = p.cls_b[0], rb0 = p.reg_b[0], rb1 = p.reg_b[1];
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const int pr = (int)(r % p.P);
+    int l = 0;
+    while (l + 1 < p.n_levels && pr >= p.lvl_off[l + 1]) ++l;
+    const int t = pr - p.lvl_off[l], T = p.lvl_len[l];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {                  // tap j multiplies the row at t + j - 1 (zero outside the level)
+      const int tt = t + j - 1;
+      if (tt >= 0 && tt < T) {
+        const long long rr = r + (j - 1);
+        a0 += cd[rr * 3 + j];
+        a1 += rd[rr * 6 + j];
+        a2 += rd[rr * 6 + 3 + j];
+      }
+    }
+    const float mk = p.mask ? (p.mask[r] ? 1.f : 0.f) : 1.f;
+    p.logits[r] = (a0 + cb) * mk;
+    const float sc = p.lvl_scale[l];
+    p.offsets[2 * r] = fmaxf(((a1 + rb0) * mk) * sc, 0.f);
+    p.offsets[2 * r + 1] = fmaxf(((a2 + rb1) * mk) * sc, 0.f);
+  }
+}
+}  // namespace avdf
+
+extern "C" int avdf_head_combine(const float* cls_dots, const float* reg_dots, const uint8_t* mask, const float* cls_b,
+                                 const float* reg_b, const float* level_scale, float* logits, float* offsets, int32_t batch,
+                                 int32_t n_levels, const int32_t* level_len, void* stream) {
+  AVDF_CHECK_ARG(cls_dots && reg_dots && cls_b && reg_b && level_scale && logits && offsets && level_len, "null pointer");
+  AVDF_CHECK_ARG(n_levels >= 1 && n_levels <= AVDF_MAX_LEVELS, "n_levels out of range");
+  HeadParams p{};
+  p.mask = mask; p.cls_b = cls_b; p.reg_b = reg_b; p.logits = logits; p.offsets = offsets; p.B = batch; p.n_levels = n_levels;
+  p.P = fill_levels(n_levels, level_len, p.lvl_off, p.lvl_len);
+  for (int l = 0; l < n_levels; ++l) p.lvl_scale[l] = level_scale[l];
+  if (batch == 0) return AVDF_OK;
+  const long long rows = (long long)batch * p.P;
+  const int grid = (int)((rows + 255) / 256);
+  head_combine_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, cls_dots, reg_dots);
+  return check_launch("head_combine_kernel");
+}
+
 extern "C" int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_wt, const float* lin1_wt, const float* ln_w,
                                const float* ln_b, const float* lin2_w, const float* lin2_b, float* out, int32_t batch,
                                int32_t t, int32_t channels, void* stream) {

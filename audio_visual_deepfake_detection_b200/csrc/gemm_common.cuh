@@ -9,6 +9,7 @@ struct EpiParams {
   const float* pe; const float* residual; const float* gamma;
   float* out_f32; void* out_h; int out_h_f16;
   int n_out;
+  const float* dot_w; int dot_n; float* dot_out;      // row dot products (avdf_conv_gemm_args.dot_*)
 };
 
 struct SegInfo {
@@ -34,6 +35,7 @@ inline void fill_epi(const avdf_conv_gemm_args* a, EpiParams& e) {
   e.pe = a->pe; e.residual = a->residual; e.gamma = a->gamma;
   e.out_f32 = a->out_f32; e.out_h = a->out_h; e.out_h_f16 = a->out_h_dtype == AVDF_DTYPE_F16;
   e.n_out = a->n_out;
+  e.dot_w = a->dot_w; e.dot_n = a->dot_n; e.dot_out = a->dot_out;
 }
 inline void fill_seg(const avdf_conv_gemm_args* a, SegInfo& s) {
   s.n_seg = a->n_seg; s.batch = a->batch;

@@ -151,6 +151,7 @@ static int conv_gemm_f32_one(const avdf_conv_gemm_args* a, cudaStream_t st) {
   p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.k_total = a->taps * a->c_in;
   p.tap_off = a->tap_mode ? 0 : (a->taps >> 1);
   AVDF_CHECK_ARG(!a->ln_after_residual, "ln_after_residual is a feature of the 16-bit path");
+  AVDF_CHECK_ARG(!a->dot_out, "dot_out is a feature of the 16-bit path");
   AVDF_CHECK_ARG(a->c_in % SBK == 0, "c_in must be a multiple of 16");
   AVDF_CHECK_ARG(a->workspace && a->workspace_bytes >= (size_t)a->batch * a->o_rows_per_video * a->n_out * sizeof(float),
                  "fp32 path needs a workspace of batch*o_rows_per_video*n_out floats");
@@ -184,7 +185,7 @@ extern "C" int avdf_conv_gemm(const avdf_conv_gemm_args* a, void* stream) {
   AVDF_CHECK_ARG(a->stride == 1 || a->stride == 2, "stride must be 1 or 2");
   AVDF_CHECK_ARG(a->n_seg >= 1 && a->n_seg <= AVDF_MAX_LEVELS, "n_seg out of range");
   AVDF_CHECK_ARG(a->a && a->w, "null operand");
-  AVDF_CHECK_ARG(a->out_f32 || a->out_h, "no output");
+  AVDF_CHECK_ARG(a->out_f32 || a->out_h || a->dot_out, "no output");
   AVDF_CHECK_ARG(!a->out_h || a->out_h_dtype == AVDF_DTYPE_BF16 || a->out_h_dtype == AVDF_DTYPE_F16, "out_h_dtype must be BF16 or F16");
   AVDF_CHECK_ARG((a->ln_w == nullptr) == (a->ln_b == nullptr), "ln_w / ln_b must come together");
   for (int i = 0; i < a->n_seg; ++i) AVDF_CHECK_ARG(a->seg_t_out[i] > 0, "seg_t_out must be positive");

@@ -105,10 +105,16 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
 
 // MODE >= 0 fixes the epilogue variant at compile time (bit 0 LayerNorm, bits 1-2 activation, bit 3 residual,
 // bit 4 positional encoding) so the epilogue carries no dead branches; MODE < 0 reads the flags at run time.
+constexpr int W8_SMEM_BYTES_FWD = 223232;      // = W8_SMEM_BYTES (defined below, next to the kernel)
 constexpr int mode_of(bool ln, int act, bool res, bool pe) { return (ln ? 1 : 0) | (act << 1) | (res ? 8 : 0) | (pe ? 16 : 0); }
 // bit 5: the LayerNorm follows the residual step (avdf_conv_gemm_args.ln_after_residual): attention projection + LN2 in
 // one launch. Only instantiated for the wide eight-epilogue-warp configuration with both outputs.
 constexpr int MODE_POSTLN = mode_of(true, AVDF_ACT_NONE, true, false) | 32;
+// bit 6: row dot products (avdf_conv_gemm_args.dot_*): the last layer of the head towers emits the per-tap partial sums of
+// the heads' final convolution instead of its 256-channel fp32 output. Wide eight-warp configuration only.
+constexpr int MODE_HEADDOT = mode_of(true, AVDF_ACT_RELU, false, false) | 64;
+constexpr int MAX_DOTS = 6;
+constexpr int W8D_SMEM_BYTES = W8_SMEM_BYTES_FWD + MAX_DOTS * MAX_BN * 4;
 
 // OUTK >= 0 fixes which outputs exist: bit 0 fp32, bit 1 16-bit copy, bit 2 the 16-bit copy is fp16 (else bf16).
 // CFG (compile-time, so that the streaming variants carry none of the other configurations' state):
@@ -118,6 +124,7 @@ constexpr int MODE_POSTLN = mode_of(true, AVDF_ACT_NONE, true, false) | 32;
 //      columns; LayerNorm statistics are exchanged through shared memory (one named barrier per row block). With four
 //      warps the LayerNorm epilogue (two TMEM passes over 256 columns) took longer than the K = 768 main loop.
 constexpr int W8_SMEM_BYTES = smem_bytes_of(MAX_BN) + 4 * 8192 /* four more staging pairs */ + 4096 /* LayerNorm partial sums */;
+static_assert(W8_SMEM_BYTES == W8_SMEM_BYTES_FWD, "keep the forward declaration in step");
 template <int MODE, int OUTK, int CFG = 0>
 __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_gemm_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -275,6 +282,9 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
     const int chunks = (p.bn >> 5) / (EPI_WARPS / 4);     // 32-column chunks this warp handles: [ch0, ch1)
     const int ch0 = team * chunks, ch1 = ch0 + chunks;
     constexpr bool POSTLN = MODE >= 0 && (MODE & 32) != 0;
+    constexpr bool HEADDOT = MODE >= 0 && (MODE & 64) != 0;
+    static_assert(!HEADDOT || CFG == 2, "row dot products run in the wide eight-warp configuration");
+    float* s_dot = reinterpret_cast<float*>(part_smem + 4096);        // HEADDOT: dot_w [dot_n][256]
     static_assert(!POSTLN || CFG == 2, "the post-residual LayerNorm runs in the wide eight-warp configuration");
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
     const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
@@ -316,6 +326,8 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
           }
           s_gam[i] = e.gamma ? __ldg(e.gamma + vec0 + i) : 1.f;
         }
+        if (HEADDOT)
+          for (int i = et; i < e.dot_n * MAX_BN; i += EPI_WARPS * 32) s_dot[i] = __ldg(e.dot_w + i);
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         loaded_n0 = vec0;
       }
@@ -561,6 +573,9 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
         if (wi == 0 && it == 1) AVDF_TS(14);        // second tile's epilogue starts
         continue;                                   // next tile
       }
+      float dots[MAX_DOTS];
+#pragma unroll
+      for (int j = 0; j < MAX_DOTS; ++j) dots[j] = 0.f;
       uint32_t vr[32];                            // accumulator block of the current chunk (raw bits)
       tmem_ld32_issue(taddr + ch0 * 32, vr);
       for (int ch = ch0; ch < ch1; ++ch) {
@@ -592,6 +607,21 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
             }
             x[4 * j] = act_tc(x[4 * j], act); x[4 * j + 1] = act_tc(x[4 * j + 1], act);
             x[4 * j + 2] = act_tc(x[4 * j + 2], act); x[4 * j + 3] = act_tc(x[4 * j + 3], act);
+          }
+        }
+        if (HEADDOT) {                            // this row's partial dot products over the chunk's 32 channels
+#pragma unroll
+          for (int j = 0; j < MAX_DOTS; ++j) {
+            if (j < e.dot_n) {
+              const float4* d4 = reinterpret_cast<const float4*>(s_dot + j * MAX_BN + cl);
+              float a_ = dots[j];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 ww = d4[i];
+                a_ = fmaf(ww.x, x[4 * i], a_); a_ = fmaf(ww.y, x[4 * i + 1], a_); a_ = fmaf(ww.z, x[4 * i + 2], a_); a_ = fmaf(ww.w, x[4 * i + 3], a_);
+              }
+              dots[j] = a_;
+            }
           }
         }
         if (has_pe && valid) {                    // + PE[t, n] * mask (embedding only: one launch per pass)
@@ -687,6 +717,17 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
       if (has_res && has16 && has32) {            // before the next tile's first residual prefetch
         if (ep_leader) tma_store_wait_read();
         __syncwarp();
+      }
+      if (HEADDOT) {
+        // the two warps of a row quarter hold the two column halves: team 0 stores its partial sums, team 1 adds to them
+        // (two addends: the order does not matter, the result is deterministic)
+        float* drow = e.dot_out + ((size_t)b * p.seg.o_rows + p.seg.o_row[tc_.seg] + t) * e.dot_n;
+        if (team == 0 && valid)
+          for (int j = 0; j < e.dot_n; ++j) drow[j] = dots[j];
+        __threadfence_block();
+        asm volatile("bar.sync %0, 64;" ::"r"(6 + q) : "memory");
+        if (team == 1 && valid)
+          for (int j = 0; j < e.dot_n; ++j) atomicAdd(drow + j, dots[j]);
       }
     }
     if (ep_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
@@ -851,9 +892,9 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     X(mode_of(true, AVDF_ACT_RELU, false, false), 1) X(mode_of(true, AVDF_ACT_RELU, false, true), 1)              \
     X(mode_of(false, AVDF_ACT_NONE, false, false), 1) X(mode_of(false, AVDF_ACT_NONE, true, false), 1)            \
     X(mode_of(false, AVDF_ACT_NONE, true, false), 7) X(mode_of(false, AVDF_ACT_NONE, true, false), 3)           \
-    X(MODE_POSTLN, 7) X(MODE_POSTLN, 3)
+    X(MODE_POSTLN, 7) X(MODE_POSTLN, 3) X(MODE_HEADDOT, 0)
 #define AVDF_SET_SMEM_WS(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
-#define AVDF_SET_SMEM_W8(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, W8_SMEM_BYTES));
+#define AVDF_SET_SMEM_W8(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ((M) >= 0 && ((M) & 64)) ? W8D_SMEM_BYTES : W8_SMEM_BYTES));
     AVDF_SET_SMEM(-1, -1)
     AVDF_TC_VARIANTS(AVDF_SET_SMEM)
     AVDF_SET_SMEM_WS(-1, -1)
@@ -869,8 +910,11 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   const int ctas_per_sm = bn <= 128 ? 2 : 1;      // narrow tiles: two co-resident CTAs per SM
   const int grid = ws ? ws_groups * ws_per : (p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm);
   const bool w8 = !ws && bn == MAX_BN && g_w8;
-  const int smem_bytes = ws ? WS_SMEM_BYTES : (w8 ? W8_SMEM_BYTES : smem_bytes_of(bn));
-  const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr) | (a->ln_after_residual ? 32 : 0);
+  const int smem_bytes = ws ? WS_SMEM_BYTES : (w8 ? (a->dot_out ? W8D_SMEM_BYTES : W8_SMEM_BYTES) : smem_bytes_of(bn));
+  const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr) | (a->ln_after_residual ? 32 : 0) | (a->dot_out ? 64 : 0);
+  if (a->dot_out) {
+    AVDF_CHECK_ARG(w8 && a->n_out == MAX_BN && a->dot_w && a->dot_n >= 1 && a->dot_n <= MAX_DOTS, "dot_out needs n_out = 256, dot_w and 1 <= dot_n <= 6");
+  }
   if (a->ln_after_residual) {
     AVDF_CHECK_ARG(w8 && a->n_out == MAX_BN, "ln_after_residual needs n_out = 256 and the eight-warp wide configuration");
   }
@@ -886,6 +930,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
 #undef AVDF_LAUNCH
 #undef AVDF_LAUNCH_WS
 #undef AVDF_LAUNCH_W8
+  if (!launched && a->dot_out) { set_error("avdf_conv_gemm: no dot_out instantiation for this epilogue / output combination"); return AVDF_ERR_UNSUPPORTED; }
   if (!launched && a->ln_after_residual) { set_error("avdf_conv_gemm: no ln_after_residual instantiation for this output combination"); return AVDF_ERR_UNSUPPORTED; }
   if (!launched) {
     if (ws) lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1, 1>, grid, WS_THREADS, smem_bytes, st, p);

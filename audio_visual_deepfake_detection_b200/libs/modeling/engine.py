@@ -158,6 +158,7 @@ class LocalizationEngine:
         self.fused_mlp_min_rows = int(os.environ.get("AVDF_FUSED_MLP_MIN_ROWS", "0"))
         self.fuse_ln2 = os.environ.get("AVDF_FUSE_LN2", "1") != "0"    # LN2 in the attention projection's epilogue (A/B switch)
         self.fuse_tail = os.environ.get("AVDF_FUSE_TAIL", "1") != "0"  # projection + LN2 + MLP as one launch (A/B switch)
+        self.head_dots = os.environ.get("AVDF_HEAD_DOTS", "1") != "0"  # heads' final conv as dot products in the tower epilogue (A/B switch)
         self.C = c["embd_dim"]
         self.n_head = c["n_head"]
         self.c_in = c["video_input_dim"] + c["audio_input_dim"]
@@ -282,7 +283,7 @@ class LocalizationEngine:
     # ------------------------------------------------------------------ building blocks
     def _gemm(self, a, wkey, *, B, taps=1, stride=1, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
               act=ops.ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_act=None, ln_after_residual=False,
-              tap_mode=0):
+              tap_mode=0, dots=None):
         w = self.w.dense(wkey, a.dtype) if isinstance(wkey, str) else self.w.stack_dense(wkey, a.dtype)
         n_out, k = w.shape
         if not isinstance(wkey, str):
@@ -302,7 +303,7 @@ class LocalizationEngine:
             ws = self.workspace(B * o_rows * n_out * 4)
         ops.conv_gemm(a, w, taps=taps, stride=stride, batch=B, c_in=c_in, n_out=n_out, segs=segs, a_rows=a_rows,
                       o_rows=o_rows, bias=bias, row_mask=row_mask, ln=ln, act=act, pe=pe, residual=residual, gamma=gamma,
-                      out_f32=out_f32, out_h=out_h, workspace=ws, ln_after_residual=ln_after_residual, tap_mode=tap_mode)
+                      out_f32=out_f32, out_h=out_h, workspace=ws, ln_after_residual=ln_after_residual, tap_mode=tap_mode, dots=dots)
 
     def _attn_and_mlp(self, pre, B, T, mask, skip, window, out_name, want_act_copy, pyr=None):
         """Shared tail of TransformerBlock / MutilModelTransformerBlock after the dwconv+LN stage:
@@ -571,12 +572,25 @@ class LocalizationEngine:
         segs = [(lens[l], offs[l], offs[l]) for l in range(self.n_levels)]
         towers = {}
         nl = self.cfg["head_num_layers"] - 1
+        # 16-bit path: the last tower layer does not write its 256-channel fp32 output at all - its epilogue emits, per row,
+        # the dot products with the three taps of the heads' final convolution (fp32, like the convolution itself), and
+        # head_combine adds the taps of neighbouring rows (av_fd_no_recon.py:82-89, 152-159)
+        head_dots = self.head_dots and adt != torch.float32 and C == 256 and nl >= 1
+        dots = {}
         for head in ("cls_head", "reg_head"):
             f = fpn
             for i in range(nl):
                 ln = w.ln(f"{head}.norm.{i}") if w.has(f"{head}.norm.{i}.weight") else None
                 bias = w.vec(f"{head}.head.{i}.conv.bias") if w.has(f"{head}.head.{i}.conv.bias") else None
                 kw = dict(B=B, taps=3, segs=segs, a_rows=P, o_rows=P, bias=bias, row_mask=masks["pyr"], ln=ln, act=ops.ACT_RELU)
+                if i == nl - 1 and head_dots and ln is not None:
+                    last = "cls_head.cls_head" if head == "cls_head" else "reg_head.offset_head"
+                    n_dot = 3 if head == "cls_head" else 6
+                    dw = w.dense(last + ".conv.weight", torch.float32).view(n_dot, C)        # [o, 3 * C] -> rows (o, tap)
+                    d = self.buf(head + "_dots", (B, P, n_dot), torch.float32)
+                    self._gemm(f, f"{head}.head.{i}.conv.weight", dots=(dw, d), **kw)
+                    dots[head] = d
+                    continue
                 if i == nl - 1:       # the last tower layer stays fp32: it feeds the fp32 logit / offset conv
                     o = self.buf(head + "_tower", (B, P, C), torch.float32)
                     self._gemm(f, f"{head}.head.{i}.conv.weight", out_f32=o, **kw)
@@ -589,6 +603,10 @@ class LocalizationEngine:
         offsets = self.buf("offsets", (B, P, 2), torch.float32)
         if not hasattr(self, "_scales"):
             self._scales = [float(self.w.sd[f"reg_head.scale.{l}.scale"]) for l in range(self.n_levels)]
+        if len(dots) == 2:
+            ops.head_combine(dots["cls_head"], dots["reg_head"], masks["pyr"], w.vec("cls_head.cls_head.conv.bias"),
+                             w.vec("reg_head.offset_head.conv.bias"), self._scales, logits, offsets, batch=B, level_len=lens)
+            return logits, offsets, vcls, masks, lens
         ops.head_final(towers["cls_head"], towers["reg_head"], masks["pyr"], w.dense("cls_head.cls_head.conv.weight", torch.float32),
                        w.vec("cls_head.cls_head.conv.bias"), w.dense("reg_head.offset_head.conv.weight", torch.float32),
                        w.vec("reg_head.offset_head.conv.bias"), self._scales, logits, offsets, batch=B, level_len=lens)

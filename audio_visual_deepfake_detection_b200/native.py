@@ -24,7 +24,7 @@ EXPORTS = [
     "avdf_nms_workspace_bytes", "avdf_nms_hard", "avdf_nms_soft",
     "avdf_postprocess_workspace_bytes", "avdf_postprocess",
     "avdf_conv_gemm_workspace_bytes", "avdf_conv_gemm", "avdf_mlp_fused", "avdf_ln_dwconv_ln", "avdf_attention",
-    "avdf_ln_rows", "avdf_instnorm_lrelu", "avdf_fpn_fuse", "avdf_head_final",
+    "avdf_ln_rows", "avdf_instnorm_lrelu", "avdf_fpn_fuse", "avdf_head_final", "avdf_head_combine",
     "avdf_vcls_exp12", "avdf_vcls_exp13", "avdf_host_pack", "avdf_host_all_pinned", "avdf_h2d_gather",
 ]
 
@@ -63,6 +63,7 @@ class ConvGemmArgs(Structure):
         ("out_f32", c_void_p), ("out_h", c_void_p), ("out_h_dtype", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("ln_after_residual", c_int32), ("tap_mode", c_int32),
+        ("dot_w", c_void_p), ("dot_n", c_int32), ("dot_out", c_void_p),
     ]
 
 
@@ -127,6 +128,7 @@ def lib():
     L.avdf_fpn_fuse.argtypes = [c_void_p] * 6 + [c_int32] * 4 + [POINTER(c_int32), c_void_p]
     L.avdf_head_final.argtypes = [c_void_p, c_void_p, c_int32] + [c_void_p] * 5 + [POINTER(c_float), c_void_p, c_void_p,
                                                                                   c_int32, c_int32, c_int32, POINTER(c_int32), c_void_p]
+    L.avdf_head_combine.argtypes = [c_void_p] * 5 + [POINTER(c_float), c_void_p, c_void_p, c_int32, c_int32, POINTER(c_int32), c_void_p]
     L.avdf_vcls_exp12.argtypes = [c_void_p, c_int32] + [c_void_p] * 7 + [c_int32] * 3 + [c_void_p]
     L.avdf_vcls_exp13.argtypes = [c_void_p, c_int32] + [c_void_p] * 6 + [c_int32] * 3 + [c_void_p]
     L.avdf_host_pack.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t), c_int32, c_int32]

@@ -200,7 +200,7 @@ def postprocess_workspace_bytes(batch, cand_cap):
 # ---------------------------------------------------------------------------- conv GEMM
 def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
               act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_h=None, workspace=None,
-              ln_after_residual=False, tap_mode=0):
+              ln_after_residual=False, tap_mode=0, dots=None):
     """segs: list of (t_out, a_row, o_row[, w_row]) per segment. a: [batch, a_rows, c_in]; w: [n_w_rows, taps*c_in]
     (same dtype as a: fp32 -> CUDA-core parity path, bf16 / fp16 -> tcgen05 path). Outputs [batch, o_rows, n_out]:
     out_f32 and/or out_h (a bf16 or fp16 copy)."""
@@ -224,6 +224,10 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
         g.ln_w, g.ln_b = ln[0].data_ptr(), ln[1].data_ptr()
     g.act = act
     g.ln_after_residual, g.tap_mode = int(bool(ln_after_residual)), int(tap_mode)
+    if dots is not None:                 # (dot_w [n, n_out] fp32, dot_out [batch, o_rows, n] fp32): row dot products of the result
+        _chk(dots[0], torch.float32, "dot_w"); _chk(dots[1], torch.float32, "dot_out")
+        assert dots[0].shape[1] == n_out and dots[1].shape[-1] == dots[0].shape[0]
+        g.dot_w, g.dot_n, g.dot_out = dots[0].data_ptr(), dots[0].shape[0], dots[1].data_ptr()
     g.pe = pe.data_ptr() if pe is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.gamma = gamma.data_ptr() if gamma is not None else None
@@ -365,6 +369,18 @@ def head_final(cls_feat, reg_feat, mask, cls_w, cls_b, reg_w, reg_b, level_scale
     _call("avdf_head_final", L.avdf_head_final, (nv.ptr(cls_feat), nv.ptr(reg_feat), _dt(cls_feat), nv.ptr(mask), nv.ptr(cls_w), nv.ptr(cls_b),
                                nv.ptr(reg_w), nv.ptr(reg_b), sc, nv.ptr(logits), nv.ptr(offsets), batch, cls_feat.shape[-1],
                                len(level_len), _levels(level_len), _stream(),), launches=1, work=None)
+
+
+def head_combine(cls_dots, reg_dots, mask, cls_b, reg_b, level_scale, logits, offsets, *, batch, level_len):
+    """logits / offsets from the per-tap partial sums the last tower layers emit (conv_gemm dots=...)."""
+    L = nv.lib()
+    for t in (cls_dots, reg_dots, cls_b, reg_b, logits, offsets):
+        _chk(t, torch.float32, "head tensor")
+    _chk(mask, torch.uint8, "mask")
+    assert cls_dots.shape[-1] == 3 and reg_dots.shape[-1] == 6
+    sc = (c_float * len(level_scale))(*[float(s) for s in level_scale])
+    _call("avdf_head_combine", L.avdf_head_combine, (nv.ptr(cls_dots), nv.ptr(reg_dots), nv.ptr(mask), nv.ptr(cls_b), nv.ptr(reg_b), sc,
+                               nv.ptr(logits), nv.ptr(offsets), batch, len(level_len), _levels(level_len), _stream(),), launches=1, work=None)
 
 
 def vcls_exp12(z, conv0_w, lin1_w, ln_w, ln_b, lin2_w, lin2_b, out, *, batch, t):

@@ -184,6 +184,13 @@ typedef struct avdf_conv_gemm_args {
    * 0 .. taps-1, stride 1 only): the row pair (x[t], x[t+1]) a stride-2 ConvTranspose1d(k=3, padding=1, output_padding=1)
    * reads for its outputs 2t and 2t+1 (blocks.py:1443-1491) - see libs/modeling/engine.py `up_block` */
   int32_t tap_mode;
+  /* Row dot products instead of (or next to) the output tensor (16-bit path, n_out = 256, wide configuration):
+   * dot_out[row, j] = sum_n dot_w[j, n] * v[row, n] for j < dot_n <= 6, v = the epilogue's result. With dot_out set,
+   * out_f32 and out_h may both be NULL: the last layer of the cls / reg towers then emits only the per-tap partial sums of
+   * the heads' final k3 convolution (av_fd_no_recon.py:82-89, 152-159), which avdf_head_combine turns into logits / offsets. */
+  const float* dot_w;            /* [dot_n, n_out] fp32 or NULL */
+  int32_t dot_n;
+  float* dot_out;                /* [batch, o_rows_per_video, dot_n] fp32 or NULL */
 } avdf_conv_gemm_args;            /* host struct */
 AVDF_API size_t avdf_conv_gemm_workspace_bytes(const avdf_conv_gemm_args* args);
 AVDF_API int avdf_conv_gemm(const avdf_conv_gemm_args* args, void* stream);
@@ -273,6 +280,13 @@ AVDF_API int avdf_head_final(const void* cls_feat, const void* reg_feat, int32_t
                     const float* reg_b, const float* level_scale /* host [n_levels] */, float* logits,
                     float* offsets, int32_t batch, int32_t channels, int32_t n_levels,
                     const int32_t* level_len /* host */, void* stream);
+
+/* The same from per-tap partial sums (avdf_conv_gemm dot_out of the last tower layers): cls_dots [batch, P, 3] holds, for
+ * every pyramid row, the dot products of its tower output with the three taps of cls_head.cls_head.conv.weight; reg_dots
+ * [batch, P, 6] = (output o, tap j) at o * 3 + j. logit[t] = dots[t-1][0] + dots[t][1] + dots[t+1][2] + bias inside the level. */
+AVDF_API int avdf_head_combine(const float* cls_dots, const float* reg_dots, const uint8_t* mask, const float* cls_b,
+                      const float* reg_b, const float* level_scale /* host [n_levels] */, float* logits, float* offsets,
+                      int32_t batch, int32_t n_levels, const int32_t* level_len /* host */, void* stream);
 
 /* ---- video-level classifier tails ---- */
 /* exp12 (blocks.py:1608-1626): z [batch, t <= 32, C] (after the last DownBlock) -> logit [batch]. The two dense

@@ -662,6 +662,48 @@ def test_conv_gemm_forward_taps_is_conv_transpose(mode):
     assert rel_err(out.view(B, 2 * T, cout).cpu(), want) < (2e-5 if mode == "fp32" else 2e-4)
 
 
+def test_conv_gemm_row_dots_and_head_combine():
+    """The last tower layer emits per-tap partial sums of the heads' final convolution instead of its 256-channel output
+    (conv_gemm dots=...), avdf_head_combine adds the neighbouring rows' taps: against avdf_head_final on the stored tower
+    outputs and against torch. Pyramid segments, ragged masks."""
+    rng = np.random.RandomState(21)
+    lens = [96, 48, 24, 12, 6, 3]
+    B, C, P = 37, 256, sum(lens)
+    offs = [sum(lens[:l]) for l in range(len(lens))]
+    adt = torch.float16
+    x = torch.from_numpy(rng.standard_normal((B, P, C)).astype(np.float32))
+    valid = rng.randint(40, 97, B); valid[0] = 96
+    mask = np.concatenate([(np.arange(n)[None] * (2 ** l)) < valid[:, None] for l, n in enumerate(lens)], axis=1).astype(np.uint8)
+    towers, dots = {}, {}
+    segs = [(lens[l], offs[l], offs[l]) for l in range(len(lens))]
+    heads = {}
+    for head, n_out in (("cls", 1), ("reg", 2)):
+        w = torch.from_numpy((rng.standard_normal((C, C, 3)) / math.sqrt(3 * C)).astype(np.float32))
+        ln = _ln_params(rng, C)
+        hw = torch.from_numpy((rng.standard_normal((n_out, C, 3)) / math.sqrt(3 * C)).astype(np.float32))
+        hb = torch.from_numpy(rng.normal(0, 0.3, n_out).astype(np.float32))
+        wp = w.permute(0, 2, 1).reshape(C, 3 * C).contiguous()
+        hwp = hw.permute(0, 2, 1).reshape(n_out, 3 * C).contiguous()              # [o, tap * C]
+        kw = dict(taps=3, stride=1, batch=B, c_in=C, n_out=C, segs=segs, a_rows=P, o_rows=P, row_mask=dev(mask),
+                  ln=(dev(ln[0]), dev(ln[1])), act=ops.ACT_RELU)
+        t32 = torch.zeros((B, P, C), device=DEV)
+        ops.conv_gemm(dev(x, adt), dev(wp, adt), out_f32=t32, **kw)
+        d = torch.full((B, P, 3 * n_out), float("nan"), device=DEV)
+        ops.conv_gemm(dev(x, adt), dev(wp, adt), dots=(dev(hwp).view(3 * n_out, C), d), **kw)
+        towers[head], dots[head], heads[head] = t32, d, (dev(hwp), dev(hb))
+        # the dot products themselves, against the stored tower output
+        want = torch.einsum("bpc,jc->bpj", t32.cpu(), hwp.view(3 * n_out, C))
+        assert rel_err(d.cpu(), want) < 1e-5
+    scales = [float(v) for v in rng.uniform(0.8, 1.6, len(lens))]
+    lg_a, of_a = torch.zeros((B, P), device=DEV), torch.zeros((B, P, 2), device=DEV)
+    lg_b, of_b = torch.zeros((B, P), device=DEV), torch.zeros((B, P, 2), device=DEV)
+    ops.head_final(towers["cls"], towers["reg"], dev(mask), heads["cls"][0], heads["cls"][1], heads["reg"][0], heads["reg"][1], scales,
+                   lg_a, of_a, batch=B, level_len=lens)
+    ops.head_combine(dots["cls"], dots["reg"], dev(mask), heads["cls"][1], heads["reg"][1], scales, lg_b, of_b, batch=B, level_len=lens)
+    torch.cuda.synchronize()
+    assert rel_err(lg_b.cpu(), lg_a.cpu()) < 1e-5 and rel_err(of_b.cpu(), of_a.cpu()) < 1e-5
+
+
 def test_attention_stacked_qkv_and_interleaved_dwconv():
     rng = np.random.RandomState(10)
     B, T, C = 3, 80, 256
