@@ -37,6 +37,10 @@ inline void fill_epi(const avdf_conv_gemm_args* a, EpiParams& e) {
   e.n_out = a->n_out;
   e.dot_w = a->dot_w; e.dot_n = a->dot_n; e.dot_out = a->dot_out;
 }
+inline void fill_taps(const avdf_conv_gemm_args* a, int* tab) {
+  for (int j = 0; j < AVDF_MAX_TAPS; ++j)
+    tab[j] = j >= a->taps ? 0 : (a->tap_rows ? a->tap_rows[j] : (a->tap_mode ? j : j - (a->taps >> 1)));
+}
 inline void fill_seg(const avdf_conv_gemm_args* a, SegInfo& s) {
   s.n_seg = a->n_seg; s.batch = a->batch;
   for (int i = 0; i < a->n_seg; ++i) { s.t_out[i] = a->seg_t_out[i]; s.a_row[i] = a->seg_a_row[i]; s.o_row[i] = a->seg_o_row[i]; s.w_row[i] = a->seg_w_row[i]; }

@@ -12,7 +12,8 @@ struct SimtParams {
   SegInfo seg;
   int seg_m_start[AVDF_MAX_LEVELS + 1];   // prefix of batch * t_out over levels
   const float* a; const float* w; float* raw;
-  int n_out, c_in, taps, stride, m_total, k_total, tap_off;
+  int n_out, c_in, taps, stride, m_total, k_total;
+  int tap_tab[AVDF_MAX_TAPS];
 };
 
 __device__ __forceinline__ void simt_decode_row(const SimtParams& p, int m, int& seg, int& b, int& t) {
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) conv_gemm_f32_kernel(const SimtParams p) 
     const int tap = kk / p.c_in, c = kk - tap * p.c_in;
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a_ok) {
-      const int ti = p.stride * a_t + tap - p.tap_off;
+      const int ti = p.stride * a_t + p.tap_tab[tap];
       if (ti >= 0 && ti < t_in_len) av = *reinterpret_cast<const float4*>(a_base + (size_t)ti * p.c_in + c + lk);
     }
     float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -149,7 +150,7 @@ static int conv_gemm_f32_one(const avdf_conv_gemm_args* a, cudaStream_t st) {
   p.a = reinterpret_cast<const float*>(a->a); p.w = reinterpret_cast<const float*>(a->w);
   p.raw = reinterpret_cast<float*>(a->workspace);
   p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.k_total = a->taps * a->c_in;
-  p.tap_off = a->tap_mode ? 0 : (a->taps >> 1);
+  fill_taps(a, p.tap_tab);
   AVDF_CHECK_ARG(!a->ln_after_residual, "ln_after_residual is a feature of the 16-bit path");
   AVDF_CHECK_ARG(!a->dot_out, "dot_out is a feature of the 16-bit path");
   AVDF_CHECK_ARG(a->c_in % SBK == 0, "c_in must be a multiple of 16");
@@ -179,7 +180,8 @@ extern "C" int avdf_conv_gemm(const avdf_conv_gemm_args* a, void* stream) {
   AVDF_CHECK_ARG(a != nullptr, "args is null");
   AVDF_CHECK_ARG(a->batch >= 0 && a->n_out > 0 && a->c_in > 0, "bad sizes");
   AVDF_CHECK_ARG(a->tap_mode == 0 || a->tap_mode == 1, "tap_mode must be 0 or 1");
-  AVDF_CHECK_ARG(a->tap_mode ? (a->taps == 2 && a->stride == 1) : (a->taps == 1 || a->taps == 3), "taps must be 1 or 3 (centred) or 2 (forward, stride 1)");
+  if (a->tap_rows) AVDF_CHECK_ARG(a->taps >= 1 && a->taps <= AVDF_MAX_TAPS && a->stride == 1 && !a->tap_mode, "tap_rows: 1 <= taps <= 9, stride 1, tap_mode 0");
+  else AVDF_CHECK_ARG(a->tap_mode ? (a->taps == 2 && a->stride == 1) : (a->taps == 1 || a->taps == 3), "taps must be 1 or 3 (centred) or 2 (forward, stride 1)");
   AVDF_CHECK_ARG(!a->ln_after_residual || (a->ln_w && a->residual && a->out_f32 && a->out_h && a->act == AVDF_ACT_NONE && !a->pe),
                  "ln_after_residual needs ln_w, residual, out_f32 and out_h, no activation and no pe");
   AVDF_CHECK_ARG(a->stride == 1 || a->stride == 2, "stride must be 1 or 2");

@@ -68,7 +68,8 @@ struct Params {
   SegInfo seg;
   int seg_tile_start[AVDF_MAX_LEVELS + 1];   // prefix of m-tiles per level
   int seg_tt[AVDF_MAX_LEVELS];               // time steps per tile (power of two <= 128)
-  int n_out, c_in, taps, stride, tap_off, bn, n_tiles_n, n_tiles_m, total_tiles;
+  int n_out, c_in, taps, stride, bn, n_tiles_n, n_tiles_m, total_tiles;
+  int tap_tab[AVDF_MAX_TAPS];        // row offset of every tap (avdf_conv_gemm_args.tap_mode / tap_rows)
   int ws, ws_groups, ws_per;                 // weight-stationary: (segment, n-tile) groups, CTAs per group
   unsigned idesc;
   EpiParams epi;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
           tma_load_2d(smem_u32(smem_b + kb * b_stage), &p.w_map, wfull_bar, kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
       }
       for (int tap = 0; tap < p.taps; ++tap) {
-        const int d = tap - p.tap_off;
+        const int d = p.tap_tab[tap];
         int par = 0, dt = d;
         if (p.stride == 2) { par = d & 1; dt = (d - par) / 2; }
         for (int kb = 0; kb < kb_per_tap; ++kb) {
@@ -783,6 +784,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   AVDF_CHECK_ARG(bn % 16 == 0 && bn >= 32, "bf16 path: unsupported n_out");
   AVDF_CHECK_ARG(!a->ln_w || a->n_out == bn, "bf16 path: fused LayerNorm needs n_out <= 256");
   AVDF_CHECK_ARG(a->stride == 1 || a->taps == 3 || a->taps == 1, "bad stride/taps");
+  AVDF_CHECK_ARG(!a->tap_rows || a->stride == 1, "tap_rows needs stride 1");
   AVDF_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0, "operands must be 16-byte aligned");
   EncodeFn encode = get_encode();
   if (!encode) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled not available from the driver"); return AVDF_ERR_CUDA; }
@@ -795,7 +797,7 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   fill_epi(a, p.epi);
   p.dbg = g_dbg;
   p.n_out = a->n_out; p.c_in = a->c_in; p.taps = a->taps; p.stride = a->stride; p.bn = bn;
-  p.tap_off = a->tap_mode ? 0 : (a->taps >> 1);
+  fill_taps(a, p.tap_tab);
   p.n_tiles_n = a->n_out / bn;
   int tiles = 0;
   for (int s = 0; s < a->n_seg; ++s) {

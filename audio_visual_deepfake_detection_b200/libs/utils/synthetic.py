@@ -108,3 +108,55 @@ def tinydataset_streams(index: int, seed: int, video_dim=256, byola_dim=2048, em
         out["byola"] = np.abs(rng.standard_normal((t_b, byola_dim))).astype(np.float32)
     out["emo"] = rng.standard_normal((t_e, emo_dim)).astype(np.float32)
     return duration, out
+
+
+# ---------------------------------------------------------------------------- BYOL-A extractor
+def byola_state_dict_spec(n_mels: int = 64, d: int = 2048) -> dict:
+    """Names and shapes of AudioNTT2020Task6's state_dict (audio_feature/content_audio/byol_a/models.py:53-76)."""
+    spec = {}
+    c_in = 1
+    for conv, bn in ((0, 1), (4, 5), (8, 9)):
+        spec[f"features.{conv}.weight"] = (64, c_in, 3, 3)
+        spec[f"features.{conv}.bias"] = (64,)
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            spec[f"features.{bn}.{k}"] = (64,)
+        c_in = 64
+    spec["fc.0.weight"] = (d, 64 * (n_mels // 8)); spec["fc.0.bias"] = (d,)
+    spec["fc.3.weight"] = (d, d); spec["fc.3.bias"] = (d,)
+    return spec
+
+
+def synthetic_byola_state_dict(seed: int = 0, n_mels: int = 64, d: int = 2048) -> dict:
+    """Seeded stand-in for pretrained_weights/AudioNTT2020-BYOLA-64x96d2048.pth (not shipped): He-scaled dense weights,
+    non-trivial BatchNorm statistics, so that every layer keeps O(1) activations with a live ReLU."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for name, shape in byola_state_dict_spec(n_mels, d).items():
+        if name.endswith("running_var"):
+            a = rng.uniform(0.5, 1.5, shape)
+        elif name.endswith("running_mean"):
+            a = rng.normal(0.0, 0.2, shape)
+        elif len(shape) == 1 and name.endswith(".weight"):          # BatchNorm gamma
+            a = rng.uniform(0.5, 1.5, shape)
+        elif name.endswith(".bias"):
+            a = rng.normal(0.0, 0.1, shape)
+        else:
+            a = rng.normal(0.0, math.sqrt(2.0 / int(np.prod(shape[1:]))), shape)
+        out[name] = torch.from_numpy(np.asarray(a, dtype=np.float32).reshape(shape).copy())
+    return out
+
+
+def synthetic_wav(n_samples: int, seed: int) -> np.ndarray:
+    """Speech-like 16 kHz test signal: a few amplitude-modulated partials plus coloured noise, peak below 1 - gives
+    the log-mel spectrogram a dynamic range (white noise alone is flat)."""
+    rng = np.random.RandomState(seed)
+    t = np.arange(n_samples, dtype=np.float64) / 16000.0
+    x = np.zeros(n_samples)
+    for _ in range(6):
+        f0 = rng.uniform(80, 3500); am = rng.uniform(0.5, 6.0); ph = rng.uniform(0, 2 * np.pi, 2)
+        x += rng.uniform(0.02, 0.2) * (0.5 + 0.5 * np.sin(2 * np.pi * am * t + ph[0])) * np.sin(2 * np.pi * f0 * t + ph[1])
+    noise = rng.standard_normal(n_samples)
+    noise = np.convolve(noise, np.ones(4) / 4.0, mode="same")
+    env = 0.5 + 0.5 * np.sin(2 * np.pi * rng.uniform(0.3, 2.0) * t + rng.uniform(0, 2 * np.pi))
+    x += 0.05 * env * noise
+    return (x / max(1.0, np.abs(x).max() * 1.05)).astype(np.float32)

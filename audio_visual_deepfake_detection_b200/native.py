@@ -26,6 +26,7 @@ EXPORTS = [
     "avdf_conv_gemm_workspace_bytes", "avdf_conv_gemm", "avdf_mlp_fused", "avdf_ln_dwconv_ln", "avdf_attention",
     "avdf_ln_rows", "avdf_instnorm_lrelu", "avdf_fpn_fuse", "avdf_head_final", "avdf_head_combine",
     "avdf_vcls_exp12", "avdf_vcls_exp13", "avdf_host_pack", "avdf_host_all_pinned", "avdf_h2d_gather",
+    "avdf_logmel", "avdf_byola_conv1_pool", "avdf_byola_pool",
 ]
 
 
@@ -64,6 +65,7 @@ class ConvGemmArgs(Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("ln_after_residual", c_int32), ("tap_mode", c_int32),
         ("dot_w", c_void_p), ("dot_n", c_int32), ("dot_out", c_void_p),
+        ("tap_rows", POINTER(c_int32)),
     ]
 
 
@@ -134,6 +136,9 @@ def lib():
     L.avdf_host_pack.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t), c_int32, c_int32]
     L.avdf_host_all_pinned.argtypes = [POINTER(c_void_p), POINTER(c_size_t), c_int32]
     L.avdf_h2d_gather.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t), c_int32, c_void_p]
+    L.avdf_logmel.argtypes = [c_void_p] * 4 + [c_int32] * 3 + [c_void_p] * 5 + [c_int32, c_float, c_float, c_void_p, c_void_p]
+    L.avdf_byola_conv1_pool.argtypes = [c_void_p] * 6 + [c_int32, c_void_p, c_int32, c_void_p, c_void_p]
+    L.avdf_byola_pool.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("avdf_last_error", "avdf_nms_workspace_bytes", "avdf_postprocess_workspace_bytes",

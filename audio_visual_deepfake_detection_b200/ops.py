@@ -200,7 +200,7 @@ def postprocess_workspace_bytes(batch, cand_cap):
 # ---------------------------------------------------------------------------- conv GEMM
 def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows, bias=None, row_mask=None, ln=None,
               act=ACT_NONE, pe=None, residual=None, gamma=None, out_f32=None, out_h=None, workspace=None,
-              ln_after_residual=False, tap_mode=0, dots=None):
+              ln_after_residual=False, tap_mode=0, dots=None, tap_rows=None):
     """segs: list of (t_out, a_row, o_row[, w_row]) per segment. a: [batch, a_rows, c_in]; w: [n_w_rows, taps*c_in]
     (same dtype as a: fp32 -> CUDA-core parity path, bf16 / fp16 -> tcgen05 path). Outputs [batch, o_rows, n_out]:
     out_f32 and/or out_h (a bf16 or fp16 copy)."""
@@ -228,6 +228,10 @@ def conv_gemm(a, w, *, taps, stride=1, batch, c_in, n_out, segs, a_rows, o_rows,
         _chk(dots[0], torch.float32, "dot_w"); _chk(dots[1], torch.float32, "dot_out")
         assert dots[0].shape[1] == n_out and dots[1].shape[-1] == dots[0].shape[0]
         g.dot_w, g.dot_n, g.dot_out = dots[0].data_ptr(), dots[0].shape[0], dots[1].data_ptr()
+    if tap_rows is not None:             # explicit row offset per tap (a 3x3 Conv2d over a flattened, padded grid)
+        assert len(tap_rows) == taps
+        tr = (c_int32 * taps)(*[int(v) for v in tap_rows])
+        g.tap_rows = tr
     g.pe = pe.data_ptr() if pe is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.gamma = gamma.data_ptr() if gamma is not None else None
@@ -399,3 +403,46 @@ def vcls_exp13(z, conv0_w, seg_w, seg_b, cls_w, cls_b, out, *, batch, t):
         _chk(x, torch.float32, "vcls tensor")
     _call("avdf_vcls_exp13", L.avdf_vcls_exp13, (nv.ptr(z), _dt(z), nv.ptr(conv0_w), nv.ptr(seg_w), nv.ptr(seg_b), nv.ptr(cls_w), nv.ptr(cls_b),
                                nv.ptr(out), batch, t, z.shape[-1], _stream(),), launches=1, work=None)
+
+
+# ---------------------------------------------------------------------------- BYOL-A extractor
+def logmel(wav, clip_sample_off, clip_frame_off, clip_pair_off, total_pairs, window, twiddle, mel, lms, *, mean, std):
+    """wav: the clips back to back (fp32); lms [total_frames, 64] receives the normalised log-mel rows.
+    mel = (lo int32 [64], cnt int32 [64], w fp32 [64, stride]): the mel triangles in sparse form."""
+    L = nv.lib()
+    mel_lo, mel_cnt, mel_w = mel
+    for t, n in ((wav, "wav"), (window, "window"), (twiddle, "twiddle"), (mel_w, "mel_w"), (lms, "lms")):
+        _chk(t, torch.float32, n)
+    _chk(clip_sample_off, torch.int64, "clip_sample_off")
+    for t in (clip_frame_off, clip_pair_off, mel_lo, mel_cnt):
+        _chk(t, torch.int32, "index array")
+    assert window.numel() == 1024 and twiddle.numel() == 2048 and mel_lo.numel() == 64 and mel_cnt.numel() == 64 and mel_w.shape[0] == 64
+    n_clips, frames = clip_frame_off.numel() - 1, lms.shape[0]
+    _call("avdf_logmel", L.avdf_logmel, (nv.ptr(wav), nv.ptr(clip_sample_off), nv.ptr(clip_frame_off), nv.ptr(clip_pair_off), n_clips, frames,
+                                         int(total_pairs), nv.ptr(window), nv.ptr(twiddle), nv.ptr(mel_lo), nv.ptr(mel_cnt), nv.ptr(mel_w),
+                                         int(mel_w.shape[1]), float(mean), float(std), nv.ptr(lms), _stream(),),
+          launches=1, work={"bytes": _nbytes(wav, lms), "flops": frames * (5.0 * 1024 * 10 / 2 + 2.0 * 970)})
+
+
+def byola_conv1_pool(lms, clip_frame_off, w, b, clip_of_step, t_of_step, out, mask_out=None):
+    L = nv.lib()
+    _chk(lms, torch.float32, "lms"); _chk(w, torch.float32, "w"); _chk(b, torch.float32, "b"); _chk(out, None, "out")
+    for t in (clip_frame_off, clip_of_step, t_of_step):
+        _chk(t, torch.int32, "index array")
+    _chk(mask_out, torch.uint8, "mask_out")
+    n_steps = clip_of_step.numel()
+    assert out.numel() == n_steps * 34 * 64 and w.numel() == 64 * 9
+    _call("avdf_byola_conv1_pool", L.avdf_byola_conv1_pool, (nv.ptr(lms), nv.ptr(clip_frame_off), nv.ptr(w), nv.ptr(b), nv.ptr(clip_of_step),
+          nv.ptr(t_of_step), n_steps, nv.ptr(out), _dt(out), nv.ptr(mask_out) if mask_out is not None else None, _stream(),),
+          launches=1, work={"bytes": _nbytes(lms, out)})
+
+
+def byola_pool(x, clip_step_in, clip_of_step, t_of_step, out, *, mel_in, pad_out, mask_out=None):
+    L = nv.lib()
+    _chk(x, None, "x"); _chk(out, x.dtype, "out"); _chk(mask_out, torch.uint8, "mask_out")
+    for t in (clip_step_in, clip_of_step, t_of_step):
+        _chk(t, torch.int32, "index array")
+    n_steps = clip_of_step.numel()
+    assert out.numel() == n_steps * (mel_in // 2 + 2 * pad_out) * 64
+    _call("avdf_byola_pool", L.avdf_byola_pool, (nv.ptr(x), _dt(x), mel_in, nv.ptr(clip_step_in), nv.ptr(clip_of_step), nv.ptr(t_of_step), n_steps,
+          int(pad_out), nv.ptr(out), nv.ptr(mask_out) if mask_out is not None else None, _stream(),), launches=1, work={"bytes": _nbytes(x, out)})

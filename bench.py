@@ -293,6 +293,77 @@ def nms_sweep(dev):
     return out
 
 
+def byola_extractor_bench(dev):
+    """the BYOL-A extractor in front of the path (wav -> [T, 2048] features), 32 clips of AV-Deepfake1M
+    lengths per batch: device-resident (wav in HBM, CUDA events), end to end from host arrays (pinned staging + copy inside
+    `extract`), the per-kernel times of one batch, the CPU oracle (torch CPU fp32, one clip per call like the reference
+    script) on a bounded sample, and the parity of the sampled clips."""
+    import torch
+    from audio_visual_deepfake_detection_b200 import ops
+    from audio_visual_deepfake_detection_b200.libs.features import AudioNTT2020Task6, BatchPlan, LogMelSpectrogram
+    from audio_visual_deepfake_detection_b200.libs.utils import synthetic as syn
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import byola_ref
+    sd = syn.synthetic_byola_state_dict(0)
+    m = AudioNTT2020Task6(n_mels=64, d=2048, precision="mixed").load_state_dict(sd).to(dev).eval()
+    durs = syn.sample_durations(8 * 32, seed=4321)
+    batches = [[syn.synthetic_wav(int(16000 * d), 9000 + 32 * b + i) for i, d in enumerate(durs[32 * b:32 * b + 32])] for b in range(8)]
+    mel = LogMelSpectrogram(dev)
+    plans = [BatchPlan([w.shape[0] for w in bt], dev) for bt in batches]
+    d_wavs = [torch.from_numpy(np.concatenate(bt)).to(dev) for bt in batches]
+
+    def resident():
+        for w, pl in zip(d_wavs, plans):
+            m.forward_packed(mel.packed(w, pl), pl)
+    for _ in range(2):
+        resident()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        resident()
+    e1.record(); torch.cuda.synchronize()
+    res_ms = e0.elapsed_time(e1) / reps / len(batches)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        for bt in batches:
+            outs = m.extract(bt)
+    torch.cuda.synchronize()
+    e2e_ms = 1000.0 * (time.perf_counter() - t0) / 2 / len(batches)
+    # per-kernel times of one batch
+    ops.Profile.on = True; ops.Profile.records = []
+    m.forward_packed(mel.packed(d_wavs[0], plans[0]), plans[0])
+    torch.cuda.synchronize()
+    ops.Profile.on = False
+    kern = {}
+    for name, work, a, b in ops.Profile.records:
+        if "k" in (work or {}):
+            name = "%s[k=%d,n=%d]" % (name, work["k"], work["n"])
+        k = kern.setdefault(name, {"us": 0.0, "launches": 0, "gflop": 0.0, "mb": 0.0})
+        k["us"] += 1000.0 * a.elapsed_time(b); k["launches"] += 1
+        k["gflop"] += (work or {}).get("flops", 0.0) / 1e9; k["mb"] += (work or {}).get("bytes", 0.0) / 1e6
+    ops.Profile.records = []
+    for k in kern.values():
+        k["tflops"] = k["gflop"] / k["us"] * 1e3 if k["gflop"] else None
+        k["gbs"] = k["mb"] / k["us"] * 1e3 if k["us"] else None
+    # CPU oracle + parity on a bounded sample (one clip per call, all host threads)
+    n_cpu = 6
+    t0 = time.perf_counter()
+    want = [byola_ref.extract(w, sd) for w in batches[0][:n_cpu]]
+    cpu_s = time.perf_counter() - t0
+    got = m.extract(batches[0])
+    err = max(float(np.abs(g.cpu().numpy() - w).max() / np.abs(w).max()) for g, w in zip(got, want))
+    secs = float(np.sum(durs)) / len(batches)
+    return {"workload": "BYOL-A AudioNTT2020Task6 (d = 2048) on 16 kHz audio, 32 clips per batch, AV-Deepfake1M durations (mean %.1f s)" % (secs / 32),
+            "value": 32.0 / res_ms * 1e3, "unit": "clips/s", "ms_per_batch": res_ms, "audio_seconds_per_second": secs / res_ms * 1e3,
+            "e2e": {"value": 32.0 / e2e_ms * 1e3, "unit": "clips/s", "note": "host float arrays in, device features out (pageable -> pinned -> H2D inside extract)"},
+            "kernels": kern, "precision": "mixed (fp16 operands, fp32 accumulate; log-mel and conv1 in fp32)",
+            "cpu_baseline": {"value": n_cpu / cpu_s, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d clips, oracle/byola_ref.py (numpy FFT + torch CPU fp32), one clip per call" % n_cpu},
+            "parity": {"max_rel_err_vs_oracle": err, "bar": 1e-2, "clips": n_cpu}}
+
+
 # --------------------------------------------------------------------------------------------- our arm
 BATCHES_PER_STEP = 32        # one step = 4 passes over the 8-batch pool = 1024 videos per GPU
 
@@ -623,6 +694,10 @@ def run_ours(args):
                              "gflop_per_video": flops_per_video(rr["cfg"]["model"], rr["name"].endswith("THE"), rr["name"].endswith("NoNorm")) / 1e9}
                 torch.cuda.empty_cache()
             extra["nms_sweep"] = nms_sweep(dev)
+            try:
+                extra["byola_extractor"] = byola_extractor_bench(dev)
+            except Exception as exc:     # an extra never costs the bench line
+                extra["byola_extractor_error"] = repr(exc)
             line["extra"] = extra
         emit(line)
     if world > 1:

@@ -159,6 +159,7 @@ AVDF_API int avdf_postprocess(const avdf_postprocess_args* args, void* stream);
  *         ln_after_residual moves the LayerNorm behind the residual step, see the field below)
  * dtype F32 -> fp32 CUDA-core path (parity mode); BF16 / F16 -> TMA + tcgen05 tensor-core path (A and W in that
  * 16-bit format, fp32 accumulate in TMEM). out_h (optional) receives a 16-bit copy in out_h_dtype (BF16 | F16). */
+#define AVDF_MAX_TAPS 9
 typedef struct avdf_conv_gemm_args {
   int32_t batch, n_out, c_in, taps, stride, n_seg;
   int32_t seg_t_out[AVDF_MAX_LEVELS];
@@ -191,6 +192,10 @@ typedef struct avdf_conv_gemm_args {
   const float* dot_w;            /* [dot_n, n_out] fp32 or NULL */
   int32_t dot_n;
   float* dot_out;                /* [batch, o_rows_per_video, dot_n] fp32 or NULL */
+  /* Explicit tap table (stride 1, tap_mode 0, taps <= AVDF_MAX_TAPS): tap j reads input row t + tap_rows[j] instead of
+   * t + j - taps/2. With the rows of a (time, mel) grid flattened and padded (csrc/byola.cu "grid layout") the nine offsets
+   * {-1,0,1} * row_pitch + {-1,0,1} make the launch a 3x3 Conv2d (audio_feature/content_audio/byol_a/models.py:59, 64). */
+  const int32_t* tap_rows;       /* host [taps] or NULL */
 } avdf_conv_gemm_args;            /* host struct */
 AVDF_API size_t avdf_conv_gemm_workspace_bytes(const avdf_conv_gemm_args* args);
 AVDF_API int avdf_conv_gemm(const avdf_conv_gemm_args* args, void* stream);
@@ -298,6 +303,35 @@ AVDF_API int avdf_vcls_exp12(const void* z, int32_t dtype, const float* conv0_wt
 AVDF_API int avdf_vcls_exp13(const void* z, int32_t dtype, const float* conv0_w /* [C,C] */, const float* seg_w /* [C] */,
                     const float* seg_b, const float* cls_w /* [2] */, const float* cls_b, float* out,
                     int32_t batch, int32_t t, int32_t channels, void* stream);
+
+/* ---- upstream BYOL-A feature extractor (audio_feature/content_audio) ----
+ * A batch of clips is packed along time. frames(clip) = 1 + samples / 160 (centre = True); all index arrays are DEVICE
+ * int arrays prepared by the host side (libs/features/byola.py `BatchPlan`). */
+/* replaces torchaudio MelSpectrogram(16 kHz, n_fft = win = 1024, hop 160, 64 mels, 60-7800 Hz) + log(x + eps) +
+ * PrecomputedNorm (extract_audio_feature_one.py:34-42, 66; byol_a/augmentations.py:218-219):
+ * wav = the clips back to back, clip c = samples [clip_sample_off[c], clip_sample_off[c+1]) (each > 512 samples),
+ * its frames are rows [clip_frame_off[c], clip_frame_off[c+1]) of lms [total_frames, 64] (time-major). One CTA transforms
+ * frames 2j and 2j+1 of a clip together: clip_pair_off[c] = sum over earlier clips of ceil(frames / 2), total_pairs its end.
+ * window [1024] (periodic Hann), twiddle [1024][2] = (cos, -sin)(2 pi j / 1024); the mel triangles in sparse form: filter m
+ * weighs the power bins mel_lo[m] .. mel_lo[m] + mel_cnt[m] - 1 with mel_w[m * mel_stride + 0 ..] (all DEVICE arrays;
+ * mel_lo[m] + mel_cnt[m] <= 513). */
+AVDF_API int avdf_logmel(const float* wav, const int64_t* clip_sample_off, const int32_t* clip_frame_off,
+                const int32_t* clip_pair_off, int32_t n_clips, int32_t total_frames, int32_t total_pairs, const float* window,
+                const float* twiddle, const int32_t* mel_lo, const int32_t* mel_cnt, const float* mel_w, int32_t mel_stride,
+                float mean, float std, float* lms, void* stream);
+/* features.0-3 of AudioNTT2020Task6 (byol_a/models.py:54-57): Conv2d(1, 64, 3, padding 1) + BatchNorm2d (eval; folded by
+ * the caller into w [64, 9] (mel tap major) and b [64]) + ReLU + MaxPool2d(2) -> level-1 grid layout
+ * out [n_steps * 34, 64] (csrc/byola.cu): step s holds pooled time step t_of_step[s] of clip clip_of_step[s] (-1: an
+ * all-zero separator step). mask_out (optional) [n_steps * 34] receives 1 for rows holding data, 0 for padding rows. */
+AVDF_API int avdf_byola_conv1_pool(const float* lms, const int32_t* clip_frame_off, const float* w, const float* b,
+                const int32_t* clip_of_step, const int32_t* t_of_step, int32_t n_steps, void* out, int32_t out_dtype,
+                uint8_t* mask_out, void* stream);
+/* MaxPool2d(2) (models.py:62, 67) from the grid layout with mel_in rows per step (clip c starts at step clip_step_in[c])
+ * into the next grid layout (pad_out 1: [n_steps_out * (mel_in / 2 + 2), 64]) or into dense rows for the fc layers
+ * (pad_out 0: [n_steps_out, (mel_in / 2) * 64], feature index = mel * 64 + channel as models.py:80-82 flattens it). */
+AVDF_API int avdf_byola_pool(const void* in, int32_t dtype, int32_t mel_in, const int32_t* clip_step_in,
+                const int32_t* clip_of_step, const int32_t* t_of_step, int32_t n_steps_out, int32_t pad_out, void* out,
+                uint8_t* mask_out, void* stream);
 
 /* ---- HOST: gather n byte spans (src[i] -> dst[i], nbytes[i] bytes; all HOST pointers, any alignment; dst is normally
  * a slice of a pinned staging buffer) with up to n_threads threads of a pool that lives inside the library

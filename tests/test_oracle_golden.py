@@ -113,3 +113,58 @@ def test_oracle_vs_live_reference_nms():
             b, d = nms_ref.softnms(segs, sc, thr, 0.75, 0.2, method)
             assert np.array_equal(a, b)
             assert np.array_equal(dets.numpy()[:len(a)], d)
+
+
+# ---------------------------------------------------------------------------- BYOL-A extractor
+def test_byola_oracle_against_reference_fixtures():
+    """oracle/byola_ref.py against tests/golden/byola.npz (the reference's AudioNTT2020Task6 class + torchaudio's
+    MelSpectrogram, run by oracle/make_golden_byola.py): the mel filters bit-equal, the log-mel spectrogram to its fp32
+    noise floor, the features within 5e-5 of the largest value."""
+    import byola_ref
+    g = np.load(os.path.join(GOLD, "byola.npz"))
+    assert np.array_equal(byola_ref.mel_filterbank(), g["mel_fb"])
+    sd = syn.synthetic_byola_state_dict(int(g["weight_seed"]))
+    for i, (n, seed) in enumerate(g["clips"]):
+        wav = syn.synthetic_wav(int(n), int(seed))
+        lms = byola_ref.log_mel(wav)
+        assert lms.shape == g[f"lms{i}"].shape == (64, byola_ref.n_frames(int(n)))
+        # bins without signal sit at log(eps): there the value is the FFT's rounding noise (fp32 in torch, fp64 in numpy)
+        assert np.abs(lms - g[f"lms{i}"]).max() < 2e-3
+        loud = g[f"lms{i}"] > -1.0            # 85 % of the bins; the error grows as a bin's energy falls towards the noise floor
+        assert np.abs(lms - g[f"lms{i}"])[loud].max() < 2e-5
+        feat = byola_ref.forward(g[f"lms{i}"], sd)
+        assert feat.shape == g[f"feat{i}"].shape == (byola_ref.n_frames(int(n)) // 8, 2048)
+        assert np.abs(feat - g[f"feat{i}"]).max() < 2e-5 * np.abs(g[f"feat{i}"]).max()
+        full = byola_ref.extract(wav, sd)
+        assert np.abs(full - g[f"feat{i}"]).max() < 5e-5 * np.abs(g[f"feat{i}"]).max()
+
+
+def test_byola_host_side_plan_and_filterbank():
+    """BatchPlan's packed layouts (csrc/byola.cu grid layout) and the product's mel filter table, no GPU."""
+    import byola_ref
+    from audio_visual_deepfake_detection_b200.libs.features import byola
+    assert np.array_equal(byola.mel_filterbank(), byola_ref.mel_filterbank())
+    plan = byola.BatchPlan([32037, 17123, 9000, 1120], "cpu")
+    assert plan.frames == [201, 108, 57, 8] and plan.t[3] == [25, 13, 7, 1]
+    assert plan.steps1 % 64 == 0 and plan.steps2 % 64 == 0 and plan.rows3 % 128 == 0
+    c1, t1, s1 = plan.d_clip1.numpy(), plan.d_t1.numpy(), plan.d_start1.numpy()
+    for c, t in enumerate(plan.t[1]):
+        assert np.array_equal(c1[s1[c]:s1[c] + t], np.full(t, c)) and np.array_equal(t1[s1[c]:s1[c] + t], np.arange(t))
+        assert c1[s1[c] - 1] == -1 and c1[s1[c] + t] == -1          # a zero step on both sides of every clip
+    assert plan.row_off3.tolist() == [0, 25, 38, 45, 46]
+    for bad in ([512], [1119]):                   # no reflect padding / fewer than 8 frames: torch refuses both too
+        with pytest.raises(ValueError):
+            byola.BatchPlan(bad, "cpu")
+    assert byola.BatchPlan(None, "cpu", frames=[96, 96]).t[3] == [12, 12]
+    m = byola.AudioNTT2020Task6(n_mels=64, d=2048)
+    with pytest.raises(KeyError):
+        m.load_state_dict({"fc.0.weight": torch.zeros(2048, 512)})
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(syn.synthetic_byola_state_dict(0)).to("cpu")
+    # load_weight's key filter (models.py:27-33): prefixes in front of features. / fc. are dropped, other keys ignored
+    sd = {"model.encoder." + k: v for k, v in syn.synthetic_byola_state_dict(0).items()}
+    sd["projector.weight"] = torch.zeros(3)
+    m2 = byola.AudioNTT2020Task6()
+    with pytest.raises(RuntimeError):            # filtered and loaded, then refuses the CPU device
+        m2.load_weight(None, "cpu", state_dict={"state_dict": sd})
+    assert sorted(m2.state_dict()) == sorted(syn.synthetic_byola_state_dict(0))
