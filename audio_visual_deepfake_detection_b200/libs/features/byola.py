@@ -13,13 +13,15 @@ BatchNorm folded into weights / bias, ReLU in the epilogue), `avdf_byola_pool`, 
 layers. A batch of clips of different lengths is packed along time (csrc/byola.cu "grid layout"): each clip sees exactly
 the zero padding it gets alone at batch size 1, which is how the reference script runs it.
 """
+import ctypes
 import math
+import os
 import re
 
 import numpy as np
 import torch
 
-from ... import ops
+from ... import native, ops
 
 CONFIG = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=160, n_mels=64, f_min=60.0, f_max=7800.0, feature_d=2048)
 NORM_STATS = (-2.2800865, 3.5897882)       # extract_audio_feature_one.py:31
@@ -276,7 +278,13 @@ class AudioNTT2020Task6:
                 self._stage = (torch.empty(max(2 * n, 1 << 22), dtype=torch.float32).pin_memory(), torch.cuda.Event())
             host, done = self._stage
             done.synchronize()            # the previous batch's copy has left the buffer
-            np.concatenate(wavs, out=host.numpy()[:n])
+            # gather into the pinned buffer with the library's host thread pool (non-temporal stores, csrc/host_pack.cu)
+            k = len(wavs)
+            base = host.data_ptr()
+            src = (ctypes.c_void_p * k)(*[w.ctypes.data for w in wavs])
+            dst = (ctypes.c_void_p * k)(*[base + 4 * int(o) for o in plan.sample_off[:-1]])
+            nb = (ctypes.c_size_t * k)(*[w.nbytes for w in wavs])
+            native.check(native.lib().avdf_host_pack(src, dst, nb, k, min(8, os.cpu_count() or 1)), "avdf_host_pack")
             wav = host[:n].to(self.device, non_blocking=True)
             done.record(torch.cuda.current_stream(self.device))
         lms = self._melspec.packed(wav, plan)
