@@ -61,6 +61,7 @@ constexpr int WS_THREADS = 128 + WS_EPI_WARPS * 32;
 struct Params {
   CUtensorMap a_map[AVDF_MAX_LEVELS];
   CUtensorMap w_map;
+  CUtensorMap w_half_map;                    // mc: box of bn / 2 weight rows (each CTA of a pair fetches one half)
   CUtensorMap o32_map[AVDF_MAX_LEVELS];      // fp32 output, 3-D (n, t, video) per segment, box = one epilogue warp's 32 rows x 32 columns
   CUtensorMap o16_map[AVDF_MAX_LEVELS];      // 16-bit output copy
   CUtensorMap o16w_map[AVDF_MAX_LEVELS];     // 16-bit output, 64-column box (32 rows x 128 B, swizzle 128B) for the wide epilogue pass
@@ -71,6 +72,8 @@ struct Params {
   int n_out, c_in, taps, stride, bn, n_tiles_n, n_tiles_m, total_tiles;
   int tap_tab[AVDF_MAX_TAPS];        // row offset of every tap (avdf_conv_gemm_args.tap_mode / tap_rows)
   int ws, ws_groups, ws_per;                 // weight-stationary: (segment, n-tile) groups, CTAs per group
+  int mc;                                    // clusters of two CTAs on adjacent row tiles share every weight tile by TMA multicast
+  int pair;                                  // wide configuration as CTA pairs: cta_group::2 MMAs (M = 256 over two SMs, each CTA holds half of W)
   unsigned idesc;
   EpiParams epi;
   unsigned long long* dbg;                   // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
@@ -132,10 +135,11 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
   // 1024 B alignment for the 128B swizzle atoms (an offset into the array keeps the shared address space visible
   // to the compiler: LDS/STS instead of generic loads)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  constexpr bool ws = CFG == 1, w8 = CFG == 2;
+  constexpr bool ws = CFG == 1, w8 = CFG == 2 || CFG == 3;      // CFG 3: the wide configuration as CTA pairs (cta_group::2)
+  constexpr bool pair = CFG == 3;
   constexpr bool OUT16_ONLY = MODE >= 0 && OUTK >= 0 && (OUTK & 3) == 2 && (MODE & 24) == 0;   // the "wide" epilogue pass
-  const int n_stages = ws ? ws_a_stages(OUT16_ONLY) : n_stages_of(p.bn);
-  const int b_stage = b_stage_of(p.bn);
+  const int n_stages = ws ? ws_a_stages(OUT16_ONLY) : (pair ? MAX_STAGES : n_stages_of(p.bn));
+  const int b_stage = pair ? (p.bn >> 1) * BK * 2 : b_stage_of(p.bn);
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + n_stages * A_STAGE;       // ws: WS_W_BLOCKS resident K blocks of the weights
   unsigned char* after = smem_b + (ws ? WS_W_BLOCKS : n_stages) * b_stage;
@@ -170,6 +174,16 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) AVDF_TS(0);
+  // CTA pairs (wide configuration only): the two CTAs of a cluster own adjacent row tiles of one n-tile; the leader (rank 0)
+  // issues ONE tcgen05.mma.cta_group::2 per K step for both (M = 256), each CTA loads its own A rows and HALF of the weight
+  // tile. Barriers the MMA warp waits on live in the leader, barriers it signals are reached in both CTAs by multicast commits
+  // (the scheme of mlp_fused.cu). What it buys: a CTA writes and reads 32 instead of 48 KB of shared memory per K step - the
+  // K >= 512 launches were bound by shared-memory bandwidth (TMA writes + operand reads), not by L2 (the multicast variant
+  // that only halved the L2 reads did not move them).
+  // A kernel that contains cta_group::2 instructions can only be launched as clusters (a plain launch fails with 'cluster
+  // misconfiguration'), hence a separate instantiation (CFG 3). A stage then holds 16 + 16 KB instead of 16 + 32 KB: FOUR stages
+  // instead of three in less shared memory - the big-K launches are bound by the latency of the TMA -> MMA -> commit -> refill
+  // chain (~1.2 us) times the bytes in flight, and a pair needs half the bytes per K step.
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.seg.n_seg; ++s)
@@ -177,18 +191,27 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.w_map) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.mc ? 2 : 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), pair ? 2 * EPI_WARPS : EPI_WARPS); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (pair) {                                  // one warp of EACH CTA of the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  // mc: the peer's barriers must exist before a multicast load or commit of ours can land on them
+  const bool clustered = !ws && (p.mc != 0 || pair);
+  const uint32_t crank = clustered ? cluster_ctarank() : 0u;
+  if (clustered) cluster_sync_all();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (warp == 0) AVDF_TS(1);
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; its outputs (A, residual) are
@@ -218,10 +241,22 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
         if (p.stride == 2) { par = d & 1; dt = (d - par) / 2; }
         for (int kb = 0; kb < kb_per_tap; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          if (leader) {
+          if (pair) {
+            // both CTAs' bytes (own A rows + own half of the weight tile) are credited to the LEADER's full barrier
+            if (leader) {
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * ((uint32_t)A_STAGE + (uint32_t)(p.bn >> 1) * 128u));
+              const uint32_t fb = mapa_rank(full_bar(stage), 0u);
+              tma_load_4d_pair(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], fb, kb * BK, par, tc_.t0 + dt, tc_.b0);
+              tma_load_2d_pair(smem_u32(smem_b + stage * b_stage), &p.w_half_map, fb, tap * p.c_in + kb * BK,
+                               tc_.n0 + p.seg.w_row[tc_.seg] + (int)crank * (p.bn >> 1));
+            }
+          } else if (leader) {
             mbar_arrive_expect_tx(full_bar(stage), ws ? (uint32_t)A_STAGE : stage_bytes);
             tma_load_4d(smem_u32(smem_a + stage * A_STAGE), &p.a_map[tc_.seg], full_bar(stage), kb * BK, par, tc_.t0 + dt, tc_.b0);
-            if (!ws) tma_load_2d(smem_u32(smem_b + stage * b_stage), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
+            if (!ws && p.mc)             // our half of the weight tile, into both CTAs of the pair
+              tma_load_2d_mc(smem_u32(smem_b + stage * b_stage) + crank * (uint32_t)(p.bn >> 1) * 128u, &p.w_half_map, full_bar(stage),
+                             tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg] + (int)crank * (p.bn >> 1), (unsigned short)3);
+            else if (!ws) tma_load_2d(smem_u32(smem_b + stage * b_stage), &p.w_map, full_bar(stage), tap * p.c_in + kb * BK, tc_.n0 + p.seg.w_row[tc_.seg]);
           }
           __syncwarp();
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -235,7 +270,7 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
     // (~53 ns per issue measured, scripts/umma_pace.py) - longer than the 35 ns a 128x128x16 instruction takes.
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
-    for (int it = 0; tile_at(it) >= 0; ++it) {
+    for (int it = 0; (!pair || crank == 0) && tile_at(it) >= 0; ++it) {      // pair: the leader CTA issues for both
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       if (ws && it == 0) mbar_wait(wfull_bar, 0);
@@ -248,11 +283,19 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
         if (leader) {
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * A_STAGE));
           const uint64_t db = make_sw128_desc(smem_u32(smem_b + (ws ? ki : stage) * b_stage));
+          if (pair) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)          // +32 B per K=16 step inside the swizzle atom
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
-          if (ki == k_iters - 1) umma_commit(tfull_bar(acc));
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(empty_bar(stage));
+            if (ki == k_iters - 1) umma_commit_pair(tfull_bar(acc));
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)          // +32 B per K=16 step inside the swizzle atom
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            if (!ws && p.mc) umma_commit_mc(empty_bar(stage), (unsigned short)3); else umma_commit(empty_bar(stage));
+            if (ki == k_iters - 1) umma_commit(tfull_bar(acc));
+          }
         }
         __syncwarp();
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -266,6 +309,10 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
     // this warp's 32 rows x 32 or 64 columns; rows beyond the batch are clipped by the tensor map); the residual
     // block of the next chunk is prefetched by TMA into a swizzled tile (mbarrier).
     const EpiParams& e = p.epi;
+    // the accumulator is free again: tell the MMA warp (pair: the leader CTA's, through shared::cluster)
+    auto release_acc = [&](int acc_) {
+      if (pair) mbar_arrive_cluster(mapa_rank(tempty_bar(acc_), 0u)); else mbar_arrive(tempty_bar(acc_));
+    };
     const bool ep_leader = elect_one();        // the lane that issues this warp's TMA loads / stores, commits and waits
     const int wi = warp - 4;                     // epilogue warp 0 .. EPI_WARPS - 1
     const int q = wi & 3;                        // TMEM lane quarter (= warp % 4) / 32-row block of the tile
@@ -284,9 +331,9 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
     const int ch0 = team * chunks, ch1 = ch0 + chunks;
     constexpr bool POSTLN = MODE >= 0 && (MODE & 32) != 0;
     constexpr bool HEADDOT = MODE >= 0 && (MODE & 64) != 0;
-    static_assert(!HEADDOT || CFG == 2, "row dot products run in the wide eight-warp configuration");
+    static_assert(!HEADDOT || CFG == 2 || CFG == 3, "row dot products run in the wide eight-warp configuration");
     float* s_dot = reinterpret_cast<float*>(part_smem + 4096);        // HEADDOT: dot_w [dot_n][256]
-    static_assert(!POSTLN || CFG == 2, "the post-residual LayerNorm runs in the wide eight-warp configuration");
+    static_assert(!POSTLN || CFG == 2 || CFG == 3, "the post-residual LayerNorm runs in the wide eight-warp configuration");
     const bool has_ln = MODE < 0 ? (e.ln_w != nullptr) : ((MODE & 1) != 0);
     const bool has_res = MODE < 0 ? (e.residual != nullptr) : ((MODE & 8) != 0);
     const bool has_pe = MODE < 0 ? (e.pe != nullptr) : ((MODE & 16) != 0);
@@ -436,7 +483,7 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
           if (ch + 2 >= ch1) {                     // all TMEM reads of this warp done: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
-            if (ep_leader) mbar_arrive(tempty_bar(acc));
+            if (ep_leader) release_acc(acc);
           }
           unsigned char* tw = t32 + (tsel << 12);
           tsel ^= 1;
@@ -517,7 +564,7 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
           if (ch + 2 >= ch1) {                     // all TMEM reads of this warp done: release the accumulator
             tcgen05_fence_before();
             __syncwarp();
-            if (ep_leader) mbar_arrive(tempty_bar(acc));
+            if (ep_leader) release_acc(acc);
           }
           unsigned char* tw = (store_seq++ & 1) ? trs : t32;
           const f32x2 mk2 = pk2(mk), nmean2 = pk2(-mean), rstd2 = pk2(rstd);
@@ -589,7 +636,7 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
         } else {                                  // all TMEM reads of this warp are issued: once they complete the
           tcgen05_fence_before();                 // MMA warp may overwrite the accumulator
           __syncwarp();
-          if (ep_leader) mbar_arrive(tempty_bar(acc));
+          if (ep_leader) release_acc(acc);
         }
         const int cl = ch * 32;
         {                                         // (acc + bias) * mask -> LayerNorm -> activation
@@ -735,9 +782,11 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();        // no CTA leaves while its peer can still write into its shared memory / barriers / TMEM
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -746,6 +795,11 @@ __global__ void __launch_bounds__(CFG ? WS_THREADS : THREADS, CFG ? 1 : 2) conv_
 static unsigned long long* g_dbg = nullptr;
 static bool g_w8 = !(getenv("AVDF_GEMM_W8") && atoi(getenv("AVDF_GEMM_W8")) == 0);   // wide tiles: eight epilogue warps (0: four)
 static int g_ws_mode = -1;                    // weight-stationary configuration: -1 auto (default), 0 never, 1 wherever it is legal
+// weight multicast between CTA pairs: smallest K (taps * c_in) it is used for; 0 switches it off (AVDF_GEMM_MC)
+// (measured: no gain - these launches are bound by shared-memory bandwidth, not by L2 - so it is off by default)
+static int g_mc_min_k = getenv("AVDF_GEMM_MC") ? atoi(getenv("AVDF_GEMM_MC")) : 0;
+// CTA pairs (cta_group::2) for wide-configuration launches with taps * c_in >= this; 0 switches them off (AVDF_GEMM_PAIR)
+static int g_pair_min_k = getenv("AVDF_GEMM_PAIR") ? atoi(getenv("AVDF_GEMM_PAIR")) : 512;
 
 int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   using namespace tc;
@@ -896,7 +950,8 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
     X(mode_of(false, AVDF_ACT_NONE, true, false), 7) X(mode_of(false, AVDF_ACT_NONE, true, false), 3)           \
     X(MODE_POSTLN, 7) X(MODE_POSTLN, 3) X(MODE_HEADDOT, 0)
 #define AVDF_SET_SMEM_WS(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
-#define AVDF_SET_SMEM_W8(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ((M) >= 0 && ((M) & 64)) ? W8D_SMEM_BYTES : W8_SMEM_BYTES));
+#define AVDF_SET_SMEM_W8(M, O) AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ((M) >= 0 && ((M) & 64)) ? W8D_SMEM_BYTES : W8_SMEM_BYTES)); \
+    AVDF_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<M, O, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ((M) >= 0 && ((M) & 64)) ? W8D_SMEM_BYTES : W8_SMEM_BYTES));
     AVDF_SET_SMEM(-1, -1)
     AVDF_TC_VARIANTS(AVDF_SET_SMEM)
     AVDF_SET_SMEM_WS(-1, -1)
@@ -910,9 +965,34 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   }
   AVDF_CHECK_ARG((long long)a->batch * a->o_rows_per_video * a->n_out < (1ll << 31), "output larger than 2^31 elements");
   const int ctas_per_sm = bn <= 128 ? 2 : 1;      // narrow tiles: two co-resident CTAs per SM
-  const int grid = ws ? ws_groups * ws_per : (p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm);
+  int grid = ws ? ws_groups * ws_per : (p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm);
+  // weight multicast: the launches whose L2 -> SM operand stream is dominated by the weight tile every CTA re-reads (the
+  // K >= 512 convolutions: embedding, video branch, head towers). CTAs 2c, 2c + 1 form a cluster and walk adjacent row tiles
+  // of the SAME n-tile in lock step (m is the fastest tile index: an even number of m-tiles and an even grid keep a pair
+  // inside one n-tile and give both CTAs the same number of tiles).
+  const bool pair = !ws && bn == MAX_BN && g_w8 && g_pair_min_k > 0 && a->taps * a->c_in >= g_pair_min_k && p.n_tiles_m % 2 == 0 && grid >= 2;
+  const bool mc = pair || (!ws && g_mc_min_k > 0 && a->taps * a->c_in >= g_mc_min_k && p.n_tiles_m % 2 == 0 && grid >= 2 && bn % 16 == 0);
+  if (mc) {
+    grid &= ~1;
+    p.mc = pair ? 0 : 1;
+    p.pair = pair ? 1 : 0;
+    if (pair) p.idesc = (p.idesc & ~(0x1fu << 24)) | ((unsigned)((2 * BM) >> 4) << 24);     // M = 256 over the two CTAs
+    cuuint64_t dims[2] = {(cuuint64_t)a->taps * a->c_in, (cuuint64_t)(a->n_w_rows > 0 ? a->n_w_rows : a->n_out)};
+    cuuint64_t strides[1] = {(cuuint64_t)a->taps * a->c_in * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(bn / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&p.w_half_map, tm_dtype, 2, const_cast<void*>(a->w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("avdf_conv_gemm: cuTensorMapEncodeTiled(W half) failed with %d", (int)r); return AVDF_ERR_CUDA; }
+  }
+  int smem_bytes_ = 0;
+  auto go = [&](auto kernel, int threads) {
+    return mc ? launch_pdl_cluster(kernel, grid, threads, smem_bytes_, st, 2, p) : launch_pdl(kernel, grid, threads, smem_bytes_, st, p);
+  };
   const bool w8 = !ws && bn == MAX_BN && g_w8;
   const int smem_bytes = ws ? WS_SMEM_BYTES : (w8 ? (a->dot_out ? W8D_SMEM_BYTES : W8_SMEM_BYTES) : smem_bytes_of(bn));
+  smem_bytes_ = smem_bytes;
   const int mode = mode_of(a->ln_w != nullptr, a->act, a->residual != nullptr, a->pe != nullptr) | (a->ln_after_residual ? 32 : 0) | (a->dot_out ? 64 : 0);
   if (a->dot_out) {
     AVDF_CHECK_ARG(w8 && a->n_out == MAX_BN && a->dot_w && a->dot_n >= 1 && a->dot_n <= MAX_DOTS, "dot_out needs n_out = 256, dot_w and 1 <= dot_n <= 6");
@@ -923,9 +1003,9 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   const int outk = (a->out_f32 ? 1 : 0) | (a->out_h ? 2 : 0) | ((a->out_h && a->out_h_dtype == AVDF_DTYPE_F16) ? 4 : 0);
   bool launched = false;
   cudaError_t lerr = cudaSuccess;
-#define AVDF_LAUNCH(M, O) if (!launched && !ws && !w8 && mode == (M) && outk == (O)) { lerr = launch_pdl(conv_gemm_tc_kernel<M, O>, grid, THREADS, smem_bytes, st, p); launched = true; }
-#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { lerr = launch_pdl(conv_gemm_tc_kernel<M, O, 1>, grid, WS_THREADS, smem_bytes, st, p); launched = true; }
-#define AVDF_LAUNCH_W8(M, O) if (!launched && w8 && mode == (M) && outk == (O)) { lerr = launch_pdl(conv_gemm_tc_kernel<M, O, 2>, grid, WS_THREADS, smem_bytes, st, p); launched = true; }
+#define AVDF_LAUNCH(M, O) if (!launched && !ws && !w8 && mode == (M) && outk == (O)) { lerr = go(conv_gemm_tc_kernel<M, O>, THREADS); launched = true; }
+#define AVDF_LAUNCH_WS(M, O) if (!launched && ws && mode == (M) && outk == (O)) { lerr = go(conv_gemm_tc_kernel<M, O, 1>, WS_THREADS); launched = true; }
+#define AVDF_LAUNCH_W8(M, O) if (!launched && w8 && mode == (M) && outk == (O)) { lerr = pair ? go(conv_gemm_tc_kernel<M, O, 3>, WS_THREADS) : go(conv_gemm_tc_kernel<M, O, 2>, WS_THREADS); launched = true; }
   AVDF_TC_VARIANTS(AVDF_LAUNCH)
   AVDF_TC_WS_VARIANTS(AVDF_LAUNCH_WS)
   AVDF_TC_W8_VARIANTS(AVDF_LAUNCH_W8)
@@ -935,11 +1015,15 @@ int conv_gemm_tc(const avdf_conv_gemm_args* a, cudaStream_t st) {
   if (!launched && a->dot_out) { set_error("avdf_conv_gemm: no dot_out instantiation for this epilogue / output combination"); return AVDF_ERR_UNSUPPORTED; }
   if (!launched && a->ln_after_residual) { set_error("avdf_conv_gemm: no ln_after_residual instantiation for this output combination"); return AVDF_ERR_UNSUPPORTED; }
   if (!launched) {
-    if (ws) lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1, 1>, grid, WS_THREADS, smem_bytes, st, p);
-    else if (w8) lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1, 2>, grid, WS_THREADS, smem_bytes, st, p);
-    else lerr = launch_pdl(conv_gemm_tc_kernel<-1, -1>, grid, THREADS, smem_bytes, st, p);
+    if (ws) lerr = go(conv_gemm_tc_kernel<-1, -1, 1>, WS_THREADS);
+    else if (w8) lerr = pair ? go(conv_gemm_tc_kernel<-1, -1, 3>, WS_THREADS) : go(conv_gemm_tc_kernel<-1, -1, 2>, WS_THREADS);
+    else lerr = go(conv_gemm_tc_kernel<-1, -1>, THREADS);
   }
-  if (lerr != cudaSuccess) { set_error("conv_gemm_tc_kernel: launch failed: %s", cudaGetErrorString(lerr)); return AVDF_ERR_CUDA; }
+  if (lerr != cudaSuccess) {
+    set_error("conv_gemm_tc_kernel: launch failed: %s (grid %d, smem %d, bn %d, ws %d, w8 %d, multicast %d, pair %d)", cudaGetErrorString(lerr), grid,
+              smem_bytes, bn, (int)ws, (int)w8, p.mc, p.pair);
+    return AVDF_ERR_CUDA;
+  }
   return check_launch("conv_gemm_tc_kernel");
 }
 
@@ -955,6 +1039,19 @@ extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_timeline(u
 extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_w8(int on) {
   const int prev = avdf::g_w8 ? 1 : 0;
   avdf::g_w8 = on != 0;
+  return prev;
+}
+// Debug / test hook: weight multicast between CTA pairs for launches with taps * c_in >= min_k (0: never). Returns the
+// previous setting.
+extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_mc(int min_k) {
+  const int prev = avdf::g_mc_min_k;
+  avdf::g_mc_min_k = min_k;
+  return prev;
+}
+// Debug / test hook: CTA pairs (cta_group::2) for wide launches with taps * c_in >= min_k (0: never). Returns the previous setting.
+extern "C" __attribute__((visibility("default"))) int avdf_debug_gemm_pair(int min_k) {
+  const int prev = avdf::g_pair_min_k;
+  avdf::g_pair_min_k = min_k;
   return prev;
 }
 // Debug / test hook: weight-stationary configuration -1 auto (default), 0 never, 1 wherever it is legal. Returns the

@@ -829,3 +829,57 @@ def test_mlp_fused_16bit_copy_into_pyramid_level():
     assert torch.equal(out2, out)
     assert torch.equal(pyr[:, row0:row0 + T].reshape(rows, C), dense)
     assert bool((pyr[:, :row0] == 7.0).all()) and bool((pyr[:, row0 + T:] == 7.0).all())
+
+
+@pytest.mark.parametrize("case", ["towers_k768_ln", "embed_k2304_s1", "down_k1536_s2_n1024", "narrow_k512_n128", "dots_k768", "odd_tiles_fallback"])
+def test_conv_gemm_weight_multicast(case):
+    """CTA pairs on adjacent row tiles of one n-tile, two ways: `pair` = cta_group::2 MMAs (M = 256 over the two SMs, each CTA
+    holds half of every weight tile; the default for K >= 512 in the wide configuration) and `mc` = independent MMAs with the
+    weight tile fetched by TMA multicast (off by default): both bit-identical to the plain launch, and against torch. Many tiles per
+    CTA (several trips around the stage ring), ragged masks, wide / narrow / strided / several n-tiles / row-dot epilogues."""
+    rng = np.random.RandomState(zlib.crc32(case.encode()) & 0xffff)
+    cfg = {"towers_k768_ln": dict(B=160, T=128, cin=256, taps=3, stride=1, nout=256, ln=True, act=ops.ACT_RELU),
+           "embed_k2304_s1": dict(B=40, T=128, cin=768, taps=3, stride=1, nout=256, ln=True, act=ops.ACT_RELU),
+           "down_k1536_s2_n1024": dict(B=12, T=128, cin=512, taps=3, stride=2, nout=1024, ln=False, act=ops.ACT_NONE),
+           "narrow_k512_n128": dict(B=340, T=128, cin=512, taps=1, stride=1, nout=128, ln=False, act=ops.ACT_GELU),
+           "dots_k768": dict(B=10, T=128, cin=256, taps=3, stride=1, nout=256, ln=True, act=ops.ACT_RELU, dots=True),
+           "odd_tiles_fallback": dict(B=7, T=128, cin=256, taps=3, stride=1, nout=256, ln=True, act=ops.ACT_RELU)}[case]
+    B, T, cin, taps, stride, nout = (cfg[k] for k in ("B", "T", "cin", "taps", "stride", "nout"))
+    adt = torch.float16
+    t_in = T * stride
+    x = torch.from_numpy(rng.standard_normal((B, t_in, cin)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((nout, cin, taps)) / math.sqrt(cin * taps)).astype(np.float32))
+    bias = torch.from_numpy(rng.normal(0, 0.3, nout).astype(np.float32))
+    ln = _ln_params(rng, nout) if cfg["ln"] else None
+    valid = rng.randint(T // 2, T + 1, B); valid[0] = T
+    mask = (np.arange(T)[None] < valid[:, None]).astype(np.uint8)
+    wp = w.permute(0, 2, 1).reshape(nout, taps * cin).contiguous()
+    dw = torch.from_numpy(rng.standard_normal((6, nout)).astype(np.float32) / 16) if cfg.get("dots") else None
+    L = nv.lib()
+    outs = {}
+    prev = (L.avdf_debug_gemm_mc(0), L.avdf_debug_gemm_pair(0))
+    try:
+        for key, (mc, pair) in {"pair": (0, 512), 512: (512, 0), 0: (0, 0)}.items():
+            L.avdf_debug_gemm_mc(mc); L.avdf_debug_gemm_pair(pair)
+            o32 = torch.full((B, T, nout), float("nan"), device=DEV)
+            o16 = torch.zeros((B, T, nout), dtype=adt, device=DEV)
+            d = torch.full((B, T, 6), float("nan"), device=DEV) if dw is not None else None
+            kw = dict(out_f32=o32, out_h=o16) if dw is None else dict(dots=(dev(dw), d))
+            ops.conv_gemm(dev(x, adt), dev(wp, adt), taps=taps, stride=stride, batch=B, c_in=cin, n_out=nout, segs=[(T, 0, 0)], a_rows=t_in,
+                          o_rows=T, bias=dev(bias), row_mask=dev(mask), ln=None if ln is None else (dev(ln[0]), dev(ln[1])), act=cfg["act"], **kw)
+            torch.cuda.synchronize()
+            outs[key] = (o32.cpu(), o16.float().cpu(), None if d is None else d.cpu())
+    finally:
+        L.avdf_debug_gemm_mc(prev[0]); L.avdf_debug_gemm_pair(prev[1])
+    xq, wq = x.to(adt).float(), w.to(adt).float()
+    y = F.conv1d(xq.transpose(1, 2), wq, bias, stride=stride, padding=taps // 2).transpose(1, 2) * torch.from_numpy(mask).float()[..., None]
+    if ln is not None:
+        y = F.layer_norm(y, (nout,), ln[0], ln[1], 1e-5)
+    y = F.relu(y) if cfg["act"] == ops.ACT_RELU else (model_ref.gelu_erf(y) if cfg["act"] == ops.ACT_GELU else y)
+    if dw is None:
+        assert rel_err(outs[512][0], y) < 2e-4 and rel_err(outs[512][1], y) < 2e-3
+        for key in (512, "pair"):
+            assert torch.equal(outs[key][0], outs[0][0]) and torch.equal(outs[key][1], outs[0][1]), key
+    else:
+        assert rel_err(outs[512][2], torch.einsum("btn,jn->btj", y, dw)) < 2e-4
+        assert torch.equal(outs[512][2], outs[0][2]) and torch.equal(outs["pair"][2], outs[0][2])
