@@ -49,7 +49,11 @@ __global__ void __launch_bounds__(256) logmel_kernel(const LogMelParams p) {
   }
   const int f0 = fo + j2;                                      // row of frame A in lms
   const int f_end = fo + nfr;
-  for (int n = tid; n < FFT_N; n += 256) {
+  // first radix-4 pass straight from global memory (all its twiddles are 1): thread i owns samples i, i + 256, i + 512, i + 768
+  float2 x4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = tid + j * (FFT_N / 4);
     const float w = __ldg(p.window + n);
     float v[2];
 #pragma unroll
@@ -62,12 +66,22 @@ __global__ void __launch_bounds__(256) logmel_kernel(const LogMelParams p) {
         v[h] = __ldg(src[h] + i) * w;
       }
     }
-    buf[0][n] = make_float2(v[0], v[1]);
+    x4[j] = make_float2(v[0], v[1]);
+  }
+  {
+    const float2 t0 = make_float2(x4[0].x + x4[2].x, x4[0].y + x4[2].y), t1 = make_float2(x4[0].x - x4[2].x, x4[0].y - x4[2].y);
+    const float2 t2 = make_float2(x4[1].x + x4[3].x, x4[1].y + x4[3].y);
+    const float2 t3 = make_float2(x4[1].y - x4[3].y, x4[3].x - x4[1].x);           // -i (x1 - x3)
+    const int o = tid << 2;
+    buf[0][o] = make_float2(t0.x + t2.x, t0.y + t2.y);
+    buf[0][o + 1] = make_float2(t1.x + t3.x, t1.y + t3.y);
+    buf[0][o + 2] = make_float2(t0.x - t2.x, t0.y - t2.y);
+    buf[0][o + 3] = make_float2(t1.x - t3.x, t1.y - t3.y);
   }
   __syncthreads();
   int cur = 0;
 #pragma unroll 1
-  for (int s = 1, sh = 8; s < FFT_N; s <<= 2, sh -= 2) {     // radix 4: thread = one butterfly; w = table[k * (256 / s)]
+  for (int s = 4, sh = 6; s < FFT_N; s <<= 2, sh -= 2) {     // radix 4: thread = one butterfly; w = table[k * (256 / s)]
     const int i = tid;
     const int k = i & (s - 1);
     const int tb = k << sh;

@@ -345,3 +345,33 @@ def test_result_record_ring():
         assert torch.equal(row[3:3 + n], w["scores"]) and torch.equal(row[3 + K:3 + K + 2 * n].reshape(n, 2), w["segments"])
         assert float(row[2]) == float(w["video_cls"][0])
         assert float(row[3 + n:3 + K].abs().sum()) == 0.0
+
+
+def test_model_on_second_device_matches_first():
+    """`devices: ['cuda:1']` (what the reference yaml ships is a non-zero ordinal): every launch, tensor map, stream and the
+    per-device kernel attributes follow the MODEL's device, not the process' current one - same records as on cuda:0, with
+    cuda:0 left current on the calling thread; the BYOL-A extractor likewise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    assert torch.cuda.current_device() == 0
+    durs = [4.03, 9.04, 7.42]
+    raw = [{"video_id": f"vid{i}", "duration": d, "streams": syn.synthetic_streams(d, 300 + i)} for i, d in enumerate(durs)]
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        model_name, overrides, _, wseed = MODEL_CASES["exp12"]
+        cfg = load_config_for(model_name, dict(overrides))
+        model = make_meta_arch(cfg["model_name"], **cfg["model"], precision="mixed", max_batch=4)
+        model.load_state_dict(syn.synthetic_state_dict(cfg["model"], model_name, seed=wseed))
+        model.to(dev).eval()
+        outs.append(model.forward_streams(raw))
+        assert torch.cuda.current_device() == 0
+    for a, b in zip(*outs):
+        assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["segments"], b["segments"]) and torch.equal(a["video_cls"], b["video_cls"])
+    from audio_visual_deepfake_detection_b200.libs.features import AudioNTT2020Task6
+    wavs = [syn.synthetic_wav(16000 * 2 + 77, 5), syn.synthetic_wav(16000 + 999, 6)]
+    feats = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = AudioNTT2020Task6().load_state_dict(syn.synthetic_byola_state_dict(0)).to(dev).eval()
+        feats.append([f.cpu() for f in m.extract(wavs)])
+    for a, b in zip(*feats):
+        assert torch.equal(a, b)
