@@ -291,10 +291,16 @@ __device__ __forceinline__ float rsqrt_fast(float x) {      // MUFU.RSQ, 2 ulp; 
 // therefore works on LDL2_PA source rows (phase A) and LDL2_RPI<STRIDE> output rows (phase B) at once, their chains
 // interleaved by the unrolled loops.
 constexpr int LDL2_PA = 3;
-template <int STRIDE> __host__ __device__ constexpr int ldl2_rpi() { return STRIDE == 1 ? 4 : 2; }
+#ifndef AVDF_LDL2_RPI1
+#define AVDF_LDL2_RPI1 4
+#endif
+#ifndef AVDF_LDL2_MINB
+#define AVDF_LDL2_MINB 2
+#endif
+template <int STRIDE> __host__ __device__ constexpr int ldl2_rpi() { return STRIDE == 1 ? AVDF_LDL2_RPI1 : 2; }
 
 template <typename OutT, int STRIDE, int NS, bool SKIP>
-__global__ void __launch_bounds__(LDL2_WARPS * 32, 2) ln_dwconv_ln2_kernel(const LdlParams p) {
+__global__ void __launch_bounds__(LDL2_WARPS * 32, AVDF_LDL2_MINB) ln_dwconv_ln2_kernel(const LdlParams p) {
   pdl_trigger();                 // the projection GEMM that follows may start its prologue now (it waits for this grid)
   constexpr int SRC = ldl2_src_rows<STRIDE>();
   constexpr int RPI = ldl2_rpi<STRIDE>();

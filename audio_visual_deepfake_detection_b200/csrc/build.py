@@ -22,7 +22,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # nms.cu restates g++-compiled float code: no fused multiply-add contraction, IEEE div/sqrt
-PER_FILE = {"nms.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"], "gemm_tc.cu": (["-DAVDF_GEMM_TIMELINE"] if os.environ.get("AVDF_GEMM_TIMELINE") else [])}
+PER_FILE = {"nms.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"], "gemm_tc.cu": (["-DAVDF_GEMM_TIMELINE"] if os.environ.get("AVDF_GEMM_TIMELINE") else []),
+            "blocks.cu": os.environ.get("AVDF_BLOCKS_FLAGS", "").split()}
 
 
 def nvcc():

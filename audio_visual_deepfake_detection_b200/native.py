@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libavdf_sm100.so")
+LIB_PATH = os.environ.get("AVDF_LIB_PATH") or os.path.join(HERE, "csrc", "libavdf_sm100.so")      # (override: kernel experiments)
 
 MAX_LEVELS = 8
 MAX_SEGS = 1024

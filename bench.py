@@ -583,6 +583,21 @@ def measure_workload(args, workload, steps, rank, world, local, dist, full):
         for nm, kv in kernels.items():                 # HBM-roofline fraction of the memory-bound kernels (algorithmic bytes)
             if kv["gbs"] and not kv["tflops"]:
                 kv["hbm_frac"] = kv["gbs"] / peak_gbs
+        # the same fraction on each kernel's LARGEST launch (the level-0 / T = 768 one): the small pyramid levels (12 MB and
+        # less per launch) are bound by launch latency, not by a roofline, and pull the all-launch figure down
+        big = {}
+        for nm, work, a, b in ops.Profile.records:
+            key = max(work.get("flops", 0.0) / (peak_tf * 1e12), work.get("bytes", 0.0) / (peak_gbs * 1e9))
+            if key > 0:
+                cur = big.setdefault(nm, {"roof_s": key, "ms": []})
+                if key > cur["roof_s"] * 1.001:
+                    cur["roof_s"], cur["ms"] = key, []
+                if key > cur["roof_s"] * 0.999:
+                    cur["ms"].append(a.elapsed_time(b))
+        for nm, v in big.items():
+            if nm in kernels and v["ms"]:
+                med = sorted(v["ms"])[len(v["ms"]) // 2]
+                kernels[nm]["largest_launch"] = {"us": 1000.0 * med, "roofline_frac": v["roof_s"] * 1e3 / med}
         traffic = None
         try:        # DRAM bytes per launch of the GEMM kernel from the committed ncu pass (profiles/), not measured live
             tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))["kernels"]["tc::conv_gemm_tc_kernel"]
