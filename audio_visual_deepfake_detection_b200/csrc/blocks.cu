@@ -286,11 +286,19 @@ __device__ __forceinline__ float rsqrt_fast(float x) {      // MUFU.RSQ, 2 ulp; 
   return r;
 }
 
+// (Measured and dropped: a persistent form with the next tile's raw rows prefetched by cp.async into a shared-memory double
+// buffer - 26.1 against 25.5 us per level-0 launch: an iteration takes as long as a whole one-tile CTA, the global loads were
+// not what the warps wait for. The kernel runs at 0.33 instructions per cycle and scheduler with 3 warps per scheduler: every
+// warp issues once in ~8 cycles - dependent FMA2 / shuffle / LDS chains - and the register file (150 per thread) caps both the
+// warps per SM and the rows a warp can interleave: 2, 3 CTAs per SM x 2, 4 rows per iteration all land on 25-27 us.)
 // Both phases are chains of dependent instructions per row (load -> sums -> 5 butterfly steps -> rsqrt -> scale), ~16
 // cycles from issue to issue (ncu: 0.28 warp instructions per cycle and scheduler with 4.5 resident warps): every warp
 // therefore works on LDL2_PA source rows (phase A) and LDL2_RPI<STRIDE> output rows (phase B) at once, their chains
 // interleaved by the unrolled loops.
-constexpr int LDL2_PA = 3;
+#ifndef AVDF_LDL2_PA
+#define AVDF_LDL2_PA 6
+#endif
+constexpr int LDL2_PA = AVDF_LDL2_PA;      // (6: every warp's source rows of a stride-1 tile are one round of loads - one exposed latency instead of two)
 #ifndef AVDF_LDL2_RPI1
 #define AVDF_LDL2_RPI1 4
 #endif
@@ -317,10 +325,47 @@ __global__ void __launch_bounds__(LDL2_WARPS * 32, AVDF_LDL2_MINB) ln_dwconv_ln2
   const float* src_b = p.src + (size_t)b * p.t_src * kC;
   const int pos_first = STRIDE * t0 - 1, pos_last = STRIDE * (t1 - 1) + 1;
   const f32x2 zero2 = pk2(0.f);
-  for (int i = threadIdx.x; i < NS * kC; i += LDL2_WARPS * 32) {
-    const int s = i / kC, c = i - s * kC;
-    const float bb = p.ln_in_b[s][c];
-    eb[s][0][c] = p.dw_w[s][3 * c] * bb; eb[s][1][c] = p.dw_w[s][3 * c + 1] * bb; eb[s][2][c] = p.dw_w[s][3 * c + 2] * bb;
+  // the tile's mask bytes, one per lane
+  unsigned tile_mask = 0xffffffffu;
+  if (p.mask_out) {
+    const bool mbit = (t0 + lane < t1) ? (p.mask_out[(size_t)b * p.t_out + t0 + lane] != 0) : true;
+    tile_mask = __ballot_sync(0xffffffffu, mbit);
+  }
+  // Interior tiles (a full tile, no tap outside the sequence, no masked row - all but the first and last tile of a video
+  // when the masks are all-true, i.e. always under force_upsampling) take the phase-B loop with every edge test compiled out:
+  // the tests, the zero fills and the divergence bookkeeping they drag in were ~25 % of the executed instructions
+  // (ncu source page: ISETP 8 %, CS2R 7 %, BRA / BSSY / BSYNC 7.6 %). Same arithmetic, same order: bit-identical results.
+  // They also never read the per-tap bias table, so only edge tiles build it (768 x NS entries from global memory: ~1 us of
+  // exposed latency at the head of every CTA).
+  const bool interior = (t1 - t0) == LDL2_ROWS && pos_first >= 0 && pos_last < p.t_virt && tile_mask == 0xffffffffu;
+  if (!interior) {
+    for (int i = threadIdx.x; i < NS * kC; i += LDL2_WARPS * 32) {
+      const int s = i / kC, c = i - s * kC;
+      const float bb = p.ln_in_b[s][c];
+      eb[s][0][c] = p.dw_w[s][3 * c] * bb; eb[s][1][c] = p.dw_w[s][3 * c + 1] * bb; eb[s][2][c] = p.dw_w[s][3 * c + 2] * bb;
+    }
+  }
+  // the constants of this warp's phase-B stream, in registers for the whole slice: fetched HERE so that their latency overlaps
+  // phase A's loads instead of following them
+  constexpr int WPS = LDL2_WARPS / NS;          // warps per stream
+  const int s = warp / WPS, part = warp - s * WPS;
+  f32x2 A0[4], A1[4], A2[4], Bs[4], Wo[4], Bo[4];
+  {
+    const float* wi = p.ln_in_w[s]; const float* bi = p.ln_in_b[s]; const float* dw = p.dw_w[s];
+    const float* wo = p.ln_out_w[s]; const float* bo = p.ln_out_b[s];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = (k < 2 ? 0 : 128) + 4 * lane + 2 * (k & 1);
+      float a0[2], a1[2], a2[2], bs[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float w = __ldg(wi + c + e), bb = __ldg(bi + c + e);
+        const float d0 = __ldg(dw + 3 * (c + e)), d1 = __ldg(dw + 3 * (c + e) + 1), d2 = __ldg(dw + 3 * (c + e) + 2);
+        a0[e] = d0 * w; a1[e] = d1 * w; a2[e] = d2 * w; bs[e] = d0 * bb + d1 * bb + d2 * bb;
+      }
+      A0[k] = pk2(a0[0], a0[1]); A1[k] = pk2(a1[0], a1[1]); A2[k] = pk2(a2[0], a2[1]); Bs[k] = pk2(bs[0], bs[1]);
+      Wo[k] = pk2(__ldg(wo + c), __ldg(wo + c + 1)); Bo[k] = pk2(__ldg(bo + c), __ldg(bo + c + 1));
+    }
   }
   // ---- phase A: normalise every source position of the tile once
   for (int base = pos_first + warp; base <= pos_last; base += LDL2_WARPS * LDL2_PA) {
@@ -376,43 +421,12 @@ __global__ void __launch_bounds__(LDL2_WARPS * 32, AVDF_LDL2_MINB) ln_dwconv_ln2
       }
     }
   }
-  // the tile's mask bytes, one per lane
-  unsigned tile_mask = 0xffffffffu;
-  if (p.mask_out) {
-    const bool mbit = (t0 + lane < t1) ? (p.mask_out[(size_t)b * p.t_out + t0 + lane] != 0) : true;
-    tile_mask = __ballot_sync(0xffffffffu, mbit);
-  }
-  // ---- phase B: this warp's stream and row slice; the stream's constants in registers
-  constexpr int WPS = LDL2_WARPS / NS;          // warps per stream
-  const int s = warp / WPS, part = warp - s * WPS;
-  f32x2 A0[4], A1[4], A2[4], Bs[4], Wo[4], Bo[4];
-  {
-    const float* wi = p.ln_in_w[s]; const float* bi = p.ln_in_b[s]; const float* dw = p.dw_w[s];
-    const float* wo = p.ln_out_w[s]; const float* bo = p.ln_out_b[s];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = (k < 2 ? 0 : 128) + 4 * lane + 2 * (k & 1);
-      float a0[2], a1[2], a2[2], bs[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float w = __ldg(wi + c + e), bb = __ldg(bi + c + e);
-        const float d0 = __ldg(dw + 3 * (c + e)), d1 = __ldg(dw + 3 * (c + e) + 1), d2 = __ldg(dw + 3 * (c + e) + 2);
-        a0[e] = d0 * w; a1[e] = d1 * w; a2[e] = d2 * w; bs[e] = d0 * bb + d1 * bb + d2 * bb;
-      }
-      A0[k] = pk2(a0[0], a0[1]); A1[k] = pk2(a1[0], a1[1]); A2[k] = pk2(a2[0], a2[1]); Bs[k] = pk2(bs[0], bs[1]);
-      Wo[k] = pk2(__ldg(wo + c), __ldg(wo + c + 1)); Bo[k] = pk2(__ldg(bo + c), __ldg(bo + c + 1));
-    }
-  }
+  // ---- phase B: this warp's stream and row slice (its constants were fetched above)
   __syncthreads();
   const int n_rows = t1 - t0;
   const int per = ((n_rows + WPS - 1) / WPS + RPI - 1) / RPI * RPI;      // rows per warp, a multiple of RPI
   const int ra = t0 + part * per, rb = min(ra + per, t1);
   OutT* out_s = reinterpret_cast<OutT*>(p.out[s]);
-  // Interior tiles (a full tile, no tap outside the sequence, no masked row - all but the first and last tile of a video
-  // when the masks are all-true, i.e. always under force_upsampling) take the same loop with every edge test compiled out:
-  // the tests, the zero fills and the divergence bookkeeping they drag in were ~25 % of the executed instructions
-  // (ncu source page: ISETP 8 %, CS2R 7 %, BRA / BSSY / BSYNC 7.6 %). Same arithmetic, same order: bit-identical results.
-  const bool interior = n_rows == LDL2_ROWS && pos_first >= 0 && pos_last < p.t_virt && tile_mask == 0xffffffffu;
   auto phase_b = [&](auto fast_tag) {
   constexpr bool FAST = decltype(fast_tag)::value;
   for (int tb = ra; tb < rb; tb += RPI) {
