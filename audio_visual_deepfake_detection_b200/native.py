@@ -144,7 +144,7 @@ def lib():
         if name not in ("avdf_last_error", "avdf_nms_workspace_bytes", "avdf_postprocess_workspace_bytes",
                         "avdf_conv_gemm_workspace_bytes", "avdf_abi_version"):
             fn.restype = c_int32
-    if L.avdf_abi_version() != 2:
+    if L.avdf_abi_version() != 3:
         raise AvdfError("libavdf_sm100.so ABI version mismatch")
     _lib = L
     return L

@@ -56,7 +56,8 @@ extern "C" {
 #define AVDF_API
 #endif
 
-#define AVDF_ABI_VERSION 2
+/* 3: avdf_conv_gemm_args grew (dot_w / dot_n / dot_out, tap_rows); avdf_head_combine, avdf_logmel, avdf_byola_* added */
+#define AVDF_ABI_VERSION 3
 #define AVDF_MAX_LEVELS 8
 #define AVDF_MAX_SEGS 1024
 

@@ -33,7 +33,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(native.EXPORTS) == syms
-    assert native.lib().avdf_abi_version() == 2
+    assert native.lib().avdf_abi_version() == 3
 
 
 def test_argument_errors_are_codes_not_crashes():
