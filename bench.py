@@ -43,7 +43,7 @@ WORKLOADS = {
     "av5": ("exp5", {}, "video+emo", "audio-visual exp5-style localization with the live reconstruction branch (1024 ch), batch 32"),
 }
 BATCH = 32
-TRAFFIC_FILE = "r2_n_step_traffic.json"    # per-kernel DRAM bytes of one pass (ncu pass, see profiles/README.md)
+TRAFFIC_FILE = "r2_o_step_traffic.json"    # per-kernel DRAM bytes of one pass (ncu pass, see profiles/README.md)
 PIPE_FILE = "r2_n_tensor_pipe.json"          # sm__pipe_tensor_cycles_active per kernel from the committed ncu --set full page
 N_POOL = 8              # distinct resident input batches rotated through the timed region (8 x ~75 MB > 126 MB L2)
 
