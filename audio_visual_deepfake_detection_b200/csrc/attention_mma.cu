@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(AM_WARPS * 32) attention_banded_mma_kernel(con
                                                                             const InT* __restrict__ v, const unsigned char* __restrict__ kv_mask,
                                                                             OutT* __restrict__ out, int B, int T, int RPV) {
   pdl_trigger();                 // the output-projection GEMM may start its prologue now (it waits for this grid)
+  pdl_wait();                    // launched as a programmatic dependent of the q/k/v GEMM: its CTAs are placed while that grid drains
   constexpr bool BF16 = std::is_same<InT, __nv_bfloat16>::value;
   constexpr int HALF = 3;
   constexpr int AM_ROWS = 16 * AM_WARPS, AM_KEYS = AM_ROWS + 16;
@@ -228,8 +229,9 @@ int attention_banded_mma(const void* q, const void* k, const void* v, const unsi
 #define AVDF_AM_W(InT, W)                                                                                                  \
   AVDF_DISPATCH_DTYPE(out_dtype, OutT, {                                                                                   \
     AVDF_SMEM_ATTR_ONCE((attention_banded_mma_kernel<InT, OutT, W>), 2 * (64 + 16) * AM_PITCH);                            \
-    attention_banded_mma_kernel<InT, OutT, W><<<grid, W * 32, smem, st>>>((const InT*)q, (const InT*)k, (const InT*)v, kv_mask, \
-                                                                             (OutT*)out, batch, t, rpv);                  \
+    cudaError_t le_ = launch_pdl(attention_banded_mma_kernel<InT, OutT, W>, grid, W * 32, smem, st, (const InT*)q, (const InT*)k,   \
+                                 (const InT*)v, kv_mask, (OutT*)out, batch, t, rpv);                                       \
+    if (le_ != cudaSuccess) { set_error("attention_banded_mma_kernel: launch failed: %s", cudaGetErrorString(le_)); return AVDF_ERR_CUDA; } \
   })
   if (in_dtype == AVDF_DTYPE_F16) AVDF_AM(__half); else AVDF_AM(__nv_bfloat16);
 #undef AVDF_AM

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(LDL_WARPS * 32, 3) ln_dwconv_ln_kernel(const L
     sp[s][3][c] = d0 * bb + d1 * bb + d2 * bb;
     sp[s][7][c] = p.ln_out_w[s][c]; sp[s][8][c] = p.ln_out_b[s][c];
   }
+  pdl_wait();                    // launched as a programmatic dependent: everything above (weights only) overlapped the previous kernel's tail
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = p.rows;
@@ -367,6 +368,9 @@ __global__ void __launch_bounds__(LDL2_WARPS * 32, AVDF_LDL2_MINB) ln_dwconv_ln2
       Wo[k] = pk2(__ldg(wo + c), __ldg(wo + c + 1)); Bo[k] = pk2(__ldg(bo + c), __ldg(bo + c + 1));
     }
   }
+  // launched as a programmatic dependent of the kernel that wrote `src`: the mask bytes, the bias table and the stream constants
+  // above are weights / host-written tables and were fetched while that kernel was still draining
+  pdl_wait();
   // ---- phase A: normalise every source position of the tile once
   for (int base = pos_first + warp; base <= pos_last; base += LDL2_WARPS * LDL2_PA) {
     f32x2 nxt[LDL2_PA][4];
@@ -1298,7 +1302,7 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, {                                                                          \
     const size_t smem = (size_t)(ldl2_src_rows<S>() * (SK ? 2 : 1) + NS * 3) * kC * sizeof(float);                   \
     AVDF_SMEM_ATTR_ONCE((ln_dwconv_ln2_kernel<OutT, S, NS, SK>), smem);                                              \
-    ln_dwconv_ln2_kernel<OutT, S, NS, SK><<<grid2, LDL2_WARPS * 32, smem, st>>>(p);                                  \
+    { cudaError_t le_ = launch_pdl(ln_dwconv_ln2_kernel<OutT, S, NS, SK>, grid2, LDL2_WARPS * 32, smem, st, p); if (le_ != cudaSuccess) { set_error("ln_dwconv_ln2_kernel: launch failed: %s", cudaGetErrorString(le_)); return AVDF_ERR_CUDA; } } \
   })
     if (a->stride == 1) { if (a->n_streams == 1) AVDF_LDL2(1, 1, false); else if (a->n_streams == 2) AVDF_LDL2(1, 2, false); else AVDF_LDL2(1, 3, false); }
     else if (a->skip_out) { if (a->n_streams == 1) AVDF_LDL2(2, 1, true); else if (a->n_streams == 2) AVDF_LDL2(2, 2, true); else AVDF_LDL2(2, 3, true); }
@@ -1321,7 +1325,7 @@ extern "C" int avdf_ln_dwconv_ln(const avdf_ln_dwconv_ln_args* a, void* stream) 
   AVDF_DISPATCH_DTYPE(a->out_dtype, OutT, {                                                                          \
     const size_t smem = (size_t)(NS * 9 + LDL_WARPS * LDL_DEPTH) * kC * sizeof(float);                               \
     AVDF_SMEM_ATTR_ONCE((ln_dwconv_ln_kernel<OutT, S, NS>), smem);                                                   \
-    ln_dwconv_ln_kernel<OutT, S, NS><<<grid, LDL_WARPS * 32, smem, st>>>(p);                                         \
+    { cudaError_t le_ = launch_pdl(ln_dwconv_ln_kernel<OutT, S, NS>, grid, LDL_WARPS * 32, smem, st, p); if (le_ != cudaSuccess) { set_error("ln_dwconv_ln_kernel: launch failed: %s", cudaGetErrorString(le_)); return AVDF_ERR_CUDA; } } \
   })
   if (a->stride == 1) { if (a->n_streams == 1) AVDF_LDL(1, 1); else if (a->n_streams == 2) AVDF_LDL(1, 2); else AVDF_LDL(1, 3); }
   else { if (a->n_streams == 1) AVDF_LDL(2, 1); else if (a->n_streams == 2) AVDF_LDL(2, 2); else AVDF_LDL(2, 3); }
