@@ -807,8 +807,17 @@ static int launch_standalone(const float* segs, const float* scores, int32_t n, 
     attr[0].val.clusterDim.x = NMS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     // a device (or partition) that cannot co-schedule NMS_CL such CTAs in one cluster takes the single-CTA path below
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, nms_cluster_kernel, &cfg) != cudaSuccess) { max_clusters = 0; (void)cudaGetLastError(); }
+    // (asked once per device, for the largest slice: the query is a host-side driver call of its own)
+    static int cluster_ok[64];              // 0 unknown, 1 yes, -1 no
+    int max_clusters = dev >= 0 && dev < 64 ? cluster_ok[dev] : 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t probe = cfg;
+      probe.dynamicSmemBytes = (size_t)NMS_CL_SLICE_MAX * 5 * sizeof(float);
+      int n_cl = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_cl, nms_cluster_kernel, &probe) != cudaSuccess) { n_cl = 0; (void)cudaGetLastError(); }
+      max_clusters = n_cl >= 1 ? 1 : -1;
+      if (dev >= 0 && dev < 64) cluster_ok[dev] = max_clusters;
+    }
     if (max_clusters >= 1) {
       const cudaError_t e = cudaLaunchKernelEx(&cfg, nms_cluster_kernel, segs, scores, (int)n, S, thr, sigma, min_score, method, (int)max_num,
                                                dets, reinterpret_cast<long long*>(out_idx), out_count, reinterpret_cast<int*>(ws));
