@@ -63,7 +63,6 @@ class BatchPlan:
         self.n_clips = len(frames)
         self.frames = frames
         self.t = [[f >> l for f in self.frames] for l in range(4)]          # time steps of a clip at pooling level l
-        ints = []
 
         def grid(tl):                 # one zero step in front of every clip and behind the last; steps padded to 64
             steps = _pad_to(1 + sum(t + 1 for t in tl), 64)
