@@ -142,9 +142,9 @@ def test_edge_cases():
 
 
 def test_extractor_feeds_the_localization_model():
-    """The extractor's output IS the model's BYOL-A stream (deepfake_video_audio.py:451-479): wav -> features -> interp /
-    concat -> localization model, all on the device; the segments equal those from the same features read back as .npy-style
-    host arrays."""
+    """The extractor's output IS the model's BYOL-A stream (deepfake_video_audio.py:451-479: the `.npy` the dataset loads and
+    truncates): wav -> GPU extractor -> raw-stream entry point of the localization model. The same pipeline fed with the CPU
+    oracle's features gives the same video-level logit to within the 16-bit operand noise."""
     from audio_visual_deepfake_detection_b200.libs.core import load_config_for
     from audio_visual_deepfake_detection_b200.libs.modeling import EXP12, make_meta_arch
     cfg = load_config_for(EXP12, {"dataset.video_input_dim": 0, "test_cfg.nms_method": "soft"})
@@ -165,3 +165,13 @@ def test_extractor_feeds_the_localization_model():
     out = model.forward_streams(raw)
     assert len(out) == 2 and all(o["segments"].shape[1] == 2 for o in out)
     assert all(np.isfinite(np.asarray(o["scores"])).all() for o in out)
+    sd = syn.synthetic_byola_state_dict(int(GOLD["weight_seed"]))
+    raw_ref = []
+    for r, w in zip(raw, wavs):
+        st = dict(r["streams"])
+        st["byola"] = byola_ref.extract(w, sd)[:st["byola"].shape[0]]
+        raw_ref.append(dict(r, streams=st))
+    out_ref = model.forward_streams(raw_ref)
+    for a, b in zip(out, out_ref):
+        va, vb = float(np.asarray(a["video_cls"]).reshape(-1)[0]), float(np.asarray(b["video_cls"]).reshape(-1)[0])
+        assert abs(va - vb) < 2e-2 * max(1.0, abs(vb)), (va, vb)
